@@ -1,0 +1,195 @@
+/* qlb200.h -- C ABI of the B200-native block-sparse contraction path.
+ *
+ * Drop-in boundary for ONE path of QuantumLiquids/TensorToolkit: qlten::Contract on
+ * block-sparse symmetric tensors.  The reference has no FFI of its own (header-only C++
+ * templates, backends chosen by macros), so the entry points below are cut at the seam the
+ * reference itself draws between "block metadata" and "raw data":
+ *
+ *   qlb200_match            replaces BlockSparseDataTensor::DataBlkGenForTenCtrct
+ *                           (include/qlten/qltensor/blk_spar_data_ten/data_blk_operations.h:411-578)
+ *                           + TenCtrctGenSavedAxesSet (:268-296) + TenCtrctNeedTransCheck
+ *                           (include/qlten/tensor_manipulation/ten_ctrct.h:396-443)
+ *                           + FermionExchangeSignForCtrct (data_blk_operations.h:351-401)
+ *                           + DataBlksOffsetRefresh (:137-145)
+ *   qlb200_task (struct)    replaces RawDataCtrctTask
+ *                           (include/qlten/qltensor/blk_spar_data_ten/raw_data_operation_tasks.h:196-270)
+ *   qlb200_plan_* / qlb200_execute
+ *                           replace BlockSparseDataTensor::CtrctTwoBSDTAndAssignIn
+ *                           (include/qlten/qltensor/blk_spar_data_ten/global_operations.h:895-992),
+ *                           i.e. every hp_numeric::TensorTranspose (framework/hp_numeric/ten_trans.h:94-114
+ *                           HPTT, :245-349 cuTENSOR) and hp_numeric::MatMultiply
+ *                           (framework/hp_numeric/blas_level3.h:35-108 CBLAS, :798-981 cuBLAS) call of a
+ *                           contraction, in two kernel launches (batched permute + grouped GEMM).
+ *   qlb200_transpose_*      replaces BlockSparseDataTensor::Transpose raw-data part
+ *                           (global_operations.h:393-441, raw_data_operations.h:201-218).
+ *   qlb200_estimate_cost    replaces EstimateContractCost
+ *                           (include/qlten/tensor_manipulation/tensor_op_cost.h:467-516).
+ *
+ * Plain C types only; every array argument is caller-owned and read during the call only.
+ * All functions return QLB200_OK (0) or a negative error code; qlb200_last_error() gives text.
+ * There is NO CPU fallback: execute functions fail with QLB200_ERR_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef QLB200_H
+#define QLB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QLB200_MAX_RANK 8
+
+enum {
+  QLB200_OK = 0,
+  QLB200_ERR_ARG = -1,      /* precondition violated (the reference only assert()s these) */
+  QLB200_ERR_CUDA = -2,     /* CUDA runtime error / no device */
+  QLB200_ERR_NOMEM = -3,
+  QLB200_ERR_UNSUPPORTED = -4
+};
+
+enum { QLB200_F64 = 0, QLB200_C64 = 1 };               /* double, complex double (interleaved re,im) */
+enum { QLB200_MEM_HOST = 0, QLB200_MEM_DEVICE = 1 };   /* where A/B/C raw buffers live */
+enum { QLB200_DIR_IN = -1, QLB200_DIR_OUT = 1 };       /* TenIndexDirType, qltensor/index.h:34-38 */
+
+/* Block "shell" of one BlockSparseDataTensor: everything the matcher reads, nothing it does not.
+ * Blocks are listed in ascending blk_idx order (std::map order, blk_spar_data_ten.h:459) where
+ * blk_idx = row-major index of blk_coors over nsct (blk_spar_data_ten.h:380-382); data offsets are
+ * the prefix sums of block sizes in that order (data_blk_operations.h:137-145). */
+typedef struct qlb200_shell {
+  int32_t rank;              /* number of indexes, 1..QLB200_MAX_RANK */
+  const uint32_t *nsct;      /* [rank]   sectors per index (BSDT blk_shape) */
+  const uint32_t *deg;       /* [sum nsct] degeneracy of every sector, index-major */
+  const uint8_t *parity;     /* [sum nsct] 1 = odd fermion parity; NULL for bosonic QN types */
+  const int8_t *dir;         /* [rank]   QLB200_DIR_IN / QLB200_DIR_OUT (only read when parity!=NULL) */
+  uint64_t nblk;             /* stored blocks */
+  const uint32_t *blk_coors; /* [nblk*rank] sector coordinates of each stored block */
+} qlb200_shell;
+
+/* One matched block pair == one GEMM.  Field meaning follows RawDataCtrctTask. Offsets are in
+ * elements into the raw buffers of A, B and C. */
+typedef struct qlb200_task {
+  uint64_t a_blk_idx, b_blk_idx, c_blk_idx;
+  uint64_t a_off, b_off, c_off;
+  uint32_t a_ord, b_ord, c_ord; /* ordinal of the block in its tensor's ascending-blk_idx list */
+  uint32_t m, k, n;
+  int8_t sign;                  /* fermion exchange sign, +1 / -1 (f_ex_sign) */
+  uint8_t first;                /* 1 = this pair creates the C block (beta = 0) */
+  uint8_t pad_[2];
+} qlb200_task;
+
+typedef struct qlb200_cost {    /* same accounting as tensor_op_cost.h:109-120 */
+  double flops;
+  uint64_t gemm_count;
+  uint64_t candidate_block_pair_count;
+  uint64_t output_block_count;
+  uint64_t output_raw_elem_count;
+  uint64_t read_bytes, write_bytes, temp_peak_bytes;
+} qlb200_cost;
+
+typedef struct qlb200_match qlb200_match;   /* result of the sector matcher (host only) */
+typedef struct qlb200_ctx qlb200_ctx;       /* one per device / host thread */
+typedef struct qlb200_plan qlb200_plan;     /* device-side descriptor tables of one contraction */
+typedef struct qlb200_tplan qlb200_tplan;   /* device-side descriptor table of a whole-tensor transpose */
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char *qlb200_version(void);
+const char *qlb200_last_error(void);        /* thread-local text of the last failure */
+
+/* ---- sector matcher (host, no CUDA calls) --------------------------------------------------- */
+int qlb200_match_create(const qlb200_shell *a, const qlb200_shell *b, int32_t nctrct,
+                        const int32_t *a_axes, const int32_t *b_axes, qlb200_match **out);
+void qlb200_match_destroy(qlb200_match *m);
+/* Restrict matching to A blocks whose coordinate on `axis` equals `sector`: the block set of
+ * dmrg::Contract1Sector (tensor_manipulation/dmrg/contract_1sector.h:181-228). */
+int qlb200_match_create_1sector(const qlb200_shell *a, int32_t axis, uint32_t sector,
+                                const qlb200_shell *b, int32_t nctrct, const int32_t *a_axes,
+                                const int32_t *b_axes, qlb200_match **out);
+int32_t qlb200_match_c_rank(const qlb200_match *m);
+uint64_t qlb200_match_c_nblk(const qlb200_match *m);
+uint64_t qlb200_match_c_elems(const qlb200_match *m);            /* raw_data_size_ of C */
+uint64_t qlb200_match_ntask(const qlb200_match *m);
+int qlb200_match_is_scalar(const qlb200_match *m);
+/* perm = saved_a ++ ctrct_a (A) / ctrct_b ++ saved_b (B); returns 1 if a transpose is needed */
+int qlb200_match_perm(const qlb200_match *m, int which /*0=A,1=B*/, int32_t *perm_out);
+/* C blocks in ascending blk_idx order */
+int qlb200_match_c_blocks(const qlb200_match *m, uint64_t *blk_idx, uint32_t *blk_coors,
+                          uint32_t *shape, uint64_t *offset);
+/* tasks: order==0 -> discovery order of the reference's (a,b) scan; order==1 -> sorted by
+ * (c_blk_idx, first-task-first), the order SortTasksByCBlkIdx establishes (stable here). */
+int qlb200_match_tasks(const qlb200_match *m, int order, qlb200_task *tasks_out);
+int qlb200_estimate_cost(const qlb200_match *m, int dtype, qlb200_cost *out);
+
+/* ---- execution ------------------------------------------------------------------------------ */
+int qlb200_ctx_create(int device, qlb200_ctx **out);
+void qlb200_ctx_destroy(qlb200_ctx *ctx);
+int qlb200_ctx_sync(qlb200_ctx *ctx);
+void *qlb200_ctx_stream(qlb200_ctx *ctx);                         /* cudaStream_t */
+int qlb200_ctx_set_stream(qlb200_ctx *ctx, void *cuda_stream);    /* run on a caller stream */
+
+/* device memory helpers for host languages without a CUDA binding */
+int qlb200_dev_alloc(qlb200_ctx *ctx, size_t bytes, void **out);
+int qlb200_dev_free(qlb200_ctx *ctx, void *p);
+int qlb200_memcpy_h2d(qlb200_ctx *ctx, void *dst, const void *src, size_t bytes);  /* async on ctx stream */
+int qlb200_memcpy_d2h(qlb200_ctx *ctx, void *dst, const void *src, size_t bytes);  /* async on ctx stream */
+int qlb200_host_register(void *p, size_t bytes);                  /* pin caller memory */
+int qlb200_host_unregister(void *p);
+
+/* Build the device descriptor tables from a match.  flags: see below.
+ * ctx == NULL builds a host-only plan: stats, partition and c_ranges work, execute does not. */
+#define QLB200_PLAN_DETERMINISTIC 1u   /* default and only mode: no atomics, fixed summation order */
+#define QLB200_PLAN_NO_SKINNY 2u       /* force every task through the DMMA kernel (testing) */
+int qlb200_plan_create(qlb200_ctx *ctx, const qlb200_match *m, const qlb200_shell *a,
+                       const qlb200_shell *b, int dtype, uint32_t flags, qlb200_plan **out);
+/* Descriptor-table entry (no shells): permute every A/B block with one perm each, then run the
+ * grouped GEMM over `tasks`.  a_shape/b_shape are [n*rank] block shapes, offsets in elements. */
+int qlb200_plan_create_raw(qlb200_ctx *ctx, int dtype, uint32_t flags, int32_t a_rank,
+                           const int32_t *a_perm, uint64_t na, const uint32_t *a_shape,
+                           const uint64_t *a_off, int32_t b_rank, const int32_t *b_perm, uint64_t nb,
+                           const uint32_t *b_shape, const uint64_t *b_off, uint64_t ntask,
+                           const qlb200_task *tasks, uint64_t c_elems, qlb200_plan **out);
+void qlb200_plan_destroy(qlb200_plan *p);
+/* Keep only the output row slabs of this rank (multi-GPU: partition by output sector / row slab).
+ * Units are whole C blocks or row ranges of C blocks, balanced by flops (LPT). */
+int qlb200_plan_partition(qlb200_plan *p, int32_t world, int32_t rank);
+/* ranges of C (element offsets, lengths) this plan writes after partitioning */
+uint64_t qlb200_plan_c_range_count(const qlb200_plan *p);
+int qlb200_plan_c_ranges(const qlb200_plan *p, uint64_t *off, uint64_t *len);
+
+typedef struct qlb200_plan_stats {
+  double flops;                 /* sum over tasks, 2mkn or 8mkn */
+  uint64_t ntask, ngroup, ntile_dmma, nrow_skinny;
+  uint64_t permute_elems_a, permute_elems_b;   /* elements moved by the batched permute */
+  uint64_t workspace_bytes;
+  uint64_t gemm_read_bytes, gemm_write_bytes;  /* (mk+kn)*s per task, mn*s per C block */
+} qlb200_plan_stats;
+int qlb200_plan_get_stats(const qlb200_plan *p, qlb200_plan_stats *out);
+
+/* C = contract(A, B).  C must hold c_elems elements (uninitialised is fine).  With
+ * QLB200_MEM_HOST the call stages A, B through device memory and copies C back, then
+ * synchronises; with QLB200_MEM_DEVICE it only enqueues work on the ctx stream. */
+int qlb200_execute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C,
+                   int mem_kind);
+/* the two phases separately (device pointers only) -- used by the benchmark to time each kernel */
+int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B);
+int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C);
+/* number of kernel launches the last execute on this ctx issued */
+uint64_t qlb200_ctx_launch_count(const qlb200_ctx *ctx);
+
+/* ---- whole-tensor transpose (BlockSparseDataTensor::Transpose) ----------------------------- */
+/* out block list: transposed shell (ascending new blk_idx), offsets; scale = fermion reorder sign. */
+int qlb200_tplan_create(qlb200_ctx *ctx, const qlb200_shell *t, const int32_t *perm, int dtype,
+                        qlb200_tplan **out);
+void qlb200_tplan_destroy(qlb200_tplan *p);
+uint64_t qlb200_tplan_nblk(const qlb200_tplan *p);
+int qlb200_tplan_blocks(const qlb200_tplan *p, uint64_t *blk_idx, uint32_t *blk_coors,
+                        uint32_t *shape, uint64_t *offset, int8_t *scale);
+int qlb200_transpose_execute(qlb200_ctx *ctx, qlb200_tplan *p, const void *src, void *dst,
+                             int mem_kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QLB200_H */

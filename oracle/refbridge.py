@@ -1,0 +1,240 @@
+"""oracle/refbridge.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes bridge to oracle/_ref/libqlref.so: the UNMODIFIED reference (TensorToolkit CPU path, HPTT +
+OpenBLAS) compiled by oracle/Makefile.  Only tests/, __graft_entry__.smoke() and the cpu_baseline /
+--impl reference legs of bench.py may import this module; the product package never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from tensortoolkit_b200.tensor import BlockSparseTensor, Index, KIND_ORDINAL
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(_HERE, "_ref", "libqlref.so")
+
+_I64P = C.POINTER(C.c_int64)
+_P = C.c_void_p
+
+
+def available() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # see BASELINE.md: active spin-wait oversubscribes
+        L = C.CDLL(REF_LIB)
+        sig = {
+            "qlref_set_seed": (None, [C.c_uint64]),
+            "qlref_set_threads": (None, [C.c_int]),
+            "qlref_index_new": (_P, [C.c_int, C.c_int, C.c_int, _I64P, _I64P]),
+            "qlref_index_free": (None, [_P]),
+            "qlref_tensor_new": (_P, [C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+            "qlref_tensor_free": (None, [_P]),
+            "qlref_tensor_clone": (_P, [_P]),
+            "qlref_tensor_rank": (C.c_int, [_P]),
+            "qlref_tensor_dtype": (C.c_int, [_P]),
+            "qlref_tensor_is_default": (C.c_int, [_P]),
+            "qlref_tensor_fermionic": (C.c_int, [_P]),
+            "qlref_tensor_nblk": (C.c_uint64, [_P]),
+            "qlref_tensor_raw_size": (C.c_uint64, [_P]),
+            "qlref_tensor_raw": (_P, [_P]),
+            "qlref_tensor_shell": (None, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_int8)]),
+            "qlref_tensor_sectors": (None, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]),
+            "qlref_tensor_blocks": (None, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+            "qlref_tensor_random": (None, [_P, _I64P]),
+            "qlref_tensor_transpose": (None, [_P, _I64P]),
+            "qlref_tensor_norm2": (C.c_double, [_P]),
+            "qlref_tensor_indexes_equal": (C.c_int, [_P, _P]),
+            "qlref_contract": (_P, [_P, _P, C.c_int, _I64P, _I64P]),
+            "qlref_contract_time": (C.c_double, [_P, _P, C.c_int, _I64P, _I64P, C.c_int]),
+            "qlref_contract_1sector": (_P, [_P, C.c_int64, C.c_int64, _P, C.c_int, _I64P, _I64P]),
+            "qlref_contract_tasks": (C.c_uint64, [_P, _P, C.c_int, _I64P, _I64P, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+            "qlref_contract_cost": (None, [_P, _P, C.c_int, _I64P, _I64P, C.POINTER(C.c_double)]),
+            "qlref_b200_contract": (_P, [_P, _P, C.c_int, _I64P, _I64P, _P]),
+            "qlref_b200_contract_1sector": (_P, [_P, C.c_int64, C.c_int64, _P, C.c_int, _I64P, _I64P, _P]),
+            "qlref_b200_transpose": (C.c_int, [_P, _I64P, _P]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _i64(v):
+    return (C.c_int64 * max(1, len(v)))(*[int(x) for x in v])
+
+
+def set_seed(seed: int):
+    lib().qlref_set_seed(seed)
+
+
+def set_threads(n: int):
+    lib().qlref_set_threads(n)
+
+
+class RefTensor:
+    """A QLTensor<double|complex, QNT> living inside the reference library."""
+
+    def __init__(self, handle, indexes, dtype):
+        self.h = handle
+        self.indexes = list(indexes) if indexes is not None else None
+        self.dtype = np.dtype(dtype)
+
+    @staticmethod
+    def new(indexes, dtype=np.float64) -> "RefTensor":
+        L = lib()
+        kind = indexes[0].kind
+        ko = KIND_ORDINAL[kind.name]
+        hs = []
+        for ix in indexes:
+            qn = [v for s in ix.sectors for v in s.qn]
+            dg = [s.dgnc for s in ix.sectors]
+            hs.append(L.qlref_index_new(ko, ix.dir, ix.nsct, _i64(qn), _i64(dg)))
+        arr = (_P * len(hs))(*hs)
+        t = L.qlref_tensor_new(ko, 0 if np.dtype(dtype) == np.float64 else 1, len(hs), arr)
+        for h in hs:
+            L.qlref_index_free(h)
+        return RefTensor(t, indexes, dtype)
+
+    def random(self, div):
+        lib().qlref_tensor_random(self.h, _i64(list(div)))
+        return self
+
+    def clone(self) -> "RefTensor":
+        return RefTensor(lib().qlref_tensor_clone(self.h), self.indexes, self.dtype)
+
+    def transpose(self, perm):
+        lib().qlref_tensor_transpose(self.h, _i64(perm))
+        self.indexes = [self.indexes[i] for i in perm]
+        return self
+
+    def b200_transpose(self, perm, ctx_handle=None):
+        rc = lib().qlref_b200_transpose(self.h, _i64(perm), ctx_handle)
+        if rc != 0:
+            raise RuntimeError("qlten::b200::Transpose failed")
+        self.indexes = [self.indexes[i] for i in perm]
+        return self
+
+    @property
+    def rank(self):
+        return lib().qlref_tensor_rank(self.h)
+
+    @property
+    def nblk(self):
+        return int(lib().qlref_tensor_nblk(self.h))
+
+    def is_default(self):
+        return bool(lib().qlref_tensor_is_default(self.h))
+
+    def norm2(self):
+        return lib().qlref_tensor_norm2(self.h)
+
+    def raw(self) -> np.ndarray:
+        n = int(lib().qlref_tensor_raw_size(self.h))
+        if n == 0:
+            return np.zeros(0, self.dtype)
+        p = lib().qlref_tensor_raw(self.h)
+        buf = (C.c_char * (n * self.dtype.itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=self.dtype, count=n).copy()
+
+    def blocks(self):
+        n, r = self.nblk, self.rank
+        idx = np.zeros(n, np.uint64); off = np.zeros(n, np.uint64)
+        coors = np.zeros((n, r), np.uint32); shape = np.zeros((n, r), np.uint32)
+        if n:
+            lib().qlref_tensor_blocks(self.h, idx.ctypes.data_as(C.POINTER(C.c_uint64)), coors.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                      shape.ctypes.data_as(C.POINTER(C.c_uint32)), off.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return idx, coors, shape, off
+
+    def shell_arrays(self):
+        r = self.rank
+        nsct = np.zeros(r, np.uint32); dirs = np.zeros(r, np.int8)
+        lib().qlref_tensor_shell(self.h, nsct.ctypes.data_as(C.POINTER(C.c_uint32)), dirs.ctypes.data_as(C.POINTER(C.c_int8)))
+        tot = int(nsct.sum())
+        deg = np.zeros(tot, np.uint32); par = np.zeros(tot, np.uint8)
+        lib().qlref_tensor_sectors(self.h, deg.ctypes.data_as(C.POINTER(C.c_uint32)), par.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return nsct, dirs, deg, par
+
+    def to_bst(self) -> BlockSparseTensor:
+        """Copy into the product's host mirror (same indexes, same block order, same raw data)."""
+        t = BlockSparseTensor(self.indexes, self.dtype)
+        if self.rank == 0:
+            t.data = self.raw()
+            return t
+        _, coors, _, _ = self.blocks()
+        t.set_blocks(coors, self.raw())
+        return t
+
+    def free(self):
+        if self.h:
+            lib().qlref_tensor_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _c_indexes(a: RefTensor, b: RefTensor, axes):
+    sa = [i for i in range(len(a.indexes)) if i not in axes[0]]
+    sb = [i for i in range(len(b.indexes)) if i not in axes[1]]
+    return [a.indexes[i] for i in sa] + [b.indexes[i] for i in sb]
+
+
+def contract(a: RefTensor, b: RefTensor, axes) -> RefTensor:
+    h = lib().qlref_contract(a.h, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]))
+    return RefTensor(h, _c_indexes(a, b, axes), a.dtype)
+
+
+def contract_time(a: RefTensor, b: RefTensor, axes, reps=1) -> float:
+    return lib().qlref_contract_time(a.h, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), reps)
+
+
+def contract_1sector(a: RefTensor, axis, sct, b: RefTensor, axes) -> RefTensor:
+    h = lib().qlref_contract_1sector(a.h, axis, sct, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]))
+    return RefTensor(h, _c_indexes(a, b, axes), a.dtype)
+
+
+def b200_contract(a: RefTensor, b: RefTensor, axes, ctx_handle=None) -> RefTensor:
+    """qlten::b200::Contract on reference QLTensors (the drop-in adapter, CUDA path)."""
+    h = lib().qlref_b200_contract(a.h, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), ctx_handle)
+    if not h:
+        raise RuntimeError("qlten::b200::Contract failed")
+    return RefTensor(h, _c_indexes(a, b, axes), a.dtype)
+
+
+def b200_contract_1sector(a: RefTensor, axis, sct, b: RefTensor, axes, ctx_handle=None) -> RefTensor:
+    h = lib().qlref_b200_contract_1sector(a.h, axis, sct, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), ctx_handle)
+    if not h:
+        raise RuntimeError("qlten::b200::Contract1Sector failed")
+    return RefTensor(h, _c_indexes(a, b, axes), a.dtype)
+
+
+def contract_tasks(a: RefTensor, b: RefTensor, axes, sorted_by_c=False):
+    """The reference's RawDataCtrctTask list as (uint64[n,9], float64[n,2]) =
+    (a_idx,b_idx,c_idx,a_off,b_off,c_off,m,k,n), (f_ex_sign, beta)."""
+    L = lib()
+    n = int(L.qlref_contract_tasks(a.h, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), int(sorted_by_c), 0, None, None))
+    u = np.zeros((n, 9), np.uint64); d = np.zeros((n, 2), np.float64)
+    if n:
+        L.qlref_contract_tasks(a.h, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), int(sorted_by_c), n,
+                               u.ctypes.data_as(C.POINTER(C.c_uint64)), d.ctypes.data_as(C.POINTER(C.c_double)))
+    return u, d
+
+
+def contract_cost(a: RefTensor, b: RefTensor, axes) -> dict:
+    out = (C.c_double * 8)()
+    lib().qlref_contract_cost(a.h, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), out)
+    keys = ["flops", "gemm_count", "candidate_block_pair_count", "output_block_count", "output_raw_elem_count",
+            "read_bytes", "write_bytes", "temp_peak_bytes"]
+    return dict(zip(keys, list(out)))

@@ -1,0 +1,135 @@
+"""ctypes binding of the C ABI in include/qlb200.h (tensortoolkit_b200/libqlb200.so).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``make -C tensortoolkit_b200/csrc``.
+There is no CPU fallback: if the library is missing, importing this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqlb200.so")
+
+QLB200_MAX_RANK = 8
+OK = 0
+F64, C64 = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+DIR_IN, DIR_OUT = -1, 1
+PLAN_DETERMINISTIC, PLAN_NO_SKINNY = 1, 2
+
+
+class Shell(C.Structure):
+    _fields_ = [
+        ("rank", C.c_int32),
+        ("nsct", C.POINTER(C.c_uint32)),
+        ("deg", C.POINTER(C.c_uint32)),
+        ("parity", C.POINTER(C.c_uint8)),
+        ("dir", C.POINTER(C.c_int8)),
+        ("nblk", C.c_uint64),
+        ("blk_coors", C.POINTER(C.c_uint32)),
+    ]
+
+
+class Task(C.Structure):
+    _fields_ = [
+        ("a_blk_idx", C.c_uint64), ("b_blk_idx", C.c_uint64), ("c_blk_idx", C.c_uint64),
+        ("a_off", C.c_uint64), ("b_off", C.c_uint64), ("c_off", C.c_uint64),
+        ("a_ord", C.c_uint32), ("b_ord", C.c_uint32), ("c_ord", C.c_uint32),
+        ("m", C.c_uint32), ("k", C.c_uint32), ("n", C.c_uint32),
+        ("sign", C.c_int8), ("first", C.c_uint8), ("pad_", C.c_uint8 * 2),
+    ]
+
+
+class Cost(C.Structure):
+    _fields_ = [
+        ("flops", C.c_double), ("gemm_count", C.c_uint64), ("candidate_block_pair_count", C.c_uint64),
+        ("output_block_count", C.c_uint64), ("output_raw_elem_count", C.c_uint64),
+        ("read_bytes", C.c_uint64), ("write_bytes", C.c_uint64), ("temp_peak_bytes", C.c_uint64),
+    ]
+
+
+class PlanStats(C.Structure):
+    _fields_ = [
+        ("flops", C.c_double), ("ntask", C.c_uint64), ("ngroup", C.c_uint64), ("ntile_dmma", C.c_uint64),
+        ("nrow_skinny", C.c_uint64), ("permute_elems_a", C.c_uint64), ("permute_elems_b", C.c_uint64),
+        ("workspace_bytes", C.c_uint64), ("gemm_read_bytes", C.c_uint64), ("gemm_write_bytes", C.c_uint64),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/qlb200.h
+_P = C.c_void_p
+_PP = C.POINTER(C.c_void_p)
+_I32P = C.POINTER(C.c_int32)
+_U32P = C.POINTER(C.c_uint32)
+_U64P = C.POINTER(C.c_uint64)
+_I8P = C.POINTER(C.c_int8)
+_SH = C.POINTER(Shell)
+SYMBOLS = {
+    "qlb200_version": (C.c_char_p, []),
+    "qlb200_last_error": (C.c_char_p, []),
+    "qlb200_match_create": (C.c_int, [_SH, _SH, C.c_int32, _I32P, _I32P, _PP]),
+    "qlb200_match_destroy": (None, [_P]),
+    "qlb200_match_create_1sector": (C.c_int, [_SH, C.c_int32, C.c_uint32, _SH, C.c_int32, _I32P, _I32P, _PP]),
+    "qlb200_match_c_rank": (C.c_int32, [_P]),
+    "qlb200_match_c_nblk": (C.c_uint64, [_P]),
+    "qlb200_match_c_elems": (C.c_uint64, [_P]),
+    "qlb200_match_ntask": (C.c_uint64, [_P]),
+    "qlb200_match_is_scalar": (C.c_int, [_P]),
+    "qlb200_match_perm": (C.c_int, [_P, C.c_int, _I32P]),
+    "qlb200_match_c_blocks": (C.c_int, [_P, _U64P, _U32P, _U32P, _U64P]),
+    "qlb200_match_tasks": (C.c_int, [_P, C.c_int, C.POINTER(Task)]),
+    "qlb200_estimate_cost": (C.c_int, [_P, C.c_int, C.POINTER(Cost)]),
+    "qlb200_ctx_create": (C.c_int, [C.c_int, _PP]),
+    "qlb200_ctx_destroy": (None, [_P]),
+    "qlb200_ctx_sync": (C.c_int, [_P]),
+    "qlb200_ctx_stream": (_P, [_P]),
+    "qlb200_ctx_set_stream": (C.c_int, [_P, _P]),
+    "qlb200_dev_alloc": (C.c_int, [_P, C.c_size_t, _PP]),
+    "qlb200_dev_free": (C.c_int, [_P, _P]),
+    "qlb200_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "qlb200_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "qlb200_host_register": (C.c_int, [_P, C.c_size_t]),
+    "qlb200_host_unregister": (C.c_int, [_P]),
+    "qlb200_plan_create": (C.c_int, [_P, _P, _SH, _SH, C.c_int, C.c_uint32, _PP]),
+    "qlb200_plan_create_raw": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_int32, _I32P, C.c_uint64, _U32P, _U64P,
+                                         C.c_int32, _I32P, C.c_uint64, _U32P, _U64P, C.c_uint64, C.POINTER(Task),
+                                         C.c_uint64, _PP]),
+    "qlb200_plan_destroy": (None, [_P]),
+    "qlb200_plan_partition": (C.c_int, [_P, C.c_int32, C.c_int32]),
+    "qlb200_plan_c_range_count": (C.c_uint64, [_P]),
+    "qlb200_plan_c_ranges": (C.c_int, [_P, _U64P, _U64P]),
+    "qlb200_plan_get_stats": (C.c_int, [_P, C.POINTER(PlanStats)]),
+    "qlb200_execute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
+    "qlb200_execute_permute": (C.c_int, [_P, _P, _P, _P]),
+    "qlb200_execute_gemm": (C.c_int, [_P, _P, _P, _P, _P]),
+    "qlb200_ctx_launch_count": (C.c_uint64, [_P]),
+    "qlb200_tplan_create": (C.c_int, [_P, _SH, _I32P, C.c_int, _PP]),
+    "qlb200_tplan_destroy": (None, [_P]),
+    "qlb200_tplan_nblk": (C.c_uint64, [_P]),
+    "qlb200_tplan_blocks": (C.c_int, [_P, _U64P, _U32P, _U32P, _U64P, _I8P]),
+    "qlb200_transpose_execute": (C.c_int, [_P, _P, _P, _P, C.c_int]),
+}
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the contraction path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = load()
+
+
+class QLB200Error(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != OK:
+        raise QLB200Error(f"{what} failed ({rc}): {lib.qlb200_last_error().decode()}")

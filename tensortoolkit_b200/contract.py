@@ -1,0 +1,254 @@
+"""Python face of the contraction path; every call goes through the C ABI (include/qlb200.h).
+
+  contract(a, b, axes)            mirrors qlten::Contract (tensor_manipulation/ten_ctrct.h:277-290)
+  contract_1sector(a, ax, s, b, axes)  mirrors qlten::dmrg::Contract1Sector (dmrg/contract_1sector.h:211-228)
+  transpose(t, order)             mirrors QLTensor::Transpose (qltensor_impl.h:449-464)
+
+`ContractionPlan` exposes the plan/execute split for device-resident, repeated use (Lanczos-style
+loops, benchmarks): match once, build the descriptor tables once, execute many times.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+from .tensor import BlockSparseTensor, _dtype_code
+
+
+class Context:
+    """One qlb200_ctx (one device, one stream). Fails loudly without a B200."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        check(lib.qlb200_ctx_create(device, C.byref(h)), "qlb200_ctx_create")
+        self.h = h
+        self.device = device
+
+    def sync(self):
+        check(lib.qlb200_ctx_sync(self.h), "qlb200_ctx_sync")
+
+    def stream(self) -> int:
+        return lib.qlb200_ctx_stream(self.h) or 0
+
+    def set_stream(self, cuda_stream: int):
+        check(lib.qlb200_ctx_set_stream(self.h, C.c_void_p(cuda_stream)), "qlb200_ctx_set_stream")
+
+    def launch_count(self) -> int:
+        return int(lib.qlb200_ctx_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            lib.qlb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _i32(v):
+    return (C.c_int32 * len(v))(*[int(x) for x in v])
+
+
+class Match:
+    """Result of the host sector matcher (qlb200_match)."""
+
+    def __init__(self, a: BlockSparseTensor, b: BlockSparseTensor, axes, one_sector=None):
+        axes_a, axes_b = list(axes[0]), list(axes[1])
+        if len(axes_a) != len(axes_b):
+            raise ValueError("axes_set must pair axes of A with axes of B")
+        for x, y in zip(axes_a, axes_b):
+            if not (0 <= x < a.rank and 0 <= y < b.rank) or a.indexes[x] != b.indexes[y].inverse():
+                raise ValueError(f"contracted indexes A[{x}] and B[{y}] do not match (need A[x] == InverseIndex(B[y]))")
+        self.a, self.b = a, b
+        self.axes = (axes_a, axes_b)
+        self.sa, self.sb = a.shell(), b.shell()
+        h = C.c_void_p()
+        if one_sector is None:
+            rc = lib.qlb200_match_create(self.sa.ptr(), self.sb.ptr(), len(axes_a), _i32(axes_a), _i32(axes_b), C.byref(h))
+        else:
+            rc = lib.qlb200_match_create_1sector(self.sa.ptr(), int(one_sector[0]), int(one_sector[1]), self.sb.ptr(),
+                                                 len(axes_a), _i32(axes_a), _i32(axes_b), C.byref(h))
+        check(rc, "qlb200_match_create")
+        self.h = h
+        self.c_rank = lib.qlb200_match_c_rank(h)
+        self.c_nblk = int(lib.qlb200_match_c_nblk(h))
+        self.c_elems = int(lib.qlb200_match_c_elems(h))
+        self.ntask = int(lib.qlb200_match_ntask(h))
+        self.is_scalar = bool(lib.qlb200_match_is_scalar(h))
+        saved_a = [i for i in range(a.rank) if i not in axes_a]
+        saved_b = [i for i in range(b.rank) if i not in axes_b]
+        self.c_indexes = [a.indexes[i] for i in saved_a] + [b.indexes[i] for i in saved_b]
+
+    def perm(self, which: int):
+        rank = self.a.rank if which == 0 else self.b.rank
+        out = (C.c_int32 * rank)()
+        need = lib.qlb200_match_perm(self.h, which, out)
+        return list(out), bool(need)
+
+    def c_blocks(self):
+        n, r = self.c_nblk, self.c_rank
+        idx = np.zeros(n, np.uint64); off = np.zeros(n, np.uint64)
+        coors = np.zeros((n, r), np.uint32); shape = np.zeros((n, r), np.uint32)
+        check(lib.qlb200_match_c_blocks(self.h, idx.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        coors.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                        shape.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                        off.ctypes.data_as(C.POINTER(C.c_uint64))), "qlb200_match_c_blocks")
+        return idx, coors, shape, off
+
+    def tasks(self, sorted_by_c: bool = False):
+        arr = (_lib.Task * self.ntask)()
+        check(lib.qlb200_match_tasks(self.h, 1 if sorted_by_c else 0, arr), "qlb200_match_tasks")
+        return arr
+
+    def cost(self, dtype) -> _lib.Cost:
+        c = _lib.Cost()
+        check(lib.qlb200_estimate_cost(self.h, _dtype_code(dtype), C.byref(c)), "qlb200_estimate_cost")
+        return c
+
+    def result_shell(self, dtype) -> BlockSparseTensor:
+        c = BlockSparseTensor(self.c_indexes, dtype)
+        if not self.is_scalar and self.c_nblk:
+            _, coors, _, _ = self.c_blocks()
+            c.set_blocks(coors)
+        elif self.is_scalar:
+            c.data = np.zeros(1 if self.ntask else 0, dtype=c.dtype)
+        return c
+
+    def close(self):
+        if self.h:
+            lib.qlb200_match_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ContractionPlan:
+    """Device descriptor tables of one contraction (qlb200_plan)."""
+
+    def __init__(self, ctx: Context, match: Match, dtype, flags: int = _lib.PLAN_DETERMINISTIC):
+        self.ctx, self.match = ctx, match
+        self.dtype = np.dtype(dtype)
+        h = C.c_void_p()
+        check(lib.qlb200_plan_create(ctx.h, match.h, match.sa.ptr(), match.sb.ptr(), _dtype_code(dtype), flags, C.byref(h)),
+              "qlb200_plan_create")
+        self.h = h
+
+    def stats(self) -> _lib.PlanStats:
+        s = _lib.PlanStats()
+        check(lib.qlb200_plan_get_stats(self.h, C.byref(s)), "qlb200_plan_get_stats")
+        return s
+
+    def partition(self, world: int, rank: int):
+        check(lib.qlb200_plan_partition(self.h, world, rank), "qlb200_plan_partition")
+
+    def c_ranges(self):
+        n = int(lib.qlb200_plan_c_range_count(self.h))
+        off = np.zeros(n, np.uint64); ln = np.zeros(n, np.uint64)
+        check(lib.qlb200_plan_c_ranges(self.h, off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                       ln.ctypes.data_as(C.POINTER(C.c_uint64))), "qlb200_plan_c_ranges")
+        return off, ln
+
+    def execute_host(self, a: np.ndarray, b: np.ndarray, c: np.ndarray):
+        check(lib.qlb200_execute(self.ctx.h, self.h, a.ctypes.data, b.ctypes.data, c.ctypes.data, _lib.MEM_HOST), "qlb200_execute")
+
+    def execute_device(self, a_ptr: int, b_ptr: int, c_ptr: int):
+        check(lib.qlb200_execute(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(c_ptr), _lib.MEM_DEVICE),
+              "qlb200_execute")
+
+    def execute_permute(self, a_ptr: int, b_ptr: int):
+        check(lib.qlb200_execute_permute(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr)), "qlb200_execute_permute")
+
+    def execute_gemm(self, a_ptr: int, b_ptr: int, c_ptr: int):
+        check(lib.qlb200_execute_gemm(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(c_ptr)),
+              "qlb200_execute_gemm")
+
+    def close(self):
+        if self.h:
+            lib.qlb200_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _run(a, b, match, ctx):
+    if a.dtype != b.dtype:
+        # mixed real/complex promotes like the reference (ten_ctrct.h:292-350)
+        if a.dtype != np.complex128:
+            a2 = BlockSparseTensor(a.indexes, np.complex128); a2.set_blocks(a.blk_coors, a.data.astype(np.complex128)); a = a2
+        if b.dtype != np.complex128:
+            b2 = BlockSparseTensor(b.indexes, np.complex128); b2.set_blocks(b.blk_coors, b.data.astype(np.complex128)); b = b2
+    c = match.result_shell(a.dtype)
+    if match.ntask == 0:
+        return c
+    ctx = ctx or default_context()
+    plan = ContractionPlan(ctx, match, a.dtype)
+    try:
+        plan.execute_host(a.data, b.data, c.data)
+    finally:
+        plan.close()
+    return c
+
+
+def contract(a: BlockSparseTensor, b: BlockSparseTensor, axes: Sequence[Sequence[int]], ctx: Context = None) -> BlockSparseTensor:
+    """C = Contract(A, B, {{a axes}, {b axes}}): C's indexes are A's free indexes then B's free indexes."""
+    m = Match(a, b, axes)
+    try:
+        return _run(a, b, m, ctx)
+    finally:
+        m.close()
+
+
+def contract_1sector(a, idx_a: int, qn_sector_idx_a: int, b, axes, ctx: Context = None) -> BlockSparseTensor:
+    if idx_a in list(axes[0]):
+        raise ValueError("the split index must be a free index of A")
+    m = Match(a, b, axes, one_sector=(idx_a, qn_sector_idx_a))
+    try:
+        return _run(a, b, m, ctx)
+    finally:
+        m.close()
+
+
+def transpose(t: BlockSparseTensor, order: Sequence[int], ctx: Context = None) -> BlockSparseTensor:
+    """Whole-tensor index permutation; fermionic tensors pick up the reorder sign per block."""
+    order = [int(x) for x in order]
+    if sorted(order) != list(range(t.rank)):
+        raise ValueError("order is not a permutation")
+    ctx = ctx or default_context()
+    sh = t.shell()
+    h = C.c_void_p()
+    check(lib.qlb200_tplan_create(ctx.h, sh.ptr(), _i32(order), _dtype_code(t.dtype), C.byref(h)), "qlb200_tplan_create")
+    try:
+        out = BlockSparseTensor([t.indexes[i] for i in order], t.dtype)
+        n = int(lib.qlb200_tplan_nblk(h))
+        coors = np.zeros((n, t.rank), np.uint32)
+        check(lib.qlb200_tplan_blocks(h, None, coors.ctypes.data_as(C.POINTER(C.c_uint32)), None, None, None), "qlb200_tplan_blocks")
+        out.set_blocks(coors)
+        if n:
+            check(lib.qlb200_transpose_execute(ctx.h, h, t.data.ctypes.data, out.data.ctypes.data, _lib.MEM_HOST),
+                  "qlb200_transpose_execute")
+        return out
+    finally:
+        lib.qlb200_tplan_destroy(h)

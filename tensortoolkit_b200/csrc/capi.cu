@@ -1,0 +1,540 @@
+// capi.cu -- the extern "C" surface declared in include/qlb200.h.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "matcher.h"
+#include "plan.h"
+#include "qlb200.h"
+
+using namespace qlb200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int Fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define QL_CUDA(call)                                                      \
+  do {                                                                     \
+    cudaError_t e_ = (call);                                               \
+    if (e_ != cudaSuccess) return Fail(QLB200_ERR_CUDA, CudaErr(#call, e_)); \
+  } while (0)
+
+template<typename T>
+int Upload(const std::vector<T> &v, T **dst, cudaStream_t s) {
+  *dst = nullptr;
+  if (v.empty()) return QLB200_OK;
+  QL_CUDA(cudaMalloc(reinterpret_cast<void **>(dst), v.size() * sizeof(T)));
+  QL_CUDA(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  return QLB200_OK;
+}
+
+int EnsureArena(void **p, size_t *cap, size_t need, cudaStream_t s) {
+  if (need <= *cap) return QLB200_OK;
+  QL_CUDA(cudaStreamSynchronize(s));
+  if (*p) { QL_CUDA(cudaFree(*p)); *p = nullptr; *cap = 0; }
+  size_t want = need + need / 8 + 256;
+  QL_CUDA(cudaMalloc(p, want));
+  *cap = want;
+  return QLB200_OK;
+}
+
+size_t ElemSize(int dtype) { return dtype == QLB200_C64 ? 16 : 8; }
+size_t Align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+int UploadGemmTables(qlb200_plan *p) {
+  cudaStream_t s = p->ctx->stream;
+  int rc;
+  if (p->d.tasks == nullptr) {
+    if ((rc = Upload(p->h.tasks, &p->d.tasks, s)) != QLB200_OK) return rc;
+  }
+  if (p->d.groups) { cudaFree(p->d.groups); p->d.groups = nullptr; }
+  if (p->d.tiles) { cudaFree(p->d.tiles); p->d.tiles = nullptr; }
+  if (p->d.items) { cudaFree(p->d.items); p->d.items = nullptr; }
+  if ((rc = Upload(p->h.part_groups, &p->d.groups, s)) != QLB200_OK) return rc;
+  if ((rc = Upload(p->h.tiles, &p->d.tiles, s)) != QLB200_OK) return rc;
+  if ((rc = Upload(p->h.items, &p->d.items, s)) != QLB200_OK) return rc;
+  QL_CUDA(cudaStreamSynchronize(s));   // host vectors may change after return
+  return QLB200_OK;
+}
+
+int FinishPlan(qlb200_ctx *ctx, qlb200_plan *p) {
+  cudaStream_t s = ctx->stream;
+  int rc;
+  QL_CUDA(cudaSetDevice(ctx->device));
+  if ((rc = Upload(p->h.perm_blks, &p->d.perm_blks, s)) != QLB200_OK) return rc;
+  if ((rc = Upload(p->h.perm_tile_base, &p->d.perm_tile_base, s)) != QLB200_OK) return rc;
+  QL_CUDA(cudaMalloc(reinterpret_cast<void **>(&p->d.counters), 2 * sizeof(unsigned int)));
+  QL_CUDA(cudaMemsetAsync(p->d.counters, 0, 2 * sizeof(unsigned int), s));
+  return UploadGemmTables(p);
+}
+
+GemmParams MakeParams(const qlb200_plan *p) {
+  GemmParams gp;
+  gp.tasks = p->d.tasks; gp.groups = p->d.groups; gp.tiles = p->d.tiles; gp.items = p->d.items;
+  gp.ntiles = static_cast<uint32_t>(p->h.tiles.size());
+  gp.nitems = static_cast<uint32_t>(p->h.items.size());
+  gp.counters = p->d.counters;
+  return gp;
+}
+
+size_t WsBytes(const qlb200_plan *p) {
+  const size_t es = ElemSize(p->h.dtype);
+  return Align256(p->h.ws_a_elems * es) + Align256(p->h.ws_b_elems * es);
+}
+
+}  // namespace
+
+void qlb200::DeviceTables::Free() {
+  cudaFree(perm_blks); cudaFree(perm_tile_base); cudaFree(tasks); cudaFree(groups); cudaFree(tiles);
+  cudaFree(items); cudaFree(counters);
+  perm_blks = nullptr; perm_tile_base = nullptr; tasks = nullptr; groups = nullptr; tiles = nullptr;
+  items = nullptr; counters = nullptr;
+}
+
+extern "C" {
+
+const char *qlb200_version(void) { return "qlb200 0.1 (sm_100a)"; }
+const char *qlb200_last_error(void) { return g_err.c_str(); }
+
+// ---- matcher -----------------------------------------------------------------------------------
+struct qlb200_match { Match m; };
+
+static int MatchCreate(const qlb200_shell *a, const qlb200_shell *b, int32_t nctrct, const int32_t *a_axes,
+                       const int32_t *b_axes, int sel_axis, uint32_t sel_sector, qlb200_match **out) {
+  if (!a || !b || !out || (nctrct > 0 && (!a_axes || !b_axes))) return Fail(QLB200_ERR_ARG, "null argument");
+  qlb200_match *m = new (std::nothrow) qlb200_match();
+  if (!m) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  std::string err = BuildMatch(a, b, nctrct, a_axes, b_axes, sel_axis, sel_sector, &m->m);
+  if (!err.empty()) { delete m; return Fail(QLB200_ERR_ARG, err); }
+  *out = m;
+  return QLB200_OK;
+}
+
+int qlb200_match_create(const qlb200_shell *a, const qlb200_shell *b, int32_t nctrct, const int32_t *a_axes,
+                        const int32_t *b_axes, qlb200_match **out) {
+  return MatchCreate(a, b, nctrct, a_axes, b_axes, -1, 0, out);
+}
+int qlb200_match_create_1sector(const qlb200_shell *a, int32_t axis, uint32_t sector, const qlb200_shell *b,
+                                int32_t nctrct, const int32_t *a_axes, const int32_t *b_axes, qlb200_match **out) {
+  if (axis < 0) return Fail(QLB200_ERR_ARG, "negative 1-sector axis");
+  return MatchCreate(a, b, nctrct, a_axes, b_axes, axis, sector, out);
+}
+void qlb200_match_destroy(qlb200_match *m) { delete m; }
+int32_t qlb200_match_c_rank(const qlb200_match *m) { return m->m.c_rank; }
+uint64_t qlb200_match_c_nblk(const qlb200_match *m) { return m->m.c_blocks.size(); }
+uint64_t qlb200_match_c_elems(const qlb200_match *m) { return m->m.c_elems; }
+uint64_t qlb200_match_ntask(const qlb200_match *m) { return m->m.tasks.size(); }
+int qlb200_match_is_scalar(const qlb200_match *m) { return m->m.scalar ? 1 : 0; }
+int qlb200_match_perm(const qlb200_match *m, int which, int32_t *perm_out) {
+  const std::vector<int> &p = which == 0 ? m->m.a_perm : m->m.b_perm;
+  for (size_t i = 0; i < p.size(); ++i) perm_out[i] = p[i];
+  return which == 0 ? (m->m.a_need_trans ? 1 : 0) : (m->m.b_need_trans ? 1 : 0);
+}
+int qlb200_match_c_blocks(const qlb200_match *m, uint64_t *blk_idx, uint32_t *blk_coors, uint32_t *shape,
+                          uint64_t *offset) {
+  const int r = m->m.c_rank;
+  for (size_t b = 0; b < m->m.c_blocks.size(); ++b) {
+    const CBlock &cb = m->m.c_blocks[b];
+    if (blk_idx) blk_idx[b] = cb.blk_idx;
+    if (offset) offset[b] = cb.offset;
+    for (int i = 0; i < r; ++i) {
+      if (blk_coors) blk_coors[b * r + i] = cb.coors[i];
+      if (shape) shape[b * r + i] = cb.shape[i];
+    }
+  }
+  return QLB200_OK;
+}
+int qlb200_match_tasks(const qlb200_match *m, int order, qlb200_task *tasks_out) {
+  if (order == 0) {
+    std::memcpy(tasks_out, m->m.tasks.data(), m->m.tasks.size() * sizeof(qlb200_task));
+  } else {
+    auto s = m->m.SortedTasks();
+    std::memcpy(tasks_out, s.data(), s.size() * sizeof(qlb200_task));
+  }
+  return QLB200_OK;
+}
+int qlb200_estimate_cost(const qlb200_match *m, int dtype, qlb200_cost *out) {
+  if (!m || !out) return Fail(QLB200_ERR_ARG, "null argument");
+  EstimateCost(m->m, dtype, out);
+  return QLB200_OK;
+}
+
+// ---- context -----------------------------------------------------------------------------------
+int qlb200_ctx_create(int device, qlb200_ctx **out) {
+  if (!out) return Fail(QLB200_ERR_ARG, "null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return Fail(QLB200_ERR_CUDA, e != cudaSuccess ? CudaErr("cudaGetDeviceCount", e) : "no CUDA device");
+  if (device < 0 || device >= ndev) return Fail(QLB200_ERR_ARG, "device ordinal out of range");
+  QL_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  QL_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return Fail(QLB200_ERR_UNSUPPORTED, "qlb200 kernels are built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor));
+  qlb200_ctx *c = new (std::nothrow) qlb200_ctx();
+  if (!c) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return Fail(QLB200_ERR_CUDA, CudaErr("cudaStreamCreate", e)); }
+  e = ConfigureKernels();
+  if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return Fail(QLB200_ERR_CUDA, CudaErr("cudaFuncSetAttribute", e)); }
+  *out = c;
+  return QLB200_OK;
+}
+void qlb200_ctx_destroy(qlb200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->ws); cudaFree(ctx->stage);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+int qlb200_ctx_sync(qlb200_ctx *ctx) { QL_CUDA(cudaStreamSynchronize(ctx->stream)); return QLB200_OK; }
+void *qlb200_ctx_stream(qlb200_ctx *ctx) { return ctx->stream; }
+int qlb200_ctx_set_stream(qlb200_ctx *ctx, void *cuda_stream) {
+  QL_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  return QLB200_OK;
+}
+uint64_t qlb200_ctx_launch_count(const qlb200_ctx *ctx) { return ctx->launches; }
+
+int qlb200_dev_alloc(qlb200_ctx *ctx, size_t bytes, void **out) {
+  QL_CUDA(cudaSetDevice(ctx->device));
+  QL_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+  return QLB200_OK;
+}
+int qlb200_dev_free(qlb200_ctx *ctx, void *p) {
+  QL_CUDA(cudaSetDevice(ctx->device));
+  QL_CUDA(cudaFree(p));
+  return QLB200_OK;
+}
+int qlb200_memcpy_h2d(qlb200_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  QL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return QLB200_OK;
+}
+int qlb200_memcpy_d2h(qlb200_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  QL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return QLB200_OK;
+}
+int qlb200_host_register(void *p, size_t bytes) { QL_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterDefault)); return QLB200_OK; }
+int qlb200_host_unregister(void *p) { QL_CUDA(cudaHostUnregister(p)); return QLB200_OK; }
+
+// ---- plans -------------------------------------------------------------------------------------
+int qlb200_plan_create(qlb200_ctx *ctx, const qlb200_match *m, const qlb200_shell *, const qlb200_shell *,
+                       int dtype, uint32_t flags, qlb200_plan **out) {
+  if (!m || !out) return Fail(QLB200_ERR_ARG, "null argument");
+  if (dtype != QLB200_F64 && dtype != QLB200_C64) return Fail(QLB200_ERR_ARG, "bad dtype");
+  const Match &mm = m->m;
+  qlb200_plan *p = new (std::nothrow) qlb200_plan();
+  if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  p->ctx = ctx;
+  std::vector<int32_t> ap(mm.a_perm.begin(), mm.a_perm.end()), bp(mm.b_perm.begin(), mm.b_perm.end());
+  std::string err = BuildPlanHost(dtype, flags, mm.a_need_trans, mm.a.rank, ap.data(), mm.a.nblk, mm.a.shape.data(),
+                                  mm.a.offset.data(), mm.a.elems, mm.b_need_trans, mm.b.rank, bp.data(), mm.b.nblk,
+                                  mm.b.shape.data(), mm.b.offset.data(), mm.b.elems, mm.SortedTasks(), mm.c_elems, &p->h);
+  if (!err.empty()) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, err); }
+  if (ctx != nullptr) {   // ctx == NULL: host-only plan (stats / partition queries, no device tables)
+    int rc = FinishPlan(ctx, p);
+    if (rc != QLB200_OK) { p->d.Free(); delete p; return rc; }
+  }
+  *out = p;
+  return QLB200_OK;
+}
+
+int qlb200_plan_create_raw(qlb200_ctx *ctx, int dtype, uint32_t flags, int32_t a_rank, const int32_t *a_perm,
+                           uint64_t na, const uint32_t *a_shape, const uint64_t *a_off, int32_t b_rank,
+                           const int32_t *b_perm, uint64_t nb, const uint32_t *b_shape, const uint64_t *b_off,
+                           uint64_t ntask, const qlb200_task *tasks, uint64_t c_elems, qlb200_plan **out) {
+  if (!ctx || !out || !a_shape || !b_shape || !a_off || !b_off || (ntask && !tasks)) return Fail(QLB200_ERR_ARG, "null argument");
+  if (dtype != QLB200_F64 && dtype != QLB200_C64) return Fail(QLB200_ERR_ARG, "bad dtype");
+  if (a_rank < 1 || a_rank > QLB200_MAX_RANK || b_rank < 1 || b_rank > QLB200_MAX_RANK) return Fail(QLB200_ERR_ARG, "bad rank");
+  auto trans = [](int rank, const int32_t *perm) {
+    if (!perm) return false;
+    for (int i = 0; i < rank; ++i) if (perm[i] != i) return true;
+    return false;
+  };
+  auto total = [](int rank, uint64_t n, const uint32_t *shape, const uint64_t *off) {
+    uint64_t e = 0;
+    for (uint64_t b = 0; b < n; ++b) {
+      uint64_t sz = 1;
+      for (int i = 0; i < rank; ++i) sz *= shape[b * rank + i];
+      e = std::max(e, off[b] + sz);
+    }
+    return e;
+  };
+  std::vector<qlb200_task> st(tasks, tasks + ntask);
+  std::stable_sort(st.begin(), st.end(), [](const qlb200_task &x, const qlb200_task &y) {
+    if (x.c_off != y.c_off) return x.c_off < y.c_off;
+    return x.first > y.first;
+  });
+  for (auto &t : st) t.c_ord = 0;   // groups are delimited by c_off here
+  {
+    uint32_t ord = 0;
+    for (size_t i = 0; i < st.size(); ++i) { if (i > 0 && st[i].c_off != st[i - 1].c_off) ++ord; st[i].c_ord = ord; }
+  }
+  qlb200_plan *p = new (std::nothrow) qlb200_plan();
+  if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  p->ctx = ctx;
+  std::string err = BuildPlanHost(dtype, flags, trans(a_rank, a_perm), a_rank, a_perm, na, a_shape, a_off,
+                                  total(a_rank, na, a_shape, a_off), trans(b_rank, b_perm), b_rank, b_perm, nb, b_shape,
+                                  b_off, total(b_rank, nb, b_shape, b_off), st, c_elems, &p->h);
+  if (!err.empty()) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, err); }
+  int rc = FinishPlan(ctx, p);
+  if (rc != QLB200_OK) { p->d.Free(); delete p; return rc; }
+  *out = p;
+  return QLB200_OK;
+}
+
+void qlb200_plan_destroy(qlb200_plan *p) {
+  if (!p) return;
+  if (!p->ctx) { delete p; return; }
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  p->d.Free();
+  delete p;
+}
+
+int qlb200_plan_partition(qlb200_plan *p, int32_t world, int32_t rank) {
+  if (!p || world < 1 || rank < 0 || rank >= world) return Fail(QLB200_ERR_ARG, "bad world/rank");
+  PartitionRows(&p->h, world, rank);
+  std::string err = BuildTiles(&p->h);
+  if (!err.empty()) return Fail(QLB200_ERR_UNSUPPORTED, err);
+  if (!p->ctx) return QLB200_OK;
+  QL_CUDA(cudaSetDevice(p->ctx->device));
+  return UploadGemmTables(p);
+}
+uint64_t qlb200_plan_c_range_count(const qlb200_plan *p) {
+  uint64_t n = 0;
+  for (const auto &g : p->h.part_groups) if (g.row_end > g.row_begin) ++n;
+  return n;
+}
+int qlb200_plan_c_ranges(const qlb200_plan *p, uint64_t *off, uint64_t *len) {
+  uint64_t i = 0;
+  for (const auto &g : p->h.part_groups) {
+    if (g.row_end <= g.row_begin) continue;
+    off[i] = g.c_off + uint64_t(g.row_begin) * g.n;
+    len[i] = uint64_t(g.row_end - g.row_begin) * g.n;
+    ++i;
+  }
+  return QLB200_OK;
+}
+int qlb200_plan_get_stats(const qlb200_plan *p, qlb200_plan_stats *out) {
+  if (!p || !out) return Fail(QLB200_ERR_ARG, "null argument");
+  std::memset(out, 0, sizeof(*out));
+  out->flops = p->h.flops;
+  out->ntask = p->h.tasks.size();
+  out->ngroup = p->h.groups.size();
+  out->ntile_dmma = p->h.tiles.size();
+  out->nrow_skinny = p->h.items.size();
+  out->permute_elems_a = p->h.permute_elems_a;
+  out->permute_elems_b = p->h.permute_elems_b;
+  out->workspace_bytes = WsBytes(p);
+  out->gemm_read_bytes = p->h.gemm_read_bytes;
+  out->gemm_write_bytes = p->h.gemm_write_bytes;
+  return QLB200_OK;
+}
+
+// ---- execution ---------------------------------------------------------------------------------
+static int ResolveOperands(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, const void **gemmA,
+                           const void **gemmB, void **wsA, void **wsB) {
+  const size_t es = ElemSize(p->h.dtype);
+  int rc = EnsureArena(&ctx->ws, &ctx->ws_bytes, WsBytes(p), ctx->stream);
+  if (rc != QLB200_OK) return rc;
+  *wsA = ctx->ws;
+  *wsB = static_cast<char *>(ctx->ws) + Align256(p->h.ws_a_elems * es);
+  *gemmA = p->h.a_trans ? *wsA : A;
+  *gemmB = p->h.b_trans ? *wsB : B;
+  return QLB200_OK;
+}
+
+int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B) {
+  if (!ctx || !p) return Fail(QLB200_ERR_ARG, "null argument");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  const void *ga, *gb; void *wa, *wb;
+  int rc = ResolveOperands(ctx, p, A, B, &ga, &gb, &wa, &wb);
+  if (rc != QLB200_OK) return rc;
+  ctx->launches = 0;
+  const uint32_t ntiles = p->h.perm_tile_base.back();
+  if (ntiles > 0) {
+    QL_CUDA(LaunchPermute(p->h.dtype, p->d.perm_blks, p->d.perm_tile_base, static_cast<uint32_t>(p->h.perm_blks.size()),
+                          ntiles, A, B, wa, wb, ctx->num_sms, ctx->stream));
+    ctx->launches += 1; ctx->total_launches += 1;
+  }
+  return QLB200_OK;
+}
+
+int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C) {
+  if (!ctx || !p) return Fail(QLB200_ERR_ARG, "null argument");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  const void *ga, *gb; void *wa, *wb;
+  int rc = ResolveOperands(ctx, p, A, B, &ga, &gb, &wa, &wb);
+  if (rc != QLB200_OK) return rc;
+  ctx->launches = 0;
+  GemmParams gp = MakeParams(p);
+  if (gp.ntiles > 0) {
+    QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, ga, gb, C, ctx->num_sms, ctx->stream));
+    ctx->launches += 1; ctx->total_launches += 1;
+  }
+  if (gp.nitems > 0) {
+    QL_CUDA(LaunchGemmSkinny(p->h.dtype, gp, ga, gb, C, ctx->num_sms, ctx->stream));
+    ctx->launches += 1; ctx->total_launches += 1;
+  }
+  return QLB200_OK;
+}
+
+int qlb200_execute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C, int mem_kind) {
+  if (!ctx || !p || !A || !B || !C) return Fail(QLB200_ERR_ARG, "null argument");
+  if (p->ctx == nullptr) return Fail(QLB200_ERR_ARG, "host-only plan (created without a context) cannot execute");
+  if (p->ctx != ctx) return Fail(QLB200_ERR_ARG, "plan belongs to another context");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  const size_t es = ElemSize(p->h.dtype);
+  const void *dA = A, *dB = B;
+  void *dC = C;
+  if (mem_kind == QLB200_MEM_HOST) {
+    const size_t ab = Align256(p->h.a_elems * es), bb = Align256(p->h.b_elems * es), cb = Align256(p->h.c_elems * es);
+    int rc = EnsureArena(&ctx->stage, &ctx->stage_bytes, ab + bb + cb, ctx->stream);
+    if (rc != QLB200_OK) return rc;
+    char *base = static_cast<char *>(ctx->stage);
+    QL_CUDA(cudaMemcpyAsync(base, A, p->h.a_elems * es, cudaMemcpyHostToDevice, ctx->stream));
+    QL_CUDA(cudaMemcpyAsync(base + ab, B, p->h.b_elems * es, cudaMemcpyHostToDevice, ctx->stream));
+    dA = base; dB = base + ab; dC = base + ab + bb;
+  } else if (mem_kind != QLB200_MEM_DEVICE) {
+    return Fail(QLB200_ERR_ARG, "bad mem_kind");
+  }
+  int rc = qlb200_execute_permute(ctx, p, dA, dB);
+  if (rc != QLB200_OK) return rc;
+  const uint64_t l0 = ctx->launches;
+  rc = qlb200_execute_gemm(ctx, p, dA, dB, dC);
+  if (rc != QLB200_OK) return rc;
+  ctx->launches += l0;
+  if (mem_kind == QLB200_MEM_HOST) {
+    // only the ranges this plan writes are copied back (whole C unless partitioned)
+    bool whole = true;
+    for (size_t i = 0; i < p->h.groups.size(); ++i)
+      if (p->h.part_groups[i].row_begin != 0 || p->h.part_groups[i].row_end != p->h.groups[i].m) { whole = false; break; }
+    if (whole) {
+      QL_CUDA(cudaMemcpyAsync(C, dC, p->h.c_elems * es, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      for (const auto &g : p->h.part_groups) {
+        if (g.row_end <= g.row_begin) continue;
+        const size_t o = (g.c_off + size_t(g.row_begin) * g.n) * es, l = size_t(g.row_end - g.row_begin) * g.n * es;
+        QL_CUDA(cudaMemcpyAsync(static_cast<char *>(C) + o, static_cast<char *>(dC) + o, l, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+    }
+    QL_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return QLB200_OK;
+}
+
+// ---- whole-tensor transpose ---------------------------------------------------------------------
+int qlb200_tplan_create(qlb200_ctx *ctx, const qlb200_shell *t, const int32_t *perm, int dtype, qlb200_tplan **out) {
+  if (!ctx || !t || !perm || !out) return Fail(QLB200_ERR_ARG, "null argument");
+  if (dtype != QLB200_F64 && dtype != QLB200_C64) return Fail(QLB200_ERR_ARG, "bad dtype");
+  Shell s;
+  std::string err = s.Load(t);
+  if (!err.empty()) return Fail(QLB200_ERR_ARG, err);
+  const int r = s.rank;
+  std::vector<char> seen(r, 0);
+  for (int i = 0; i < r; ++i) {
+    if (perm[i] < 0 || perm[i] >= r || seen[perm[i]]) return Fail(QLB200_ERR_ARG, "perm is not a permutation");
+    seen[perm[i]] = 1;
+  }
+  qlb200_tplan *p = new (std::nothrow) qlb200_tplan();
+  if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  p->ctx = ctx; p->dtype = dtype; p->elems = s.elems; p->rank = r;
+  // transposed blocks: new coordinates/shape, new blk_idx over the permuted sector counts
+  struct TB { uint64_t idx; uint64_t src; };
+  std::vector<TB> tb(s.nblk);
+  std::vector<uint32_t> nsct_t(r);
+  for (int i = 0; i < r; ++i) nsct_t[i] = s.nsct[perm[i]];
+  for (uint64_t b = 0; b < s.nblk; ++b) {
+    uint64_t idx = 0;
+    for (int i = 0; i < r; ++i) idx = idx * nsct_t[i] + s.coors[b * r + perm[i]];
+    tb[b] = {idx, b};
+  }
+  std::sort(tb.begin(), tb.end(), [](const TB &x, const TB &y) { return x.idx < y.idx; });
+  p->blk_idx.resize(s.nblk); p->offset.resize(s.nblk); p->scale.resize(s.nblk);
+  p->coors.resize(s.nblk * r); p->shape.resize(s.nblk * r);
+  uint64_t off = 0;
+  p->perm_tile_base.push_back(0);
+  uint8_t par[QLB200_MAX_RANK];
+  for (uint64_t i = 0; i < s.nblk; ++i) {
+    const uint64_t b = tb[i].src;
+    p->blk_idx[i] = tb[i].idx; p->offset[i] = off;
+    for (int a = 0; a < r; ++a) { p->coors[i * r + a] = s.coors[b * r + perm[a]]; p->shape[i * r + a] = s.shape[b * r + perm[a]]; }
+    int sign = 1;
+    if (s.fermionic()) {
+      for (int a = 0; a < r; ++a) par[a] = s.parity[s.sct_base[a] + s.coors[b * r + a]];
+      sign = FermionReorderSign(par, r, perm);
+    }
+    p->scale[i] = static_cast<int8_t>(sign);
+    if (s.size[b] >= (1ull << 32)) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, "block with 2^32 or more elements"); }
+    uint64_t nt = 0;
+    PermBlk d = MakePermBlk(r, &s.shape[b * r], perm, s.offset[b], off, 0, float(sign), &nt);
+    if (p->perm_tile_base.back() + nt >= (1ull << 32)) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, "too many permute tiles"); }
+    p->perm_blks.push_back(d);
+    p->perm_tile_base.push_back(static_cast<uint32_t>(p->perm_tile_base.back() + nt));
+    off += s.size[b];
+  }
+  QL_CUDA(cudaSetDevice(ctx->device));
+  int rc = Upload(p->perm_blks, &p->d.perm_blks, ctx->stream);
+  if (rc == QLB200_OK) rc = Upload(p->perm_tile_base, &p->d.perm_tile_base, ctx->stream);
+  if (rc != QLB200_OK) { p->d.Free(); delete p; return rc; }
+  QL_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = p;
+  return QLB200_OK;
+}
+void qlb200_tplan_destroy(qlb200_tplan *p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  p->d.Free();
+  delete p;
+}
+uint64_t qlb200_tplan_nblk(const qlb200_tplan *p) { return p->blk_idx.size(); }
+int qlb200_tplan_blocks(const qlb200_tplan *p, uint64_t *blk_idx, uint32_t *blk_coors, uint32_t *shape,
+                        uint64_t *offset, int8_t *scale) {
+  const size_t n = p->blk_idx.size();
+  if (blk_idx) std::memcpy(blk_idx, p->blk_idx.data(), n * sizeof(uint64_t));
+  if (offset) std::memcpy(offset, p->offset.data(), n * sizeof(uint64_t));
+  if (blk_coors) std::memcpy(blk_coors, p->coors.data(), n * p->rank * sizeof(uint32_t));
+  if (shape) std::memcpy(shape, p->shape.data(), n * p->rank * sizeof(uint32_t));
+  if (scale) std::memcpy(scale, p->scale.data(), n * sizeof(int8_t));
+  return QLB200_OK;
+}
+int qlb200_transpose_execute(qlb200_ctx *ctx, qlb200_tplan *p, const void *src, void *dst, int mem_kind) {
+  if (!ctx || !p || !src || !dst) return Fail(QLB200_ERR_ARG, "null argument");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  const size_t es = ElemSize(p->dtype);
+  const void *ds = src; void *dd = dst;
+  const size_t bytes = p->elems * es;
+  if (mem_kind == QLB200_MEM_HOST) {
+    int rc = EnsureArena(&ctx->stage, &ctx->stage_bytes, 2 * Align256(bytes), ctx->stream);
+    if (rc != QLB200_OK) return rc;
+    char *base = static_cast<char *>(ctx->stage);
+    QL_CUDA(cudaMemcpyAsync(base, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ds = base; dd = base + Align256(bytes);
+  }
+  ctx->launches = 0;
+  const uint32_t ntiles = p->perm_tile_base.back();
+  if (ntiles > 0) {
+    QL_CUDA(LaunchPermute(p->dtype, p->d.perm_blks, p->d.perm_tile_base, static_cast<uint32_t>(p->perm_blks.size()), ntiles,
+                          ds, ds, dd, dd, ctx->num_sms, ctx->stream));
+    ctx->launches += 1; ctx->total_launches += 1;
+  }
+  if (mem_kind == QLB200_MEM_HOST) {
+    QL_CUDA(cudaMemcpyAsync(dst, dd, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    QL_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return QLB200_OK;
+}
+
+}  // extern "C"

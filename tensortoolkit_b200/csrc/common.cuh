@@ -1,0 +1,95 @@
+// common.cuh -- device descriptor tables shared by the plan builder and the kernels.
+#ifndef QLB200_COMMON_CUH
+#define QLB200_COMMON_CUH
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+
+namespace qlb200 {
+
+// ------------------------------------------------------------------------------------------------
+// Batched permute.  One PermBlk per block, already canonicalised on the host:
+//   * size-1 axes dropped, axes that stay adjacent (and in order) merged;
+//   * axes listed in OUTPUT order (ext[nd-1] is the output-fastest axis), sstr[] = source stride.
+// The tile of a block spans TI elements of the source-fastest axis (`jin`, source stride 1) and TO
+// elements of the output-fastest axis (nd-1); all remaining axes enumerate tiles.  When the two
+// axes coincide (jin == nd-1) the block is a batch of contiguous runs ("row copy") and TO
+// enumerates the next-outer output axis instead.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPermMaxDims = 8;
+constexpr int kPermTileElems = 2048;   // elements staged in shared memory per tile
+
+struct PermBlk {
+  unsigned long long src_off, dst_off;  // elements, relative to the source / destination buffer
+  uint32_t ext[kPermMaxDims];           // extents in output order
+  uint32_t sstr[kPermMaxDims];          // source stride of each output axis
+  uint32_t dstr[kPermMaxDims];          // destination stride of each output axis (row-major over ext)
+  uint32_t nd;
+  uint32_t jin;                         // output axis with source stride 1
+  uint32_t jout;                        // axis tiled by TO (nd-1, or the next-outer one for row copies)
+  uint32_t TI, TO;                      // tile extents
+  uint32_t nti, nto;                    // tiles along jin / jout
+  uint32_t txi_log2, txo_log2;          // log2 of the thread-row width used in the load / store phase
+  uint32_t src_sel;                     // 0 = operand A buffer, 1 = operand B buffer
+  float scale;                          // +1 / -1 (fermionic whole-tensor transpose), applied on the fly
+  uint32_t pad_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Grouped GEMM.  A "group" is one output block; its tasks are the matched input pairs that
+// accumulate into it.  Offsets are in elements.
+// ------------------------------------------------------------------------------------------------
+struct GemmTask {
+  unsigned long long a_off, b_off;  // into the (possibly permuted) A / B operand buffers
+  uint32_t k;
+  int32_t sign;                     // +1 / -1
+};
+
+struct GemmGroup {
+  unsigned long long c_off;
+  uint32_t m, n;
+  uint32_t task_begin, task_end;
+  uint32_t row_begin, row_end;      // rows of the block this plan computes (multi-GPU slabs)
+};
+
+struct GemmTile {       // DMMA tile: rows [tm*BM, ..) x cols [tn*BN, ..) of a group
+  uint32_t group;
+  uint16_t tm, tn;
+};
+
+struct SkinnyItem {     // rows [row0, row0+rows) of a narrow group, one thread per row
+  uint32_t group;
+  uint32_t row0;
+};
+
+struct GemmParams {
+  const GemmTask *tasks;
+  const GemmGroup *groups;
+  const GemmTile *tiles;
+  const SkinnyItem *items;
+  uint32_t ntiles, nitems;
+  unsigned int *counters;           // [0] next tile, [1] finished CTAs (self-resetting)
+};
+
+inline std::string CudaErr(const char *what, cudaError_t e) {
+  return std::string(what) + ": " + cudaGetErrorString(e);
+}
+
+// launchers (defined in permute.cu / gemm.cu); all enqueue on `stream` and return the launch error
+cudaError_t LaunchPermute(int dtype, const PermBlk *blks, const uint32_t *tile_base, uint32_t nblk,
+                          uint32_t ntiles, const void *srcA, const void *srcB, void *dstA, void *dstB,
+                          int num_sms, cudaStream_t stream);
+cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, const void *A, const void *B, void *C,
+                           int num_sms, cudaStream_t stream);
+cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, const void *A, const void *B, void *C,
+                             int num_sms, cudaStream_t stream);
+cudaError_t ConfigureKernels();   // one-time cudaFuncSetAttribute calls
+
+// tile shapes of the DMMA kernel, needed by the host-side tiler
+constexpr int kRealBM = 128, kRealBN = 128, kRealBK = 16;
+constexpr int kCplxBM = 64, kCplxBN = 128, kCplxBK = 8;
+constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyRows = 256;
+
+}  // namespace qlb200
+#endif

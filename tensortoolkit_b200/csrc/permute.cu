@@ -1,0 +1,143 @@
+// permute.cu -- batched N-D permute: every block of both operands in ONE launch.
+//
+// Replaces the per-block hp_numeric::TensorTranspose calls of the reference's contraction loop
+// (include/qlten/qltensor/blk_spar_data_ten/global_operations.h:922-964; HPTT
+// framework/hp_numeric/ten_trans.h:94-114, cuTENSOR :245-349) and the per-block loop of
+// BlockSparseDataTensor::Transpose (raw_data_operations.h:201-218).
+// Semantics (ten_trans.h:130-186): out[i_perm[0], i_perm[1], ...] = scale * in[i_0, i_1, ...], both
+// row-major, i.e. output axis j is input axis perm[j].  Pure data movement: bit-exact.
+//
+// HBM-bound.  Persistent CTAs walk a flat tile list (prefix sums over blocks, binary search), stage
+// a TI x TO tile in shared memory so that global reads run along the source-fastest axis and
+// global writes along the destination-fastest axis.  Algorithmic bytes: 2 * elements * sizeof(T).
+#include "common.cuh"
+
+namespace qlb200 {
+
+namespace {
+
+constexpr int kPermThreads = 256;
+constexpr int kPermSmemElems = 2304;   // (TI|1) * TO never exceeds this (host tiler guarantees)
+
+template<typename T> __device__ __forceinline__ T ScaleBy(T v, float s);
+template<> __device__ __forceinline__ double ScaleBy<double>(double v, float s) { return s < 0.f ? -v : v; }
+template<> __device__ __forceinline__ double2 ScaleBy<double2>(double2 v, float s) {
+  return s < 0.f ? make_double2(-v.x, -v.y) : v;
+}
+
+template<typename T>
+__global__ void __launch_bounds__(kPermThreads)
+PermuteKernel(const PermBlk *__restrict__ blks, const uint32_t *__restrict__ tile_base, uint32_t nblk,
+              uint32_t ntiles, const T *__restrict__ srcA, const T *__restrict__ srcB,
+              T *__restrict__ dstA, T *__restrict__ dstB) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *s = reinterpret_cast<T *>(smem_raw);
+  __shared__ PermBlk sd;
+  __shared__ uint32_t s_blk;
+  const int tid = threadIdx.x;
+  uint32_t cur_blk = 0xffffffffu;
+
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // --- locate the block owning this tile (largest b with tile_base[b] <= tile) ---
+    if (tid == 0) {
+      uint32_t lo = 0, hi = nblk;
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (tile_base[mid] <= tile) lo = mid; else hi = mid;
+      }
+      s_blk = lo;
+    }
+    __syncthreads();
+    const uint32_t b = s_blk;
+    if (b != cur_blk) {
+      // cooperative copy of the descriptor into shared memory
+      const uint32_t *g = reinterpret_cast<const uint32_t *>(blks + b);
+      uint32_t *d = reinterpret_cast<uint32_t *>(&sd);
+      for (int i = tid; i < int(sizeof(PermBlk) / 4); i += kPermThreads) d[i] = g[i];
+      cur_blk = b;
+    }
+    __syncthreads();
+
+    uint32_t lt = tile - tile_base[b];
+    const uint32_t nd = sd.nd, jin = sd.jin, jout = sd.jout;
+    const uint32_t ti0 = (lt % sd.nti) * sd.TI; lt /= sd.nti;
+    const uint32_t to0 = (lt % sd.nto) * sd.TO; lt /= sd.nto;
+    unsigned long long so = sd.src_off + ti0, dofs = sd.dst_off + (unsigned long long) ti0 * sd.dstr[jin];
+    if (jout != jin) {
+      so += (unsigned long long) to0 * sd.sstr[jout];
+      dofs += (unsigned long long) to0 * sd.dstr[jout];
+    }
+    for (int j = int(nd) - 1; j >= 0; --j) {
+      if (uint32_t(j) == jin || uint32_t(j) == jout) continue;
+      const uint32_t e = sd.ext[j];
+      const uint32_t c = lt % e; lt /= e;
+      so += (unsigned long long) c * sd.sstr[j];
+      dofs += (unsigned long long) c * sd.dstr[j];
+    }
+    const uint32_t TIa = min(sd.TI, sd.ext[jin] - ti0);
+    const uint32_t TOa = (jout != jin) ? min(sd.TO, sd.ext[jout] - to0) : 1u;
+    const T *__restrict__ src = (sd.src_sel ? srcB : srcA) + so;
+    T *__restrict__ dst = (sd.src_sel ? dstB : dstA) + dofs;
+    const float scale = sd.scale;
+    const uint32_t s_out = sd.sstr[jout], d_in = sd.dstr[jin], d_out = sd.dstr[jout];
+
+    if (jin == nd - 1) {
+      // source-fastest axis is also destination-fastest: contiguous runs, no staging needed
+      const uint32_t tx = tid & ((1u << sd.txi_log2) - 1u), ty = tid >> sd.txi_log2;
+      const uint32_t TX = 1u << sd.txi_log2, RY = kPermThreads >> sd.txi_log2;
+      for (uint32_t to = ty; to < TOa; to += RY) {
+        const T *sp = src + (unsigned long long) to * s_out;
+        T *dp = dst + (unsigned long long) to * d_out;
+#pragma unroll 4
+        for (uint32_t ti = tx; ti < TIa; ti += TX) dp[ti] = ScaleBy(sp[ti], scale);
+      }
+    } else {
+      const uint32_t TIp = sd.TI | 1u;
+      {
+        const uint32_t tx = tid & ((1u << sd.txi_log2) - 1u), ty = tid >> sd.txi_log2;
+        const uint32_t TX = 1u << sd.txi_log2, RY = kPermThreads >> sd.txi_log2;
+        for (uint32_t to = ty; to < TOa; to += RY) {
+          const T *sp = src + (unsigned long long) to * s_out;
+          T *ss = s + to * TIp;
+#pragma unroll 4
+          for (uint32_t ti = tx; ti < TIa; ti += TX) ss[ti] = sp[ti];
+        }
+      }
+      __syncthreads();
+      {
+        const uint32_t tx = tid & ((1u << sd.txo_log2) - 1u), ty = tid >> sd.txo_log2;
+        const uint32_t TX = 1u << sd.txo_log2, RY = kPermThreads >> sd.txo_log2;
+        for (uint32_t ti = ty; ti < TIa; ti += RY) {
+          T *dp = dst + (unsigned long long) ti * d_in;
+          const T *ss = s + ti;
+#pragma unroll 4
+          for (uint32_t to = tx; to < TOa; to += TX) dp[to] = ScaleBy(ss[to * TIp], scale);
+        }
+      }
+    }
+    __syncthreads();   // shared tile / descriptor are reused by the next iteration
+  }
+}
+
+}  // namespace
+
+cudaError_t LaunchPermute(int dtype, const PermBlk *blks, const uint32_t *tile_base, uint32_t nblk,
+                          uint32_t ntiles, const void *srcA, const void *srcB, void *dstA, void *dstB,
+                          int num_sms, cudaStream_t stream) {
+  if (ntiles == 0) return cudaSuccess;
+  const uint32_t grid = ntiles < uint32_t(num_sms) * 6u ? ntiles : uint32_t(num_sms) * 6u;
+  if (dtype == 0) {
+    const size_t smem = kPermSmemElems * sizeof(double);
+    PermuteKernel<double><<<grid, kPermThreads, smem, stream>>>(
+        blks, tile_base, nblk, ntiles, static_cast<const double *>(srcA), static_cast<const double *>(srcB),
+        static_cast<double *>(dstA), static_cast<double *>(dstB));
+  } else {
+    const size_t smem = kPermSmemElems * sizeof(double2);
+    PermuteKernel<double2><<<grid, kPermThreads, smem, stream>>>(
+        blks, tile_base, nblk, ntiles, static_cast<const double2 *>(srcA), static_cast<const double2 *>(srcB),
+        static_cast<double2 *>(dstA), static_cast<double2 *>(dstB));
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace qlb200

@@ -1,0 +1,97 @@
+// plan.h -- execution context and per-contraction device plans (internal).
+#ifndef QLB200_PLAN_H
+#define QLB200_PLAN_H
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "matcher.h"
+
+struct qlb200_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  // grow-only arenas: `ws` holds the permuted operands, `stage` the device copies of host tensors
+  void *ws = nullptr; size_t ws_bytes = 0;
+  void *stage = nullptr; size_t stage_bytes = 0;
+  uint64_t launches = 0;          // kernels launched by the last execute call
+  uint64_t total_launches = 0;
+};
+
+namespace qlb200 {
+
+struct DeviceTables {
+  PermBlk *perm_blks = nullptr;
+  uint32_t *perm_tile_base = nullptr;
+  GemmTask *tasks = nullptr;
+  GemmGroup *groups = nullptr;
+  GemmTile *tiles = nullptr;
+  SkinnyItem *items = nullptr;
+  unsigned int *counters = nullptr;
+  void Free();
+};
+
+struct PlanHost {
+  int dtype = 0;
+  uint32_t flags = 0;
+  uint64_t a_elems = 0, b_elems = 0, c_elems = 0;      // raw sizes of the three tensors
+  bool a_trans = false, b_trans = false;
+  uint64_t ws_a_elems = 0, ws_b_elems = 0;             // permuted operand sizes (workspace)
+  std::vector<PermBlk> perm_blks;
+  std::vector<uint32_t> perm_tile_base;                // [nblk+1]
+  std::vector<GemmTask> tasks;
+  std::vector<GemmGroup> groups;                       // full row ranges
+  std::vector<uint64_t> group_ksum;
+  std::vector<GemmGroup> part_groups;                  // row ranges after partitioning
+  std::vector<GemmTile> tiles;
+  std::vector<SkinnyItem> items;
+  double flops = 0;
+  uint64_t permute_elems_a = 0, permute_elems_b = 0;
+  uint64_t gemm_read_bytes = 0, gemm_write_bytes = 0;
+};
+
+}  // namespace qlb200
+
+struct qlb200_plan {
+  qlb200_ctx *ctx = nullptr;
+  qlb200::PlanHost h;
+  qlb200::DeviceTables d;
+};
+
+struct qlb200_tplan {
+  qlb200_ctx *ctx = nullptr;
+  int dtype = 0;
+  uint64_t elems = 0;
+  int rank = 0;
+  std::vector<uint64_t> blk_idx, offset;
+  std::vector<uint32_t> coors, shape;
+  std::vector<int8_t> scale;
+  std::vector<qlb200::PermBlk> perm_blks;
+  std::vector<uint32_t> perm_tile_base;
+  qlb200::DeviceTables d;
+};
+
+namespace qlb200 {
+
+/// Canonicalise one block permutation and choose its tiling. `perm[j]` = input axis of output axis j.
+PermBlk MakePermBlk(int rank, const uint32_t *shape, const int32_t *perm, uint64_t src_off, uint64_t dst_off,
+                    uint32_t src_sel, float scale, uint64_t *ntiles_out);
+
+/// Build the host-side tables of a contraction from sorted tasks.
+std::string BuildPlanHost(int dtype, uint32_t flags, bool a_trans, int a_rank, const int32_t *a_perm,
+                          uint64_t na, const uint32_t *a_shape, const uint64_t *a_off, uint64_t a_elems,
+                          bool b_trans, int b_rank, const int32_t *b_perm, uint64_t nb, const uint32_t *b_shape,
+                          const uint64_t *b_off, uint64_t b_elems, const std::vector<qlb200_task> &sorted_tasks,
+                          uint64_t c_elems, PlanHost *out);
+
+/// (Re)build tile and item lists from part_groups.
+std::string BuildTiles(PlanHost *h);
+
+/// Restrict part_groups to the rows owned by `rank` of `world` (cost-balanced contiguous cut).
+void PartitionRows(PlanHost *h, int world, int rank);
+
+}  // namespace qlb200
+#endif
