@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: block-sparse contraction useful FP64 GFLOP/s and % of the
+measured FP64 tensor-core GEMM peak.
+
+Workload at N=1 (config.workload): BASELINE configs[2], the headline -- U(1) two-site
+effective-Hamiltonian apply at D=4096, complex double (four chained Contract calls).
+One "step" = one H_eff apply.  `value` = algorithmic flops (the reference's own cost model,
+tensor_op_cost.h: 8*m*k*n per complex pair) / device time with all operands resident in HBM.
+`e2e` = the same apply through the public chain API with psi in pinned HOST memory: H2D of psi,
+four steps, D2H of the result inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--D 4096] [--dtype c128|f64]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEEDS = {"f64": 20260002, "c128": 20260003}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--D", type=int, default=4096)
+    ap.add_argument("--dtype", default="c128", choices=["c128", "f64"])
+    ap.add_argument("--cpu-sample-D", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
+    return ap.parse_args()
+
+
+def np_dtype(name):
+    return np.complex128 if name == "c128" else np.float64
+
+
+def workload_name(D, dtype):
+    return (f"U(1) spin-1/2 Heisenberg two-site effective-Hamiltonian apply (lenv x psi x W1 x W2 x renv, 4 chained Contract), "
+            f"D={D}, {'complex double' if dtype == 'c128' else 'double'}")
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max((float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()), default=None),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def build_tensors(D, dtype, rng):
+    import tensortoolkit_b200 as tk
+    from tensortoolkit_b200 import workloads as wl
+    ti = wl.heff_tensor_indexes(wl.u1_heisenberg_indexes(D))
+    return {name: tk.BlockSparseTensor(idxs, np_dtype(dtype)).random((0,), rng) for name, idxs in ti.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_apply(D, dtype, reps, threads):
+    """The reference's own CPU path (oracle/_ref: TensorToolkit + HPTT + OpenBLAS) on one H_eff apply.
+    Returns (best seconds per apply, flops per apply)."""
+    from oracle import refbridge as ref
+    from tensortoolkit_b200 import workloads as wl
+    ref.lib()
+    ref.set_threads(threads)
+    ref.set_seed(SEEDS[dtype])
+    ti = wl.heff_tensor_indexes(wl.u1_heisenberg_indexes(D))
+    r = {name: ref.RefTensor.new(idxs, np_dtype(dtype)).random((0,)) for name, idxs in ti.items()}
+    flops = 0.0
+    for lhs, rhs, axes, out in wl.HEFF_STEPS:          # warm-up pass, also builds the intermediates
+        flops += ref.contract_cost(r[lhs], r[rhs], axes)["flops"]
+        r[out] = ref.contract(r[lhs], r[rhs], axes)
+    best = float("inf")
+    for _ in range(reps):
+        t = 0.0
+        for lhs, rhs, axes, out in wl.HEFF_STEPS:
+            t += ref.contract_time(r[lhs], r[rhs], axes, 1)
+        best = min(best, t)
+    return best, flops
+
+
+def pick_threads():
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = pick_threads()
+    D = args.cpu_sample_D
+    times = []
+    flops = None
+    for _ in range(max(1, args.warmup)):
+        cpu_reference_apply(D, args.dtype, 1, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sec, flops = cpu_reference_apply(D, args.dtype, 1, threads)
+        times.append(sec)
+        if time.perf_counter() - t0 > 240:
+            break
+    sec = float(np.mean(times))
+    val = flops / sec / 1e9
+    sample = f"one H_eff apply at D={D} ({flops / 1e9:.1f} GFLOP; the D={args.D} workload is {(args.D / D) ** 3:.0f}x the flops), Contract calls only"
+    line = {
+        "impl": "reference", "metric": "block-sparse contraction useful FP64 GFLOP/s", "value": val, "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "c64(f64 pairs)" if args.dtype == "c128" else "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.D, args.dtype), "bounded_sample": sample},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def measure_fp64_peak(torch, dtype):
+    """cuBLAS GEMM peak for the arithmetic type, measured here (MEASURED_PEAKS.json has no FP64 entry)."""
+    n = 4096 if dtype == "c128" else 8192
+    tdt = torch.complex128 if dtype == "c128" else torch.float64
+    a = torch.randn(n, n, dtype=tdt, device="cuda")
+    b = torch.randn(n, n, dtype=tdt, device="cuda")
+    fl = (8.0 if dtype == "c128" else 2.0) * n ** 3
+    best = float("inf")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    # sustained: back to back for ~1.5 s
+    reps = max(3, int(1.5 / best))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b)
+    e1.record(); torch.cuda.synchronize()
+    sustained = fl * reps / (e0.elapsed_time(e1) * 1e-3)
+    del a, b
+    return fl / best / 1e12, sustained / 1e12, f"torch.matmul {'complex128' if dtype == 'c128' else 'float64'} {n}^3 (cuBLAS), best of 6 / back-to-back {reps} calls"
+
+
+def run_ours(args):
+    import torch
+    import tensortoolkit_b200 as tk
+    from tensortoolkit_b200 import workloads as wl
+    from tensortoolkit_b200.heff import ContractionChain
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    stream = torch.cuda.Stream()
+    ctx = tk.Context(local)
+    ctx.set_stream(stream.cuda_stream)
+
+    dtype = args.dtype
+    es = 16 if dtype == "c128" else 8
+    rng = np.random.default_rng(SEEDS[dtype])
+    tensors = build_tensors(args.D, dtype, rng)
+    if world > 1:
+        from tensortoolkit_b200.sharding import shard_heff_tensors
+        tensors, shard_info = shard_heff_tensors(tensors, world, rank)
+    chain = ContractionChain(ctx, tensors, wl.HEFF_STEPS, np_dtype(dtype))
+    stats = chain.stats()
+    flops_local = chain.flops()
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, args.warmup)):
+            chain.apply_device()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        # ---- timed region: K applies, per-step events, L2 flushed between steps ----
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            launches = chain.apply_device()
+            e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        dev_ms = [a.elapsed_time(b) for a, b in evs]
+        # ---- per-kernel breakdown (same stream, CUDA events around each launch group) ----
+        kern = []
+        for si, ((lhs, rhs, axes, out), plan) in enumerate(zip(chain.steps, chain.plans)):
+            tp, tg = [], []
+            for _ in range(max(3, min(args.steps, 5))):
+                flush.zero_()
+                a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a0.record(stream)
+                plan.execute_permute(chain.buf[lhs].ptr, chain.buf[rhs].ptr)
+                a1.record(stream)
+                plan.execute_gemm(chain.buf[lhs].ptr, chain.buf[rhs].ptr, chain.buf[out].ptr)
+                a2.record(stream)
+                torch.cuda.synchronize()
+                tp.append(a0.elapsed_time(a1)); tg.append(a1.elapsed_time(a2))
+            st = stats[si]
+            pel = st.permute_elems_a + st.permute_elems_b
+            kern.append({"step": si + 1, "kernel": "batched_permute", "ms": float(np.mean(tp)), "bound": "hbm",
+                         "alg_bytes": 2 * pel * es, "achieved": (2 * pel * es / (np.mean(tp) * 1e-3) / 1e9) if pel else 0.0, "unit": "GB/s"})
+            kname = "grouped_gemm_dmma" if st.ntile_dmma else "grouped_gemm_skinny"
+            if st.ntile_dmma:
+                kern.append({"step": si + 1, "kernel": kname, "ms": float(np.mean(tg)), "bound": "tensor", "alg_flops": st.flops,
+                             "achieved": st.flops / (np.mean(tg) * 1e-3) / 1e12, "unit": "TFLOP/s"})
+            else:
+                byts = st.gemm_read_bytes + st.gemm_write_bytes
+                kern.append({"step": si + 1, "kernel": kname, "ms": float(np.mean(tg)), "bound": "hbm", "alg_bytes": byts,
+                             "achieved": byts / (np.mean(tg) * 1e-3) / 1e9, "unit": "GB/s"})
+        sampler.stop_flag = True
+        # ---- e2e: psi in pinned host memory, H2D + 4 steps + D2H per step ----
+        psi_host = tensors["psi"].data
+        out_host = np.empty(chain.shells["out"].data.size, np_dtype(dtype))
+        tk._lib.check(tk._lib.lib.qlb200_host_register(psi_host.ctypes.data, psi_host.nbytes), "host_register")
+        tk._lib.check(tk._lib.lib.qlb200_host_register(out_host.ctypes.data, out_host.nbytes), "host_register")
+        for _ in range(2):
+            chain.apply_host("psi", psi_host, "out", out_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            chain.apply_host("psi", psi_host, "out", out_host)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.steps
+        tk._lib.lib.qlb200_host_unregister(psi_host.ctypes.data)
+        tk._lib.lib.qlb200_host_unregister(out_host.ctypes.data)
+        peak_burst, peak_sust, peak_how = measure_fp64_peak(torch, dtype)
+
+    ms = float(np.mean(dev_ms))
+    tot_ms, flops_total, e2e_max = ms, flops_local, e2e_s
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        f = torch.tensor([flops_local], device="cuda", dtype=torch.float64)
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+        tot_ms, e2e_max, flops_total = float(t[0]), float(t[1]), float(f[0])
+    if rank != 0:
+        return
+
+    value = flops_total / (tot_ms * 1e-3) / 1e9
+    dom = max((k for k in kern), key=lambda k: k["ms"])
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    if dom["bound"] == "tensor":
+        roof = {"bound": "tensor", "kernel": f"step{dom['step']}:{dom['kernel']}", "achieved": dom["achieved"], "peak": peak_burst,
+                "unit": "TFLOP/s", "frac": dom["achieved"] / peak_burst, "traffic": None,
+                "peak_source": f"FP64 GEMM peak measured in this run: {peak_how}; burst {peak_burst:.2f} / sustained {peak_sust:.2f} TFLOP/s "
+                               "(MEASURED_PEAKS.json has no FP64 entry; tcgen05 has no FP64 kind, DMMA via mma.sync is the FP64 tensor path)"}
+    else:
+        roof = {"bound": "hbm", "kernel": f"step{dom['step']}:{dom['kernel']}", "achieved": dom["achieved"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": dom["achieved"] / hbm_peak, "traffic": None, "peak_source": hbm_src}
+    for k in kern:
+        k["frac"] = k["achieved"] / (peak_burst if k["bound"] == "tensor" else hbm_peak)
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            threads = pick_threads()
+            sec, fl = cpu_reference_apply(args.cpu_sample_D, dtype, 2, threads)
+            cpu = {"value": fl / sec / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": "reference",
+                   "sample": f"one H_eff apply at D={args.cpu_sample_D} {dtype} ({fl / 1e9:.1f} GFLOP, {sec:.2f} s best of 2) with the reference's own "
+                             "CPU path (TensorToolkit Contract + HPTT + OpenBLAS 0.3.15), Contract calls only"}
+        except Exception as e:   # the oracle library is test infrastructure; never fatal for the product bench
+            cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+
+    line = {
+        "metric": "block-sparse contraction useful FP64 GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "c64(f64 pairs)" if dtype == "c128" else "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.D, dtype), "l2": "512 MiB flush written between timed applies; operands+intermediates (>1 GB) exceed the 126 MB L2",
+                   "parallelism": f"output-sector/row-slab x{world}" if world > 1 else "single GPU", "flops_per_step": flops_total,
+                   "tasks_per_step": int(sum(s.ntask for s in stats))},
+        "pct_fp64_peak": 100.0 * value / 1e3 / peak_burst / world, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sust, "how": peak_how},
+        "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+        "e2e": {"value": flops_total / e2e_max / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_max * 1e3,
+                "h2d_bytes_per_step": int(psi_host.nbytes), "d2h_bytes_per_step": int(out_host.nbytes)},
+        "gpu_launches": int(launches) * args.steps, "clocks": sampler.summary(),
+    }
+    if args.breakdown:
+        for k in kern:
+            print(f"  step {k['step']} {k['kernel']:22s} {k['ms']:8.3f} ms  {k['achieved']:9.2f} {k['unit']:8s} frac {k['frac']:.3f}", file=sys.stderr)
+    print(json.dumps(line))
+    chain.close()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

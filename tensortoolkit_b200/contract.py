@@ -148,7 +148,7 @@ class ContractionPlan:
         self.ctx, self.match = ctx, match
         self.dtype = np.dtype(dtype)
         h = C.c_void_p()
-        check(lib.qlb200_plan_create(ctx.h, match.h, match.sa.ptr(), match.sb.ptr(), _dtype_code(dtype), flags, C.byref(h)),
+        check(lib.qlb200_plan_create(ctx.h if ctx is not None else None, match.h, match.sa.ptr(), match.sb.ptr(), _dtype_code(dtype), flags, C.byref(h)),
               "qlb200_plan_create")
         self.h = h
 

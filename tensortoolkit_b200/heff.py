@@ -1,0 +1,106 @@
+"""Device-resident chain of contractions: plan once, apply many times (Lanczos-style mat-vec).
+
+The reference's recipe for the two-site effective-Hamiltonian apply is four chained Contract calls
+(tests/test_tensor_manipulation/test_ten_ctrct_1sct.cc:253-257); its block topology is constant
+across iterations, so matches, descriptor tables and buffers are built once here and every apply
+only enqueues kernels on the context's stream (no host round trips between steps).
+"""
+import ctypes as C
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+from .contract import Context, ContractionPlan, Match
+from .tensor import BlockSparseTensor
+
+
+class DeviceBuffer:
+    def __init__(self, ctx: Context, nbytes: int):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(lib.qlb200_dev_alloc(ctx.h, max(self.nbytes, 16), C.byref(p)), "qlb200_dev_alloc")
+        self.ptr = p.value
+
+    def upload(self, host: np.ndarray):
+        assert host.nbytes <= self.nbytes
+        check(lib.qlb200_memcpy_h2d(self.ctx.h, C.c_void_p(self.ptr), host.ctypes.data, host.nbytes), "qlb200_memcpy_h2d")
+
+    def download(self, host: np.ndarray):
+        assert host.nbytes <= self.nbytes
+        check(lib.qlb200_memcpy_d2h(self.ctx.h, host.ctypes.data, C.c_void_p(self.ptr), host.nbytes), "qlb200_memcpy_d2h")
+
+    def free(self):
+        if self.ptr:
+            lib.qlb200_dev_free(self.ctx.h, C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+class ContractionChain:
+    """steps: list of (lhs name, rhs name, axes, out name); `tensors` holds the host operands."""
+
+    def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps: Sequence[Tuple[str, str, tuple, str]],
+                 dtype, flags: int = _lib.PLAN_DETERMINISTIC):
+        self.ctx, self.dtype, self.steps = ctx, np.dtype(dtype), list(steps)
+        self.shells: Dict[str, BlockSparseTensor] = dict(tensors)
+        self.matches: List[Match] = []
+        self.plans: List[ContractionPlan] = []
+        for lhs, rhs, axes, out in self.steps:
+            m = Match(self.shells[lhs], self.shells[rhs], axes)
+            self.matches.append(m)
+            self.shells[out] = m.result_shell(self.dtype)
+            self.plans.append(ContractionPlan(ctx, m, self.dtype, flags))
+        self.buf: Dict[str, DeviceBuffer] = {}
+        for name, t in self.shells.items():
+            self.buf[name] = DeviceBuffer(ctx, t.data.size * self.dtype.itemsize)
+        for name, t in tensors.items():
+            self.buf[name].upload(t.data)
+        ctx.sync()
+        self.launches_per_apply = 0
+
+    def stats(self):
+        return [p.stats() for p in self.plans]
+
+    def flops(self) -> float:
+        return float(sum(s.flops for s in self.stats()))
+
+    def upload(self, name: str, host: np.ndarray):
+        self.buf[name].upload(host)
+
+    def apply_device(self):
+        """Enqueue all steps; returns the number of kernels launched."""
+        n = 0
+        for (lhs, rhs, _, out), plan in zip(self.steps, self.plans):
+            plan.execute_device(self.buf[lhs].ptr, self.buf[rhs].ptr, self.buf[out].ptr)
+            n += self.ctx.launch_count()
+        self.launches_per_apply = n
+        return n
+
+    def apply_host(self, in_name: str, host_in: np.ndarray, out_name: str, host_out: np.ndarray):
+        """End-to-end apply: input H2D, all steps, result D2H, synchronise."""
+        self.buf[in_name].upload(host_in)
+        self.apply_device()
+        self.buf[out_name].download(host_out)
+        self.ctx.sync()
+
+    def result(self, name: str) -> BlockSparseTensor:
+        t = self.shells[name]
+        out = BlockSparseTensor(t.indexes, self.dtype)
+        if t.rank:
+            out.set_blocks(t.blk_coors)
+        else:
+            out.data = np.zeros(t.data.size, self.dtype)
+        self.buf[name].download(out.data)
+        self.ctx.sync()
+        return out
+
+    def close(self):
+        for p in self.plans:
+            p.close()
+        for m in self.matches:
+            m.close()
+        for b in self.buf.values():
+            b.free()
+        self.plans, self.matches, self.buf = [], [], {}
