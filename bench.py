@@ -16,7 +16,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -30,7 +29,7 @@ SEEDS = {"f64": 20260002, "c128": 20260003}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--D", type=int, default=4096)
@@ -51,35 +50,47 @@ def workload_name(D, dtype):
 
 
 # ------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region
+    (B200_PROFILING.md recipe: start before, stop after)."""
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.proc, self.samples = index, None, []
 
-    def run(self):
+    def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) >= 7:
+                self.samples.append(f)
 
     def summary(self):
+        num = lambda x: float(x) if x.replace(".", "", 1).isdigit() else None
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        sm = sorted(v for v in (num(s[0]) for s in self.samples) if v is not None)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
-                "power_w_max": max((float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()), default=None),
-                "reasons": reasons, "samples": len(self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        pw = [v for v in (num(s[2]) for s in self.samples) if v is not None]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": num(self.samples[0][1]),
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.samples)}
 
 
 def build_tensors(D, dtype, rng):
@@ -200,10 +211,17 @@ def run_ours(args):
     es = 16 if dtype == "c128" else 8
     rng = np.random.default_rng(SEEDS[dtype])
     tensors = build_tensors(args.D, dtype, rng)
+    sharded = None
     if world > 1:
-        from tensortoolkit_b200.sharding import shard_heff_tensors
-        tensors, shard_info = shard_heff_tensors(tensors, world, rank)
-    chain = ContractionChain(ctx, tensors, wl.HEFF_STEPS, np_dtype(dtype))
+        # partition by output sector / row slab of lenv's free bond; all-gather of disjoint slabs per apply
+        from tensortoolkit_b200.heff import ShardedChain
+        with torch.cuda.stream(stream):
+            sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank)
+        chain = sharded.chain
+        apply_fn = sharded.apply
+    else:
+        chain = ContractionChain(ctx, tensors, wl.HEFF_STEPS, np_dtype(dtype))
+        apply_fn = chain.apply_device
     stats = chain.stats()
     flops_local = chain.flops()
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -215,7 +233,7 @@ def run_ours(args):
 
     with torch.cuda.stream(stream):
         for _ in range(max(3, args.warmup)):
-            chain.apply_device()
+            apply_fn()
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
@@ -225,7 +243,7 @@ def run_ours(args):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            launches = chain.apply_device()
+            launches = apply_fn()
             e1.record(stream)
             evs.append((e0, e1))
         barrier()
@@ -256,18 +274,26 @@ def run_ours(args):
                 byts = st.gemm_read_bytes + st.gemm_write_bytes
                 kern.append({"step": si + 1, "kernel": kname, "ms": float(np.mean(tg)), "bound": "hbm", "alg_bytes": byts,
                              "achieved": byts / (np.mean(tg) * 1e-3) / 1e9, "unit": "GB/s"})
-        sampler.stop_flag = True
+        sampler.stop()
         # ---- e2e: psi in pinned host memory, H2D + 4 steps + D2H per step ----
         psi_host = tensors["psi"].data
-        out_host = np.empty(chain.shells["out"].data.size, np_dtype(dtype))
+        out_host = np.empty(sharded.info.full_elems if sharded is not None else chain.shells["out"].data.size, np_dtype(dtype))
         tk._lib.check(tk._lib.lib.qlb200_host_register(psi_host.ctypes.data, psi_host.nbytes), "host_register")
         tk._lib.check(tk._lib.lib.qlb200_host_register(out_host.ctypes.data, out_host.nbytes), "host_register")
+        def e2e_apply():
+            if sharded is None:
+                chain.apply_host("psi", psi_host, "out", out_host)
+            else:   # psi H2D on every rank, local steps + all-gather + unpack, full result D2H on every rank
+                chain.buf["psi"].upload(psi_host)
+                sharded.apply()
+                tk._lib.check(tk._lib.lib.qlb200_memcpy_d2h(ctx.h, out_host.ctypes.data, sharded.full.data_ptr(), out_host.nbytes), "d2h")
+                ctx.sync()
         for _ in range(2):
-            chain.apply_host("psi", psi_host, "out", out_host)
+            e2e_apply()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            chain.apply_host("psi", psi_host, "out", out_host)
+            e2e_apply()
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.steps
         tk._lib.lib.qlb200_host_unregister(psi_host.ctypes.data)

@@ -189,6 +189,13 @@ int qlb200_tplan_blocks(const qlb200_tplan *p, uint64_t *blk_idx, uint32_t *blk_
 int qlb200_transpose_execute(qlb200_ctx *ctx, qlb200_tplan *p, const void *src, void *dst,
                              int mem_kind);
 
+/* ---- batched range copy (multi-GPU: unpack all-gathered output slabs into the full layout) --- */
+/* dst[dst_off[i] .. +len[i]) = src[src_off[i] .. +len[i]) for every i, one launch of the permute
+ * kernel in its contiguous-run mode.  Offsets / lengths in elements; device pointers only. */
+int qlb200_cplan_create(qlb200_ctx *ctx, int dtype, uint64_t n, const uint64_t *src_off,
+                        const uint64_t *dst_off, const uint64_t *len, qlb200_tplan **out);
+int qlb200_copy_execute(qlb200_ctx *ctx, qlb200_tplan *p, const void *src, void *dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,8 @@ SYMBOLS = {
     "qlb200_tplan_nblk": (C.c_uint64, [_P]),
     "qlb200_tplan_blocks": (C.c_int, [_P, _U64P, _U32P, _U32P, _U64P, _I8P]),
     "qlb200_transpose_execute": (C.c_int, [_P, _P, _P, _P, C.c_int]),
+    "qlb200_cplan_create": (C.c_int, [_P, C.c_int, C.c_uint64, _U64P, _U64P, _U64P, _PP]),
+    "qlb200_copy_execute": (C.c_int, [_P, _P, _P, _P]),
 }
 
 

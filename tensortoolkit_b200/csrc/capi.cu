@@ -537,4 +537,49 @@ int qlb200_transpose_execute(qlb200_ctx *ctx, qlb200_tplan *p, const void *src, 
   return QLB200_OK;
 }
 
+// ---- batched range copy ---------------------------------------------------------------------------
+int qlb200_cplan_create(qlb200_ctx *ctx, int dtype, uint64_t n, const uint64_t *src_off, const uint64_t *dst_off,
+                        const uint64_t *len, qlb200_tplan **out) {
+  if (!ctx || !out || (n && (!src_off || !dst_off || !len))) return Fail(QLB200_ERR_ARG, "null argument");
+  if (dtype != QLB200_F64 && dtype != QLB200_C64) return Fail(QLB200_ERR_ARG, "bad dtype");
+  qlb200_tplan *p = new (std::nothrow) qlb200_tplan();
+  if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  p->ctx = ctx; p->dtype = dtype; p->rank = 1;
+  p->perm_tile_base.push_back(0);
+  const int32_t ident[1] = {0};
+  for (uint64_t i = 0; i < n; ++i) {
+    // ranges longer than 2^31 elements are split so extents stay 32-bit
+    for (uint64_t done = 0; done < len[i];) {
+      const uint64_t chunk = std::min<uint64_t>(len[i] - done, 1ull << 31);
+      const uint32_t shape[1] = {static_cast<uint32_t>(chunk)};
+      uint64_t nt = 0;
+      PermBlk d = MakePermBlk(1, shape, ident, src_off[i] + done, dst_off[i] + done, 0, 1.0f, &nt);
+      if (p->perm_tile_base.back() + nt >= (1ull << 32)) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, "too many copy tiles"); }
+      p->perm_blks.push_back(d);
+      p->perm_tile_base.push_back(static_cast<uint32_t>(p->perm_tile_base.back() + nt));
+      p->elems += chunk;
+      done += chunk;
+    }
+  }
+  QL_CUDA(cudaSetDevice(ctx->device));
+  int rc = Upload(p->perm_blks, &p->d.perm_blks, ctx->stream);
+  if (rc == QLB200_OK) rc = Upload(p->perm_tile_base, &p->d.perm_tile_base, ctx->stream);
+  if (rc != QLB200_OK) { p->d.Free(); delete p; return rc; }
+  QL_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = p;
+  return QLB200_OK;
+}
+int qlb200_copy_execute(qlb200_ctx *ctx, qlb200_tplan *p, const void *src, void *dst) {
+  if (!ctx || !p || !src || !dst) return Fail(QLB200_ERR_ARG, "null argument");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  ctx->launches = 0;
+  const uint32_t ntiles = p->perm_tile_base.back();
+  if (ntiles > 0) {
+    QL_CUDA(LaunchPermute(p->dtype, p->d.perm_blks, p->d.perm_tile_base, static_cast<uint32_t>(p->perm_blks.size()), ntiles,
+                          src, src, dst, dst, ctx->num_sms, ctx->stream));
+    ctx->launches += 1; ctx->total_launches += 1;
+  }
+  return QLB200_OK;
+}
+
 }  // extern "C"

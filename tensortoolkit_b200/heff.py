@@ -38,11 +38,21 @@ class DeviceBuffer:
             self.ptr = None
 
 
+class ExternalBuffer(DeviceBuffer):
+    """Device memory owned by the caller."""
+
+    def __init__(self, ctx: Context, ptr: int, nbytes: int):
+        self.ctx, self.ptr, self.nbytes = ctx, int(ptr), int(nbytes)
+
+    def free(self):
+        self.ptr = None
+
+
 class ContractionChain:
     """steps: list of (lhs name, rhs name, axes, out name); `tensors` holds the host operands."""
 
     def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps: Sequence[Tuple[str, str, tuple, str]],
-                 dtype, flags: int = _lib.PLAN_DETERMINISTIC):
+                 dtype, flags: int = _lib.PLAN_DETERMINISTIC, external: Dict[str, int] = None):
         self.ctx, self.dtype, self.steps = ctx, np.dtype(dtype), list(steps)
         self.shells: Dict[str, BlockSparseTensor] = dict(tensors)
         self.matches: List[Match] = []
@@ -54,7 +64,10 @@ class ContractionChain:
             self.plans.append(ContractionPlan(ctx, m, self.dtype, flags))
         self.buf: Dict[str, DeviceBuffer] = {}
         for name, t in self.shells.items():
-            self.buf[name] = DeviceBuffer(ctx, t.data.size * self.dtype.itemsize)
+            if external and name in external:      # caller-owned device memory (e.g. a torch tensor)
+                self.buf[name] = ExternalBuffer(ctx, external[name], t.data.size * self.dtype.itemsize)
+            else:
+                self.buf[name] = DeviceBuffer(ctx, t.data.size * self.dtype.itemsize)
         for name, t in tensors.items():
             self.buf[name].upload(t.data)
         ctx.sync()
@@ -104,3 +117,57 @@ class ContractionChain:
         for b in self.buf.values():
             b.free()
         self.plans, self.matches, self.buf = [], [], {}
+
+
+class ShardedChain:
+    """One rank's share of a contraction chain plus the exchange that rebuilds the full result on
+    every GPU: local steps -> NCCL all-gather of the packed row slabs (NVLink/NVSwitch) -> one
+    batched-copy launch that scatters every rank's slabs into the full raw-buffer layout.
+    No reduction is needed because ranks own disjoint output rows (see sharding.py)."""
+
+    def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, dtype,
+                 world: int, rank: int, group=None):
+        import torch
+        from .sharding import shard_chain
+        self.torch, self.group = torch, group
+        self.ctx, self.world, self.rank = ctx, world, rank
+        mine, self.info = shard_chain(tensors, steps, name, axis, world, rank, dtype)
+        self.dtype = np.dtype(dtype)
+        tdt = torch.complex128 if self.dtype == np.complex128 else torch.float64
+        dev = torch.device("cuda", ctx.device)
+        self.stride = max(max(self.info.local_elems), 1)
+        self.local = torch.zeros(self.stride, dtype=tdt, device=dev)
+        self.gathered = torch.zeros(world * self.stride, dtype=tdt, device=dev)
+        self.full = torch.zeros(max(self.info.full_elems, 1), dtype=tdt, device=dev)
+        self.out_name = steps[-1][3]
+        self.chain = ContractionChain(ctx, mine, steps, dtype, external={self.out_name: self.local.data_ptr()})
+        src, dst, ln = [], [], []
+        for r in range(world):
+            for s in self.info.slabs[r]:
+                src.append(r * self.stride + s.local_offset); dst.append(s.full_offset); ln.append(s.length)
+        n = len(src)
+        arr = lambda v: (C.c_uint64 * max(n, 1))(*v)
+        h = C.c_void_p()
+        check(lib.qlb200_cplan_create(ctx.h, _lib.C64 if self.dtype == np.complex128 else _lib.F64, n, arr(src), arr(dst), arr(ln),
+                                      C.byref(h)), "qlb200_cplan_create")
+        self.cplan = h
+
+    def flops_local(self) -> float:
+        return self.chain.flops()
+
+    def apply(self) -> int:
+        """Local steps + all-gather + unpack, all enqueued on the current torch stream (== ctx stream)."""
+        n = self.chain.apply_device()
+        if self.world > 1:
+            self.torch.distributed.all_gather_into_tensor(self.gathered, self.local, group=self.group)
+        else:
+            self.gathered.copy_(self.local)
+        check(lib.qlb200_copy_execute(self.ctx.h, self.cplan, C.c_void_p(self.gathered.data_ptr()), C.c_void_p(self.full.data_ptr())),
+              "qlb200_copy_execute")
+        return n + 1
+
+    def close(self):
+        self.chain.close()
+        if self.cplan:
+            lib.qlb200_tplan_destroy(self.cplan)
+            self.cplan = None

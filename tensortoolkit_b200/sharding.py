@@ -1,0 +1,178 @@
+"""Multi-GPU partition of a contraction chain by OUTPUT quantum-number sector and row slab.
+
+The reference distributes the DMRG mat-vec over MPI ranks by restricting one FREE index of the
+first operand to a single QN sector per work unit (dmrg::Contract1Sector,
+tensor_manipulation/dmrg/contract_1sector.h:181-228; recipe in
+tests/test_tensor_manipulation/test_ten_ctrct_1sct.cc:265-279) and summing the partial results.
+Because that index stays free through every step of the chain, each unit's intermediates never
+leave its rank.  Here the same idea is taken one step further for 8 GPUs behind one NVSwitch:
+
+  * work unit = a RANGE OF ROWS (degeneracy sub-range) of one sector of the split index, so the
+    dominant sector (17 % of the flops for the Gaussian bond of the benchmark) can be cut;
+  * all rows of the split index form one line, weighted by the flops they cause in every step;
+    rank r owns the r-th equal-cost segment of that line (all ranks compute the same cuts);
+  * each rank's result blocks are row slabs of the full result's blocks, i.e. contiguous ranges of
+    the full raw buffer -- no reduction is needed, only an all-gather of disjoint ranges.
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+from .contract import Match
+from .tensor import BlockSparseTensor, Index, QNSector
+
+
+@dataclass
+class Slab:
+    full_offset: int     # element offset in the full (unsharded) result raw buffer
+    local_offset: int    # element offset in the owning rank's packed result raw buffer
+    length: int
+
+
+@dataclass
+class ShardInfo:
+    world: int
+    rank: int
+    sector_ranges: List[List[Tuple[int, int]]]   # [rank][sector] -> (lo, hi) rows of the split index
+    slabs: List[List[Slab]]                      # [rank] -> slabs of that rank's result
+    local_elems: List[int]                       # [rank] packed result size
+    full_elems: int
+    cost_share: List[float]                      # [rank] fraction of the chain's flops
+
+
+def _track_axis(steps, tensors_rank: Dict[str, int], name: str, axis: int):
+    """Position of the split index in the lhs operand of every step (it must stay a free lhs axis)."""
+    pos = {name: axis}
+    out = []
+    ranks = dict(tensors_rank)
+    for lhs, rhs, axes, res in steps:
+        if lhs not in pos:
+            raise ValueError("the split index must travel through the lhs operands of the chain")
+        p = pos[lhs]
+        if p in axes[0]:
+            raise ValueError("the split index is contracted inside the chain")
+        saved = [i for i in range(ranks[lhs]) if i not in axes[0]]
+        out.append(p)
+        pos[res] = saved.index(p)
+        ranks[res] = len(saved) + (ranks[rhs] - len(axes[1]))
+    return out, pos[steps[-1][3]]
+
+
+def sector_costs(tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, dtype) -> Tuple[np.ndarray, Dict[str, BlockSparseTensor], int]:
+    """Flops of the whole chain attributed to each sector of the split index."""
+    shells = dict(tensors)
+    ranks = {k: v.rank for k, v in tensors.items()}
+    track, out_axis = _track_axis(steps, ranks, name, axis)
+    nsct = tensors[name].indexes[axis].nsct
+    cost = np.zeros(nsct)
+    f = 8.0 if np.dtype(dtype) == np.complex128 else 2.0
+    for (lhs, rhs, axes, res), p in zip(steps, track):
+        m = Match(shells[lhs], shells[rhs], axes)
+        a_coors = shells[lhs].blk_coors
+        for t in m.tasks():
+            cost[int(a_coors[t.a_ord, p])] += f * t.m * t.k * t.n
+        shells[res] = m.result_shell(dtype)
+        m.close()
+    return cost, shells, out_axis
+
+
+def row_line_cuts(cost: np.ndarray, degs: Sequence[int], world: int, snap: int = 8) -> List[List[Tuple[int, int]]]:
+    """Cut the line of rows (sector-major) into `world` segments of equal cost."""
+    degs = [int(d) for d in degs]
+    per_row = [c / d if d else 0.0 for c, d in zip(cost, degs)]
+    total = float(sum(cost))
+    # cumulative position -> (sector, row)
+    def locate(target):
+        acc = 0.0
+        for s, d in enumerate(degs):
+            c = per_row[s] * d
+            if acc + c > target and c > 0:
+                r = int(round((target - acc) / per_row[s] / snap)) * snap
+                return s, max(0, min(d, r))
+            acc += c
+        return len(degs), 0
+    cuts = [(0, 0)] + [locate(total * r / world) for r in range(1, world)] + [(len(degs), 0)]
+    out = []
+    for r in range(world):
+        (s0, r0), (s1, r1) = cuts[r], cuts[r + 1]
+        ranges = []
+        for s, d in enumerate(degs):
+            lo, hi = 0, d
+            if s < s0 or s > s1:
+                lo = hi = 0
+            else:
+                if s == s0:
+                    lo = r0
+                if s == s1:
+                    hi = r1
+            ranges.append((lo, max(lo, hi)))
+        out.append(ranges)
+    return out
+
+
+def restrict_tensor(t: BlockSparseTensor, axis: int, ranges: Sequence[Tuple[int, int]]) -> BlockSparseTensor:
+    """Sub-tensor keeping rows [lo, hi) of every sector of index `axis` (empty sectors dropped)."""
+    ix = t.indexes[axis]
+    keep = [s for s, (lo, hi) in enumerate(ranges) if hi > lo]
+    new_pos = {s: i for i, s in enumerate(keep)}
+    new_ix = Index(ix.kind, [QNSector(ix.sectors[s].qn, ranges[s][1] - ranges[s][0]) for s in keep], ix.dir)
+    idxs = list(t.indexes)
+    idxs[axis] = new_ix
+    out = BlockSparseTensor(idxs, t.dtype)
+    sel = [b for b in range(t.nblk) if int(t.blk_coors[b, axis]) in new_pos]
+    if not sel or not keep:
+        return out
+    coors = t.blk_coors[sel].copy()
+    coors[:, axis] = [new_pos[int(c)] for c in coors[:, axis]]
+    out.set_blocks(coors)          # relabelling is monotone, so block order is preserved
+    for nb, b in enumerate(sel):
+        lo, hi = ranges[int(t.blk_coors[b, axis])]
+        sl = [slice(None)] * t.rank
+        sl[axis] = slice(lo, hi)
+        out.block(nb)[...] = t.block(b)[tuple(sl)]
+    return out
+
+
+def shard_chain(tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, world: int, rank: int,
+                dtype=None) -> Tuple[Dict[str, BlockSparseTensor], ShardInfo]:
+    """Returns this rank's operand set (only `name` differs) and the slab map of every rank."""
+    dtype = dtype or tensors[name].dtype
+    cost, shells, out_axis = sector_costs(tensors, steps, name, axis, dtype)
+    if out_axis != 0:
+        raise ValueError("the split index must end up as the first index of the result (row slabs must be contiguous)")
+    degs = tensors[name].indexes[axis].degs()
+    ranges = row_line_cuts(cost, degs, world)
+    full_out = shells[steps[-1][3]]
+    per_row = [c / d if d else 0.0 for c, d in zip(cost, degs)]
+    total = float(cost.sum()) or 1.0
+    slabs, local_elems, share = [], [], []
+    for r in range(world):
+        lst, loc = [], 0
+        for b in range(full_out.nblk):           # ascending blk_idx == the rank's own packed block order
+            s = int(full_out.blk_coors[b, 0])
+            lo, hi = ranges[r][s]
+            if hi <= lo:
+                continue
+            rest = int(full_out.blk_size[b]) // int(full_out.blk_shape[b, 0])
+            lst.append(Slab(int(full_out.blk_offset[b]) + lo * rest, loc, (hi - lo) * rest))
+            loc += (hi - lo) * rest
+        slabs.append(lst)
+        local_elems.append(loc)
+        share.append(sum(per_row[s] * (hi - lo) for s, (lo, hi) in enumerate(ranges[r])) / total)
+    mine = dict(tensors)
+    mine[name] = restrict_tensor(tensors[name], axis, ranges[rank])
+    return mine, ShardInfo(world, rank, ranges, slabs, local_elems, int(full_out.data.size), share)
+
+
+def shard_heff_tensors(tensors, world, rank):
+    """Two-site H_eff apply (workloads.HEFF_STEPS): split lenv's free ket-side bond (axis 2)."""
+    from .workloads import HEFF_STEPS
+    return shard_chain(tensors, HEFF_STEPS, "lenv", 2, world, rank)
+
+
+def unpack_slabs(info: ShardInfo, gathered: np.ndarray, stride: int, full: np.ndarray):
+    """Host model of the unpack step: gathered[r*stride + local] -> full[full_offset] (tests)."""
+    for r in range(info.world):
+        for s in info.slabs[r]:
+            full[s.full_offset:s.full_offset + s.length] = gathered[r * stride + s.local_offset:r * stride + s.local_offset + s.length]
