@@ -83,6 +83,12 @@ GemmParams MakeParams(const qlb200_plan *p) {
   return gp;
 }
 
+void SetPlanKnobs(const qlb200_ctx *ctx, uint32_t flags, PlanHost *h) {
+  h->num_sms = ctx ? ctx->num_sms : 148;
+  h->forced_shape = (flags & QLB200_PLAN_FORCE_SHAPE) ? int((flags >> 8) & 3u) : -1;
+  if (flags & QLB200_PLAN_LEGACY_GEMM) h->forced_shape = 0;   // the cp.async kernel only has the 64x128 tile
+}
+
 size_t WsBytes(const qlb200_plan *p) {
   const size_t es = ElemSize(p->h.dtype);
   return Align256(p->h.ws_a_elems * es) + Align256(p->h.ws_b_elems * es);
@@ -236,6 +242,7 @@ int qlb200_plan_create(qlb200_ctx *ctx, const qlb200_match *m, const qlb200_shel
   qlb200_plan *p = new (std::nothrow) qlb200_plan();
   if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
   p->ctx = ctx;
+  SetPlanKnobs(ctx, flags, &p->h);
   std::vector<int32_t> ap(mm.a_perm.begin(), mm.a_perm.end()), bp(mm.b_perm.begin(), mm.b_perm.end());
   std::string err = BuildPlanHost(dtype, flags, mm.a_need_trans, mm.a.rank, ap.data(), mm.a.nblk, mm.a.shape.data(),
                                   mm.a.offset.data(), mm.a.elems, mm.b_need_trans, mm.b.rank, bp.data(), mm.b.nblk,
@@ -283,6 +290,7 @@ int qlb200_plan_create_raw(qlb200_ctx *ctx, int dtype, uint32_t flags, int32_t a
   qlb200_plan *p = new (std::nothrow) qlb200_plan();
   if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
   p->ctx = ctx;
+  SetPlanKnobs(ctx, flags, &p->h);
   std::string err = BuildPlanHost(dtype, flags, trans(a_rank, a_perm), a_rank, a_perm, na, a_shape, a_off,
                                   total(a_rank, na, a_shape, a_off), trans(b_rank, b_perm), b_rank, b_perm, nb, b_shape,
                                   b_off, total(b_rank, nb, b_shape, b_off), st, c_elems, &p->h);
@@ -380,7 +388,10 @@ int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const vo
   ctx->launches = 0;
   GemmParams gp = MakeParams(p);
   if (gp.ntiles > 0) {
-    QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, ga, gb, C, ctx->num_sms, ctx->stream));
+    if (p->h.dtype == QLB200_C64 && !(p->h.flags & QLB200_PLAN_LEGACY_GEMM))
+      QL_CUDA(LaunchGemmWsCplx(p->h.shape, gp, ga, gb, C, ctx->num_sms, ctx->stream));
+    else
+      QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, ga, gb, C, ctx->num_sms, ctx->stream));
     ctx->launches += 1; ctx->total_launches += 1;
   }
   if (gp.nitems > 0) {

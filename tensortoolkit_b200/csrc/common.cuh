@@ -85,6 +85,11 @@ cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, const void *A, const 
 cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, const void *A, const void *B, void *C,
                              int num_sms, cudaStream_t stream);
 cudaError_t ConfigureKernels();   // one-time cudaFuncSetAttribute calls
+// warp-specialised complex kernel (gemm_ws.cu); shape: 0 = 64x128, 1 = 32x128, 2 = 64x64, 3 = 32x64
+cudaError_t LaunchGemmWsCplx(int shape, const GemmParams &p, const void *A, const void *B, void *C, int num_sms,
+                             cudaStream_t stream);
+void WsTileShape(int shape, int *bm, int *bn);
+constexpr int kWsNumShapes = 4;
 
 // tile shapes of the DMMA kernel, needed by the host-side tiler
 constexpr int kRealBM = 128, kRealBN = 128, kRealBK = 16;

@@ -276,3 +276,26 @@ def test_full_size_properties_heff_d4096_complex(ctx):
     y12 = apply(both)
     assert y1.indexes == t["psi"].indexes and np.array_equal(y1.blk_coors, t["psi"].blk_coors)
     assert util.rel_fro(y12.data, y1.data + (0.5 - 2j) * y2.data) <= TOL
+
+
+@pytest.mark.parametrize("variant", ["shape0", "shape1", "shape2", "shape3", "legacy", "auto"])
+def test_complex_gemm_kernel_variants(ref, ctx, variant):
+    """Every tile shape of the warp-specialised complex kernel (and the cp.async kernel) against the
+    reference on a fermionic chain with ragged K tails, -1 exchange signs and several pairs per block."""
+    flags = {"legacy": _lib.PLAN_LEGACY_GEMM, "auto": 0}.get(variant)
+    if flags is None:
+        flags = _lib.plan_shape_flag(int(variant[-1]))
+    flags |= _lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY
+    ti = wl.heff_tensor_indexes(wl.hubbard_indexes(150))
+    ref.set_seed(77)
+    r = {name: ref.RefTensor.new(idxs, np.complex128).random((0, 0)) for name, idxs in ti.items()}
+    t = {name: x.to_bst() for name, x in r.items()}
+    for lhs, rhs, axes, out in wl.HEFF_STEPS:
+        r[out] = ref.contract(r[lhs], r[rhs], axes)
+        m = tk.Match(t[lhs], t[rhs], axes)
+        plan = tk.ContractionPlan(ctx, m, np.complex128, flags)
+        c = m.result_shell(np.complex128)
+        plan.execute_host(t[lhs].data, t[rhs].data, c.data)
+        plan.close(); m.close()
+        util.assert_same_as_ref(c, r[out], TOL)
+        t[out] = c
