@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--cpu-sample-D", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
+    ap.add_argument("--plan-flags", type=int, default=1, help="qlb200_plan_create flags (kernel A/B testing; 1 = default)")
     return ap.parse_args()
 
 
@@ -220,7 +221,7 @@ def run_ours(args):
         chain = sharded.chain
         apply_fn = sharded.apply
     else:
-        chain = ContractionChain(ctx, tensors, wl.HEFF_STEPS, np_dtype(dtype))
+        chain = ContractionChain(ctx, tensors, wl.HEFF_STEPS, np_dtype(dtype), args.plan_flags)
         apply_fn = chain.apply_device
     stats = chain.stats()
     flops_local = chain.flops()
