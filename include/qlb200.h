@@ -142,7 +142,6 @@ int qlb200_host_unregister(void *p);
 #define QLB200_PLAN_DETERMINISTIC 1u   /* default and only mode: no atomics, fixed summation order */
 #define QLB200_PLAN_NO_SKINNY 2u       /* force every task through the DMMA kernel (testing) */
 #define QLB200_PLAN_LEGACY_GEMM 4u     /* complex: use the cp.async kernel instead of the warp-specialised one */
-#define QLB200_PLAN_FORCE_SHAPE 8u     /* complex: tile shape class given in bits 8..9 (0=64x128,1=32x128,2=64x64,3=32x64) */
 int qlb200_plan_create(qlb200_ctx *ctx, const qlb200_match *m, const qlb200_shell *a,
                        const qlb200_shell *b, int dtype, uint32_t flags, qlb200_plan **out);
 /* Descriptor-table entry (no shells): permute every A/B block with one perm each, then run the

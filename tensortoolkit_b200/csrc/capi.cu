@@ -85,8 +85,7 @@ GemmParams MakeParams(const qlb200_plan *p) {
 
 void SetPlanKnobs(const qlb200_ctx *ctx, uint32_t flags, PlanHost *h) {
   h->num_sms = ctx ? ctx->num_sms : 148;
-  h->forced_shape = (flags & QLB200_PLAN_FORCE_SHAPE) ? int((flags >> 8) & 3u) : -1;
-  if (flags & QLB200_PLAN_LEGACY_GEMM) h->forced_shape = 0;   // the cp.async kernel only has the 64x128 tile
+  (void) flags;
 }
 
 size_t WsBytes(const qlb200_plan *p) {
@@ -389,7 +388,7 @@ int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const vo
   GemmParams gp = MakeParams(p);
   if (gp.ntiles > 0) {
     if (p->h.dtype == QLB200_C64 && !(p->h.flags & QLB200_PLAN_LEGACY_GEMM))
-      QL_CUDA(LaunchGemmWsCplx(p->h.shape, gp, ga, gb, C, ctx->num_sms, ctx->stream));
+      QL_CUDA(LaunchGemmWsCplx(gp, ga, gb, C, ctx->num_sms, ctx->stream));
     else
       QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, ga, gb, C, ctx->num_sms, ctx->stream));
     ctx->launches += 1; ctx->total_launches += 1;

@@ -85,15 +85,15 @@ cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, const void *A, const 
 cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, const void *A, const void *B, void *C,
                              int num_sms, cudaStream_t stream);
 cudaError_t ConfigureKernels();   // one-time cudaFuncSetAttribute calls
-// warp-specialised complex kernel (gemm_ws.cu); shape: 0 = 64x128, 1 = 32x128, 2 = 64x64, 3 = 32x64
-cudaError_t LaunchGemmWsCplx(int shape, const GemmParams &p, const void *A, const void *B, void *C, int num_sms,
+// warp-specialised complex kernel (gemm_ws.cu), CTA tile kWsBM x kWsBN
+cudaError_t LaunchGemmWsCplx(const GemmParams &p, const void *A, const void *B, void *C, int num_sms,
                              cudaStream_t stream);
-void WsTileShape(int shape, int *bm, int *bn);
-constexpr int kWsNumShapes = 4;
+cudaError_t ConfigureWsKernel();
 
 // tile shapes of the DMMA kernel, needed by the host-side tiler
 constexpr int kRealBM = 128, kRealBN = 128, kRealBK = 16;
-constexpr int kCplxBM = 64, kCplxBN = 128, kCplxBK = 8;
+constexpr int kCplxBM = 64, kCplxBN = 128, kCplxBK = 8;   // legacy cp.async kernel
+constexpr int kWsBM = 32, kWsBN = 128;                     // warp-specialised kernel
 constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyRows = 256;
 
 }  // namespace qlb200

@@ -377,7 +377,9 @@ GemmSkinny(GemmParams p, const typename Elem<CPLX>::T *__restrict__ A, const typ
 cudaError_t ConfigureKernels() {
   cudaError_t e = cudaFuncSetAttribute(GemmDmmaReal, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRealSmem));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(GemmDmmaCplx, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCplxSmem));
+  e = cudaFuncSetAttribute(GemmDmmaCplx, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCplxSmem));
+  if (e != cudaSuccess) return e;
+  return ConfigureWsKernel();
 }
 
 cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, const void *A, const void *B, void *C, int num_sms,

@@ -158,12 +158,6 @@ std::string BuildPlanHost(int dtype, uint32_t flags, bool a_trans, int a_rank, c
 
 namespace {
 
-// CTA tile shapes of the complex kernel; kept in sync with WsTileShape() in gemm_ws.cu (which is
-// device code and not linked into host-only unit tests of this file).
-const int kShapeBm[4] = {64, 32, 64, 32}, kShapeBn[4] = {128, 128, 64, 64};
-// relative DMMA-pipe efficiency of a shape's inner loop (fragment loads per MMA), measured
-const double kShapeEff[4] = {1.0, 0.96, 0.96, 0.90};
-
 struct GroupClass { bool skinny; uint64_t kpad; };
 
 GroupClass Classify(const PlanHost *h, const GemmGroup &g, int bk) {
@@ -177,50 +171,14 @@ GroupClass Classify(const PlanHost *h, const GemmGroup &g, int bk) {
   return {skinny, kpad};
 }
 
-// Modelled makespan of the DMMA tiles of a shape: greedy LPT onto num_sms persistent CTAs.
-double ShapeMakespan(const PlanHost *h, int shape) {
-  const int BM = kShapeBm[shape], BN = kShapeBn[shape];
-  std::vector<double> cost;
-  for (size_t gi = 0; gi < h->part_groups.size(); ++gi) {
-    const GemmGroup &g = h->part_groups[gi];
-    if (g.row_end <= g.row_begin) continue;
-    const GroupClass gc = Classify(h, g, 8);
-    if (gc.skinny) continue;
-    const uint64_t tm = (g.row_end - g.row_begin + BM - 1) / BM, tn = (g.n + BN - 1) / BN;
-    const double c = double(BM) * BN * double(gc.kpad + 64) / kShapeEff[shape];   // +64: per-tile prologue/epilogue
-    for (uint64_t i = 0; i < tm * tn; ++i) cost.push_back(c);
-  }
-  if (cost.empty()) return 0.0;
-  std::sort(cost.begin(), cost.end(), std::greater<double>());
-  std::vector<double> bins(std::max(1, h->num_sms), 0.0);
-  // bins kept as a min-heap
-  auto cmp = [](double x, double y) { return x > y; };
-  for (double c : cost) {
-    std::pop_heap(bins.begin(), bins.end(), cmp);
-    bins.back() += c;
-    std::push_heap(bins.begin(), bins.end(), cmp);
-  }
-  return *std::max_element(bins.begin(), bins.end());
-}
-
 }  // namespace
 
 std::string BuildTiles(PlanHost *h) {
   h->tiles.clear(); h->items.clear();
   int BM = kRealBM, BN = kRealBN;
   if (h->dtype == QLB200_C64) {
-    int best = 0;
-    if (h->forced_shape >= 0) {
-      best = h->forced_shape & 3;
-    } else {
-      double best_t = -1;
-      for (int s = 0; s < 4; ++s) {
-        const double t = ShapeMakespan(h, s);
-        if (best_t < 0 || t < best_t * 0.995) { best_t = t; best = s; }
-      }
-    }
-    h->shape = best;
-    BM = kShapeBm[best]; BN = kShapeBn[best];
+    const bool legacy = (h->flags & QLB200_PLAN_LEGACY_GEMM) != 0;
+    BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : kWsBN;
   }
   std::vector<uint32_t> order(h->part_groups.size());
   std::iota(order.begin(), order.end(), 0u);

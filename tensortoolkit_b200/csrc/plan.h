@@ -38,8 +38,6 @@ struct PlanHost {
   int dtype = 0;
   uint32_t flags = 0;
   int num_sms = 148;
-  int shape = 0;                                       // complex DMMA tile shape class (gemm_ws.cu)
-  int forced_shape = -1;                               // >= 0: skip the heuristic (testing / tuning)
   uint64_t a_elems = 0, b_elems = 0, c_elems = 0;      // raw sizes of the three tensors
   bool a_trans = false, b_trans = false;
   uint64_t ws_a_elems = 0, ws_b_elems = 0;             // permuted operand sizes (workspace)

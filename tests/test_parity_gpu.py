@@ -278,13 +278,11 @@ def test_full_size_properties_heff_d4096_complex(ctx):
     assert util.rel_fro(y12.data, y1.data + (0.5 - 2j) * y2.data) <= TOL
 
 
-@pytest.mark.parametrize("variant", ["shape0", "shape1", "shape2", "shape3", "legacy", "auto"])
+@pytest.mark.parametrize("variant", ["ws", "legacy"])
 def test_complex_gemm_kernel_variants(ref, ctx, variant):
-    """Every tile shape of the warp-specialised complex kernel (and the cp.async kernel) against the
-    reference on a fermionic chain with ragged K tails, -1 exchange signs and several pairs per block."""
-    flags = {"legacy": _lib.PLAN_LEGACY_GEMM, "auto": 0}.get(variant)
-    if flags is None:
-        flags = _lib.plan_shape_flag(int(variant[-1]))
+    """The warp-specialised complex kernel and the cp.async kernel against the reference on a
+    fermionic chain with ragged K tails, ragged tile edges, -1 exchange signs and several pairs per block."""
+    flags = {"legacy": _lib.PLAN_LEGACY_GEMM, "ws": 0}[variant]
     flags |= _lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY
     ti = wl.heff_tensor_indexes(wl.hubbard_indexes(150))
     ref.set_seed(77)
