@@ -26,7 +26,7 @@ namespace {
 constexpr int kConsumerWarps = 4;
 // consumer warpgroup + producer warpgroup (only its first warp works).  Two CTAs x 8 warps leave 128
 // registers per thread at launch; the budget is re-split at run time with setmaxnreg (consumers 208,
-// producer warpgroup 40: per SM sub-partition 2 x (208 + 40) = 496 <= 512 registers per lane).
+// producer warpgroup 48: per SM sub-partition 2 x (208 + 48) = 512 registers per lane).
 constexpr int kWsThreads = (kConsumerWarps + 4) * 32;
 constexpr int WBM = kWsBM, WBN = kWsBN, WBK = 8;
 constexpr int WLDA = WBK + 4;          // 12 complex per A row: (row*12 + k) mod 8 distinct over a quarter-warp
@@ -81,47 +81,50 @@ struct WsSmem {
                                    STAGES * sizeof(StageMeta);
 };
 
-// One k-stage (WBK = 8 -> two k4 steps) of a warp's 32 x 32 sub-tile.  FULL: every m8 / n8 group is valid.
-template<bool FULL>
+// One k-stage (WBK = 8 -> two k4 steps) of a warp's sub-tile: MT valid m8 row groups x NT valid n8 column
+// groups.  Specialised at compile time so that skipped MMAs are not even issued.
+template<int MT, int NT>
 __device__ __forceinline__ void ComputeStage(double (&cr)[4][4][2], double (&ci)[4][4][2], const double2 *cA, const double2 *cB,
-                                             uint32_t smask, int mt, int nt) {
+                                             uint32_t smask) {
 #pragma unroll
   for (int ks = 0; ks < WBK / 4; ++ks) {
-    double ax[4], ay[4], nay[4];
-    double2 b[4];
+    double ax[MT], ay[MT], nay[MT];
+    double2 b[NT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < MT; ++i) {
       const double2 a = cA[i * 8 * WLDA + ks * 4];
       ax[i] = FlipSign(a.x, smask);
       ay[i] = FlipSign(a.y, smask);
       nay[i] = FlipSign(a.y, smask ^ 0x80000000u);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) b[j] = cB[ks * 4 * WLDB + j * 32];
+    for (int j = 0; j < NT; ++j) b[j] = cB[ks * 4 * WLDB + j * 32];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (FULL || i < mt) {
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (FULL || j < nt) {
-            DmmaNv(cr[i][j][0], cr[i][j][1], ax[i], b[j].x);
-            DmmaNv(ci[i][j][0], ci[i][j][1], ax[i], b[j].y);
-          }
-        }
+      for (int j = 0; j < NT; ++j) {
+        DmmaNv(cr[i][j][0], cr[i][j][1], ax[i], b[j].x);
+        DmmaNv(ci[i][j][0], ci[i][j][1], ax[i], b[j].y);
       }
-    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (FULL || i < mt) {
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (FULL || j < nt) {
-            DmmaNv(cr[i][j][0], cr[i][j][1], nay[i], b[j].y);
-            DmmaNv(ci[i][j][0], ci[i][j][1], ay[i], b[j].x);
-          }
-        }
+      for (int j = 0; j < NT; ++j) {
+        DmmaNv(cr[i][j][0], cr[i][j][1], nay[i], b[j].y);
+        DmmaNv(ci[i][j][0], ci[i][j][1], ay[i], b[j].x);
       }
-    }
+  }
+}
+
+template<int MT>
+__device__ __forceinline__ void ComputeStageN(double (&cr)[4][4][2], double (&ci)[4][4][2], const double2 *cA, const double2 *cB,
+                                              uint32_t smask, int nt) {
+  switch (nt) {
+    case 4: ComputeStage<MT, 4>(cr, ci, cA, cB, smask); break;
+    case 3: ComputeStage<MT, 3>(cr, ci, cA, cB, smask); break;
+    case 2: ComputeStage<MT, 2>(cr, ci, cA, cB, smask); break;
+    case 1: ComputeStage<MT, 1>(cr, ci, cA, cB, smask); break;
+    default: break;
   }
 }
 
@@ -144,7 +147,7 @@ GemmWsCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restric
 
   if (warp >= kConsumerWarps) {
     // ================================ producer warpgroup ================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp != kConsumerWarps) return;
     const uint32_t a_kc = lane & 7, a_r = lane >> 3;
     uint32_t it = 0;
@@ -238,8 +241,16 @@ GemmWsCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restric
     const double2 *cA = stages + size_t(s) * STAGE_ELEMS + g4 * WLDA + t4;
     const double2 *cB = stages + size_t(s) * STAGE_ELEMS + A_ELEMS + t4 * WLDB + q * 8 + g4;
     const uint32_t smask = (sm.flags & kFlagNeg) ? 0x80000000u : 0u;
-    if (mt == 4 && nt == 4) ComputeStage<true>(cr, ci, cA, cB, smask, 4, 4);
-    else ComputeStage<false>(cr, ci, cA, cB, smask, mt, nt);
+    if (mt == 4 && nt == 4) {
+      ComputeStage<4, 4>(cr, ci, cA, cB, smask);
+    } else {
+      switch (mt) {
+        case 4: ComputeStageN<4>(cr, ci, cA, cB, smask, nt); break;
+        case 3: ComputeStageN<3>(cr, ci, cA, cB, smask, nt); break;
+        case 2: ComputeStageN<2>(cr, ci, cA, cB, smask, nt); break;
+        default: ComputeStageN<1>(cr, ci, cA, cB, smask, nt); break;
+      }
+    }
     __syncwarp();
     if (lane == 0) MbarArrive(&empty[s]);
     if (sm.flags & kFlagLast) {
@@ -263,7 +274,7 @@ GemmWsCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restric
   }
 }
 
-constexpr int kWsStages = 4;
+constexpr int kWsStages = 5;
 
 }  // namespace
 
