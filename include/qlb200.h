@@ -142,6 +142,9 @@ int qlb200_host_unregister(void *p);
 #define QLB200_PLAN_DETERMINISTIC 1u   /* default and only mode: no atomics, fixed summation order */
 #define QLB200_PLAN_NO_SKINNY 2u       /* force every task through the DMMA kernel (testing) */
 #define QLB200_PLAN_LEGACY_GEMM 4u     /* complex: use the cp.async kernel instead of the warp-specialised one */
+#define QLB200_PLAN_PERMUTE_ALL 8u     /* send every block of a transposed operand through the permute kernel
+                                          (default: blocks whose permutation is trivial or one 2-D transposition
+                                          are read in place by the GEMM) */
 int qlb200_plan_create(qlb200_ctx *ctx, const qlb200_match *m, const qlb200_shell *a,
                        const qlb200_shell *b, int dtype, uint32_t flags, qlb200_plan **out);
 /* Descriptor-table entry (no shells): permute every A/B block with one perm each, then run the

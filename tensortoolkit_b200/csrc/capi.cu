@@ -74,8 +74,9 @@ int FinishPlan(qlb200_ctx *ctx, qlb200_plan *p) {
   return UploadGemmTables(p);
 }
 
-GemmParams MakeParams(const qlb200_plan *p) {
+GemmParams MakeParams(const qlb200_plan *p, const void *A, const void *B, const void *wsA, const void *wsB) {
   GemmParams gp;
+  gp.a_src = A; gp.b_src = B; gp.a_ws = wsA; gp.b_ws = wsB;
   gp.tasks = p->d.tasks; gp.groups = p->d.groups; gp.tiles = p->d.tiles; gp.items = p->d.items;
   gp.ntiles = static_cast<uint32_t>(p->h.tiles.size());
   gp.nitems = static_cast<uint32_t>(p->h.items.size());
@@ -243,8 +244,8 @@ int qlb200_plan_create(qlb200_ctx *ctx, const qlb200_match *m, const qlb200_shel
   p->ctx = ctx;
   SetPlanKnobs(ctx, flags, &p->h);
   std::vector<int32_t> ap(mm.a_perm.begin(), mm.a_perm.end()), bp(mm.b_perm.begin(), mm.b_perm.end());
-  std::string err = BuildPlanHost(dtype, flags, mm.a_need_trans, mm.a.rank, ap.data(), mm.a.nblk, mm.a.shape.data(),
-                                  mm.a.offset.data(), mm.a.elems, mm.b_need_trans, mm.b.rank, bp.data(), mm.b.nblk,
+  std::string err = BuildPlanHost(dtype, flags, static_cast<int>(mm.a_ctrct.size()), mm.a.rank, ap.data(), mm.a.nblk,
+                                  mm.a.shape.data(), mm.a.offset.data(), mm.a.elems, mm.b.rank, bp.data(), mm.b.nblk,
                                   mm.b.shape.data(), mm.b.offset.data(), mm.b.elems, mm.SortedTasks(), mm.c_elems, &p->h);
   if (!err.empty()) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, err); }
   if (ctx != nullptr) {   // ctx == NULL: host-only plan (stats / partition queries, no device tables)
@@ -262,11 +263,6 @@ int qlb200_plan_create_raw(qlb200_ctx *ctx, int dtype, uint32_t flags, int32_t a
   if (!ctx || !out || !a_shape || !b_shape || !a_off || !b_off || (ntask && !tasks)) return Fail(QLB200_ERR_ARG, "null argument");
   if (dtype != QLB200_F64 && dtype != QLB200_C64) return Fail(QLB200_ERR_ARG, "bad dtype");
   if (a_rank < 1 || a_rank > QLB200_MAX_RANK || b_rank < 1 || b_rank > QLB200_MAX_RANK) return Fail(QLB200_ERR_ARG, "bad rank");
-  auto trans = [](int rank, const int32_t *perm) {
-    if (!perm) return false;
-    for (int i = 0; i < rank; ++i) if (perm[i] != i) return true;
-    return false;
-  };
   auto total = [](int rank, uint64_t n, const uint32_t *shape, const uint64_t *off) {
     uint64_t e = 0;
     for (uint64_t b = 0; b < n; ++b) {
@@ -290,9 +286,8 @@ int qlb200_plan_create_raw(qlb200_ctx *ctx, int dtype, uint32_t flags, int32_t a
   if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
   p->ctx = ctx;
   SetPlanKnobs(ctx, flags, &p->h);
-  std::string err = BuildPlanHost(dtype, flags, trans(a_rank, a_perm), a_rank, a_perm, na, a_shape, a_off,
-                                  total(a_rank, na, a_shape, a_off), trans(b_rank, b_perm), b_rank, b_perm, nb, b_shape,
-                                  b_off, total(b_rank, nb, b_shape, b_off), st, c_elems, &p->h);
+  std::string err = BuildPlanHost(dtype, flags, 0, a_rank, a_perm, na, a_shape, a_off, total(a_rank, na, a_shape, a_off),
+                                  b_rank, b_perm, nb, b_shape, b_off, total(b_rank, nb, b_shape, b_off), st, c_elems, &p->h);
   if (!err.empty()) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, err); }
   int rc = FinishPlan(ctx, p);
   if (rc != QLB200_OK) { p->d.Free(); delete p; return rc; }
@@ -350,23 +345,20 @@ int qlb200_plan_get_stats(const qlb200_plan *p, qlb200_plan_stats *out) {
 }
 
 // ---- execution ---------------------------------------------------------------------------------
-static int ResolveOperands(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, const void **gemmA,
-                           const void **gemmB, void **wsA, void **wsB) {
+static int ResolveWorkspace(qlb200_ctx *ctx, qlb200_plan *p, void **wsA, void **wsB) {
   const size_t es = ElemSize(p->h.dtype);
   int rc = EnsureArena(&ctx->ws, &ctx->ws_bytes, WsBytes(p), ctx->stream);
   if (rc != QLB200_OK) return rc;
   *wsA = ctx->ws;
   *wsB = static_cast<char *>(ctx->ws) + Align256(p->h.ws_a_elems * es);
-  *gemmA = p->h.a_trans ? *wsA : A;
-  *gemmB = p->h.b_trans ? *wsB : B;
   return QLB200_OK;
 }
 
 int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B) {
   if (!ctx || !p) return Fail(QLB200_ERR_ARG, "null argument");
   QL_CUDA(cudaSetDevice(ctx->device));
-  const void *ga, *gb; void *wa, *wb;
-  int rc = ResolveOperands(ctx, p, A, B, &ga, &gb, &wa, &wb);
+  void *wa, *wb;
+  int rc = ResolveWorkspace(ctx, p, &wa, &wb);
   if (rc != QLB200_OK) return rc;
   ctx->launches = 0;
   const uint32_t ntiles = p->h.perm_tile_base.back();
@@ -381,20 +373,20 @@ int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const
 int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C) {
   if (!ctx || !p) return Fail(QLB200_ERR_ARG, "null argument");
   QL_CUDA(cudaSetDevice(ctx->device));
-  const void *ga, *gb; void *wa, *wb;
-  int rc = ResolveOperands(ctx, p, A, B, &ga, &gb, &wa, &wb);
+  void *wa, *wb;
+  int rc = ResolveWorkspace(ctx, p, &wa, &wb);
   if (rc != QLB200_OK) return rc;
   ctx->launches = 0;
-  GemmParams gp = MakeParams(p);
+  GemmParams gp = MakeParams(p, A, B, wa, wb);
   if (gp.ntiles > 0) {
     if (p->h.dtype == QLB200_C64 && !(p->h.flags & QLB200_PLAN_LEGACY_GEMM))
-      QL_CUDA(LaunchGemmWsCplx(gp, ga, gb, C, ctx->num_sms, ctx->stream));
+      QL_CUDA(LaunchGemmWsCplx(gp, C, ctx->num_sms, ctx->stream));
     else
-      QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, ga, gb, C, ctx->num_sms, ctx->stream));
+      QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, C, ctx->num_sms, ctx->stream));
     ctx->launches += 1; ctx->total_launches += 1;
   }
   if (gp.nitems > 0) {
-    QL_CUDA(LaunchGemmSkinny(p->h.dtype, gp, ga, gb, C, ctx->num_sms, ctx->stream));
+    QL_CUDA(LaunchGemmSkinny(p->h.dtype, gp, C, ctx->num_sms, ctx->stream));
     ctx->launches += 1; ctx->total_launches += 1;
   }
   return QLB200_OK;

@@ -41,10 +41,15 @@ struct PermBlk {
 // accumulate into it.  Offsets are in elements.
 // ------------------------------------------------------------------------------------------------
 struct GemmTask {
-  unsigned long long a_off, b_off;  // into the (possibly permuted) A / B operand buffers
+  unsigned long long a_off, b_off;  // elements, into the caller's buffer (kTask?Src) or the permuted workspace
   uint32_t k;
-  int32_t sign;                     // +1 / -1
+  int16_t sign;                     // +1 / -1
+  uint16_t flags;                   // kTask* bits
 };
+constexpr uint16_t kTaskASrc = 1;    // A block is read from the caller's buffer, not the workspace
+constexpr uint16_t kTaskATrans = 2;  // ... where it is stored as a row-major k x m matrix
+constexpr uint16_t kTaskBSrc = 4;    // B block is read from the caller's buffer
+constexpr uint16_t kTaskBTrans = 8;  // ... where it is stored as a row-major n x k matrix
 
 struct GemmGroup {
   unsigned long long c_off;
@@ -64,6 +69,7 @@ struct SkinnyItem {     // rows [row0, row0+rows) of a narrow group, one thread 
 };
 
 struct GemmParams {
+  const void *a_src, *a_ws, *b_src, *b_ws;   // caller's raw buffers / permuted workspace (set per launch)
   const GemmTask *tasks;
   const GemmGroup *groups;
   const GemmTile *tiles;
@@ -80,21 +86,18 @@ inline std::string CudaErr(const char *what, cudaError_t e) {
 cudaError_t LaunchPermute(int dtype, const PermBlk *blks, const uint32_t *tile_base, uint32_t nblk,
                           uint32_t ntiles, const void *srcA, const void *srcB, void *dstA, void *dstB,
                           int num_sms, cudaStream_t stream);
-cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, const void *A, const void *B, void *C,
-                           int num_sms, cudaStream_t stream);
-cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, const void *A, const void *B, void *C,
-                             int num_sms, cudaStream_t stream);
+cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, void *C, int num_sms, cudaStream_t stream);
+cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, void *C, int num_sms, cudaStream_t stream);
 cudaError_t ConfigureKernels();   // one-time cudaFuncSetAttribute calls
 // warp-specialised complex kernel (gemm_ws.cu), CTA tile kWsBM x kWsBN
-cudaError_t LaunchGemmWsCplx(const GemmParams &p, const void *A, const void *B, void *C, int num_sms,
-                             cudaStream_t stream);
+cudaError_t LaunchGemmWsCplx(const GemmParams &p, void *C, int num_sms, cudaStream_t stream);
 cudaError_t ConfigureWsKernel();
 
 // tile shapes of the DMMA kernel, needed by the host-side tiler
 constexpr int kRealBM = 128, kRealBN = 128, kRealBK = 16;
 constexpr int kCplxBM = 64, kCplxBN = 128, kCplxBK = 8;   // legacy cp.async kernel
 constexpr int kWsBM = 32, kWsBN = 128;                     // warp-specialised kernel
-constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyRows = 256;
+constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyRows = 256, kSkinnyThreads = 256;
 
 }  // namespace qlb200
 #endif

@@ -43,21 +43,25 @@ __device__ __forceinline__ void Dmma(double &d0, double &d1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-// Walks the concatenated k-space of a group's tasks in BK-sized chunks.
+// Walks the concatenated k-space of a group's tasks in BK-sized chunks.  The cp.async kernels only
+// read row-major operands; a task's block lives either in the caller's buffer or in the workspace.
+template<typename T>
 struct ChunkCursor {
   uint32_t task, task_end, k0, k;
-  unsigned long long a_off, b_off;
+  const T *a, *b;
   int sign;
-  __device__ __forceinline__ void Load(const GemmTask *tasks) {
+  __device__ __forceinline__ void Load(const GemmParams &p) {
     if (task < task_end) {
-      const GemmTask t = tasks[task];
-      a_off = t.a_off; b_off = t.b_off; k = t.k; sign = t.sign;
+      const GemmTask t = p.tasks[task];
+      a = static_cast<const T *>((t.flags & kTaskASrc) ? p.a_src : p.a_ws) + t.a_off;
+      b = static_cast<const T *>((t.flags & kTaskBSrc) ? p.b_src : p.b_ws) + t.b_off;
+      k = t.k; sign = t.sign;
     }
   }
   __device__ __forceinline__ bool Valid() const { return task < task_end; }
-  template<int BK> __device__ __forceinline__ void Advance(const GemmTask *tasks) {
+  template<int BK> __device__ __forceinline__ void Advance(const GemmParams &p) {
     k0 += BK;
-    if (k0 >= k) { ++task; k0 = 0; Load(tasks); }
+    if (k0 >= k) { ++task; k0 = 0; Load(p); }
   }
 };
 
@@ -71,7 +75,7 @@ constexpr int RA_ELEMS = RBM * RLDA, RB_ELEMS = RBK * RLDB;
 constexpr size_t kRealSmem = size_t(RSTAGES) * (RA_ELEMS + RB_ELEMS) * sizeof(double);
 
 __global__ void __launch_bounds__(kThreads, 1)
-GemmDmmaReal(GemmParams p, const double *__restrict__ A, const double *__restrict__ B, double *__restrict__ C) {
+GemmDmmaReal(GemmParams p, double *__restrict__ C) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sA = reinterpret_cast<double *>(smem_raw);
   double *sB = sA + RSTAGES * RA_ELEMS;
@@ -100,9 +104,9 @@ GemmDmmaReal(GemmParams p, const double *__restrict__ A, const double *__restric
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    ChunkCursor pc;   // producer cursor
-    pc.task = g.task_begin; pc.task_end = g.task_end; pc.k0 = 0; pc.k = 0; pc.a_off = pc.b_off = 0; pc.sign = 1;
-    pc.Load(p.tasks);
+    ChunkCursor<double> pc;   // producer cursor
+    pc.task = g.task_begin; pc.task_end = g.task_end; pc.k0 = 0; pc.k = 0; pc.a = pc.b = nullptr; pc.sign = 1;
+    pc.Load(p);
     uint32_t nchunks = 0;
     for (uint32_t t = g.task_begin; t < g.task_end; ++t) nchunks += (p.tasks[t].k + RBK - 1) / RBK;
 
@@ -110,8 +114,8 @@ GemmDmmaReal(GemmParams p, const double *__restrict__ A, const double *__restric
       if (pc.Valid()) {
         double *dA = sA + stage * RA_ELEMS;
         double *dB = sB + stage * RB_ELEMS;
-        const double *gA = A + pc.a_off;
-        const double *gB = B + pc.b_off;
+        const double *gA = pc.a;
+        const double *gB = pc.b;
         const uint32_t kk = pc.k0 + a_col;
         const bool kok = kk < pc.k;
 #pragma unroll
@@ -129,7 +133,7 @@ GemmDmmaReal(GemmParams p, const double *__restrict__ A, const double *__restric
           CpAsync8(dB + (b_row + r * 2) * RLDB + b_col, ok ? gB + (unsigned long long) krow * n + col : gB, ok);
         }
         if (tid == 0) s_sign[stage] = pc.sign;
-        pc.Advance<RBK>(p.tasks);
+        pc.Advance<RBK>(p);
       }
       CpAsyncCommit();
     };
@@ -193,7 +197,7 @@ constexpr int CA_ELEMS = CBM * CLDA, CB_ELEMS = CBK * CLDB;
 constexpr size_t kCplxSmem = size_t(CSTAGES) * (CA_ELEMS + CB_ELEMS) * sizeof(double2);
 
 __global__ void __launch_bounds__(kThreads, 1)
-GemmDmmaCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restrict__ B, double2 *__restrict__ C) {
+GemmDmmaCplx(GemmParams p, double2 *__restrict__ C) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *sA = reinterpret_cast<double2 *>(smem_raw);
   double2 *sB = sA + CSTAGES * CA_ELEMS;
@@ -221,9 +225,9 @@ GemmDmmaCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restr
 #pragma unroll
       for (int j = 0; j < 4; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
 
-    ChunkCursor pc;
-    pc.task = g.task_begin; pc.task_end = g.task_end; pc.k0 = 0; pc.k = 0; pc.a_off = pc.b_off = 0; pc.sign = 1;
-    pc.Load(p.tasks);
+    ChunkCursor<double2> pc;
+    pc.task = g.task_begin; pc.task_end = g.task_end; pc.k0 = 0; pc.k = 0; pc.a = pc.b = nullptr; pc.sign = 1;
+    pc.Load(p);
     uint32_t nchunks = 0;
     for (uint32_t t = g.task_begin; t < g.task_end; ++t) nchunks += (p.tasks[t].k + CBK - 1) / CBK;
 
@@ -231,8 +235,8 @@ GemmDmmaCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restr
       if (pc.Valid()) {
         double2 *dA = sA + stage * CA_ELEMS;
         double2 *dB = sB + stage * CB_ELEMS;
-        const double2 *gA = A + pc.a_off;
-        const double2 *gB = B + pc.b_off;
+        const double2 *gA = pc.a;
+        const double2 *gB = pc.b;
         const uint32_t kk = pc.k0 + a_col;
         const bool kok = kk < pc.k;
 #pragma unroll
@@ -250,7 +254,7 @@ GemmDmmaCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restr
           CpAsync16(dB + (b_row + r * 2) * CLDB + b_col, ok ? gB + (unsigned long long) krow * n + col : gB, ok);
         }
         if (tid == 0) s_sign[stage] = pc.sign;
-        pc.Advance<CBK>(p.tasks);
+        pc.Advance<CBK>(p);
       }
       CpAsyncCommit();
     };
@@ -318,15 +322,18 @@ GemmDmmaCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restr
 }
 
 // ================================================================================================
-// Narrow pairs: one thread per output row, n <= kSkinnyMaxN accumulators in registers.
-// HBM-bound: reads m*k per pair, writes m*n once.
+// Narrow pairs (n <= kSkinnyMaxN, k <= kSkinnyMaxK): HBM-bound, reads m*k per pair, writes m*n once.
+// One thread per OUTPUT ELEMENT: a work item is kSkinnyRows rows of one output block; consecutive
+// threads own consecutive elements of C (fully coalesced stores), the n threads of a row share their
+// A loads through one broadcast transaction.  A and B blocks are read in place: row-major, or
+// 2-D transposed in the caller's buffer (kTask?Trans), so these steps need no permute pass.
 // ================================================================================================
 template<bool CPLX> struct Elem;
 template<> struct Elem<false> {
   using T = double;
   static __device__ __forceinline__ T Zero() { return 0.0; }
   static __device__ __forceinline__ void Fma(T &acc, T a, T b) { acc = fma(a, b, acc); }
-  static __device__ __forceinline__ T Neg(T a) { return -a; }
+  static __device__ __forceinline__ void Axpy(T &acc, int sign, T v) { acc += sign < 0 ? -v : v; }
 };
 template<> struct Elem<true> {
   using T = double2;
@@ -335,40 +342,41 @@ template<> struct Elem<true> {
     acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
     acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
   }
-  static __device__ __forceinline__ T Neg(T a) { return make_double2(-a.x, -a.y); }
+  static __device__ __forceinline__ void Axpy(T &acc, int sign, T v) {
+    if (sign < 0) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
+  }
 };
 
 template<bool CPLX>
-__global__ void __launch_bounds__(kSkinnyRows)
-GemmSkinny(GemmParams p, const typename Elem<CPLX>::T *__restrict__ A, const typename Elem<CPLX>::T *__restrict__ B,
-           typename Elem<CPLX>::T *__restrict__ C) {
+__global__ void __launch_bounds__(kSkinnyThreads)
+GemmSkinny(GemmParams p, typename Elem<CPLX>::T *__restrict__ C) {
   using E = Elem<CPLX>;
   using T = typename E::T;
   for (uint32_t it = blockIdx.x; it < p.nitems; it += gridDim.x) {
     const SkinnyItem item = p.items[it];
     const GemmGroup g = p.groups[item.group];
-    const uint32_t row = item.row0 + threadIdx.x;
-    if (row >= g.row_end) continue;
     const uint32_t n = g.n;
-    T acc[kSkinnyMaxN];
-#pragma unroll
-    for (int j = 0; j < kSkinnyMaxN; ++j) acc[j] = E::Zero();
-    for (uint32_t t = g.task_begin; t < g.task_end; ++t) {
-      const GemmTask tk = p.tasks[t];
-      const T *ar = A + tk.a_off + (unsigned long long) row * tk.k;
-      const T *bb = B + tk.b_off;
-      for (uint32_t kk = 0; kk < tk.k; ++kk) {
-        T a = ar[kk];
-        if (tk.sign < 0) a = E::Neg(a);
-#pragma unroll
-        for (int j = 0; j < kSkinnyMaxN; ++j)
-          if (j < int(n)) E::Fma(acc[j], a, __ldg(bb + kk * n + j));
+    const uint32_t rows = min(uint32_t(kSkinnyRows), g.row_end - item.row0);
+    const uint32_t total = rows * n;
+    T *cb = C + g.c_off + (unsigned long long) item.row0 * n;
+    for (uint32_t e = threadIdx.x; e < total; e += kSkinnyThreads) {
+      const uint32_t r = e / n, j = e - r * n;
+      const unsigned long long row = item.row0 + r;
+      T acc = E::Zero();
+      for (uint32_t t = g.task_begin; t < g.task_end; ++t) {
+        const GemmTask tk = p.tasks[t];
+        const T *a = static_cast<const T *>((tk.flags & kTaskASrc) ? p.a_src : p.a_ws) + tk.a_off;
+        const T *b = static_cast<const T *>((tk.flags & kTaskBSrc) ? p.b_src : p.b_ws) + tk.b_off;
+        unsigned long long as, bs;
+        if (tk.flags & kTaskATrans) { a += row; as = g.m; } else { a += row * tk.k; as = 1; }
+        if (tk.flags & kTaskBTrans) { b += (unsigned long long) j * tk.k; bs = 1; } else { b += j; bs = n; }
+        T part = E::Zero();
+#pragma unroll 4
+        for (uint32_t kk = 0; kk < tk.k; ++kk) E::Fma(part, a[kk * as], __ldg(b + kk * bs));
+        E::Axpy(acc, tk.sign, part);
       }
+      cb[e] = acc;
     }
-    T *cr = C + g.c_off + (unsigned long long) row * n;
-#pragma unroll
-    for (int j = 0; j < kSkinnyMaxN; ++j)
-      if (j < int(n)) cr[j] = acc[j];
   }
 }
 
@@ -382,32 +390,20 @@ cudaError_t ConfigureKernels() {
   return ConfigureWsKernel();
 }
 
-cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, const void *A, const void *B, void *C, int num_sms,
-                           cudaStream_t stream) {
+cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, void *C, int num_sms, cudaStream_t stream) {
   if (p.ntiles == 0) return cudaSuccess;
   const uint32_t grid = p.ntiles < uint32_t(num_sms) ? p.ntiles : uint32_t(num_sms);
-  if (dtype == 0) {
-    GemmDmmaReal<<<grid, kThreads, kRealSmem, stream>>>(p, static_cast<const double *>(A), static_cast<const double *>(B),
-                                                        static_cast<double *>(C));
-  } else {
-    GemmDmmaCplx<<<grid, kThreads, kCplxSmem, stream>>>(p, static_cast<const double2 *>(A), static_cast<const double2 *>(B),
-                                                        static_cast<double2 *>(C));
-  }
+  if (dtype == 0) GemmDmmaReal<<<grid, kThreads, kRealSmem, stream>>>(p, static_cast<double *>(C));
+  else GemmDmmaCplx<<<grid, kThreads, kCplxSmem, stream>>>(p, static_cast<double2 *>(C));
   return cudaGetLastError();
 }
 
-cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, const void *A, const void *B, void *C, int num_sms,
-                             cudaStream_t stream) {
+cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, void *C, int num_sms, cudaStream_t stream) {
   if (p.nitems == 0) return cudaSuccess;
   const uint32_t cap = uint32_t(num_sms) * 8u;
   const uint32_t grid = p.nitems < cap ? p.nitems : cap;
-  if (dtype == 0) {
-    GemmSkinny<false><<<grid, kSkinnyRows, 0, stream>>>(p, static_cast<const double *>(A), static_cast<const double *>(B),
-                                                        static_cast<double *>(C));
-  } else {
-    GemmSkinny<true><<<grid, kSkinnyRows, 0, stream>>>(p, static_cast<const double2 *>(A), static_cast<const double2 *>(B),
-                                                       static_cast<double2 *>(C));
-  }
+  if (dtype == 0) GemmSkinny<false><<<grid, kSkinnyThreads, 0, stream>>>(p, static_cast<double *>(C));
+  else GemmSkinny<true><<<grid, kSkinnyThreads, 0, stream>>>(p, static_cast<double2 *>(C));
   return cudaGetLastError();
 }
 

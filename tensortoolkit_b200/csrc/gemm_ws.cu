@@ -14,6 +14,10 @@
 //   * Every stage carries {tile id, first/last/sign flags, valid extents}; the producer runs ahead
 //     across tile boundaries (dynamic atomic tile counter), so the next tile's prologue overlaps this
 //     tile's epilogue stores.
+//   * Operand blocks are read where they lie: row-major (A: m x k, B: k x n) or 2-D transposed
+//     (A stored k x m, B stored n x k; GemmTask::flags) -- the producer picks the copy pattern that
+//     keeps global reads contiguous, the consumers only change their shared-memory strides.  Most
+//     blocks of a DMRG contraction therefore never pass through the permute kernel.
 //   * Ragged tiles cost what they use: a warp owns the n8 column groups {q, q+4, q+8, q+12} of the
 //     tile (interleaved, so valid columns spread evenly over the four sub-partitions) and skips the
 //     MMAs of m8 row groups / n8 column groups that lie outside the output block.
@@ -25,14 +29,21 @@ namespace {
 
 constexpr int kConsumerWarps = 4;
 // consumer warpgroup + producer warpgroup (only its first warp works).  Two CTAs x 8 warps leave 128
-// registers per thread at launch; the budget is re-split at run time with setmaxnreg (consumers 208,
-// producer warpgroup 48: per SM sub-partition 2 x (208 + 48) = 512 registers per lane).
+// registers per thread at launch; the budget is re-split at run time with setmaxnreg (consumers 200,
+// producer warpgroup 56: per SM sub-partition 2 x (200 + 56) = 512 registers per lane).
 constexpr int kWsThreads = (kConsumerWarps + 4) * 32;
 constexpr int WBM = kWsBM, WBN = kWsBN, WBK = 8;
-constexpr int WLDA = WBK + 4;          // 12 complex per A row: (row*12 + k) mod 8 distinct over a quarter-warp
-constexpr int WLDB = WBN + 2;          // (k*130 + n) mod 8 = 2k + n distinct over a quarter-warp
+// Shared-memory tile layouts (units: complex elements = one 16-byte bank group); every fragment load
+// of a quarter-warp (lanes g4 in {2p, 2p+1}, t4 in 0..3) hits 8 distinct bank groups:
+//   A row-major   [32 m][12]      (12*g4 + t4)  mod 8 distinct
+//   A transposed  [8 k][34]       (34*t4 + g4)  mod 8 = 2*t4 + g4 distinct
+//   B row-major   [8 k][130]      (130*t4 + g4) mod 8 = 2*t4 + g4 distinct
+//   B transposed  [128 n][8] with the k4 halves of odd rows swapped (k ^ 4*(n&1)): 4*(g4&1) + t4 distinct
+constexpr int WLDA = WBK + 4, WLDAT = WBM + 2;
+constexpr int WLDB = WBN + 2;
 constexpr int A_ELEMS = WBM * WLDA, B_ELEMS = WBK * WLDB, STAGE_ELEMS = A_ELEMS + B_ELEMS;
-constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u, kFlagNeg = 4u;
+static_assert(WBK * WLDAT <= A_ELEMS && WBN * WBK <= B_ELEMS, "transposed tiles must fit the stage");
+constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u, kFlagNeg = 4u, kFlagATrans = 8u, kFlagBTrans = 16u;
 constexpr uint32_t kSentinel = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t SmemAddr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -81,24 +92,32 @@ struct WsSmem {
                                    STAGES * sizeof(StageMeta);
 };
 
+// Fragment addressing of one stage (element units, relative to the stage's A / B regions).
+struct FragAddr {
+  const double2 *a, *b;     // lane's base inside the A / B tile
+  uint32_t a_i, a_k1;       // A: + i * a_i (m8 group)  + ks * a_k1 (second k4 step)
+  uint32_t b_j, b_k0, b_k1; // B: + j * b_j (owned n8 group) + b_k0 / b_k1 (first / second k4 step)
+};
+
 // One k-stage (WBK = 8 -> two k4 steps) of a warp's sub-tile: MT valid m8 row groups x NT valid n8 column
 // groups.  Specialised at compile time so that skipped MMAs are not even issued.
 template<int MT, int NT>
-__device__ __forceinline__ void ComputeStage(double (&cr)[4][4][2], double (&ci)[4][4][2], const double2 *cA, const double2 *cB,
-                                             uint32_t smask) {
+__device__ __forceinline__ void ComputeStage(double (&cr)[4][4][2], double (&ci)[4][4][2], const FragAddr &f, uint32_t smask) {
 #pragma unroll
   for (int ks = 0; ks < WBK / 4; ++ks) {
     double ax[MT], ay[MT], nay[MT];
     double2 b[NT];
+    const double2 *pa = f.a + (ks ? f.a_k1 : 0u);
+    const double2 *pb = f.b + (ks ? f.b_k1 : f.b_k0);
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
-      const double2 a = cA[i * 8 * WLDA + ks * 4];
+      const double2 a = pa[i * f.a_i];
       ax[i] = FlipSign(a.x, smask);
       ay[i] = FlipSign(a.y, smask);
       nay[i] = FlipSign(a.y, smask ^ 0x80000000u);
     }
 #pragma unroll
-    for (int j = 0; j < NT; ++j) b[j] = cB[ks * 4 * WLDB + j * 32];
+    for (int j = 0; j < NT; ++j) b[j] = pb[j * f.b_j];
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -117,20 +136,19 @@ __device__ __forceinline__ void ComputeStage(double (&cr)[4][4][2], double (&ci)
 }
 
 template<int MT>
-__device__ __forceinline__ void ComputeStageN(double (&cr)[4][4][2], double (&ci)[4][4][2], const double2 *cA, const double2 *cB,
-                                              uint32_t smask, int nt) {
+__device__ __forceinline__ void ComputeStageN(double (&cr)[4][4][2], double (&ci)[4][4][2], const FragAddr &f, uint32_t smask, int nt) {
   switch (nt) {
-    case 4: ComputeStage<MT, 4>(cr, ci, cA, cB, smask); break;
-    case 3: ComputeStage<MT, 3>(cr, ci, cA, cB, smask); break;
-    case 2: ComputeStage<MT, 2>(cr, ci, cA, cB, smask); break;
-    case 1: ComputeStage<MT, 1>(cr, ci, cA, cB, smask); break;
+    case 4: ComputeStage<MT, 4>(cr, ci, f, smask); break;
+    case 3: ComputeStage<MT, 3>(cr, ci, f, smask); break;
+    case 2: ComputeStage<MT, 2>(cr, ci, f, smask); break;
+    case 1: ComputeStage<MT, 1>(cr, ci, f, smask); break;
     default: break;
   }
 }
 
 template<int STAGES>
 __global__ void __launch_bounds__(kWsThreads, 2)
-GemmWsCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restrict__ B, double2 *__restrict__ C) {
+GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2 *stages = reinterpret_cast<double2 *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + size_t(STAGES) * STAGE_ELEMS * sizeof(double2));
@@ -147,7 +165,7 @@ GemmWsCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restric
 
   if (warp >= kConsumerWarps) {
     // ================================ producer warpgroup ================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp != kConsumerWarps) return;
     const uint32_t a_kc = lane & 7, a_r = lane >> 3;
     uint32_t it = 0;
@@ -163,38 +181,60 @@ GemmWsCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restric
       const uint32_t extents = (((rows + 7u) >> 3) << 8) | (((cols + 7u) >> 3) << 16);
       for (uint32_t t = g.task_begin; t < g.task_end; ++t) {
         const GemmTask task = p.tasks[t];
-        const double2 *gA = A + task.a_off + (unsigned long long) row0 * task.k;
-        const double2 *gB = B + task.b_off + col0;
+        const double2 *aBase = static_cast<const double2 *>((task.flags & kTaskASrc) ? p.a_src : p.a_ws) + task.a_off;
+        const double2 *bBase = static_cast<const double2 *>((task.flags & kTaskBSrc) ? p.b_src : p.b_ws) + task.b_off;
+        const bool ta = (task.flags & kTaskATrans) != 0, tb = (task.flags & kTaskBTrans) != 0;
+        const uint32_t tflags = extents | (task.sign < 0 ? kFlagNeg : 0u) | (ta ? kFlagATrans : 0u) | (tb ? kFlagBTrans : 0u);
         for (uint32_t k0 = 0; k0 < task.k; k0 += WBK, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
           MbarWait(&empty[s], ph ^ 1u);
           const uint32_t sA = SmemAddr(stages + size_t(s) * STAGE_ELEMS);
           const uint32_t sB = sA + A_ELEMS * 16u;
-          {   // A: 32 rows x 8 k, a lane copies element (a_r + 4r, a_kc)
+          if (!ta) {   // A row-major m x k: a lane copies element (a_r + 4r, a_kc) of the 32 x 8 tile
             const uint32_t kk = k0 + a_kc;
             const bool kok = kk < task.k;
-            const double2 *src = gA + (unsigned long long) a_r * task.k + kk;
+            const double2 *src = aBase + (unsigned long long) (row0 + a_r) * task.k + kk;
 #pragma unroll
             for (uint32_t r = 0; r < 8; ++r) {
               const uint32_t row = a_r + 4u * r;
               const bool ok = kok && row < rows;
-              CpAsync16Z(sA + (row * WLDA + a_kc) * 16u, ok ? src + (unsigned long long) (4u * r) * task.k : gA, ok);
+              CpAsync16Z(sA + (row * WLDA + a_kc) * 16u, ok ? src + (unsigned long long) (4u * r) * task.k : aBase, ok);
+            }
+          } else {     // A stored k x m: 8 k-rows of 32 contiguous elements
+            const double2 *src = aBase + (unsigned long long) k0 * g.m + row0 + lane;
+            const bool mok = uint32_t(lane) < rows;
+#pragma unroll
+            for (uint32_t kr = 0; kr < uint32_t(WBK); ++kr) {
+              const bool ok = mok && k0 + kr < task.k;
+              CpAsync16Z(sA + (kr * WLDAT + lane) * 16u, ok ? src + (unsigned long long) kr * g.m : aBase, ok);
             }
           }
+          if (!tb) {   // B row-major k x n: 8 k-rows x 128 columns, 512 contiguous bytes per copy
 #pragma unroll
-          for (uint32_t kr = 0; kr < uint32_t(WBK); ++kr) {   // B: 8 k-rows x 128 columns, 512 contiguous bytes per copy
-            const bool rok = k0 + kr < task.k;
-            const double2 *src = gB + (unsigned long long) (k0 + kr) * g.n + lane;
+            for (uint32_t kr = 0; kr < uint32_t(WBK); ++kr) {
+              const bool rok = k0 + kr < task.k;
+              const double2 *src = bBase + (unsigned long long) (k0 + kr) * g.n + col0 + lane;
 #pragma unroll
-            for (uint32_t c = 0; c < 4; ++c) {
-              const uint32_t col = lane + 32u * c;
-              const bool ok = rok && col < cols;
-              CpAsync16Z(sB + (kr * WLDB + col) * 16u, ok ? src + 32u * c : gB, ok);
+              for (uint32_t c = 0; c < 4; ++c) {
+                const uint32_t col = lane + 32u * c;
+                const bool ok = rok && col < cols;
+                CpAsync16Z(sB + (kr * WLDB + col) * 16u, ok ? src + 32u * c : bBase, ok);
+              }
+            }
+          } else {     // B stored n x k: a lane copies element (a_r + 4r, a_kc) of the 128 x 8 tile
+            const uint32_t kk = k0 + a_kc;
+            const bool kok = kk < task.k;
+            const double2 *src = bBase + (unsigned long long) (col0 + a_r) * task.k + kk;
+#pragma unroll 8
+            for (uint32_t r = 0; r < 32; ++r) {
+              const uint32_t nl = a_r + 4u * r;
+              const bool ok = kok && nl < cols;
+              CpAsync16Z(sB + (nl * WBK + (a_kc ^ ((nl & 1u) << 2))) * 16u, ok ? src + (unsigned long long) (4u * r) * task.k : bBase, ok);
             }
           }
           CpAsyncMbarArrive(&full[s]);
           if (lane == 0) {
-            uint32_t fl = extents | (task.sign < 0 ? kFlagNeg : 0u);
+            uint32_t fl = tflags;
             if (t == g.task_begin && k0 == 0) fl |= kFlagFirst;
             if (t + 1 == g.task_end && k0 + WBK >= task.k) fl |= kFlagLast;
             meta[s].tile = tile_id; meta[s].flags = fl;
@@ -218,7 +258,7 @@ GemmWsCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restric
   }
 
   // ==================================== consumer warps ====================================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
   // warp q owns all 32 rows and the n8 column groups {q, q+4, q+8, q+12} of the CTA tile
   const int q = warp;
   const int g4 = lane >> 2, t4 = lane & 3;
@@ -238,17 +278,22 @@ GemmWsCplx(GemmParams p, const double2 *__restrict__ A, const double2 *__restric
     const int mt = int((sm.flags >> 8) & 0xfu);
     const int n8 = int((sm.flags >> 16) & 0x1fu);
     const int nt = n8 > q ? (n8 - q + 3) >> 2 : 0;
-    const double2 *cA = stages + size_t(s) * STAGE_ELEMS + g4 * WLDA + t4;
-    const double2 *cB = stages + size_t(s) * STAGE_ELEMS + A_ELEMS + t4 * WLDB + q * 8 + g4;
+    const double2 *tileA = stages + size_t(s) * STAGE_ELEMS;
+    const double2 *tileB = tileA + A_ELEMS;
+    FragAddr f;
+    if (sm.flags & kFlagATrans) { f.a = tileA + t4 * WLDAT + g4; f.a_i = 8; f.a_k1 = 4 * WLDAT; }
+    else { f.a = tileA + g4 * WLDA + t4; f.a_i = 8 * WLDA; f.a_k1 = 4; }
+    if (sm.flags & kFlagBTrans) { f.b = tileB + (q * 8 + g4) * WBK + t4; f.b_j = 32 * WBK; f.b_k0 = (g4 & 1) << 2; f.b_k1 = f.b_k0 ^ 4u; }
+    else { f.b = tileB + t4 * WLDB + q * 8 + g4; f.b_j = 32; f.b_k0 = 0; f.b_k1 = 4 * WLDB; }
     const uint32_t smask = (sm.flags & kFlagNeg) ? 0x80000000u : 0u;
     if (mt == 4 && nt == 4) {
-      ComputeStage<4, 4>(cr, ci, cA, cB, smask);
+      ComputeStage<4, 4>(cr, ci, f, smask);
     } else {
       switch (mt) {
-        case 4: ComputeStageN<4>(cr, ci, cA, cB, smask, nt); break;
-        case 3: ComputeStageN<3>(cr, ci, cA, cB, smask, nt); break;
-        case 2: ComputeStageN<2>(cr, ci, cA, cB, smask, nt); break;
-        default: ComputeStageN<1>(cr, ci, cA, cB, smask, nt); break;
+        case 4: ComputeStageN<4>(cr, ci, f, smask, nt); break;
+        case 3: ComputeStageN<3>(cr, ci, f, smask, nt); break;
+        case 2: ComputeStageN<2>(cr, ci, f, smask, nt); break;
+        default: ComputeStageN<1>(cr, ci, f, smask, nt); break;
       }
     }
     __syncwarp();
@@ -282,13 +327,12 @@ cudaError_t ConfigureWsKernel() {
   return cudaFuncSetAttribute(GemmWsCplx<kWsStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WsSmem<kWsStages>::kBytes));
 }
 
-cudaError_t LaunchGemmWsCplx(const GemmParams &p, const void *A, const void *B, void *C, int num_sms, cudaStream_t stream) {
+cudaError_t LaunchGemmWsCplx(const GemmParams &p, void *C, int num_sms, cudaStream_t stream) {
   if (p.ntiles == 0) return cudaSuccess;
   constexpr size_t smem = WsSmem<kWsStages>::kBytes;
   const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
   const uint32_t grid = p.ntiles < cap ? p.ntiles : cap;
-  GemmWsCplx<kWsStages><<<grid, kWsThreads, smem, stream>>>(p, static_cast<const double2 *>(A), static_cast<const double2 *>(B),
-                                                         static_cast<double2 *>(C));
+  GemmWsCplx<kWsStages><<<grid, kWsThreads, smem, stream>>>(p, static_cast<double2 *>(C));
   return cudaGetLastError();
 }
 

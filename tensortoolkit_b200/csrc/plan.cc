@@ -72,14 +72,65 @@ PermBlk MakePermBlk(int rank, const uint32_t *shape, const int32_t *perm, uint64
   return d;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Operand layouts.  After the permutation an operand block is a row-major R x Cc matrix (A: m x k,
+// B: k x n).  Many blocks do not need the permute kernel at all:
+//   kBlkDirect  the canonicalised permutation is the identity (all moved axes have extent 1, as the
+//               physical legs of a DMRG tensor block do) -> the GEMM reads the caller's buffer;
+//   kBlkTrans   it is one 2-D transposition whose cut coincides with the row/column cut -> the block
+//               is a row-major Cc x R matrix in the caller's buffer and the GEMM loads it transposed;
+//   kBlkPermute everything else goes through the batched permute kernel into the workspace.
+// ------------------------------------------------------------------------------------------------
+enum : uint8_t { kBlkDirect = 0, kBlkTrans = 1, kBlkPermute = 2 };
+
+static uint8_t ClassifyBlock(int rank, const uint32_t *shape, const int32_t *perm, uint64_t rows, bool allow_trans) {
+  uint64_t istr[QLB200_MAX_RANK];
+  uint64_t s = 1;
+  for (int i = rank - 1; i >= 0; --i) { istr[i] = s; s *= shape[i]; }
+  uint64_t ext[QLB200_MAX_RANK], sst[QLB200_MAX_RANK];
+  int nd = 0;
+  for (int j = 0; j < rank; ++j) {
+    const uint64_t e = shape[perm[j]], st = istr[perm[j]];
+    if (e == 1) continue;
+    if (nd > 0 && sst[nd - 1] == st * e) { ext[nd - 1] *= e; sst[nd - 1] = st; }
+    else { ext[nd] = e; sst[nd] = st; ++nd; }
+  }
+  if (nd <= 1) return kBlkDirect;
+  if (nd == 2 && allow_trans && ext[0] == rows) return kBlkTrans;
+  return kBlkPermute;
+}
+
+struct OperandPlan {
+  std::vector<uint8_t> mode;      // per block (unused blocks: kBlkDirect)
+  uint64_t permute_elems = 0;
+};
+
+static OperandPlan ClassifyOperand(int rank, const int32_t *perm, uint64_t n, const uint32_t *shape,
+                                   const std::vector<char> &used, const std::vector<uint64_t> &rows,
+                                   bool tensor_trans, bool per_block, bool allow_trans) {
+  OperandPlan op;
+  op.mode.assign(n, kBlkDirect);
+  if (!tensor_trans) return op;
+  for (uint64_t b = 0; b < n; ++b) {
+    if (!used[b]) continue;
+    op.mode[b] = per_block ? ClassifyBlock(rank, shape + b * rank, perm, rows[b], allow_trans) : uint8_t(kBlkPermute);
+    if (op.mode[b] == kBlkPermute) {
+      uint64_t sz = 1;
+      for (int i = 0; i < rank; ++i) sz *= shape[b * rank + i];
+      op.permute_elems += sz;
+    }
+  }
+  return op;
+}
+
 static std::string AddPermBlocks(PlanHost *h, int rank, const int32_t *perm, const uint32_t *shape,
-                                 const uint64_t *off, const std::vector<char> &used, uint32_t src_sel,
-                                 std::vector<uint64_t> *new_off, uint64_t *ws_elems, uint64_t *moved) {
+                                 const uint64_t *off, const std::vector<uint8_t> &mode, const std::vector<char> &used,
+                                 uint32_t src_sel, std::vector<uint64_t> *new_off, uint64_t *ws_elems, uint64_t *moved) {
   const uint64_t n = used.size();
   new_off->assign(n, 0);
   uint64_t ws = 0;
   for (uint64_t b = 0; b < n; ++b) {
-    if (!used[b]) continue;
+    if (!used[b] || mode[b] != kBlkPermute) continue;
     uint64_t sz = 1;
     for (int i = 0; i < rank; ++i) sz *= shape[b * rank + i];
     if (sz >= (1ull << 32)) return "block with 2^32 or more elements";
@@ -98,27 +149,74 @@ static std::string AddPermBlocks(PlanHost *h, int rank, const int32_t *perm, con
   return "";
 }
 
-std::string BuildPlanHost(int dtype, uint32_t flags, bool a_trans, int a_rank, const int32_t *a_perm,
+std::string BuildPlanHost(int dtype, uint32_t flags, int nctrct, int a_rank, const int32_t *a_perm_in,
                           uint64_t na, const uint32_t *a_shape, const uint64_t *a_off, uint64_t a_elems,
-                          bool b_trans, int b_rank, const int32_t *b_perm, uint64_t nb, const uint32_t *b_shape,
+                          int b_rank, const int32_t *b_perm_in, uint64_t nb, const uint32_t *b_shape,
                           const uint64_t *b_off, uint64_t b_elems, const std::vector<qlb200_task> &st,
                           uint64_t c_elems, PlanHost *h) {
   h->dtype = dtype; h->flags = flags;
   h->a_elems = a_elems; h->b_elems = b_elems; h->c_elems = c_elems;
-  h->a_trans = a_trans; h->b_trans = b_trans;
   std::vector<char> a_used(na, 0), b_used(nb, 0);
+  std::vector<uint64_t> a_rows(na, 0), b_rows(nb, 0);   // row count of the permuted block: m for A, k for B
   for (const auto &t : st) {
     if (t.a_ord >= na || t.b_ord >= nb) return "task references a block ordinal out of range";
     a_used[t.a_ord] = 1; b_used[t.b_ord] = 1;
+    a_rows[t.a_ord] = t.m; b_rows[t.b_ord] = t.k;
   }
+  auto is_ident = [](int rank, const int32_t *perm) {
+    if (!perm) return true;
+    for (int i = 0; i < rank; ++i) if (perm[i] != i) return false;
+    return true;
+  };
+  std::vector<int32_t> a_perm(a_rank), b_perm(b_rank);
+  for (int i = 0; i < a_rank; ++i) a_perm[i] = a_perm_in ? a_perm_in[i] : i;
+  for (int i = 0; i < b_rank; ++i) b_perm[i] = b_perm_in ? b_perm_in[i] : i;
+
+  // The complex warp-specialised kernel and the narrow-pair kernel read blocks in place (direct or
+  // 2-D transposed); the cp.async kernels only understand row-major operands.
+  const bool legacy = dtype != QLB200_C64 || (flags & QLB200_PLAN_LEGACY_GEMM);
+  const bool per_block = !(flags & QLB200_PLAN_PERMUTE_ALL);
+  const bool allow_trans = per_block && !legacy;
+
+  // The order of the contracted axes inside the k index is free as long as A and B agree (it only
+  // permutes the terms of each dot product).  Candidates: the caller's order, A's storage order,
+  // B's storage order; keep the one that sends the fewest elements through the permute kernel.
+  OperandPlan opa, opb;
+  {
+    std::vector<std::vector<int>> cands;
+    std::vector<int> id(std::max(nctrct, 0));
+    std::iota(id.begin(), id.end(), 0);
+    cands.push_back(id);
+    if (nctrct > 1 && per_block) {
+      std::vector<int> sa = id, sb = id;
+      const int32_t *ac = a_perm.data() + (a_rank - nctrct), *bc = b_perm.data();
+      std::sort(sa.begin(), sa.end(), [&](int x, int y) { return ac[x] < ac[y]; });
+      std::sort(sb.begin(), sb.end(), [&](int x, int y) { return bc[x] < bc[y]; });
+      if (sa != id) cands.push_back(sa);
+      if (sb != id && sb != sa) cands.push_back(sb);
+    }
+    uint64_t best_cost = ~0ull;
+    std::vector<int32_t> best_a, best_b;
+    for (const auto &sig : cands) {
+      std::vector<int32_t> pa = a_perm, pb = b_perm;
+      for (int i = 0; i < nctrct; ++i) { pa[a_rank - nctrct + i] = a_perm[a_rank - nctrct + sig[i]]; pb[i] = b_perm[sig[i]]; }
+      OperandPlan ca = ClassifyOperand(a_rank, pa.data(), na, a_shape, a_used, a_rows, !is_ident(a_rank, pa.data()), per_block, allow_trans);
+      OperandPlan cb = ClassifyOperand(b_rank, pb.data(), nb, b_shape, b_used, b_rows, !is_ident(b_rank, pb.data()), per_block, allow_trans);
+      const uint64_t cost = ca.permute_elems + cb.permute_elems;
+      if (cost < best_cost) { best_cost = cost; best_a = pa; best_b = pb; opa = std::move(ca); opb = std::move(cb); }
+    }
+    a_perm = best_a; b_perm = best_b;
+  }
+  h->a_trans = opa.permute_elems > 0; h->b_trans = opb.permute_elems > 0;
+
   std::vector<uint64_t> a_new, b_new;
   std::string err;
-  if (a_trans) {
-    err = AddPermBlocks(h, a_rank, a_perm, a_shape, a_off, a_used, 0, &a_new, &h->ws_a_elems, &h->permute_elems_a);
+  if (h->a_trans) {
+    err = AddPermBlocks(h, a_rank, a_perm.data(), a_shape, a_off, opa.mode, a_used, 0, &a_new, &h->ws_a_elems, &h->permute_elems_a);
     if (!err.empty()) return err;
   }
-  if (b_trans) {
-    err = AddPermBlocks(h, b_rank, b_perm, b_shape, b_off, b_used, 1, &b_new, &h->ws_b_elems, &h->permute_elems_b);
+  if (h->b_trans) {
+    err = AddPermBlocks(h, b_rank, b_perm.data(), b_shape, b_off, opb.mode, b_used, 1, &b_new, &h->ws_b_elems, &h->permute_elems_b);
     if (!err.empty()) return err;
   }
   if (h->perm_tile_base.empty()) h->perm_tile_base.push_back(0);
@@ -137,9 +235,12 @@ std::string BuildPlanHost(int dtype, uint32_t flags, bool a_trans, int a_rank, c
     for (size_t t = i; t < e; ++t) {
       if (st[t].m != g.m || st[t].n != g.n) return "tasks of one output block disagree on m/n";
       GemmTask gt;
-      gt.a_off = a_trans ? a_new[st[t].a_ord] : st[t].a_off;
-      gt.b_off = b_trans ? b_new[st[t].b_ord] : st[t].b_off;
+      const uint8_t ma = opa.mode[st[t].a_ord], mb = opb.mode[st[t].b_ord];
+      gt.a_off = ma == kBlkPermute ? a_new[st[t].a_ord] : st[t].a_off;
+      gt.b_off = mb == kBlkPermute ? b_new[st[t].b_ord] : st[t].b_off;
       gt.k = st[t].k; gt.sign = st[t].sign < 0 ? -1 : 1;
+      gt.flags = uint16_t((ma != kBlkPermute ? kTaskASrc : 0) | (ma == kBlkTrans ? kTaskATrans : 0) |
+                          (mb != kBlkPermute ? kTaskBSrc : 0) | (mb == kBlkTrans ? kTaskBTrans : 0));
       h->tasks.push_back(gt);
       ksum += gt.k;
       h->flops += fl * double(g.m) * double(gt.k) * double(g.n);

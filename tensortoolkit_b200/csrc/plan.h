@@ -39,7 +39,7 @@ struct PlanHost {
   uint32_t flags = 0;
   int num_sms = 148;
   uint64_t a_elems = 0, b_elems = 0, c_elems = 0;      // raw sizes of the three tensors
-  bool a_trans = false, b_trans = false;
+  bool a_trans = false, b_trans = false;               // some block of A / B goes through the permute kernel
   uint64_t ws_a_elems = 0, ws_b_elems = 0;             // permuted operand sizes (workspace)
   std::vector<PermBlk> perm_blks;
   std::vector<uint32_t> perm_tile_base;                // [nblk+1]
@@ -81,10 +81,11 @@ namespace qlb200 {
 PermBlk MakePermBlk(int rank, const uint32_t *shape, const int32_t *perm, uint64_t src_off, uint64_t dst_off,
                     uint32_t src_sel, float scale, uint64_t *ntiles_out);
 
-/// Build the host-side tables of a contraction from sorted tasks.
-std::string BuildPlanHost(int dtype, uint32_t flags, bool a_trans, int a_rank, const int32_t *a_perm,
+/// Build the host-side tables of a contraction from sorted tasks.  `nctrct` = number of contracted
+/// axes (the last nctrct entries of a_perm and the first nctrct of b_perm; 0 = unknown, keep order).
+std::string BuildPlanHost(int dtype, uint32_t flags, int nctrct, int a_rank, const int32_t *a_perm,
                           uint64_t na, const uint32_t *a_shape, const uint64_t *a_off, uint64_t a_elems,
-                          bool b_trans, int b_rank, const int32_t *b_perm, uint64_t nb, const uint32_t *b_shape,
+                          int b_rank, const int32_t *b_perm, uint64_t nb, const uint32_t *b_shape,
                           const uint64_t *b_off, uint64_t b_elems, const std::vector<qlb200_task> &sorted_tasks,
                           uint64_t c_elems, PlanHost *out);
 

@@ -278,11 +278,12 @@ def test_full_size_properties_heff_d4096_complex(ctx):
     assert util.rel_fro(y12.data, y1.data + (0.5 - 2j) * y2.data) <= TOL
 
 
-@pytest.mark.parametrize("variant", ["ws", "legacy"])
+@pytest.mark.parametrize("variant", ["ws", "legacy", "ws_permute_all", "legacy_permute_all"])
 def test_complex_gemm_kernel_variants(ref, ctx, variant):
     """The warp-specialised complex kernel and the cp.async kernel against the reference on a
     fermionic chain with ragged K tails, ragged tile edges, -1 exchange signs and several pairs per block."""
-    flags = {"legacy": _lib.PLAN_LEGACY_GEMM, "ws": 0}[variant]
+    flags = {"legacy": _lib.PLAN_LEGACY_GEMM, "ws": 0, "ws_permute_all": _lib.PLAN_PERMUTE_ALL,
+             "legacy_permute_all": _lib.PLAN_LEGACY_GEMM | _lib.PLAN_PERMUTE_ALL}[variant]
     flags |= _lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY
     ti = wl.heff_tensor_indexes(wl.hubbard_indexes(150))
     ref.set_seed(77)

@@ -146,3 +146,27 @@ def test_sharded_chain_world1_unpack(ctx):
     got = sc.full.cpu().numpy()
     sc.close()
     assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-12
+
+
+def test_plan_reads_heff_blocks_in_place():
+    """Host-only plans of the U(1) H_eff chain: with one-dimensional physical sectors every block's
+    permutation is trivial or one 2-D transposition (after re-ordering the contracted axes), so the
+    complex plan sends nothing through the permute kernel; PERMUTE_ALL restores the reference's
+    block-by-block transposes (global_operations.h:922-964)."""
+    from tensortoolkit_b200 import _lib
+    ts = make_tensors(96, np.complex128, 4)
+    shells = dict(ts)
+    moved_default, moved_all = 0, 0
+    for lhs, rhs, axes, out in wl.HEFF_STEPS:
+        m = tk.Match(shells[lhs], shells[rhs], axes)
+        shells[out] = m.result_shell(np.complex128)
+        for flags, acc in ((_lib.PLAN_DETERMINISTIC, "d"), (_lib.PLAN_DETERMINISTIC | _lib.PLAN_PERMUTE_ALL, "a")):
+            p = tk.ContractionPlan(None, m, np.complex128, flags)
+            s = p.stats()
+            if acc == "d":
+                moved_default += s.permute_elems_a + s.permute_elems_b
+            else:
+                moved_all += s.permute_elems_a + s.permute_elems_b
+            p.close()
+    assert moved_default == 0
+    assert moved_all > 0
