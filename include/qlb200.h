@@ -141,7 +141,7 @@ int qlb200_host_unregister(void *p);
  * ctx == NULL builds a host-only plan: stats, partition and c_ranges work, execute does not. */
 #define QLB200_PLAN_DETERMINISTIC 1u   /* default and only mode: no atomics, fixed summation order */
 #define QLB200_PLAN_NO_SKINNY 2u       /* force every task through the DMMA kernel (testing) */
-#define QLB200_PLAN_LEGACY_GEMM 4u     /* complex: use the cp.async kernel instead of the warp-specialised one */
+#define QLB200_PLAN_LEGACY_GEMM 4u     /* use the cp.async kernels instead of the warp-specialised ones */
 #define QLB200_PLAN_PERMUTE_ALL 8u     /* send every block of a transposed operand through the permute kernel
                                           (default: blocks whose permutation is trivial or one 2-D transposition
                                           are read in place by the GEMM) */

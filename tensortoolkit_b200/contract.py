@@ -193,6 +193,38 @@ class ContractionPlan:
             pass
 
 
+class RawPlan(ContractionPlan):
+    """Descriptor-table plan without QLTensor shells (qlb200_plan_create_raw): the caller lists block
+    shapes / offsets of A and B, one permutation per operand and the task table.  `tasks` is a list of
+    dicts with a_ord, b_ord, a_off, b_off, c_off, m, k, n, sign, first."""
+
+    def __init__(self, ctx: Context, dtype, a_rank, a_perm, a_shape, a_off, b_rank, b_perm, b_shape, b_off, tasks, c_elems,
+                 flags: int = _lib.PLAN_DETERMINISTIC):
+        self.ctx, self.match = ctx, None
+        self.dtype = np.dtype(dtype)
+        ash = np.ascontiguousarray(np.asarray(a_shape, np.uint32).reshape(-1))
+        bsh = np.ascontiguousarray(np.asarray(b_shape, np.uint32).reshape(-1))
+        aof = np.ascontiguousarray(np.asarray(a_off, np.uint64)); bof = np.ascontiguousarray(np.asarray(b_off, np.uint64))
+        if isinstance(tasks, np.ndarray):       # structured array with the layout of qlb200_task
+            assert tasks.dtype.itemsize == C.sizeof(_lib.Task)
+            tarr, nt = tasks.ctypes.data_as(C.POINTER(_lib.Task)), len(tasks)
+        else:
+            tarr = (_lib.Task * max(len(tasks), 1))()
+            for i, d in enumerate(tasks):
+                t = tarr[i]
+                t.a_ord, t.b_ord, t.c_ord = d["a_ord"], d["b_ord"], d.get("c_ord", 0)
+                t.a_off, t.b_off, t.c_off = d["a_off"], d["b_off"], d["c_off"]
+                t.m, t.k, t.n, t.sign, t.first = d["m"], d["k"], d["n"], d.get("sign", 1), d.get("first", 0)
+            nt = len(tasks)
+        h = C.c_void_p()
+        u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+        check(lib.qlb200_plan_create_raw(
+            ctx.h, _dtype_code(dtype), flags, a_rank, (C.c_int32 * a_rank)(*a_perm), len(aof), ash.ctypes.data_as(u32p),
+            aof.ctypes.data_as(u64p), b_rank, (C.c_int32 * b_rank)(*b_perm), len(bof), bsh.ctypes.data_as(u32p),
+            bof.ctypes.data_as(u64p), nt, tarr, int(c_elems), C.byref(h)), "qlb200_plan_create_raw")
+        self.h = h
+
+
 def _run(a, b, match, ctx):
     if a.dtype != b.dtype:
         # mixed real/complex promotes like the reference (ten_ctrct.h:292-350)

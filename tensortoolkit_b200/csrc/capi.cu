@@ -379,10 +379,12 @@ int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const vo
   ctx->launches = 0;
   GemmParams gp = MakeParams(p, A, B, wa, wb);
   if (gp.ntiles > 0) {
-    if (p->h.dtype == QLB200_C64 && !(p->h.flags & QLB200_PLAN_LEGACY_GEMM))
+    if (p->h.flags & QLB200_PLAN_LEGACY_GEMM)
+      QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, C, ctx->num_sms, ctx->stream));
+    else if (p->h.dtype == QLB200_C64)
       QL_CUDA(LaunchGemmWsCplx(gp, C, ctx->num_sms, ctx->stream));
     else
-      QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, C, ctx->num_sms, ctx->stream));
+      QL_CUDA(LaunchGemmWsReal(gp, C, ctx->num_sms, ctx->stream));
     ctx->launches += 1; ctx->total_launches += 1;
   }
   if (gp.nitems > 0) {

@@ -63,7 +63,7 @@ struct GemmTile {       // DMMA tile: rows [tm*BM, ..) x cols [tn*BN, ..) of a g
   uint16_t tm, tn;
 };
 
-struct SkinnyItem {     // rows [row0, row0+rows) of a narrow group, one thread per row
+struct SkinnyItem {     // rows [row0, row0 + kSkinnyElems / n) of a narrow group
   uint32_t group;
   uint32_t row0;
 };
@@ -92,12 +92,17 @@ cudaError_t ConfigureKernels();   // one-time cudaFuncSetAttribute calls
 // warp-specialised complex kernel (gemm_ws.cu), CTA tile kWsBM x kWsBN
 cudaError_t LaunchGemmWsCplx(const GemmParams &p, void *C, int num_sms, cudaStream_t stream);
 cudaError_t ConfigureWsKernel();
+// warp-specialised real-double kernel (gemm_ws_real.cu), CTA tile kWsRealBM x kWsRealBN
+cudaError_t LaunchGemmWsReal(const GemmParams &p, void *C, int num_sms, cudaStream_t stream);
+cudaError_t ConfigureWsRealKernel();
 
 // tile shapes of the DMMA kernel, needed by the host-side tiler
 constexpr int kRealBM = 128, kRealBN = 128, kRealBK = 16;
 constexpr int kCplxBM = 64, kCplxBN = 128, kCplxBK = 8;   // legacy cp.async kernel
-constexpr int kWsBM = 32, kWsBN = 128;                     // warp-specialised kernel
-constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyRows = 256, kSkinnyThreads = 256;
+constexpr int kWsBM = 32, kWsBN = 128;                     // warp-specialised complex kernel
+constexpr int kWsRealBM = 64, kWsRealBN = 128;             // warp-specialised real kernel
+constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyThreads = 256, kSkinnyPerThread = 8;
+constexpr int kSkinnyElems = kSkinnyThreads * kSkinnyPerThread;   // output elements per work item
 
 }  // namespace qlb200
 #endif

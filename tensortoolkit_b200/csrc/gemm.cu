@@ -323,17 +323,21 @@ GemmDmmaCplx(GemmParams p, double2 *__restrict__ C) {
 
 // ================================================================================================
 // Narrow pairs (n <= kSkinnyMaxN, k <= kSkinnyMaxK): HBM-bound, reads m*k per pair, writes m*n once.
-// One thread per OUTPUT ELEMENT: a work item is kSkinnyRows rows of one output block; consecutive
-// threads own consecutive elements of C (fully coalesced stores), the n threads of a row share their
-// A loads through one broadcast transaction.  A and B blocks are read in place: row-major, or
-// 2-D transposed in the caller's buffer (kTask?Trans), so these steps need no permute pass.
+//
+// A work item is a run of rows of one output block holding about kSkinnyElems output elements; one
+// thread owns up to kSkinnyPerThread of them (element e = tid + 256*u: consecutive threads write
+// consecutive elements of C).  The (pair, kk) terms of the block are first flattened into a small
+// shared-memory table {A pointer, A row stride, B coefficients with the sign folded in}; the main
+// loop then issues one A load per owned element per term -- up to 8 independent loads in flight per
+// thread -- and multiplies by coefficients broadcast from shared memory.  A and B blocks are read in
+// place: row-major, or 2-D transposed in the caller's buffer (kTask?Trans).
 // ================================================================================================
 template<bool CPLX> struct Elem;
 template<> struct Elem<false> {
   using T = double;
   static __device__ __forceinline__ T Zero() { return 0.0; }
   static __device__ __forceinline__ void Fma(T &acc, T a, T b) { acc = fma(a, b, acc); }
-  static __device__ __forceinline__ void Axpy(T &acc, int sign, T v) { acc += sign < 0 ? -v : v; }
+  static __device__ __forceinline__ T Signed(T v, int sign) { return sign < 0 ? -v : v; }
 };
 template<> struct Elem<true> {
   using T = double2;
@@ -342,40 +346,77 @@ template<> struct Elem<true> {
     acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
     acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
   }
-  static __device__ __forceinline__ void Axpy(T &acc, int sign, T v) {
-    if (sign < 0) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
-  }
+  static __device__ __forceinline__ T Signed(T v, int sign) { return sign < 0 ? make_double2(-v.x, -v.y) : v; }
 };
+
+constexpr int kSkinnyTermChunk = 64;
 
 template<bool CPLX>
 __global__ void __launch_bounds__(kSkinnyThreads)
 GemmSkinny(GemmParams p, typename Elem<CPLX>::T *__restrict__ C) {
   using E = Elem<CPLX>;
   using T = typename E::T;
+  __shared__ const T *s_ap[kSkinnyTermChunk];
+  __shared__ uint32_t s_as[kSkinnyTermChunk];
+  __shared__ T s_coef[kSkinnyTermChunk][kSkinnyMaxN];
+  const uint32_t tid = threadIdx.x;
   for (uint32_t it = blockIdx.x; it < p.nitems; it += gridDim.x) {
     const SkinnyItem item = p.items[it];
     const GemmGroup g = p.groups[item.group];
     const uint32_t n = g.n;
-    const uint32_t rows = min(uint32_t(kSkinnyRows), g.row_end - item.row0);
+    const uint32_t rows = min(uint32_t(kSkinnyElems) / n, g.row_end - item.row0);
     const uint32_t total = rows * n;
-    T *cb = C + g.c_off + (unsigned long long) item.row0 * n;
-    for (uint32_t e = threadIdx.x; e < total; e += kSkinnyThreads) {
-      const uint32_t r = e / n, j = e - r * n;
-      const unsigned long long row = item.row0 + r;
-      T acc = E::Zero();
-      for (uint32_t t = g.task_begin; t < g.task_end; ++t) {
-        const GemmTask tk = p.tasks[t];
-        const T *a = static_cast<const T *>((tk.flags & kTaskASrc) ? p.a_src : p.a_ws) + tk.a_off;
-        const T *b = static_cast<const T *>((tk.flags & kTaskBSrc) ? p.b_src : p.b_ws) + tk.b_off;
-        unsigned long long as, bs;
-        if (tk.flags & kTaskATrans) { a += row; as = g.m; } else { a += row * tk.k; as = 1; }
-        if (tk.flags & kTaskBTrans) { b += (unsigned long long) j * tk.k; bs = 1; } else { b += j; bs = n; }
-        T part = E::Zero();
-#pragma unroll 4
-        for (uint32_t kk = 0; kk < tk.k; ++kk) E::Fma(part, a[kk * as], __ldg(b + kk * bs));
-        E::Axpy(acc, tk.sign, part);
+    uint32_t row[kSkinnyPerThread], col[kSkinnyPerThread];
+    T acc[kSkinnyPerThread];
+#pragma unroll
+    for (int u = 0; u < kSkinnyPerThread; ++u) {
+      const uint32_t e = tid + u * kSkinnyThreads;
+      const uint32_t r = e / n;
+      row[u] = item.row0 + r; col[u] = e - r * n;
+      acc[u] = E::Zero();
+    }
+    // walk the group's (pair, kk) terms in chunks of kSkinnyTermChunk
+    uint32_t t = g.task_begin, kk0 = 0;
+    while (t < g.task_end) {
+      __syncthreads();   // previous chunk (or previous item) fully consumed
+      // every thread walks the same short task list; thread x fills term x
+      uint32_t nterm = 0, tt = t, kk = kk0;
+      while (tt < g.task_end && nterm < uint32_t(kSkinnyTermChunk)) {
+        const GemmTask tk = p.tasks[tt];
+        const uint32_t take = min(tk.k - kk, uint32_t(kSkinnyTermChunk) - nterm);
+        if (tid >= nterm && tid < nterm + take) {
+          const uint32_t k1 = kk + (tid - nterm);
+          const T *a = static_cast<const T *>((tk.flags & kTaskASrc) ? p.a_src : p.a_ws) + tk.a_off;
+          const T *b = static_cast<const T *>((tk.flags & kTaskBSrc) ? p.b_src : p.b_ws) + tk.b_off;
+          if (tk.flags & kTaskATrans) { s_ap[tid] = a + (unsigned long long) k1 * g.m; s_as[tid] = 1; }
+          else { s_ap[tid] = a + k1; s_as[tid] = tk.k; }
+          for (uint32_t j = 0; j < n; ++j) {
+            const T v = (tk.flags & kTaskBTrans) ? b[(unsigned long long) j * tk.k + k1] : b[(unsigned long long) k1 * n + j];
+            s_coef[tid][j] = E::Signed(v, tk.sign);
+          }
+        }
+        nterm += take; kk += take;
+        if (kk >= tk.k) { ++tt; kk = 0; }
       }
-      cb[e] = acc;
+      t = tt; kk0 = kk;
+      __syncthreads();
+      for (uint32_t x = 0; x < nterm; ++x) {
+        const T *ap = s_ap[x];
+        const unsigned long long as = s_as[x];
+        T av[kSkinnyPerThread];
+#pragma unroll
+        for (int u = 0; u < kSkinnyPerThread; ++u)
+          if (tid + u * kSkinnyThreads < total) av[u] = ap[row[u] * as];
+#pragma unroll
+        for (int u = 0; u < kSkinnyPerThread; ++u)
+          if (tid + u * kSkinnyThreads < total) E::Fma(acc[u], av[u], s_coef[x][col[u]]);
+      }
+    }
+    T *cb = C + g.c_off + (unsigned long long) item.row0 * n;
+#pragma unroll
+    for (int u = 0; u < kSkinnyPerThread; ++u) {
+      const uint32_t e = tid + u * kSkinnyThreads;
+      if (e < total) cb[e] = acc[u];
     }
   }
 }
@@ -387,7 +428,9 @@ cudaError_t ConfigureKernels() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(GemmDmmaCplx, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kCplxSmem));
   if (e != cudaSuccess) return e;
-  return ConfigureWsKernel();
+  e = ConfigureWsKernel();
+  if (e != cudaSuccess) return e;
+  return ConfigureWsRealKernel();
 }
 
 cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, void *C, int num_sms, cudaStream_t stream) {

@@ -22,16 +22,12 @@
 //     tile (interleaved, so valid columns spread evenly over the four sub-partitions) and skips the
 //     MMAs of m8 row groups / n8 column groups that lie outside the output block.
 #include "common.cuh"
+#include "ws_common.cuh"
 
 namespace qlb200 {
 
 namespace {
 
-constexpr int kConsumerWarps = 4;
-// consumer warpgroup + producer warpgroup (only its first warp works).  Two CTAs x 8 warps leave 128
-// registers per thread at launch; the budget is re-split at run time with setmaxnreg (consumers 200,
-// producer warpgroup 56: per SM sub-partition 2 x (200 + 56) = 512 registers per lane).
-constexpr int kWsThreads = (kConsumerWarps + 4) * 32;
 constexpr int WBM = kWsBM, WBN = kWsBN, WBK = 8;
 // Shared-memory tile layouts (units: complex elements = one 16-byte bank group); every fragment load
 // of a quarter-warp (lanes g4 in {2p, 2p+1}, t4 in 0..3) hits 8 distinct bank groups:
@@ -43,48 +39,6 @@ constexpr int WLDA = WBK + 4, WLDAT = WBM + 2;
 constexpr int WLDB = WBN + 2;
 constexpr int A_ELEMS = WBM * WLDA, B_ELEMS = WBK * WLDB, STAGE_ELEMS = A_ELEMS + B_ELEMS;
 static_assert(WBK * WLDAT <= A_ELEMS && WBN * WBK <= B_ELEMS, "transposed tiles must fit the stage");
-constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u, kFlagNeg = 4u, kFlagATrans = 8u, kFlagBTrans = 16u;
-constexpr uint32_t kSentinel = 0xffffffffu;
-
-__device__ __forceinline__ uint32_t SmemAddr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void MbarInit(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void MbarArrive(uint64_t *bar) {
-  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(SmemAddr(bar)) : "memory");
-}
-// arrives on `bar` once all cp.async issued so far by this thread have landed (does not change the expected count)
-__device__ __forceinline__ void CpAsyncMbarArrive(uint64_t *bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(SmemAddr(bar)) : "memory");
-}
-__device__ __forceinline__ void MbarWait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      " @p bra WAIT_DONE;\n"
-      " bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}" ::"r"(SmemAddr(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void CpAsync16Z(uint32_t smem, const void *gmem, bool pred) {
-  const int sz = pred ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "r"(sz) : "memory");
-}
-
-__device__ __forceinline__ void DmmaNv(double &d0, double &d1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
-// sign flip on the integer pipe (a DADD would compete with DMMA for the FP64 datapath)
-__device__ __forceinline__ double FlipSign(double v, uint32_t mask) {
-  return __hiloint2double(__double2hiint(v) ^ int(mask), __double2loint(v));
-}
-
-// flags word of a stage: bits 0..2 first/last/neg, 8..11 valid m8 groups, 16..20 valid n8 groups
-struct StageMeta { uint32_t tile, flags; };
 
 template<int STAGES>
 struct WsSmem {

@@ -1,0 +1,253 @@
+// gemm_ws_real.cu -- warp-specialised grouped FP64 GEMM for real double tensors.
+//
+// Same pipeline as the complex kernel (gemm_ws.cu: 4 consumer warps + 1 cp.async producer warp,
+// full/empty mbarrier ring, two CTAs per SM, dynamic tile counter, operands read in place row-major
+// or 2-D transposed, ragged tiles specialised at compile time); the differences are the shapes:
+//   * CTA tile 64 x 128, k-stage 16: a warp owns all 64 rows (8 m8 groups) and the n8 column groups
+//     {q, q+4, q+8, q+12}: 32 DMMA.8x8x4 per k4 step, 64 accumulator doubles per lane -- the same
+//     MMA count per stage and the same register budget as the complex kernel;
+//   * elements are 8 bytes, so copies are 8-byte cp.async (any block offset / leading dimension is
+//     legal) and a fragment load is an LDS.64 served per half-warp (lanes g4 in {4h..4h+3}, t4 in 0..3):
+//       A row-major   [64 m][20]    (20*g4 + t4)  mod 16 = 4*g4 + t4 distinct
+//       A transposed  [16 k][68]    (68*t4 + g4)  mod 16 = 4*t4 + g4 distinct
+//       B row-major   [16 k][132]   (132*t4 + g4) mod 16 = 4*t4 + g4 distinct
+//       B transposed  [128 n][16] with k ^ 4*(n&3): 4*((g4&3) ^ ks) + t4 distinct
+#include "common.cuh"
+#include "ws_common.cuh"
+
+namespace qlb200 {
+
+namespace {
+
+constexpr int RBM = kWsRealBM, RBN = kWsRealBN, RBK = 16;
+constexpr int RLDA = RBK + 4, RLDAT = RBM + 4, RLDB = RBN + 4;
+constexpr int RA_ELEMS = RBM * RLDA, RB_ELEMS = RBK * RLDB, RSTAGE_ELEMS = RA_ELEMS + RB_ELEMS;
+static_assert(RBK * RLDAT <= RA_ELEMS && RBN * RBK <= RB_ELEMS, "transposed tiles must fit the stage");
+constexpr int kRealStages = 4;
+constexpr size_t kRealWsSmem = size_t(kRealStages) * RSTAGE_ELEMS * sizeof(double) + 2 * kRealStages * sizeof(uint64_t) +
+                               kRealStages * sizeof(StageMeta);
+
+struct FragAddrR {
+  const double *a, *b;
+  uint32_t a_i, a_k;        // A: + i * a_i (m8 group) + ks * a_k
+  uint32_t b_j, b_k, b_x;   // B: + j * b_j (owned n8 group) + (ks ^ b_x) * b_k
+};
+
+template<int MT, int NT>
+__device__ __forceinline__ void ComputeStageR(double (&acc)[8][4][2], const FragAddrR &f, uint32_t smask) {
+#pragma unroll
+  for (int ks = 0; ks < RBK / 4; ++ks) {
+    double a[MT], b[NT];
+    const double *pa = f.a + ks * f.a_k;
+    const double *pb = f.b + (uint32_t(ks) ^ f.b_x) * f.b_k;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) a[i] = FlipSign(pa[i * f.a_i], smask);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) b[j] = pb[j * f.b_j];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) DmmaNv(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+template<int MT>
+__device__ __forceinline__ void ComputeStageRN(double (&acc)[8][4][2], const FragAddrR &f, uint32_t smask, int nt) {
+  switch (nt) {
+    case 4: ComputeStageR<MT, 4>(acc, f, smask); break;
+    case 3: ComputeStageR<MT, 3>(acc, f, smask); break;
+    case 2: ComputeStageR<MT, 2>(acc, f, smask); break;
+    case 1: ComputeStageR<MT, 1>(acc, f, smask); break;
+    default: break;
+  }
+}
+
+__global__ void __launch_bounds__(kWsThreads, 2)
+GemmWsReal(GemmParams p, double *__restrict__ C) {
+  constexpr int STAGES = kRealStages;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *stages = reinterpret_cast<double *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + size_t(STAGES) * RSTAGE_ELEMS * sizeof(double));
+  uint64_t *empty = full + STAGES;
+  StageMeta *meta = reinterpret_cast<StageMeta *>(empty + STAGES);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { MbarInit(&full[s], 33); MbarInit(&empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp >= kConsumerWarps) {
+    // ================================ producer warpgroup ================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp != kConsumerWarps) return;
+    const uint32_t a_kc = lane & 15, a_r = lane >> 4;
+    uint32_t it = 0;
+    for (;;) {
+      uint32_t tile_id = 0;
+      if (lane == 0) tile_id = atomicAdd(&p.counters[0], 1u);
+      tile_id = __shfl_sync(0xffffffffu, tile_id, 0);
+      if (tile_id >= p.ntiles) break;
+      const GemmTile tile = p.tiles[tile_id];
+      const GemmGroup g = p.groups[tile.group];
+      const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * RBM, col0 = uint32_t(tile.tn) * RBN;
+      const uint32_t rows = min(uint32_t(RBM), g.row_end - row0), cols = min(uint32_t(RBN), g.n - col0);
+      const uint32_t extents = (((rows + 7u) >> 3) << 8) | (((cols + 7u) >> 3) << 16);
+      for (uint32_t t = g.task_begin; t < g.task_end; ++t) {
+        const GemmTask task = p.tasks[t];
+        const double *aBase = static_cast<const double *>((task.flags & kTaskASrc) ? p.a_src : p.a_ws) + task.a_off;
+        const double *bBase = static_cast<const double *>((task.flags & kTaskBSrc) ? p.b_src : p.b_ws) + task.b_off;
+        const bool ta = (task.flags & kTaskATrans) != 0, tb = (task.flags & kTaskBTrans) != 0;
+        const uint32_t tflags = extents | (task.sign < 0 ? kFlagNeg : 0u) | (ta ? kFlagATrans : 0u) | (tb ? kFlagBTrans : 0u);
+        for (uint32_t k0 = 0; k0 < task.k; k0 += RBK, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+          MbarWait(&empty[s], ph ^ 1u);
+          const uint32_t sA = SmemAddr(stages + size_t(s) * RSTAGE_ELEMS);
+          const uint32_t sB = sA + RA_ELEMS * 8u;
+          if (!ta) {   // A row-major m x k: a lane copies element (a_r + 2r, a_kc) of the 64 x 16 tile
+            const uint32_t kk = k0 + a_kc;
+            const bool kok = kk < task.k;
+            const double *src = aBase + (unsigned long long) (row0 + a_r) * task.k + kk;
+#pragma unroll 8
+            for (uint32_t r = 0; r < 32; ++r) {
+              const uint32_t row = a_r + 2u * r;
+              const bool ok = kok && row < rows;
+              CpAsync8Z(sA + (row * RLDA + a_kc) * 8u, ok ? src + (unsigned long long) (2u * r) * task.k : aBase, ok);
+            }
+          } else {     // A stored k x m: 16 k-rows of 64 contiguous elements
+            const double *src = aBase + (unsigned long long) k0 * g.m + row0 + lane;
+#pragma unroll 4
+            for (uint32_t kr = 0; kr < uint32_t(RBK); ++kr) {
+              const bool kok = k0 + kr < task.k;
+#pragma unroll
+              for (uint32_t c = 0; c < 2; ++c) {
+                const uint32_t ml = lane + 32u * c;
+                const bool ok = kok && ml < rows;
+                CpAsync8Z(sA + (kr * RLDAT + ml) * 8u, ok ? src + (unsigned long long) kr * g.m + 32u * c : aBase, ok);
+              }
+            }
+          }
+          if (!tb) {   // B row-major k x n: 16 k-rows x 128 columns, 256 contiguous bytes per copy
+#pragma unroll 4
+            for (uint32_t kr = 0; kr < uint32_t(RBK); ++kr) {
+              const bool rok = k0 + kr < task.k;
+              const double *src = bBase + (unsigned long long) (k0 + kr) * g.n + col0 + lane;
+#pragma unroll
+              for (uint32_t c = 0; c < 4; ++c) {
+                const uint32_t col = lane + 32u * c;
+                const bool ok = rok && col < cols;
+                CpAsync8Z(sB + (kr * RLDB + col) * 8u, ok ? src + 32u * c : bBase, ok);
+              }
+            }
+          } else {     // B stored n x k: a lane copies element (a_r + 2r, a_kc) of the 128 x 16 tile
+            const uint32_t kk = k0 + a_kc;
+            const bool kok = kk < task.k;
+            const double *src = bBase + (unsigned long long) (col0 + a_r) * task.k + kk;
+#pragma unroll 8
+            for (uint32_t r = 0; r < 64; ++r) {
+              const uint32_t nl = a_r + 2u * r;
+              const bool ok = kok && nl < cols;
+              CpAsync8Z(sB + (nl * RBK + (a_kc ^ ((nl & 3u) << 2))) * 8u, ok ? src + (unsigned long long) (2u * r) * task.k : bBase, ok);
+            }
+          }
+          CpAsyncMbarArrive(&full[s]);
+          if (lane == 0) {
+            uint32_t fl = tflags;
+            if (t == g.task_begin && k0 == 0) fl |= kFlagFirst;
+            if (t + 1 == g.task_end && k0 + RBK >= task.k) fl |= kFlagLast;
+            meta[s].tile = tile_id; meta[s].flags = fl;
+            MbarArrive(&full[s]);
+          }
+        }
+      }
+    }
+    {   // sentinel stage: tells every consumer warp to leave
+      const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+      MbarWait(&empty[s], ph ^ 1u);
+      CpAsyncMbarArrive(&full[s]);
+      if (lane == 0) { meta[s].tile = kSentinel; meta[s].flags = 0; MbarArrive(&full[s]); }
+    }
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(&p.counters[1], 1u) == gridDim.x - 1) { p.counters[0] = 0; p.counters[1] = 0; __threadfence(); }
+    }
+    return;
+  }
+
+  // ==================================== consumer warps ====================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+  const int q = warp;
+  const int g4 = lane >> 2, t4 = lane & 3;
+  double acc[8][4][2];
+  uint32_t it = 0;
+  for (;; ++it) {
+    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+    MbarWait(&full[s], ph);
+    const StageMeta sm = meta[s];
+    if (sm.tile == kSentinel) break;
+    if (sm.flags & kFlagFirst) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
+    const int mt = int((sm.flags >> 8) & 0xfu);
+    const int n8 = int((sm.flags >> 16) & 0x1fu);
+    const int nt = n8 > q ? (n8 - q + 3) >> 2 : 0;
+    const double *tileA = stages + size_t(s) * RSTAGE_ELEMS;
+    const double *tileB = tileA + RA_ELEMS;
+    FragAddrR f;
+    if (sm.flags & kFlagATrans) { f.a = tileA + t4 * RLDAT + g4; f.a_i = 8; f.a_k = 4 * RLDAT; }
+    else { f.a = tileA + g4 * RLDA + t4; f.a_i = 8 * RLDA; f.a_k = 4; }
+    if (sm.flags & kFlagBTrans) { f.b = tileB + (q * 8 + g4) * RBK + t4; f.b_j = 32 * RBK; f.b_k = 4; f.b_x = g4 & 3; }
+    else { f.b = tileB + t4 * RLDB + q * 8 + g4; f.b_j = 32; f.b_k = 4 * RLDB; f.b_x = 0; }
+    const uint32_t smask = (sm.flags & kFlagNeg) ? 0x80000000u : 0u;
+    if (mt == 8 && nt == 4) {
+      ComputeStageR<8, 4>(acc, f, smask);
+    } else {
+      switch ((mt + 1) >> 1) {      // m8 groups are specialised in pairs
+        case 4: ComputeStageRN<8>(acc, f, smask, nt); break;
+        case 3: ComputeStageRN<6>(acc, f, smask, nt); break;
+        case 2: ComputeStageRN<4>(acc, f, smask, nt); break;
+        default: ComputeStageRN<2>(acc, f, smask, nt); break;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) MbarArrive(&empty[s]);
+    if (sm.flags & kFlagLast) {
+      const GemmTile tile = p.tiles[sm.tile];
+      const GemmGroup g = p.groups[tile.group];
+      const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * RBM, col0 = uint32_t(tile.tn) * RBN;
+      double *Cg = C + g.c_off;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t row = row0 + i * 8 + g4;
+        if (row >= g.row_end) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+          double *dst = Cg + (unsigned long long) row * g.n + col;
+          if (col < g.n) dst[0] = acc[i][j][0];
+          if (col + 1 < g.n) dst[1] = acc[i][j][1];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t ConfigureWsRealKernel() {
+  return cudaFuncSetAttribute(GemmWsReal, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRealWsSmem));
+}
+
+cudaError_t LaunchGemmWsReal(const GemmParams &p, void *C, int num_sms, cudaStream_t stream) {
+  if (p.ntiles == 0) return cudaSuccess;
+  const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
+  const uint32_t grid = p.ntiles < cap ? p.ntiles : cap;
+  GemmWsReal<<<grid, kWsThreads, kRealWsSmem, stream>>>(p, static_cast<double *>(C));
+  return cudaGetLastError();
+}
+
+}  // namespace qlb200

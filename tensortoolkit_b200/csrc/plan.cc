@@ -172,9 +172,9 @@ std::string BuildPlanHost(int dtype, uint32_t flags, int nctrct, int a_rank, con
   for (int i = 0; i < a_rank; ++i) a_perm[i] = a_perm_in ? a_perm_in[i] : i;
   for (int i = 0; i < b_rank; ++i) b_perm[i] = b_perm_in ? b_perm_in[i] : i;
 
-  // The complex warp-specialised kernel and the narrow-pair kernel read blocks in place (direct or
-  // 2-D transposed); the cp.async kernels only understand row-major operands.
-  const bool legacy = dtype != QLB200_C64 || (flags & QLB200_PLAN_LEGACY_GEMM);
+  // The warp-specialised kernels and the narrow-pair kernel read blocks in place (direct or 2-D
+  // transposed); the legacy cp.async kernels only understand row-major operands.
+  const bool legacy = (flags & QLB200_PLAN_LEGACY_GEMM) != 0;
   const bool per_block = !(flags & QLB200_PLAN_PERMUTE_ALL);
   const bool allow_trans = per_block && !legacy;
 
@@ -276,11 +276,10 @@ GroupClass Classify(const PlanHost *h, const GemmGroup &g, int bk) {
 
 std::string BuildTiles(PlanHost *h) {
   h->tiles.clear(); h->items.clear();
-  int BM = kRealBM, BN = kRealBN;
-  if (h->dtype == QLB200_C64) {
-    const bool legacy = (h->flags & QLB200_PLAN_LEGACY_GEMM) != 0;
-    BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : kWsBN;
-  }
+  const bool legacy = (h->flags & QLB200_PLAN_LEGACY_GEMM) != 0;
+  int BM, BN;
+  if (h->dtype == QLB200_C64) { BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : kWsBN; }
+  else { BM = legacy ? kRealBM : kWsRealBM; BN = legacy ? kRealBN : kWsRealBN; }
   std::vector<uint32_t> order(h->part_groups.size());
   std::iota(order.begin(), order.end(), 0u);
   // heaviest k-loops first: persistent CTAs then finish with the short tiles (LPT)
@@ -290,7 +289,8 @@ std::string BuildTiles(PlanHost *h) {
     if (g.row_end <= g.row_begin) continue;
     const uint32_t rows = g.row_end - g.row_begin;
     if (Classify(h, g, 8).skinny) {
-      for (uint32_t r = 0; r < rows; r += kSkinnyRows) h->items.push_back({gi, g.row_begin + r});
+      const uint32_t per = uint32_t(kSkinnyElems) / g.n;   // rows per work item (n <= kSkinnyMaxN)
+      for (uint32_t r = 0; r < rows; r += per) h->items.push_back({gi, g.row_begin + r});
     } else {
       const uint32_t tm = (rows + BM - 1) / BM, tn = (g.n + BN - 1) / BN;
       if (tm > 65535 || tn > 65535) return "output block too large for 16-bit tile coordinates";

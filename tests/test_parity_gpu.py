@@ -278,23 +278,54 @@ def test_full_size_properties_heff_d4096_complex(ctx):
     assert util.rel_fro(y12.data, y1.data + (0.5 - 2j) * y2.data) <= TOL
 
 
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
 @pytest.mark.parametrize("variant", ["ws", "legacy", "ws_permute_all", "legacy_permute_all"])
-def test_complex_gemm_kernel_variants(ref, ctx, variant):
-    """The warp-specialised complex kernel and the cp.async kernel against the reference on a
-    fermionic chain with ragged K tails, ragged tile edges, -1 exchange signs and several pairs per block."""
+def test_gemm_kernel_variants(ref, ctx, variant, dtype):
+    """The warp-specialised kernels (blocks read in place or through the permute kernel) and the
+    cp.async kernels against the reference on a fermionic chain with ragged K tails, ragged tile
+    edges, -1 exchange signs and several pairs per block."""
     flags = {"legacy": _lib.PLAN_LEGACY_GEMM, "ws": 0, "ws_permute_all": _lib.PLAN_PERMUTE_ALL,
              "legacy_permute_all": _lib.PLAN_LEGACY_GEMM | _lib.PLAN_PERMUTE_ALL}[variant]
     flags |= _lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY
     ti = wl.heff_tensor_indexes(wl.hubbard_indexes(150))
     ref.set_seed(77)
-    r = {name: ref.RefTensor.new(idxs, np.complex128).random((0, 0)) for name, idxs in ti.items()}
+    r = {name: ref.RefTensor.new(idxs, dtype).random((0, 0)) for name, idxs in ti.items()}
     t = {name: x.to_bst() for name, x in r.items()}
     for lhs, rhs, axes, out in wl.HEFF_STEPS:
         r[out] = ref.contract(r[lhs], r[rhs], axes)
         m = tk.Match(t[lhs], t[rhs], axes)
-        plan = tk.ContractionPlan(ctx, m, np.complex128, flags)
-        c = m.result_shell(np.complex128)
+        plan = tk.ContractionPlan(ctx, m, dtype, flags)
+        c = m.result_shell(dtype)
         plan.execute_host(t[lhs].data, t[rhs].data, c.data)
         plan.close(); m.close()
         util.assert_same_as_ref(c, r[out], TOL)
         t[out] = c
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
+def test_transposed_operand_modes_vs_numpy(ctx, dtype):
+    """Raw plans whose A blocks are stored k x m and whose B blocks are stored n x k (both read in
+    place, transposed, by the GEMM producer), with ragged sizes around the tile edges; against numpy."""
+    rng = np.random.default_rng(5)
+    cplx = dtype == np.complex128
+    sizes = [(1, 1, 1), (7, 5, 3), (33, 17, 129), (64, 40, 128), (65, 9, 131), (100, 70, 260), (31, 8, 127), (200, 33, 40)]
+    a_shape, b_shape, a_off, b_off, tasks = [], [], [], [], []
+    ao = bo = co = 0
+    a_data, b_data, want = [], [], []
+    for i, (m, k, n) in enumerate(sizes):
+        a = rng.standard_normal((k, m)) + (1j * rng.standard_normal((k, m)) if cplx else 0)     # stored k x m
+        b = rng.standard_normal((n, k)) + (1j * rng.standard_normal((n, k)) if cplx else 0)     # stored n x k
+        a_shape += [k, m]; b_shape += [n, k]; a_off.append(ao); b_off.append(bo)
+        tasks.append(dict(a_ord=i, b_ord=i, a_off=ao, b_off=bo, c_off=co, m=m, k=k, n=n, sign=-1 if i % 3 == 2 else 1, first=1))
+        want.append((-1 if i % 3 == 2 else 1) * (a.T @ b.T))
+        a_data.append(a.ravel()); b_data.append(b.ravel())
+        ao += a.size; bo += b.size; co += m * n
+    A = np.concatenate(a_data).astype(dtype); B = np.concatenate(b_data).astype(dtype)
+    Cw = np.concatenate([w.ravel() for w in want]).astype(dtype)
+    for flags in (_lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY, _lib.PLAN_DETERMINISTIC,
+                  _lib.PLAN_DETERMINISTIC | _lib.PLAN_PERMUTE_ALL | _lib.PLAN_NO_SKINNY):
+        plan = tk.RawPlan(ctx, dtype, 2, [1, 0], a_shape, a_off, 2, [1, 0], b_shape, b_off, tasks, co, flags)
+        Cg = np.zeros(co, dtype)
+        plan.execute_host(A, B, Cg)
+        plan.close()
+        assert util.rel_fro(Cg, Cw) <= TOL
