@@ -3,10 +3,11 @@
 // Same contract as gemm.cu (C = sum over the group's pairs of sign * A[m x k] * B[k x n], written
 // once, deterministic), different machine mapping:
 //
-//   * CTA = 4 consumer warps + 1 producer warp (registers re-split with setmaxnreg), CTA tile 32 x 128, TWO CTAs resident per SM.  The two
+//   * CTA = 4 consumer warps + 4 producer warps (registers re-split with setmaxnreg), CTA tile 32 x 128,
+//     TWO CTAs resident per SM.  The two
 //     CTAs of an SM drift apart, so one CTA's epilogue / prologue is covered by the other CTA's main
 //     loop and the FP64 tensor pipe (DMMA.8x8x4) of every SM sub-partition always has a warp to feed it.
-//   * The producer warp moves operand tiles global -> shared with 16-byte asynchronous copies
+//   * The producer warps move operand tiles global -> shared with 16-byte asynchronous copies
 //     (cp.async, SASS LDGSTS; complex elements are 16 bytes, so any block offset / leading dimension
 //     is legal) and signals completion through an mbarrier (cp.async.mbarrier.arrive).  Ragged edges
 //     and the K tail are zero-filled by the copy itself (src-size 0).
@@ -108,11 +109,12 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + size_t(STAGES) * STAGE_ELEMS * sizeof(double2));
   uint64_t *empty = full + STAGES;
   StageMeta *meta = reinterpret_cast<StageMeta *>(empty + STAGES);
+  __shared__ uint32_t s_tile[2];      // tile id handed from producer warp 0 to the other producer warps
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    // full: 32 asynchronous copy-completion arrivals + lane 0's own (releases the stage meta)
-    for (int s = 0; s < STAGES; ++s) { MbarInit(&full[s], 33); MbarInit(&empty[s], kConsumerWarps); }
+    // full: one asynchronous copy-completion arrival per producer lane + one plain arrival (releases the stage meta)
+    for (int s = 0; s < STAGES; ++s) { MbarInit(&full[s], kFullArrivals); MbarInit(&empty[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -120,13 +122,14 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
   if (warp >= kConsumerWarps) {
     // ================================ producer warpgroup ================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp != kConsumerWarps) return;
+    // the four producer warps walk the same tile / stage sequence and each issue a quarter of a stage's copies
+    const uint32_t pw = warp - kConsumerWarps;
     const uint32_t a_kc = lane & 7, a_r = lane >> 3;
-    uint32_t it = 0;
-    for (;;) {
-      uint32_t tile_id = 0;
-      if (lane == 0) tile_id = atomicAdd(&p.counters[0], 1u);
-      tile_id = __shfl_sync(0xffffffffu, tile_id, 0);
+    uint32_t it = 0, tcount = 0;
+    for (;; ++tcount) {
+      if (pw == 0 && lane == 0) s_tile[tcount & 1u] = atomicAdd(&p.counters[0], 1u);
+      ProducerBarrier();
+      const uint32_t tile_id = s_tile[tcount & 1u];
       if (tile_id >= p.ntiles) break;
       const GemmTile tile = p.tiles[tile_id];
       const GemmGroup g = p.groups[tile.group];
@@ -149,8 +152,8 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
             const bool kok = kk < task.k;
             const double2 *src = aBase + (unsigned long long) (row0 + a_r) * task.k + kk;
 #pragma unroll
-            for (uint32_t r = 0; r < 8; ++r) {
-              const uint32_t row = a_r + 4u * r;
+            for (uint32_t rr = 0; rr < 2; ++rr) {
+              const uint32_t r = 2u * pw + rr, row = a_r + 4u * r;
               const bool ok = kok && row < rows;
               CpAsync16Z(sA + (row * WLDA + a_kc) * 16u, ok ? src + (unsigned long long) (4u * r) * task.k : aBase, ok);
             }
@@ -158,14 +161,16 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
             const double2 *src = aBase + (unsigned long long) k0 * g.m + row0 + lane;
             const bool mok = uint32_t(lane) < rows;
 #pragma unroll
-            for (uint32_t kr = 0; kr < uint32_t(WBK); ++kr) {
+            for (uint32_t rr = 0; rr < 2; ++rr) {
+              const uint32_t kr = 2u * pw + rr;
               const bool ok = mok && k0 + kr < task.k;
               CpAsync16Z(sA + (kr * WLDAT + lane) * 16u, ok ? src + (unsigned long long) kr * g.m : aBase, ok);
             }
           }
           if (!tb) {   // B row-major k x n: 8 k-rows x 128 columns, 512 contiguous bytes per copy
 #pragma unroll
-            for (uint32_t kr = 0; kr < uint32_t(WBK); ++kr) {
+            for (uint32_t rr = 0; rr < 2; ++rr) {
+              const uint32_t kr = 2u * pw + rr;
               const bool rok = k0 + kr < task.k;
               const double2 *src = bBase + (unsigned long long) (k0 + kr) * g.n + col0 + lane;
 #pragma unroll
@@ -179,15 +184,15 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
             const uint32_t kk = k0 + a_kc;
             const bool kok = kk < task.k;
             const double2 *src = bBase + (unsigned long long) (col0 + a_r) * task.k + kk;
-#pragma unroll 8
-            for (uint32_t r = 0; r < 32; ++r) {
-              const uint32_t nl = a_r + 4u * r;
+#pragma unroll
+            for (uint32_t rr = 0; rr < 8; ++rr) {
+              const uint32_t r = 8u * pw + rr, nl = a_r + 4u * r;
               const bool ok = kok && nl < cols;
               CpAsync16Z(sB + (nl * WBK + (a_kc ^ ((nl & 1u) << 2))) * 16u, ok ? src + (unsigned long long) (4u * r) * task.k : bBase, ok);
             }
           }
           CpAsyncMbarArrive(&full[s]);
-          if (lane == 0) {
+          if (pw == 0 && lane == 0) {
             uint32_t fl = tflags;
             if (t == g.task_begin && k0 == 0) fl |= kFlagFirst;
             if (t + 1 == g.task_end && k0 + WBK >= task.k) fl |= kFlagLast;
@@ -202,9 +207,9 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
       const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
       MbarWait(&empty[s], ph ^ 1u);
       CpAsyncMbarArrive(&full[s]);
-      if (lane == 0) { meta[s].tile = kSentinel; meta[s].flags = 0; MbarArrive(&full[s]); }
+      if (pw == 0 && lane == 0) { meta[s].tile = kSentinel; meta[s].flags = 0; MbarArrive(&full[s]); }
     }
-    if (lane == 0) {
+    if (pw == 0 && lane == 0) {
       __threadfence();
       if (atomicAdd(&p.counters[1], 1u) == gridDim.x - 1) { p.counters[0] = 0; p.counters[1] = 0; __threadfence(); }
     }

@@ -1,6 +1,6 @@
 // gemm_ws_real.cu -- warp-specialised grouped FP64 GEMM for real double tensors.
 //
-// Same pipeline as the complex kernel (gemm_ws.cu: 4 consumer warps + 1 cp.async producer warp,
+// Same pipeline as the complex kernel (gemm_ws.cu: 4 consumer warps + 4 cp.async producer warps,
 // full/empty mbarrier ring, two CTAs per SM, dynamic tile counter, operands read in place row-major
 // or 2-D transposed, ragged tiles specialised at compile time); the differences are the shapes:
 //   * CTA tile 64 x 128, k-stage 16: a warp owns all 64 rows (8 m8 groups) and the n8 column groups
@@ -70,10 +70,11 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + size_t(STAGES) * RSTAGE_ELEMS * sizeof(double));
   uint64_t *empty = full + STAGES;
   StageMeta *meta = reinterpret_cast<StageMeta *>(empty + STAGES);
+  __shared__ uint32_t s_tile[2];      // tile id handed from producer warp 0 to the other producer warps
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { MbarInit(&full[s], 33); MbarInit(&empty[s], kConsumerWarps); }
+    for (int s = 0; s < STAGES; ++s) { MbarInit(&full[s], kFullArrivals); MbarInit(&empty[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -81,13 +82,13 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
   if (warp >= kConsumerWarps) {
     // ================================ producer warpgroup ================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp != kConsumerWarps) return;
+    const uint32_t pw = warp - kConsumerWarps;     // each producer warp issues a quarter of a stage's copies
     const uint32_t a_kc = lane & 15, a_r = lane >> 4;
-    uint32_t it = 0;
-    for (;;) {
-      uint32_t tile_id = 0;
-      if (lane == 0) tile_id = atomicAdd(&p.counters[0], 1u);
-      tile_id = __shfl_sync(0xffffffffu, tile_id, 0);
+    uint32_t it = 0, tcount = 0;
+    for (;; ++tcount) {
+      if (pw == 0 && lane == 0) s_tile[tcount & 1u] = atomicAdd(&p.counters[0], 1u);
+      ProducerBarrier();
+      const uint32_t tile_id = s_tile[tcount & 1u];
       if (tile_id >= p.ntiles) break;
       const GemmTile tile = p.tiles[tile_id];
       const GemmGroup g = p.groups[tile.group];
@@ -109,16 +110,17 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
             const uint32_t kk = k0 + a_kc;
             const bool kok = kk < task.k;
             const double *src = aBase + (unsigned long long) (row0 + a_r) * task.k + kk;
-#pragma unroll 8
-            for (uint32_t r = 0; r < 32; ++r) {
-              const uint32_t row = a_r + 2u * r;
+#pragma unroll
+            for (uint32_t rr = 0; rr < 8; ++rr) {
+              const uint32_t r = 8u * pw + rr, row = a_r + 2u * r;
               const bool ok = kok && row < rows;
               CpAsync8Z(sA + (row * RLDA + a_kc) * 8u, ok ? src + (unsigned long long) (2u * r) * task.k : aBase, ok);
             }
           } else {     // A stored k x m: 16 k-rows of 64 contiguous elements
             const double *src = aBase + (unsigned long long) k0 * g.m + row0 + lane;
-#pragma unroll 4
-            for (uint32_t kr = 0; kr < uint32_t(RBK); ++kr) {
+#pragma unroll
+            for (uint32_t rr = 0; rr < 4; ++rr) {
+              const uint32_t kr = 4u * pw + rr;
               const bool kok = k0 + kr < task.k;
 #pragma unroll
               for (uint32_t c = 0; c < 2; ++c) {
@@ -129,8 +131,9 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
             }
           }
           if (!tb) {   // B row-major k x n: 16 k-rows x 128 columns, 256 contiguous bytes per copy
-#pragma unroll 4
-            for (uint32_t kr = 0; kr < uint32_t(RBK); ++kr) {
+#pragma unroll
+            for (uint32_t rr = 0; rr < 4; ++rr) {
+              const uint32_t kr = 4u * pw + rr;
               const bool rok = k0 + kr < task.k;
               const double *src = bBase + (unsigned long long) (k0 + kr) * g.n + col0 + lane;
 #pragma unroll
@@ -144,15 +147,15 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
             const uint32_t kk = k0 + a_kc;
             const bool kok = kk < task.k;
             const double *src = bBase + (unsigned long long) (col0 + a_r) * task.k + kk;
-#pragma unroll 8
-            for (uint32_t r = 0; r < 64; ++r) {
-              const uint32_t nl = a_r + 2u * r;
+#pragma unroll
+            for (uint32_t rr = 0; rr < 16; ++rr) {
+              const uint32_t r = 16u * pw + rr, nl = a_r + 2u * r;
               const bool ok = kok && nl < cols;
               CpAsync8Z(sB + (nl * RBK + (a_kc ^ ((nl & 3u) << 2))) * 8u, ok ? src + (unsigned long long) (2u * r) * task.k : bBase, ok);
             }
           }
           CpAsyncMbarArrive(&full[s]);
-          if (lane == 0) {
+          if (pw == 0 && lane == 0) {
             uint32_t fl = tflags;
             if (t == g.task_begin && k0 == 0) fl |= kFlagFirst;
             if (t + 1 == g.task_end && k0 + RBK >= task.k) fl |= kFlagLast;
@@ -166,9 +169,9 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
       const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
       MbarWait(&empty[s], ph ^ 1u);
       CpAsyncMbarArrive(&full[s]);
-      if (lane == 0) { meta[s].tile = kSentinel; meta[s].flags = 0; MbarArrive(&full[s]); }
+      if (pw == 0 && lane == 0) { meta[s].tile = kSentinel; meta[s].flags = 0; MbarArrive(&full[s]); }
     }
-    if (lane == 0) {
+    if (pw == 0 && lane == 0) {
       __threadfence();
       if (atomicAdd(&p.counters[1], 1u) == gridDim.x - 1) { p.counters[0] = 0; p.counters[1] = 0; __threadfence(); }
     }

@@ -9,12 +9,17 @@ namespace qlb200 {
 namespace {
 
 constexpr int kConsumerWarps = 4;
-// consumer warpgroup + producer warpgroup (only its first warp works).  Two CTAs x 8 warps leave 128
+// consumer warpgroup + producer warpgroup.  Two CTAs x 8 warps leave 128
 // registers per thread at launch; the budget is re-split at run time with setmaxnreg (consumers 200,
 // producer warpgroup 56: per SM sub-partition 2 x (200 + 56) = 512 registers per lane).
 constexpr int kWsThreads = (kConsumerWarps + 4) * 32;
 constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u, kFlagNeg = 4u, kFlagATrans = 8u, kFlagBTrans = 16u;
 constexpr uint32_t kSentinel = 0xffffffffu;
+constexpr int kProducerWarps = 4;
+constexpr uint32_t kFullArrivals = kProducerWarps * 32 + 1;   // async copy arrivals of every producer lane + the meta release
+
+// named barrier 1: the producer warps only
+__device__ __forceinline__ void ProducerBarrier() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory"); }
 
 __device__ __forceinline__ uint32_t SmemAddr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
