@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--plan-flags", type=int, default=1, help="qlb200_plan_create flags (kernel A/B testing; 1 = default)")
+    ap.add_argument("--shard-of", default="", help="W:r -- time rank r's share of a W-GPU run on one GPU, no collective (tuning aid)")
     return ap.parse_args()
 
 
@@ -213,11 +214,18 @@ def run_ours(args):
     rng = np.random.default_rng(SEEDS[dtype])
     tensors = build_tensors(args.D, dtype, rng)
     sharded = None
-    if world > 1:
+    if args.shard_of:
+        from tensortoolkit_b200.heff import ShardedChain
+        ew, er = (int(x) for x in args.shard_of.split(":"))
+        with torch.cuda.stream(stream):
+            sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), ew, er, flags=args.plan_flags, exchange=False)
+        chain = sharded.chain
+        apply_fn = sharded.apply
+    elif world > 1:
         # partition by output sector / row slab of lenv's free bond; all-gather of disjoint slabs per apply
         from tensortoolkit_b200.heff import ShardedChain
         with torch.cuda.stream(stream):
-            sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank)
+            sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags)
         chain = sharded.chain
         apply_fn = sharded.apply
     else:
@@ -365,10 +373,15 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner) write to fd 1 too
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

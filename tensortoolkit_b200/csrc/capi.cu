@@ -59,6 +59,11 @@ int UploadGemmTables(qlb200_plan *p) {
   if ((rc = Upload(p->h.part_groups, &p->d.groups, s)) != QLB200_OK) return rc;
   if ((rc = Upload(p->h.tiles, &p->d.tiles, s)) != QLB200_OK) return rc;
   if ((rc = Upload(p->h.items, &p->d.items, s)) != QLB200_OK) return rc;
+  // [0] next unit, [1] finished CTAs, [2..] split-K arrival counters; the kernels leave them all zero
+  if (p->d.counters) { cudaFree(p->d.counters); p->d.counters = nullptr; }
+  const size_t nctr = 2 + size_t(p->h.n_split_ctrs);
+  QL_CUDA(cudaMalloc(reinterpret_cast<void **>(&p->d.counters), nctr * sizeof(unsigned int)));
+  QL_CUDA(cudaMemsetAsync(p->d.counters, 0, nctr * sizeof(unsigned int), s));
   QL_CUDA(cudaStreamSynchronize(s));   // host vectors may change after return
   return QLB200_OK;
 }
@@ -69,14 +74,12 @@ int FinishPlan(qlb200_ctx *ctx, qlb200_plan *p) {
   QL_CUDA(cudaSetDevice(ctx->device));
   if ((rc = Upload(p->h.perm_blks, &p->d.perm_blks, s)) != QLB200_OK) return rc;
   if ((rc = Upload(p->h.perm_tile_base, &p->d.perm_tile_base, s)) != QLB200_OK) return rc;
-  QL_CUDA(cudaMalloc(reinterpret_cast<void **>(&p->d.counters), 2 * sizeof(unsigned int)));
-  QL_CUDA(cudaMemsetAsync(p->d.counters, 0, 2 * sizeof(unsigned int), s));
   return UploadGemmTables(p);
 }
 
-GemmParams MakeParams(const qlb200_plan *p, const void *A, const void *B, const void *wsA, const void *wsB) {
+GemmParams MakeParams(const qlb200_plan *p, const void *A, const void *B, const void *wsA, const void *wsB, void *partials) {
   GemmParams gp;
-  gp.a_src = A; gp.b_src = B; gp.a_ws = wsA; gp.b_ws = wsB;
+  gp.a_src = A; gp.b_src = B; gp.a_ws = wsA; gp.b_ws = wsB; gp.partials = partials;
   gp.tasks = p->d.tasks; gp.groups = p->d.groups; gp.tiles = p->d.tiles; gp.items = p->d.items;
   gp.ntiles = static_cast<uint32_t>(p->h.tiles.size());
   gp.nitems = static_cast<uint32_t>(p->h.items.size());
@@ -91,7 +94,7 @@ void SetPlanKnobs(const qlb200_ctx *ctx, uint32_t flags, PlanHost *h) {
 
 size_t WsBytes(const qlb200_plan *p) {
   const size_t es = ElemSize(p->h.dtype);
-  return Align256(p->h.ws_a_elems * es) + Align256(p->h.ws_b_elems * es);
+  return Align256(p->h.ws_a_elems * es) + Align256(p->h.ws_b_elems * es) + Align256(p->h.n_part_slots * p->h.part_slot_elems * es);
 }
 
 }  // namespace
@@ -345,12 +348,13 @@ int qlb200_plan_get_stats(const qlb200_plan *p, qlb200_plan_stats *out) {
 }
 
 // ---- execution ---------------------------------------------------------------------------------
-static int ResolveWorkspace(qlb200_ctx *ctx, qlb200_plan *p, void **wsA, void **wsB) {
+static int ResolveWorkspace(qlb200_ctx *ctx, qlb200_plan *p, void **wsA, void **wsB, void **partials = nullptr) {
   const size_t es = ElemSize(p->h.dtype);
   int rc = EnsureArena(&ctx->ws, &ctx->ws_bytes, WsBytes(p), ctx->stream);
   if (rc != QLB200_OK) return rc;
   *wsA = ctx->ws;
   *wsB = static_cast<char *>(ctx->ws) + Align256(p->h.ws_a_elems * es);
+  if (partials) *partials = static_cast<char *>(*wsB) + Align256(p->h.ws_b_elems * es);
   return QLB200_OK;
 }
 
@@ -373,11 +377,11 @@ int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const
 int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C) {
   if (!ctx || !p) return Fail(QLB200_ERR_ARG, "null argument");
   QL_CUDA(cudaSetDevice(ctx->device));
-  void *wa, *wb;
-  int rc = ResolveWorkspace(ctx, p, &wa, &wb);
+  void *wa, *wb, *parts;
+  int rc = ResolveWorkspace(ctx, p, &wa, &wb, &parts);
   if (rc != QLB200_OK) return rc;
   ctx->launches = 0;
-  GemmParams gp = MakeParams(p, A, B, wa, wb);
+  GemmParams gp = MakeParams(p, A, B, wa, wb, parts);
   if (gp.ntiles > 0) {
     if (p->h.flags & QLB200_PLAN_LEGACY_GEMM)
       QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, C, ctx->num_sms, ctx->stream));

@@ -58,9 +58,18 @@ struct GemmGroup {
   uint32_t row_begin, row_end;      // rows of the block this plan computes (multi-GPU slabs)
 };
 
-struct GemmTile {       // DMMA tile: rows [tm*BM, ..) x cols [tn*BN, ..) of a group
+// DMMA work unit: rows [tm*BM, ..) x cols [tn*BN, ..) of a group, k-stages [s_begin, s_end) of the
+// group's concatenated k loop.  A tile whose k loop is long compared with a CTA's share of the launch
+// is split into `nsplit` units (deterministic split-K): every unit stores its partial tile into slot
+// part_base + split of the workspace; the unit that arrives last (counter `ctr`) adds the partials in
+// slot order 0..nsplit-1 -- a fixed order, whichever unit happens to be last -- and writes C.
+struct GemmTile {
   uint32_t group;
   uint16_t tm, tn;
+  uint32_t s_begin, s_end;
+  uint32_t part_base, ctr;
+  uint16_t split, nsplit;
+  uint32_t pad_;
 };
 
 struct SkinnyItem {     // rows [row0, row0 + kSkinnyElems / n) of a narrow group
@@ -75,7 +84,8 @@ struct GemmParams {
   const GemmTile *tiles;
   const SkinnyItem *items;
   uint32_t ntiles, nitems;
-  unsigned int *counters;           // [0] next tile, [1] finished CTAs (self-resetting)
+  unsigned int *counters;           // [0] next tile, [1] finished CTAs, [2 + ctr] split-K arrivals (all self-resetting)
+  void *partials;                   // split-K partial tiles, slot = BM x BN elements
 };
 
 inline std::string CudaErr(const char *what, cudaError_t e) {
@@ -101,6 +111,7 @@ constexpr int kRealBM = 128, kRealBN = 128, kRealBK = 16;
 constexpr int kCplxBM = 64, kCplxBN = 128, kCplxBK = 8;   // legacy cp.async kernel
 constexpr int kWsBM = 32, kWsBN = 128;                     // warp-specialised complex kernel
 constexpr int kWsRealBM = 64, kWsRealBN = 128;             // warp-specialised real kernel
+constexpr int kWsBK = 8, kWsRealBK = 16;                   // k extent of one pipeline stage
 constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyThreads = 256, kSkinnyPerThread = 8;
 constexpr int kSkinnyElems = kSkinnyThreads * kSkinnyPerThread;   // output elements per work item
 

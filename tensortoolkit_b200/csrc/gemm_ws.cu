@@ -29,7 +29,7 @@ namespace qlb200 {
 
 namespace {
 
-constexpr int WBM = kWsBM, WBN = kWsBN, WBK = 8;
+constexpr int WBM = kWsBM, WBN = kWsBN, WBK = kWsBK;
 // Shared-memory tile layouts (units: complex elements = one 16-byte bank group); every fragment load
 // of a quarter-warp (lanes g4 in {2p, 2p+1}, t4 in 0..3) hits 8 distinct bank groups:
 //   A row-major   [32 m][12]      (12*g4 + t4)  mod 8 distinct
@@ -101,6 +101,43 @@ __device__ __forceinline__ void ComputeStageN(double (&cr)[4][4][2], double (&ci
   }
 }
 
+// Split-K fix-up, run by the unit that arrived last: add the tile's partial tiles in slot order (a fixed
+// order, whichever unit happens to be last) one m8 row group at a time and write C.  Kept out of line:
+// it needs only a handful of registers and must not disturb the register allocation of the main loop.
+__device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile, const GemmGroup &g, double2 *__restrict__ C,
+                                       int q, int g4, int t4) {
+  __threadfence();
+  const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * WBM, col0 = uint32_t(tile.tn) * WBN;
+  const double2 *src0 = static_cast<const double2 *>(p.partials) + (unsigned long long) tile.part_base * (WBM * WBN) +
+                        g4 * WBN + q * 8 + 2 * t4;
+  double2 *Cg = C + g.c_off;
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    double2 sum[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sum[j][0] = sum[j][1] = make_double2(0.0, 0.0);
+    const double2 *src = src0 + i * 8 * WBN;
+    for (uint32_t sp = 0; sp < tile.nsplit; ++sp, src += WBM * WBN) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 v0 = __ldcg(src + j * 32), v1 = __ldcg(src + j * 32 + 1);
+        sum[j][0].x += v0.x; sum[j][0].y += v0.y; sum[j][1].x += v1.x; sum[j][1].y += v1.y;
+      }
+    }
+    const uint32_t row = row0 + i * 8 + g4;
+    if (row < g.row_end) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+        double2 *dst = Cg + (unsigned long long) row * g.n + col;
+        if (col < g.n) dst[0] = sum[j][0];
+        if (col + 1 < g.n) dst[1] = sum[j][1];
+      }
+    }
+  }
+  if (q == 0 && g4 == 0 && t4 == 0) p.counters[2 + tile.ctr] = 0;
+}
+
 template<int STAGES>
 __global__ void __launch_bounds__(kWsThreads, 2)
 GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
@@ -110,6 +147,7 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
   uint64_t *empty = full + STAGES;
   StageMeta *meta = reinterpret_cast<StageMeta *>(empty + STAGES);
   __shared__ uint32_t s_tile[2];      // tile id handed from producer warp 0 to the other producer warps
+  __shared__ uint32_t s_last;         // split-K: this CTA holds the last unit of its tile
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -121,7 +159,7 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
 
   if (warp >= kConsumerWarps) {
     // ================================ producer warpgroup ================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     // the four producer warps walk the same tile / stage sequence and each issue a quarter of a stage's copies
     const uint32_t pw = warp - kConsumerWarps;
     const uint32_t a_kc = lane & 7, a_r = lane >> 3;
@@ -136,13 +174,19 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
       const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * WBM, col0 = uint32_t(tile.tn) * WBN;
       const uint32_t rows = min(uint32_t(WBM), g.row_end - row0), cols = min(uint32_t(WBN), g.n - col0);
       const uint32_t extents = (((rows + 7u) >> 3) << 8) | (((cols + 7u) >> 3) << 16);
-      for (uint32_t t = g.task_begin; t < g.task_end; ++t) {
+      uint32_t sidx = 0;     // stage index of the current pair's first stage in the group's concatenated k loop
+      for (uint32_t t = g.task_begin; t < g.task_end && sidx < tile.s_end; ++t) {
         const GemmTask task = p.tasks[t];
+        const uint32_t nst = (task.k + WBK - 1) / WBK;
+        const uint32_t st_lo = max(sidx, tile.s_begin), st_hi = min(sidx + nst, tile.s_end);
+        const uint32_t st_base = sidx;
+        sidx += nst;
+        if (st_lo >= st_hi) continue;
         const double2 *aBase = static_cast<const double2 *>((task.flags & kTaskASrc) ? p.a_src : p.a_ws) + task.a_off;
         const double2 *bBase = static_cast<const double2 *>((task.flags & kTaskBSrc) ? p.b_src : p.b_ws) + task.b_off;
         const bool ta = (task.flags & kTaskATrans) != 0, tb = (task.flags & kTaskBTrans) != 0;
         const uint32_t tflags = extents | (task.sign < 0 ? kFlagNeg : 0u) | (ta ? kFlagATrans : 0u) | (tb ? kFlagBTrans : 0u);
-        for (uint32_t k0 = 0; k0 < task.k; k0 += WBK, ++it) {
+        for (uint32_t st = st_lo, k0 = (st_lo - st_base) * WBK; st < st_hi; ++st, ++it, k0 += WBK) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
           MbarWait(&empty[s], ph ^ 1u);
           const uint32_t sA = SmemAddr(stages + size_t(s) * STAGE_ELEMS);
@@ -194,8 +238,8 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
           CpAsyncMbarArrive(&full[s]);
           if (pw == 0 && lane == 0) {
             uint32_t fl = tflags;
-            if (t == g.task_begin && k0 == 0) fl |= kFlagFirst;
-            if (t + 1 == g.task_end && k0 + WBK >= task.k) fl |= kFlagLast;
+            if (st == tile.s_begin) fl |= kFlagFirst;
+            if (st + 1 == tile.s_end) fl |= kFlagLast;
             meta[s].tile = tile_id; meta[s].flags = fl;
             MbarArrive(&full[s]);
           }
@@ -217,14 +261,13 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
   }
 
   // ==================================== consumer warps ====================================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
   // warp q owns all 32 rows and the n8 column groups {q, q+4, q+8, q+12} of the CTA tile
   const int q = warp;
   const int g4 = lane >> 2, t4 = lane & 3;
   double cr[4][4][2], ci[4][4][2];
-  uint32_t it = 0;
-  for (;; ++it) {
-    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+  uint32_t s = 0, ph = 0;     // ring position and phase parity
+  for (;; ph ^= (++s == uint32_t(STAGES)) ? 1u : 0u, s = (s == uint32_t(STAGES)) ? 0u : s) {
     MbarWait(&full[s], ph);
     const StageMeta sm = meta[s];
     if (sm.tile == kSentinel) break;
@@ -261,17 +304,38 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
       const GemmTile tile = p.tiles[sm.tile];
       const GemmGroup g = p.groups[tile.group];
       const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * WBM, col0 = uint32_t(tile.tn) * WBN;
-      double2 *Cg = C + g.c_off;
+      bool write_c = true;
+      if (tile.nsplit > 1) {
+        // deterministic split-K: park this unit's partial tile, the last unit to arrive adds all of them
+        double2 *slots = static_cast<double2 *>(p.partials) + (unsigned long long) tile.part_base * (WBM * WBN);
+        double2 *mine = slots + (unsigned long long) tile.split * (WBM * WBN) + g4 * WBN + q * 8 + 2 * t4;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t row = row0 + i * 8 + g4;
-        if (row >= g.row_end) continue;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-          double2 *dst = Cg + (unsigned long long) row * g.n + col;
-          if (col < g.n) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
-          if (col + 1 < g.n) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
+          for (int j = 0; j < 4; ++j) {
+            mine[i * 8 * WBN + j * 32] = make_double2(cr[i][j][0], ci[i][j][0]);
+            mine[i * 8 * WBN + j * 32 + 1] = make_double2(cr[i][j][1], ci[i][j][1]);
+          }
+        __threadfence();
+        ConsumerBarrier();
+        if (warp == 0 && lane == 0) s_last = atomicAdd(&p.counters[2 + tile.ctr], 1u) == uint32_t(tile.nsplit) - 1u ? 1u : 0u;
+        ConsumerBarrier();
+        write_c = false;
+        if (s_last != 0) FixupTile(p, tile, g, C, q, g4, t4);
+      }
+      if (write_c) {
+        double2 *Cg = C + g.c_off;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t row = row0 + i * 8 + g4;
+          if (row >= g.row_end) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+            double2 *dst = Cg + (unsigned long long) row * g.n + col;
+            if (col < g.n) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
+            if (col + 1 < g.n) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
+          }
         }
       }
     }

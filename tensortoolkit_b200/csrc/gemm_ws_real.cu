@@ -19,7 +19,7 @@ namespace qlb200 {
 
 namespace {
 
-constexpr int RBM = kWsRealBM, RBN = kWsRealBN, RBK = 16;
+constexpr int RBM = kWsRealBM, RBN = kWsRealBN, RBK = kWsRealBK;
 constexpr int RLDA = RBK + 4, RLDAT = RBM + 4, RLDB = RBN + 4;
 constexpr int RA_ELEMS = RBM * RLDA, RB_ELEMS = RBK * RLDB, RSTAGE_ELEMS = RA_ELEMS + RB_ELEMS;
 static_assert(RBK * RLDAT <= RA_ELEMS && RBN * RBK <= RB_ELEMS, "transposed tiles must fit the stage");
@@ -62,6 +62,41 @@ __device__ __forceinline__ void ComputeStageRN(double (&acc)[8][4][2], const Fra
   }
 }
 
+// Split-K fix-up (see gemm_ws.cu FixupTile): out of line, sums the partial tiles in slot order, writes C.
+__device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &tile, const GemmGroup &g, double *__restrict__ C,
+                                        int q, int g4, int t4) {
+  __threadfence();
+  const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * RBM, col0 = uint32_t(tile.tn) * RBN;
+  const double *src0 = static_cast<const double *>(p.partials) + (unsigned long long) tile.part_base * (RBM * RBN) +
+                       g4 * RBN + q * 8 + 2 * t4;
+  double *Cg = C + g.c_off;
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    double2 sum[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sum[j] = make_double2(0.0, 0.0);
+    const double *src = src0 + i * 8 * RBN;
+    for (uint32_t sp = 0; sp < tile.nsplit; ++sp, src += RBM * RBN) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 v = __ldcg(reinterpret_cast<const double2 *>(src + j * 32));
+        sum[j].x += v.x; sum[j].y += v.y;
+      }
+    }
+    const uint32_t row = row0 + i * 8 + g4;
+    if (row < g.row_end) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+        double *dst = Cg + (unsigned long long) row * g.n + col;
+        if (col < g.n) dst[0] = sum[j].x;
+        if (col + 1 < g.n) dst[1] = sum[j].y;
+      }
+    }
+  }
+  if (q == 0 && g4 == 0 && t4 == 0) p.counters[2 + tile.ctr] = 0;
+}
+
 __global__ void __launch_bounds__(kWsThreads, 2)
 GemmWsReal(GemmParams p, double *__restrict__ C) {
   constexpr int STAGES = kRealStages;
@@ -71,6 +106,7 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
   uint64_t *empty = full + STAGES;
   StageMeta *meta = reinterpret_cast<StageMeta *>(empty + STAGES);
   __shared__ uint32_t s_tile[2];      // tile id handed from producer warp 0 to the other producer warps
+  __shared__ uint32_t s_last;         // split-K: this CTA holds the last unit of its tile
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -81,7 +117,7 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
 
   if (warp >= kConsumerWarps) {
     // ================================ producer warpgroup ================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     const uint32_t pw = warp - kConsumerWarps;     // each producer warp issues a quarter of a stage's copies
     const uint32_t a_kc = lane & 15, a_r = lane >> 4;
     uint32_t it = 0, tcount = 0;
@@ -95,13 +131,19 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
       const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * RBM, col0 = uint32_t(tile.tn) * RBN;
       const uint32_t rows = min(uint32_t(RBM), g.row_end - row0), cols = min(uint32_t(RBN), g.n - col0);
       const uint32_t extents = (((rows + 7u) >> 3) << 8) | (((cols + 7u) >> 3) << 16);
-      for (uint32_t t = g.task_begin; t < g.task_end; ++t) {
+      uint32_t sidx = 0;     // stage index of the current pair's first stage in the group's concatenated k loop
+      for (uint32_t t = g.task_begin; t < g.task_end && sidx < tile.s_end; ++t) {
         const GemmTask task = p.tasks[t];
+        const uint32_t nst = (task.k + RBK - 1) / RBK;
+        const uint32_t st_lo = max(sidx, tile.s_begin), st_hi = min(sidx + nst, tile.s_end);
+        const uint32_t st_base = sidx;
+        sidx += nst;
+        if (st_lo >= st_hi) continue;
         const double *aBase = static_cast<const double *>((task.flags & kTaskASrc) ? p.a_src : p.a_ws) + task.a_off;
         const double *bBase = static_cast<const double *>((task.flags & kTaskBSrc) ? p.b_src : p.b_ws) + task.b_off;
         const bool ta = (task.flags & kTaskATrans) != 0, tb = (task.flags & kTaskBTrans) != 0;
         const uint32_t tflags = extents | (task.sign < 0 ? kFlagNeg : 0u) | (ta ? kFlagATrans : 0u) | (tb ? kFlagBTrans : 0u);
-        for (uint32_t k0 = 0; k0 < task.k; k0 += RBK, ++it) {
+        for (uint32_t st = st_lo, k0 = (st_lo - st_base) * RBK; st < st_hi; ++st, ++it, k0 += RBK) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
           MbarWait(&empty[s], ph ^ 1u);
           const uint32_t sA = SmemAddr(stages + size_t(s) * RSTAGE_ELEMS);
@@ -157,8 +199,8 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
           CpAsyncMbarArrive(&full[s]);
           if (pw == 0 && lane == 0) {
             uint32_t fl = tflags;
-            if (t == g.task_begin && k0 == 0) fl |= kFlagFirst;
-            if (t + 1 == g.task_end && k0 + RBK >= task.k) fl |= kFlagLast;
+            if (st == tile.s_begin) fl |= kFlagFirst;
+            if (st + 1 == tile.s_end) fl |= kFlagLast;
             meta[s].tile = tile_id; meta[s].flags = fl;
             MbarArrive(&full[s]);
           }
@@ -179,13 +221,12 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
   }
 
   // ==================================== consumer warps ====================================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
   const int q = warp;
   const int g4 = lane >> 2, t4 = lane & 3;
   double acc[8][4][2];
-  uint32_t it = 0;
-  for (;; ++it) {
-    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+  uint32_t s = 0, ph = 0;     // ring position and phase parity
+  for (;; ph ^= (++s == uint32_t(STAGES)) ? 1u : 0u, s = (s == uint32_t(STAGES)) ? 0u : s) {
     MbarWait(&full[s], ph);
     const StageMeta sm = meta[s];
     if (sm.tile == kSentinel) break;
@@ -222,17 +263,36 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
       const GemmTile tile = p.tiles[sm.tile];
       const GemmGroup g = p.groups[tile.group];
       const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * RBM, col0 = uint32_t(tile.tn) * RBN;
-      double *Cg = C + g.c_off;
+      bool write_c = true;
+      if (tile.nsplit > 1) {
+        // deterministic split-K: park this unit's partial tile, the last unit to arrive adds all of them
+        double *slots = static_cast<double *>(p.partials) + (unsigned long long) tile.part_base * (RBM * RBN);
+        double *mine = slots + (unsigned long long) tile.split * (RBM * RBN) + g4 * RBN + q * 8 + 2 * t4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t row = row0 + i * 8 + g4;
-        if (row >= g.row_end) continue;
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-          double *dst = Cg + (unsigned long long) row * g.n + col;
-          if (col < g.n) dst[0] = acc[i][j][0];
-          if (col + 1 < g.n) dst[1] = acc[i][j][1];
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<double2 *>(mine + i * 8 * RBN + j * 32) = make_double2(acc[i][j][0], acc[i][j][1]);
+        __threadfence();
+        ConsumerBarrier();
+        if (warp == 0 && lane == 0) s_last = atomicAdd(&p.counters[2 + tile.ctr], 1u) == uint32_t(tile.nsplit) - 1u ? 1u : 0u;
+        ConsumerBarrier();
+        write_c = false;
+        if (s_last != 0) FixupTileR(p, tile, g, C, q, g4, t4);
+      }
+      if (write_c) {
+        double *Cg = C + g.c_off;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t row = row0 + i * 8 + g4;
+          if (row >= g.row_end) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+            double *dst = Cg + (unsigned long long) row * g.n + col;
+            if (col < g.n) dst[0] = acc[i][j][0];
+            if (col + 1 < g.n) dst[1] = acc[i][j][1];
+          }
         }
       }
     }

@@ -276,28 +276,113 @@ GroupClass Classify(const PlanHost *h, const GemmGroup &g, int bk) {
 
 std::string BuildTiles(PlanHost *h) {
   h->tiles.clear(); h->items.clear();
+  h->n_split_ctrs = 0; h->n_part_slots = 0;
   const bool legacy = (h->flags & QLB200_PLAN_LEGACY_GEMM) != 0;
-  int BM, BN;
-  if (h->dtype == QLB200_C64) { BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : kWsBN; }
-  else { BM = legacy ? kRealBM : kWsRealBM; BN = legacy ? kRealBN : kWsRealBN; }
-  std::vector<uint32_t> order(h->part_groups.size());
-  std::iota(order.begin(), order.end(), 0u);
-  // heaviest k-loops first: persistent CTAs then finish with the short tiles (LPT)
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return h->group_ksum[x] > h->group_ksum[y]; });
-  for (uint32_t gi : order) {
+  int BM, BN, BK;
+  if (h->dtype == QLB200_C64) { BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : kWsBN; BK = legacy ? kCplxBK : kWsBK; }
+  else { BM = legacy ? kRealBM : kWsRealBM; BN = legacy ? kRealBN : kWsRealBN; BK = legacy ? kRealBK : kWsRealBK; }
+  h->part_slot_elems = uint64_t(BM) * BN;
+
+  struct GInfo { uint32_t gi, tm, tn, stages; };
+  std::vector<GInfo> dm;
+  uint64_t total_stage_tiles = 0;
+  for (uint32_t gi = 0; gi < h->part_groups.size(); ++gi) {
     const GemmGroup &g = h->part_groups[gi];
     if (g.row_end <= g.row_begin) continue;
     const uint32_t rows = g.row_end - g.row_begin;
     if (Classify(h, g, 8).skinny) {
       const uint32_t per = uint32_t(kSkinnyElems) / g.n;   // rows per work item (n <= kSkinnyMaxN)
       for (uint32_t r = 0; r < rows; r += per) h->items.push_back({gi, g.row_begin + r});
-    } else {
-      const uint32_t tm = (rows + BM - 1) / BM, tn = (g.n + BN - 1) / BN;
-      if (tm > 65535 || tn > 65535) return "output block too large for 16-bit tile coordinates";
-      for (uint32_t i = 0; i < tm; ++i)
-        for (uint32_t j = 0; j < tn; ++j) h->tiles.push_back({gi, uint16_t(i), uint16_t(j)});
+      continue;
+    }
+    const uint32_t tm = (rows + BM - 1) / BM, tn = (g.n + BN - 1) / BN;
+    if (tm > 65535 || tn > 65535) return "output block too large for 16-bit tile coordinates";
+    uint64_t stages = 0;
+    for (uint32_t t = g.task_begin; t < g.task_end; ++t) stages += (uint64_t(h->tasks[t].k) + BK - 1) / BK;
+    if (stages >= (1ull << 31)) return "k loop of one output block too long";
+    dm.push_back({gi, tm, tn, uint32_t(stages)});
+    total_stage_tiles += uint64_t(tm) * tn * stages;
+  }
+  // Split-K.  The dynamic scheduler balances the SMs well as long as no unit is long compared with a
+  // CTA's share of the launch; when one output block has a very long k loop (multi-GPU row slabs,
+  // small bond dimensions) its tiles are cut along k.  A cut is not free (the partial tile makes a
+  // round trip through L2/HBM), so the cut length is chosen by simulating the greedy schedule for a
+  // few candidates and keeping the shortest modelled makespan.
+  const uint64_t slots = uint64_t(std::max(1, h->num_sms)) * 2;
+  const int mt_full = BM / 8;
+  auto tile_weight = [&](const GInfo &d, uint32_t i, uint32_t j) {
+    const GemmGroup &g = h->part_groups[d.gi];
+    const uint32_t rows = std::min<uint32_t>(BM, g.row_end - g.row_begin - i * BM), cols = std::min<uint32_t>(BN, g.n - j * BN);
+    const uint32_t mt = (rows + 7) / 8, nt = ((cols + 7) / 8 + 3) / 4;
+    return double(mt * nt) / double(mt_full * 4);
+  };
+  constexpr double kSplitOverheadStages = 4.0;   // pipeline refill + partial-tile round trip, in stage units
+  auto split_of = [](uint32_t stages, uint64_t chunk, uint32_t *len) {
+    uint32_t nsplit = uint32_t(std::min<uint64_t>((stages + chunk - 1) / chunk, 64));
+    if (nsplit < 1) nsplit = 1;
+    *len = (stages + nsplit - 1) / nsplit;
+    return (stages + *len - 1) / *len;
+  };
+  auto makespan = [&](uint64_t chunk) {
+    std::vector<double> cost;
+    for (const GInfo &d : dm) {
+      uint32_t len;
+      const uint32_t nsplit = split_of(d.stages, chunk, &len);
+      for (uint32_t i = 0; i < d.tm; ++i)
+        for (uint32_t j = 0; j < d.tn; ++j) {
+          const double w = tile_weight(d, i, j);
+          for (uint32_t sp = 0; sp < nsplit; ++sp) {
+            const uint32_t n = std::min(d.stages, (sp + 1) * len) - sp * len;
+            cost.push_back(n * w + (nsplit > 1 ? kSplitOverheadStages : 0.0));
+          }
+        }
+    }
+    std::sort(cost.begin(), cost.end(), std::greater<double>());
+    std::vector<double> bins(slots, 0.0);
+    auto cmp = [](double x, double y) { return x > y; };   // min-heap
+    for (double cst : cost) {
+      std::pop_heap(bins.begin(), bins.end(), cmp);
+      bins.back() += cst;
+      std::push_heap(bins.begin(), bins.end(), cmp);
+    }
+    return *std::max_element(bins.begin(), bins.end());
+  };
+  uint64_t chunk = ~0ull;
+  if (!legacy && !dm.empty() && !(h->flags & QLB200_PLAN_NO_SPLIT_K)) {
+    constexpr uint64_t kMinChunk = 16;
+    const uint64_t budget = std::max<uint64_t>(1, total_stage_tiles / slots);
+    double best = makespan(~0ull);
+    for (uint64_t div = 2; div <= 32; div *= 2) {
+      const uint64_t cand = std::max<uint64_t>(kMinChunk, budget / div);
+      const double t = makespan(cand);
+      if (t < best * 0.98) { best = t; chunk = cand; }
+      if (cand == kMinChunk) break;
     }
   }
+  for (const GInfo &d : dm) {
+    uint32_t len;
+    const uint32_t nsplit = split_of(d.stages, chunk, &len);
+    for (uint32_t i = 0; i < d.tm; ++i)
+      for (uint32_t j = 0; j < d.tn; ++j) {
+        GemmTile t;
+        std::memset(&t, 0, sizeof(t));
+        t.group = d.gi; t.tm = uint16_t(i); t.tn = uint16_t(j); t.nsplit = uint16_t(nsplit);
+        if (nsplit > 1) {
+          t.ctr = h->n_split_ctrs++;
+          t.part_base = static_cast<uint32_t>(h->n_part_slots);
+          h->n_part_slots += nsplit;
+        }
+        for (uint32_t sp = 0; sp < nsplit; ++sp) {
+          t.split = uint16_t(sp);
+          t.s_begin = sp * len; t.s_end = std::min(d.stages, (sp + 1) * len);
+          h->tiles.push_back(t);
+        }
+      }
+  }
+  if (h->n_part_slots >= (1ull << 32)) return "too many split-K slots";
+  // longest units first: persistent CTAs then finish with the short ones (LPT)
+  std::stable_sort(h->tiles.begin(), h->tiles.end(),
+                   [](const GemmTile &x, const GemmTile &y) { return x.s_end - x.s_begin > y.s_end - y.s_begin; });
   if (h->tiles.size() >= (1ull << 32) || h->items.size() >= (1ull << 32)) return "too many tiles";
   return "";
 }

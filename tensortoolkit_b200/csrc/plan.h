@@ -48,6 +48,9 @@ struct PlanHost {
   std::vector<uint64_t> group_ksum;
   std::vector<GemmGroup> part_groups;                  // row ranges after partitioning
   std::vector<GemmTile> tiles;
+  uint32_t n_split_ctrs = 0;                           // split-K tiles (one arrival counter each)
+  uint64_t n_part_slots = 0;                           // split-K partial-tile slots
+  uint64_t part_slot_elems = 0;                        // elements per slot (BM x BN)
   std::vector<SkinnyItem> items;
   double flops = 0;
   uint64_t permute_elems_a = 0, permute_elems_b = 0;

@@ -10,14 +10,16 @@ namespace {
 
 constexpr int kConsumerWarps = 4;
 // consumer warpgroup + producer warpgroup.  Two CTAs x 8 warps leave 128
-// registers per thread at launch; the budget is re-split at run time with setmaxnreg (consumers 200,
-// producer warpgroup 56: per SM sub-partition 2 x (200 + 56) = 512 registers per lane).
+// registers per thread at launch; the budget is re-split at run time with setmaxnreg (consumers 208,
+// producer warpgroup 48: per SM sub-partition 2 x (208 + 48) = 512 registers per lane).
 constexpr int kWsThreads = (kConsumerWarps + 4) * 32;
 constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u, kFlagNeg = 4u, kFlagATrans = 8u, kFlagBTrans = 16u;
 constexpr uint32_t kSentinel = 0xffffffffu;
 constexpr int kProducerWarps = 4;
 constexpr uint32_t kFullArrivals = kProducerWarps * 32 + 1;   // async copy arrivals of every producer lane + the meta release
 
+// named barrier 2: the consumer warps only (split-K fix-up)
+__device__ __forceinline__ void ConsumerBarrier() { asm volatile("bar.sync 2, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
 // named barrier 1: the producer warps only
 __device__ __forceinline__ void ProducerBarrier() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory"); }
 

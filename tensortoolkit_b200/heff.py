@@ -126,7 +126,7 @@ class ShardedChain:
     No reduction is needed because ranks own disjoint output rows (see sharding.py)."""
 
     def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, dtype,
-                 world: int, rank: int, group=None):
+                 world: int, rank: int, group=None, flags: int = _lib.PLAN_DETERMINISTIC, exchange: bool = True):
         import torch
         from .sharding import shard_chain
         self.torch, self.group = torch, group
@@ -140,7 +140,8 @@ class ShardedChain:
         self.gathered = torch.zeros(world * self.stride, dtype=tdt, device=dev)
         self.full = torch.zeros(max(self.info.full_elems, 1), dtype=tdt, device=dev)
         self.out_name = steps[-1][3]
-        self.chain = ContractionChain(ctx, mine, steps, dtype, external={self.out_name: self.local.data_ptr()})
+        self.exchange = exchange      # False: time one rank's share on a single GPU (no collective)
+        self.chain = ContractionChain(ctx, mine, steps, dtype, flags, external={self.out_name: self.local.data_ptr()})
         src, dst, ln = [], [], []
         for r in range(world):
             for s in self.info.slabs[r]:
@@ -158,6 +159,8 @@ class ShardedChain:
     def apply(self) -> int:
         """Local steps + all-gather + unpack, all enqueued on the current torch stream (== ctx stream)."""
         n = self.chain.apply_device()
+        if self.world > 1 and not self.exchange:
+            return n
         if self.world > 1:
             self.torch.distributed.all_gather_into_tensor(self.gathered, self.local, group=self.group)
         else:
