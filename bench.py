@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--plan-flags", type=int, default=1, help="qlb200_plan_create flags (kernel A/B testing; 1 = default)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "allgather"],
+                    help="N>1: output exchange fused into the last GEMM's epilogue (peer stores over NVLink) or NCCL all-gather + unpack")
     ap.add_argument("--shard-of", default="", help="W:r -- time rank r's share of a W-GPU run on one GPU, no collective (tuning aid)")
     return ap.parse_args()
 
@@ -218,19 +220,38 @@ def run_ours(args):
         from tensortoolkit_b200.heff import ShardedChain
         ew, er = (int(x) for x in args.shard_of.split(":"))
         with torch.cuda.stream(stream):
-            sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), ew, er, flags=args.plan_flags, exchange=False)
+            sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), ew, er, flags=args.plan_flags, exchange=None)
         chain = sharded.chain
         apply_fn = sharded.apply
     elif world > 1:
         # partition by output sector / row slab of lenv's free bond; all-gather of disjoint slabs per apply
         from tensortoolkit_b200.heff import ShardedChain
         with torch.cuda.stream(stream):
-            sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags)
+            sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags,
+                                   exchange=args.exchange)
         chain = sharded.chain
         apply_fn = sharded.apply
     else:
         chain = ContractionChain(ctx, tensors, wl.HEFF_STEPS, np_dtype(dtype), args.plan_flags)
         apply_fn = chain.apply_device
+    verified = None
+    if world > 1:
+        # parity of the sharded path on this very input: every rank rebuilds the full result and checks it
+        # against its own unsharded apply (relative Frobenius error, tolerance 1e-12)
+        with torch.cuda.stream(stream):
+            ref_chain = ContractionChain(ctx, tensors, wl.HEFF_STEPS, np_dtype(dtype), args.plan_flags)
+            ref_chain.apply_device()
+            want = ref_chain.result("out").data
+            ref_chain.close()
+            sharded.apply()
+            torch.distributed.barrier()
+            got = np.empty_like(want)
+            sharded.download_full(got)
+            ctx.sync()
+        verified = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        if not verified <= 1e-12:
+            raise SystemExit(f"rank {rank}: sharded apply differs from the unsharded one, rel err {verified:.3e}")
+        del want, got
     stats = chain.stats()
     flops_local = chain.flops()
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -267,7 +288,9 @@ def run_ours(args):
                 a0.record(stream)
                 plan.execute_permute(chain.buf[lhs].ptr, chain.buf[rhs].ptr)
                 a1.record(stream)
-                plan.execute_gemm(chain.buf[lhs].ptr, chain.buf[rhs].ptr, chain.buf[out].ptr)
+                # a fused-exchange plan addresses its output in the full result layout
+                fused_last = sharded is not None and sharded.exchange == "fused" and si == len(chain.plans) - 1
+                plan.execute_gemm(chain.buf[lhs].ptr, chain.buf[rhs].ptr, sharded.full_ptr if fused_last else chain.buf[out].ptr)
                 a2.record(stream)
                 torch.cuda.synchronize()
                 tp.append(a0.elapsed_time(a1)); tg.append(a1.elapsed_time(a2))
@@ -296,7 +319,7 @@ def run_ours(args):
             else:   # psi H2D on every rank, local steps + all-gather + unpack, full result D2H on every rank
                 chain.buf["psi"].upload(psi_host)
                 sharded.apply()
-                tk._lib.check(tk._lib.lib.qlb200_memcpy_d2h(ctx.h, out_host.ctypes.data, sharded.full.data_ptr(), out_host.nbytes), "d2h")
+                sharded.download_full(out_host)
                 ctx.sync()
         for _ in range(2):
             e2e_apply()
@@ -356,7 +379,7 @@ def run_ours(args):
         "warmup": max(3, args.warmup), "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "c64(f64 pairs)" if dtype == "c128" else "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.D, dtype), "l2": "512 MiB flush written between timed applies; operands+intermediates (>1 GB) exceed the 126 MB L2",
-                   "parallelism": f"output-sector/row-slab x{world}" if world > 1 else "single GPU", "flops_per_step": flops_total,
+                   "parallelism": (f"output-sector/row-slab x{world}, exchange={args.exchange}" + (" (peer stores over NVLink from the GEMM epilogue)" if args.exchange == "fused" else " (NCCL)")) if world > 1 else "single GPU", "flops_per_step": flops_total,
                    "tasks_per_step": int(sum(s.ntask for s in stats))},
         "pct_fp64_peak": 100.0 * value / 1e3 / peak_burst / world, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sust, "how": peak_how},
         "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
@@ -364,6 +387,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(psi_host.nbytes), "d2h_bytes_per_step": int(out_host.nbytes)},
         "gpu_launches": int(launches) * args.steps, "clocks": sampler.summary(),
     }
+    if verified is not None:
+        line["sharded_vs_unsharded_rel_err"] = verified
     if args.breakdown:
         for k in kern:
             print(f"  step {k['step']} {k['kernel']:22s} {k['ms']:8.3f} ms  {k['achieved']:9.2f} {k['unit']:8s} frac {k['frac']:.3f}", file=sys.stderr)

@@ -180,6 +180,23 @@ int qlb200_execute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B
 /* the two phases separately (device pointers only) -- used by the benchmark to time each kernel */
 int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B);
 int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C);
+/* ---- multi-GPU: exchange fused into the GEMM epilogue ---------------------------------------- */
+/* Ranks that own disjoint row slabs of one result (qlb200_plan_partition, or operands restricted to
+ * a row range) can write them straight into the full result on EVERY GPU of the NVLink domain: the
+ * output tiles of the grouped GEMM are stored to all `npeers` buffers (the caller's own and its peers',
+ * mapped with qlb200_ipc_open) from inside the kernel, so no separate all-gather is needed -- only a
+ * barrier before the result is read.  Device pointers only; npeers <= 8. */
+int qlb200_execute_bcast(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *const *C_peers,
+                         int32_t npeers);
+/* Rebase output blocks: the block the plan would write at element offset from_off[i] is written at
+ * to_off[i] instead (a rank's packed row slabs -> their place in the full result layout). */
+int qlb200_plan_remap_output(qlb200_plan *p, uint64_t n, const uint64_t *from_off, const uint64_t *to_off);
+/* CUDA IPC plumbing for host languages without a CUDA binding: export a 64-byte handle of a buffer
+ * obtained from qlb200_dev_alloc, open a peer's handle (enables peer access), close it. */
+int qlb200_ipc_export(qlb200_ctx *ctx, const void *dev_ptr, unsigned char *handle64);
+int qlb200_ipc_open(qlb200_ctx *ctx, const unsigned char *handle64, void **peer_ptr);
+int qlb200_ipc_close(qlb200_ctx *ctx, void *peer_ptr);
+
 /* number of kernel launches the last execute on this ctx issued */
 uint64_t qlb200_ctx_launch_count(const qlb200_ctx *ctx);
 

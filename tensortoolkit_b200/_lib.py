@@ -101,6 +101,11 @@ SYMBOLS = {
     "qlb200_execute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "qlb200_execute_permute": (C.c_int, [_P, _P, _P, _P]),
     "qlb200_execute_gemm": (C.c_int, [_P, _P, _P, _P, _P]),
+    "qlb200_execute_bcast": (C.c_int, [_P, _P, _P, _P, _PP, C.c_int32]),
+    "qlb200_plan_remap_output": (C.c_int, [_P, C.c_uint64, _U64P, _U64P]),
+    "qlb200_ipc_export": (C.c_int, [_P, _P, C.c_char_p]),
+    "qlb200_ipc_open": (C.c_int, [_P, C.c_char_p, _PP]),
+    "qlb200_ipc_close": (C.c_int, [_P, _P]),
     "qlb200_ctx_launch_count": (C.c_uint64, [_P]),
     "qlb200_tplan_create": (C.c_int, [_P, _SH, _I32P, C.c_int, _PP]),
     "qlb200_tplan_destroy": (None, [_P]),

@@ -174,6 +174,17 @@ class ContractionPlan:
         check(lib.qlb200_execute(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(c_ptr), _lib.MEM_DEVICE),
               "qlb200_execute")
 
+    def execute_bcast(self, a_ptr: int, b_ptr: int, c_ptrs):
+        """Device-resident execute whose output tiles are stored to every buffer of `c_ptrs` (this GPU's and
+        its NVLink peers') from inside the GEMM epilogue."""
+        arr = (C.c_void_p * len(c_ptrs))(*[int(x) for x in c_ptrs])
+        check(lib.qlb200_execute_bcast(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), arr, len(c_ptrs)), "qlb200_execute_bcast")
+
+    def remap_output(self, from_off, to_off):
+        f = np.ascontiguousarray(np.asarray(from_off, np.uint64)); t = np.ascontiguousarray(np.asarray(to_off, np.uint64))
+        check(lib.qlb200_plan_remap_output(self.h, len(f), f.ctypes.data_as(C.POINTER(C.c_uint64)), t.ctypes.data_as(C.POINTER(C.c_uint64))),
+              "qlb200_plan_remap_output")
+
     def execute_permute(self, a_ptr: int, b_ptr: int):
         check(lib.qlb200_execute_permute(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr)), "qlb200_execute_permute")
 

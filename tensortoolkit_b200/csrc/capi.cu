@@ -77,9 +77,12 @@ int FinishPlan(qlb200_ctx *ctx, qlb200_plan *p) {
   return UploadGemmTables(p);
 }
 
-GemmParams MakeParams(const qlb200_plan *p, const void *A, const void *B, const void *wsA, const void *wsB, void *partials) {
+GemmParams MakeParams(const qlb200_plan *p, const void *A, const void *B, const void *wsA, const void *wsB, void *partials,
+                      void *const *c_out, uint32_t n_out) {
   GemmParams gp;
   gp.a_src = A; gp.b_src = B; gp.a_ws = wsA; gp.b_ws = wsB; gp.partials = partials;
+  for (uint32_t d = 0; d < uint32_t(kMaxOut); ++d) gp.c_out[d] = d < n_out ? c_out[d] : nullptr;
+  gp.n_out = n_out;
   gp.tasks = p->d.tasks; gp.groups = p->d.groups; gp.tiles = p->d.tiles; gp.items = p->d.items;
   gp.ntiles = static_cast<uint32_t>(p->h.tiles.size());
   gp.nitems = static_cast<uint32_t>(p->h.items.size());
@@ -374,27 +377,89 @@ int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const
   return QLB200_OK;
 }
 
-int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C) {
-  if (!ctx || !p) return Fail(QLB200_ERR_ARG, "null argument");
+static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *const *c_out, uint32_t n_out) {
   QL_CUDA(cudaSetDevice(ctx->device));
   void *wa, *wb, *parts;
   int rc = ResolveWorkspace(ctx, p, &wa, &wb, &parts);
   if (rc != QLB200_OK) return rc;
   ctx->launches = 0;
-  GemmParams gp = MakeParams(p, A, B, wa, wb, parts);
+  GemmParams gp = MakeParams(p, A, B, wa, wb, parts, c_out, n_out);
   if (gp.ntiles > 0) {
-    if (p->h.flags & QLB200_PLAN_LEGACY_GEMM)
-      QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, C, ctx->num_sms, ctx->stream));
-    else if (p->h.dtype == QLB200_C64)
-      QL_CUDA(LaunchGemmWsCplx(gp, C, ctx->num_sms, ctx->stream));
-    else
-      QL_CUDA(LaunchGemmWsReal(gp, C, ctx->num_sms, ctx->stream));
+    if (p->h.flags & QLB200_PLAN_LEGACY_GEMM) {
+      if (n_out != 1) return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels cannot broadcast their output");
+      QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, ctx->num_sms, ctx->stream));
+    } else if (p->h.dtype == QLB200_C64) {
+      QL_CUDA(LaunchGemmWsCplx(gp, ctx->num_sms, ctx->stream));
+    } else {
+      QL_CUDA(LaunchGemmWsReal(gp, ctx->num_sms, ctx->stream));
+    }
     ctx->launches += 1; ctx->total_launches += 1;
   }
   if (gp.nitems > 0) {
-    QL_CUDA(LaunchGemmSkinny(p->h.dtype, gp, C, ctx->num_sms, ctx->stream));
+    QL_CUDA(LaunchGemmSkinny(p->h.dtype, gp, ctx->num_sms, ctx->stream));
     ctx->launches += 1; ctx->total_launches += 1;
   }
+  return QLB200_OK;
+}
+
+int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C) {
+  if (!ctx || !p) return Fail(QLB200_ERR_ARG, "null argument");
+  void *outs[1] = {C};
+  return ExecuteGemm(ctx, p, A, B, outs, 1);
+}
+
+int qlb200_execute_bcast(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *const *C_peers, int32_t npeers) {
+  if (!ctx || !p || !A || !B || !C_peers) return Fail(QLB200_ERR_ARG, "null argument");
+  if (npeers < 1 || npeers > kMaxOut) return Fail(QLB200_ERR_ARG, "npeers must be 1..8");
+  for (int32_t d = 0; d < npeers; ++d) if (!C_peers[d]) return Fail(QLB200_ERR_ARG, "null output pointer");
+  if (p->ctx != ctx) return Fail(QLB200_ERR_ARG, "plan belongs to another context");
+  int rc = qlb200_execute_permute(ctx, p, A, B);
+  if (rc != QLB200_OK) return rc;
+  const uint64_t l0 = ctx->launches;
+  rc = ExecuteGemm(ctx, p, A, B, C_peers, static_cast<uint32_t>(npeers));
+  if (rc != QLB200_OK) return rc;
+  ctx->launches += l0;
+  return QLB200_OK;
+}
+
+int qlb200_plan_remap_output(qlb200_plan *p, uint64_t n, const uint64_t *from_off, const uint64_t *to_off) {
+  if (!p || (n && (!from_off || !to_off))) return Fail(QLB200_ERR_ARG, "null argument");
+  std::vector<std::pair<uint64_t, uint64_t>> map(n);
+  for (uint64_t i = 0; i < n; ++i) map[i] = {from_off[i], to_off[i]};
+  std::sort(map.begin(), map.end());
+  for (size_t gi = 0; gi < p->h.groups.size(); ++gi) {
+    const uint64_t off = p->h.groups[gi].c_off;
+    auto it = std::lower_bound(map.begin(), map.end(), std::make_pair(off, uint64_t(0)));
+    if (it == map.end() || it->first != off) return Fail(QLB200_ERR_ARG, "output block offset missing from the remap table");
+    p->h.groups[gi].c_off = it->second;
+    p->h.part_groups[gi].c_off = it->second;
+  }
+  if (!p->ctx) return QLB200_OK;
+  QL_CUDA(cudaSetDevice(p->ctx->device));
+  return UploadGemmTables(p);
+}
+
+int qlb200_ipc_export(qlb200_ctx *ctx, const void *dev_ptr, unsigned char *handle64) {
+  if (!ctx || !dev_ptr || !handle64) return Fail(QLB200_ERR_ARG, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  QL_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+  std::memcpy(handle64, &h, 64);
+  return QLB200_OK;
+}
+int qlb200_ipc_open(qlb200_ctx *ctx, const unsigned char *handle64, void **peer_ptr) {
+  if (!ctx || !handle64 || !peer_ptr) return Fail(QLB200_ERR_ARG, "null argument");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  QL_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return QLB200_OK;
+}
+int qlb200_ipc_close(qlb200_ctx *ctx, void *peer_ptr) {
+  if (!ctx || !peer_ptr) return Fail(QLB200_ERR_ARG, "null argument");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  QL_CUDA(cudaIpcCloseMemHandle(peer_ptr));
   return QLB200_OK;
 }
 

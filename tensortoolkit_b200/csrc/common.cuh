@@ -77,8 +77,12 @@ struct SkinnyItem {     // rows [row0, row0 + kSkinnyElems / n) of a narrow grou
   uint32_t row0;
 };
 
+constexpr int kMaxOut = 8;        // output replicas (this GPU + NVLink peers)
+
 struct GemmParams {
   const void *a_src, *a_ws, *b_src, *b_ws;   // caller's raw buffers / permuted workspace (set per launch)
+  void *c_out[kMaxOut];                      // every output element is stored to c_out[0 .. n_out): the caller's C and,
+  uint32_t n_out;                            // for a fused multi-GPU exchange, the same buffer on each NVLink peer
   const GemmTask *tasks;
   const GemmGroup *groups;
   const GemmTile *tiles;
@@ -96,14 +100,14 @@ inline std::string CudaErr(const char *what, cudaError_t e) {
 cudaError_t LaunchPermute(int dtype, const PermBlk *blks, const uint32_t *tile_base, uint32_t nblk,
                           uint32_t ntiles, const void *srcA, const void *srcB, void *dstA, void *dstB,
                           int num_sms, cudaStream_t stream);
-cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, void *C, int num_sms, cudaStream_t stream);
-cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, void *C, int num_sms, cudaStream_t stream);
+cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, int num_sms, cudaStream_t stream);     // writes c_out[0] only
+cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, int num_sms, cudaStream_t stream);
 cudaError_t ConfigureKernels();   // one-time cudaFuncSetAttribute calls
 // warp-specialised complex kernel (gemm_ws.cu), CTA tile kWsBM x kWsBN
-cudaError_t LaunchGemmWsCplx(const GemmParams &p, void *C, int num_sms, cudaStream_t stream);
+cudaError_t LaunchGemmWsCplx(const GemmParams &p, int num_sms, cudaStream_t stream);
 cudaError_t ConfigureWsKernel();
 // warp-specialised real-double kernel (gemm_ws_real.cu), CTA tile kWsRealBM x kWsRealBN
-cudaError_t LaunchGemmWsReal(const GemmParams &p, void *C, int num_sms, cudaStream_t stream);
+cudaError_t LaunchGemmWsReal(const GemmParams &p, int num_sms, cudaStream_t stream);
 cudaError_t ConfigureWsRealKernel();
 
 // tile shapes of the DMMA kernel, needed by the host-side tiler

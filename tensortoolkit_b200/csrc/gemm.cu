@@ -75,7 +75,8 @@ constexpr int RA_ELEMS = RBM * RLDA, RB_ELEMS = RBK * RLDB;
 constexpr size_t kRealSmem = size_t(RSTAGES) * (RA_ELEMS + RB_ELEMS) * sizeof(double);
 
 __global__ void __launch_bounds__(kThreads, 1)
-GemmDmmaReal(GemmParams p, double *__restrict__ C) {
+GemmDmmaReal(GemmParams p) {
+  double *__restrict__ C = static_cast<double *>(p.c_out[0]);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sA = reinterpret_cast<double *>(smem_raw);
   double *sB = sA + RSTAGES * RA_ELEMS;
@@ -197,7 +198,8 @@ constexpr int CA_ELEMS = CBM * CLDA, CB_ELEMS = CBK * CLDB;
 constexpr size_t kCplxSmem = size_t(CSTAGES) * (CA_ELEMS + CB_ELEMS) * sizeof(double2);
 
 __global__ void __launch_bounds__(kThreads, 1)
-GemmDmmaCplx(GemmParams p, double2 *__restrict__ C) {
+GemmDmmaCplx(GemmParams p) {
+  double2 *__restrict__ C = static_cast<double2 *>(p.c_out[0]);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *sA = reinterpret_cast<double2 *>(smem_raw);
   double2 *sB = sA + CSTAGES * CA_ELEMS;
@@ -353,7 +355,7 @@ constexpr int kSkinnyTermChunk = 64;
 
 template<bool CPLX>
 __global__ void __launch_bounds__(kSkinnyThreads)
-GemmSkinny(GemmParams p, typename Elem<CPLX>::T *__restrict__ C) {
+GemmSkinny(GemmParams p) {
   using E = Elem<CPLX>;
   using T = typename E::T;
   __shared__ const T *s_ap[kSkinnyTermChunk];
@@ -412,11 +414,14 @@ GemmSkinny(GemmParams p, typename Elem<CPLX>::T *__restrict__ C) {
           if (tid + u * kSkinnyThreads < total) E::Fma(acc[u], av[u], s_coef[x][col[u]]);
       }
     }
-    T *cb = C + g.c_off + (unsigned long long) item.row0 * n;
+    const unsigned long long cbase = g.c_off + (unsigned long long) item.row0 * n;
+    for (uint32_t d = 0; d < p.n_out; ++d) {
+      T *cb = static_cast<T *>(p.c_out[d]) + cbase;
 #pragma unroll
-    for (int u = 0; u < kSkinnyPerThread; ++u) {
-      const uint32_t e = tid + u * kSkinnyThreads;
-      if (e < total) cb[e] = acc[u];
+      for (int u = 0; u < kSkinnyPerThread; ++u) {
+        const uint32_t e = tid + u * kSkinnyThreads;
+        if (e < total) cb[e] = acc[u];
+      }
     }
   }
 }
@@ -433,20 +438,20 @@ cudaError_t ConfigureKernels() {
   return ConfigureWsRealKernel();
 }
 
-cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, void *C, int num_sms, cudaStream_t stream) {
+cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, int num_sms, cudaStream_t stream) {
   if (p.ntiles == 0) return cudaSuccess;
   const uint32_t grid = p.ntiles < uint32_t(num_sms) ? p.ntiles : uint32_t(num_sms);
-  if (dtype == 0) GemmDmmaReal<<<grid, kThreads, kRealSmem, stream>>>(p, static_cast<double *>(C));
-  else GemmDmmaCplx<<<grid, kThreads, kCplxSmem, stream>>>(p, static_cast<double2 *>(C));
+  if (dtype == 0) GemmDmmaReal<<<grid, kThreads, kRealSmem, stream>>>(p);
+  else GemmDmmaCplx<<<grid, kThreads, kCplxSmem, stream>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, void *C, int num_sms, cudaStream_t stream) {
+cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, int num_sms, cudaStream_t stream) {
   if (p.nitems == 0) return cudaSuccess;
   const uint32_t cap = uint32_t(num_sms) * 8u;
   const uint32_t grid = p.nitems < cap ? p.nitems : cap;
-  if (dtype == 0) GemmSkinny<false><<<grid, kSkinnyThreads, 0, stream>>>(p, static_cast<double *>(C));
-  else GemmSkinny<true><<<grid, kSkinnyThreads, 0, stream>>>(p, static_cast<double2 *>(C));
+  if (dtype == 0) GemmSkinny<false><<<grid, kSkinnyThreads, 0, stream>>>(p);
+  else GemmSkinny<true><<<grid, kSkinnyThreads, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

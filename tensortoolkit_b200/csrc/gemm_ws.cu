@@ -104,13 +104,11 @@ __device__ __forceinline__ void ComputeStageN(double (&cr)[4][4][2], double (&ci
 // Split-K fix-up, run by the unit that arrived last: add the tile's partial tiles in slot order (a fixed
 // order, whichever unit happens to be last) one m8 row group at a time and write C.  Kept out of line:
 // it needs only a handful of registers and must not disturb the register allocation of the main loop.
-__device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile, const GemmGroup &g, double2 *__restrict__ C,
-                                       int q, int g4, int t4) {
+__device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile, const GemmGroup &g, int q, int g4, int t4) {
   __threadfence();
   const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * WBM, col0 = uint32_t(tile.tn) * WBN;
   const double2 *src0 = static_cast<const double2 *>(p.partials) + (unsigned long long) tile.part_base * (WBM * WBN) +
                         g4 * WBN + q * 8 + 2 * t4;
-  double2 *Cg = C + g.c_off;
 #pragma unroll 1
   for (int i = 0; i < 4; ++i) {
     double2 sum[4][2];
@@ -126,12 +124,14 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
     }
     const uint32_t row = row0 + i * 8 + g4;
     if (row < g.row_end) {
+      for (uint32_t d = 0; d < p.n_out; ++d) {
+        double2 *Cg = static_cast<double2 *>(p.c_out[d]) + g.c_off + (unsigned long long) row * g.n;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-        double2 *dst = Cg + (unsigned long long) row * g.n + col;
-        if (col < g.n) dst[0] = sum[j][0];
-        if (col + 1 < g.n) dst[1] = sum[j][1];
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+          if (col < g.n) Cg[col] = sum[j][0];
+          if (col + 1 < g.n) Cg[col + 1] = sum[j][1];
+        }
       }
     }
   }
@@ -140,7 +140,7 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
 
 template<int STAGES>
 __global__ void __launch_bounds__(kWsThreads, 2)
-GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
+GemmWsCplx(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2 *stages = reinterpret_cast<double2 *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + size_t(STAGES) * STAGE_ELEMS * sizeof(double2));
@@ -321,20 +321,22 @@ GemmWsCplx(GemmParams p, double2 *__restrict__ C) {
         if (warp == 0 && lane == 0) s_last = atomicAdd(&p.counters[2 + tile.ctr], 1u) == uint32_t(tile.nsplit) - 1u ? 1u : 0u;
         ConsumerBarrier();
         write_c = false;
-        if (s_last != 0) FixupTile(p, tile, g, C, q, g4, t4);
+        if (s_last != 0) FixupTile(p, tile, g, q, g4, t4);
       }
       if (write_c) {
-        double2 *Cg = C + g.c_off;
+        for (uint32_t d = 0; d < p.n_out; ++d) {     // n_out > 1: fused exchange, the same tile goes to every NVLink peer
+          double2 *Cg = static_cast<double2 *>(p.c_out[d]) + g.c_off;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t row = row0 + i * 8 + g4;
-          if (row >= g.row_end) continue;
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t row = row0 + i * 8 + g4;
+            if (row >= g.row_end) continue;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-            double2 *dst = Cg + (unsigned long long) row * g.n + col;
-            if (col < g.n) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
-            if (col + 1 < g.n) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+              double2 *dst = Cg + (unsigned long long) row * g.n + col;
+              if (col < g.n) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
+              if (col + 1 < g.n) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
+            }
           }
         }
       }
@@ -350,12 +352,12 @@ cudaError_t ConfigureWsKernel() {
   return cudaFuncSetAttribute(GemmWsCplx<kWsStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WsSmem<kWsStages>::kBytes));
 }
 
-cudaError_t LaunchGemmWsCplx(const GemmParams &p, void *C, int num_sms, cudaStream_t stream) {
+cudaError_t LaunchGemmWsCplx(const GemmParams &p, int num_sms, cudaStream_t stream) {
   if (p.ntiles == 0) return cudaSuccess;
   constexpr size_t smem = WsSmem<kWsStages>::kBytes;
   const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
   const uint32_t grid = p.ntiles < cap ? p.ntiles : cap;
-  GemmWsCplx<kWsStages><<<grid, kWsThreads, smem, stream>>>(p, static_cast<double2 *>(C));
+  GemmWsCplx<kWsStages><<<grid, kWsThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -63,13 +63,11 @@ __device__ __forceinline__ void ComputeStageRN(double (&acc)[8][4][2], const Fra
 }
 
 // Split-K fix-up (see gemm_ws.cu FixupTile): out of line, sums the partial tiles in slot order, writes C.
-__device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &tile, const GemmGroup &g, double *__restrict__ C,
-                                        int q, int g4, int t4) {
+__device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &tile, const GemmGroup &g, int q, int g4, int t4) {
   __threadfence();
   const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * RBM, col0 = uint32_t(tile.tn) * RBN;
   const double *src0 = static_cast<const double *>(p.partials) + (unsigned long long) tile.part_base * (RBM * RBN) +
                        g4 * RBN + q * 8 + 2 * t4;
-  double *Cg = C + g.c_off;
 #pragma unroll 1
   for (int i = 0; i < 8; ++i) {
     double2 sum[4];
@@ -85,12 +83,14 @@ __device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &til
     }
     const uint32_t row = row0 + i * 8 + g4;
     if (row < g.row_end) {
+      for (uint32_t d = 0; d < p.n_out; ++d) {
+        double *Cg = static_cast<double *>(p.c_out[d]) + g.c_off + (unsigned long long) row * g.n;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-        double *dst = Cg + (unsigned long long) row * g.n + col;
-        if (col < g.n) dst[0] = sum[j].x;
-        if (col + 1 < g.n) dst[1] = sum[j].y;
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+          if (col < g.n) Cg[col] = sum[j].x;
+          if (col + 1 < g.n) Cg[col + 1] = sum[j].y;
+        }
       }
     }
   }
@@ -98,7 +98,7 @@ __device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &til
 }
 
 __global__ void __launch_bounds__(kWsThreads, 2)
-GemmWsReal(GemmParams p, double *__restrict__ C) {
+GemmWsReal(const __grid_constant__ GemmParams p) {
   constexpr int STAGES = kRealStages;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *stages = reinterpret_cast<double *>(smem_raw);
@@ -278,20 +278,22 @@ GemmWsReal(GemmParams p, double *__restrict__ C) {
         if (warp == 0 && lane == 0) s_last = atomicAdd(&p.counters[2 + tile.ctr], 1u) == uint32_t(tile.nsplit) - 1u ? 1u : 0u;
         ConsumerBarrier();
         write_c = false;
-        if (s_last != 0) FixupTileR(p, tile, g, C, q, g4, t4);
+        if (s_last != 0) FixupTileR(p, tile, g, q, g4, t4);
       }
       if (write_c) {
-        double *Cg = C + g.c_off;
+        for (uint32_t d = 0; d < p.n_out; ++d) {     // n_out > 1: fused exchange, the same tile goes to every NVLink peer
+          double *Cg = static_cast<double *>(p.c_out[d]) + g.c_off;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t row = row0 + i * 8 + g4;
-          if (row >= g.row_end) continue;
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t row = row0 + i * 8 + g4;
+            if (row >= g.row_end) continue;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-            double *dst = Cg + (unsigned long long) row * g.n + col;
-            if (col < g.n) dst[0] = acc[i][j][0];
-            if (col + 1 < g.n) dst[1] = acc[i][j][1];
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+              double *dst = Cg + (unsigned long long) row * g.n + col;
+              if (col < g.n) dst[0] = acc[i][j][0];
+              if (col + 1 < g.n) dst[1] = acc[i][j][1];
+            }
           }
         }
       }
@@ -305,11 +307,11 @@ cudaError_t ConfigureWsRealKernel() {
   return cudaFuncSetAttribute(GemmWsReal, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRealWsSmem));
 }
 
-cudaError_t LaunchGemmWsReal(const GemmParams &p, void *C, int num_sms, cudaStream_t stream) {
+cudaError_t LaunchGemmWsReal(const GemmParams &p, int num_sms, cudaStream_t stream) {
   if (p.ntiles == 0) return cudaSuccess;
   const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
   const uint32_t grid = p.ntiles < cap ? p.ntiles : cap;
-  GemmWsReal<<<grid, kWsThreads, kRealWsSmem, stream>>>(p, static_cast<double *>(C));
+  GemmWsReal<<<grid, kWsThreads, kRealWsSmem, stream>>>(p);
   return cudaGetLastError();
 }
 

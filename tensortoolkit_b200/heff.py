@@ -121,12 +121,18 @@ class ContractionChain:
 
 class ShardedChain:
     """One rank's share of a contraction chain plus the exchange that rebuilds the full result on
-    every GPU: local steps -> NCCL all-gather of the packed row slabs (NVLink/NVSwitch) -> one
-    batched-copy launch that scatters every rank's slabs into the full raw-buffer layout.
-    No reduction is needed because ranks own disjoint output rows (see sharding.py)."""
+    every GPU.  Ranks own disjoint output rows (see sharding.py), so no reduction is needed.
+
+    exchange="fused" (default for world > 1): the last step's grouped GEMM stores its output tiles straight
+        into the full result buffer of EVERY rank -- its own and, through CUDA-IPC-mapped NVLink peer
+        pointers, the others' -- from inside the kernel epilogue (qlb200_execute_bcast); the only collective
+        left is a one-element all-reduce that acts as the barrier before the result is read.
+    exchange="allgather": local steps -> NCCL all-gather of the packed row slabs -> one batched-copy launch
+        that scatters every rank's slabs into the full raw-buffer layout (the library-collective baseline).
+    exchange=None: no exchange at all (time one rank's share on a single GPU)."""
 
     def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, dtype,
-                 world: int, rank: int, group=None, flags: int = _lib.PLAN_DETERMINISTIC, exchange: bool = True):
+                 world: int, rank: int, group=None, flags: int = _lib.PLAN_DETERMINISTIC, exchange="fused", peers=None):
         import torch
         from .sharding import shard_chain
         self.torch, self.group = torch, group
@@ -135,42 +141,91 @@ class ShardedChain:
         self.dtype = np.dtype(dtype)
         tdt = torch.complex128 if self.dtype == np.complex128 else torch.float64
         dev = torch.device("cuda", ctx.device)
+        self.exchange = exchange
         self.stride = max(max(self.info.local_elems), 1)
         self.local = torch.zeros(self.stride, dtype=tdt, device=dev)
-        self.gathered = torch.zeros(world * self.stride, dtype=tdt, device=dev)
-        self.full = torch.zeros(max(self.info.full_elems, 1), dtype=tdt, device=dev)
         self.out_name = steps[-1][3]
-        self.exchange = exchange      # False: time one rank's share on a single GPU (no collective)
+        self.cplan, self.full_buf, self.peer_ptrs, self.opened = None, None, None, []
         self.chain = ContractionChain(ctx, mine, steps, dtype, flags, external={self.out_name: self.local.data_ptr()})
-        src, dst, ln = [], [], []
-        for r in range(world):
-            for s in self.info.slabs[r]:
-                src.append(r * self.stride + s.local_offset); dst.append(s.full_offset); ln.append(s.length)
-        n = len(src)
-        arr = lambda v: (C.c_uint64 * max(n, 1))(*v)
-        h = C.c_void_p()
-        check(lib.qlb200_cplan_create(ctx.h, _lib.C64 if self.dtype == np.complex128 else _lib.F64, n, arr(src), arr(dst), arr(ln),
-                                      C.byref(h)), "qlb200_cplan_create")
-        self.cplan = h
+        full_bytes = max(self.info.full_elems, 1) * self.dtype.itemsize
+        if exchange == "fused":
+            # the full result lives in a cudaMalloc'ed buffer of its own so that it can be exported over CUDA IPC
+            self.full_buf = DeviceBuffer(ctx, full_bytes)
+            self.full_ptr = self.full_buf.ptr
+            my = self.info.slabs[rank]
+            self.chain.plans[-1].remap_output([s.local_offset for s in my], [s.full_offset for s in my])
+            if peers is not None:                       # caller-supplied replicas (single-process tests)
+                self.peer_ptrs = [self.full_ptr] + [int(x) for x in peers]
+            elif world > 1:
+                handle = C.create_string_buffer(64)
+                check(lib.qlb200_ipc_export(ctx.h, C.c_void_p(self.full_ptr), handle), "qlb200_ipc_export")
+                handles = [None] * world
+                torch.distributed.all_gather_object(handles, bytes(handle.raw), group=group)
+                self.peer_ptrs = [self.full_ptr]
+                for r in range(world):
+                    if r == rank:
+                        continue
+                    pp = C.c_void_p()
+                    check(lib.qlb200_ipc_open(ctx.h, handles[r], C.byref(pp)), "qlb200_ipc_open")
+                    self.opened.append(pp.value)
+                    self.peer_ptrs.append(pp.value)
+            else:
+                self.peer_ptrs = [self.full_ptr]
+            self.flag = torch.zeros(1, dtype=torch.float32, device=dev)
+        else:
+            self.gathered = torch.zeros(world * self.stride, dtype=tdt, device=dev)
+            self.full = torch.zeros(max(self.info.full_elems, 1), dtype=tdt, device=dev)
+            self.full_ptr = self.full.data_ptr()
+            src, dst, ln = [], [], []
+            for r in range(world):
+                for s in self.info.slabs[r]:
+                    src.append(r * self.stride + s.local_offset); dst.append(s.full_offset); ln.append(s.length)
+            n = len(src)
+            arr = lambda v: (C.c_uint64 * max(n, 1))(*v)
+            h = C.c_void_p()
+            check(lib.qlb200_cplan_create(ctx.h, _lib.C64 if self.dtype == np.complex128 else _lib.F64, n, arr(src), arr(dst), arr(ln),
+                                          C.byref(h)), "qlb200_cplan_create")
+            self.cplan = h
 
     def flops_local(self) -> float:
         return self.chain.flops()
 
     def apply(self) -> int:
-        """Local steps + all-gather + unpack, all enqueued on the current torch stream (== ctx stream)."""
-        n = self.chain.apply_device()
-        if self.world > 1 and not self.exchange:
+        """All steps of this rank plus the exchange, enqueued on the current torch stream (== ctx stream)."""
+        ch = self.chain
+        if self.exchange == "fused":
+            n = 0
+            for (lhs, rhs, _, out), plan in zip(ch.steps[:-1], ch.plans[:-1]):
+                plan.execute_device(ch.buf[lhs].ptr, ch.buf[rhs].ptr, ch.buf[out].ptr)
+                n += self.ctx.launch_count()
+            lhs, rhs, _, _ = ch.steps[-1]
+            ch.plans[-1].execute_bcast(ch.buf[lhs].ptr, ch.buf[rhs].ptr, self.peer_ptrs)
+            n += self.ctx.launch_count()
+            if self.world > 1 and self.opened:
+                self.torch.distributed.all_reduce(self.flag, group=self.group)    # barrier: every peer's tiles have landed
+            return n
+        n = ch.apply_device()
+        if self.exchange is None:
             return n
         if self.world > 1:
             self.torch.distributed.all_gather_into_tensor(self.gathered, self.local, group=self.group)
         else:
             self.gathered.copy_(self.local)
-        check(lib.qlb200_copy_execute(self.ctx.h, self.cplan, C.c_void_p(self.gathered.data_ptr()), C.c_void_p(self.full.data_ptr())),
+        check(lib.qlb200_copy_execute(self.ctx.h, self.cplan, C.c_void_p(self.gathered.data_ptr()), C.c_void_p(self.full_ptr)),
               "qlb200_copy_execute")
         return n + 1
 
+    def download_full(self, host: np.ndarray):
+        check(lib.qlb200_memcpy_d2h(self.ctx.h, host.ctypes.data, C.c_void_p(self.full_ptr), host.nbytes), "qlb200_memcpy_d2h")
+
     def close(self):
+        for pp in self.opened:
+            lib.qlb200_ipc_close(self.ctx.h, C.c_void_p(pp))
+        self.opened = []
         self.chain.close()
+        if self.full_buf is not None:
+            self.full_buf.free()
+            self.full_buf = None
         if self.cplan:
             lib.qlb200_tplan_destroy(self.cplan)
             self.cplan = None

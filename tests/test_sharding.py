@@ -140,12 +140,48 @@ def test_sharded_chain_world1_unpack(ctx):
     full_chain.close()
     st = torch.cuda.Stream()
     ctx.sync()
-    sc = ShardedChain(ctx, ts, wl.HEFF_STEPS, "lenv", 2, np.complex128, 1, 0)
+    sc = ShardedChain(ctx, ts, wl.HEFF_STEPS, "lenv", 2, np.complex128, 1, 0, exchange="allgather")
     sc.apply()
     ctx.sync(); torch.cuda.synchronize()
     got = sc.full.cpu().numpy()
     sc.close()
     assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_fused_exchange_writes_every_replica(ctx, dtype):
+    """The fused exchange on one device: every rank's last-step GEMM stores its row slabs into THREE
+    replicas of the full result (its own + two stand-ins for NVLink peers) from inside the kernel
+    epilogue; after all ranks ran, every replica equals the unsharded apply."""
+    from tensortoolkit_b200.heff import ContractionChain, ShardedChain, DeviceBuffer
+    ts = make_tensors(220, dtype, 9)
+    full_chain = ContractionChain(ctx, ts, wl.HEFF_STEPS, dtype)
+    full_chain.apply_device()
+    want = full_chain.result("out").data
+    full_chain.close()
+    world = 3
+    nbytes = want.nbytes
+    replicas = [DeviceBuffer(ctx, nbytes) for _ in range(2)]
+    chains = []
+    for r in range(world):
+        sc = ShardedChain(ctx, ts, wl.HEFF_STEPS, "lenv", 2, dtype, world, r, exchange="fused", peers=[b.ptr for b in replicas])
+        chains.append(sc)
+    # rank 0's own buffer is the third replica: make ranks 1, 2 write into it as well
+    for sc in chains[1:]:
+        sc.peer_ptrs.append(chains[0].full_ptr)
+    for sc in chains:
+        sc.apply()
+    ctx.sync()
+    for ptr in [chains[0].full_ptr] + [b.ptr for b in replicas]:
+        got = np.empty_like(want)
+        tk._lib.check(tk._lib.lib.qlb200_memcpy_d2h(ctx.h, got.ctypes.data, ptr, got.nbytes), "d2h")
+        ctx.sync()
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-12
+    for sc in chains:
+        sc.close()
+    for b in replicas:
+        b.free()
 
 
 def test_plan_reads_heff_blocks_in_place():
