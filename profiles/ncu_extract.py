@@ -23,17 +23,26 @@ for r in rows[2:]:
             print(f"{h:90s} {u:12s} {v}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr = rows[hi]
-ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) >= len(hdr)]
-tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
-print("total samples", tot)
-keys = [k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
-agg = {k: sum(int(r[ix[k]] or 0) for r in data) for k in keys}
-print("stall totals:", {k: v for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v > tot * 0.005})
-for r in data:
-    s = int(r[ix["# Samples"]] or 0)
-    if s >= tot * share:
-        st = {k[6:]: int(r[ix[k]] or 0) for k in keys if int(r[ix[k]] or 0) > s * 0.1}
-        print(r[ix["Address"]][-5:], r[ix["Source"]][:64].ljust(64), s, r[ix["Instructions Executed"]], st)
+sections, cur = [], None          # one section per profiled launch
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        cur = {"name": r[1], "hdr": None, "data": []}
+        sections.append(cur)
+    elif r and r[0] == "Address" and cur is not None:
+        cur["hdr"] = r
+    elif cur is not None and cur["hdr"] is not None and len(r) >= len(cur["hdr"]):
+        cur["data"].append(r)
+for sec in sections:
+    hdr, data = sec["hdr"], sec["data"]
+    ix = {h: i for i, h in enumerate(hdr)}
+    tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
+    print("-" * 100)
+    print(sec["name"][:90], "total samples", tot)
+    keys = [k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
+    agg = {k: sum(int(r[ix[k]] or 0) for r in data) for k in keys}
+    print("stall totals:", {k: v for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v > tot * 0.005})
+    for r in data:
+        s = int(r[ix["# Samples"]] or 0)
+        if s >= tot * share:
+            st = {k[6:]: int(r[ix[k]] or 0) for k in keys if int(r[ix[k]] or 0) > s * 0.1}
+            print(r[ix["Address"]][-5:], r[ix["Source"]][:64].ljust(64), s, r[ix["Instructions Executed"]], st)
