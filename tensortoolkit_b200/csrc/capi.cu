@@ -389,7 +389,7 @@ static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const voi
       if (n_out != 1) return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels cannot broadcast their output");
       QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, ctx->num_sms, ctx->stream));
     } else if (p->h.dtype == QLB200_C64) {
-      QL_CUDA(LaunchGemmWsCplx(gp, ctx->num_sms, ctx->stream));
+      QL_CUDA(LaunchGemmWsCplx(gp, !(p->h.flags & QLB200_PLAN_CPLX_4M), ctx->num_sms, ctx->stream));
     } else {
       QL_CUDA(LaunchGemmWsReal(gp, ctx->num_sms, ctx->stream));
     }

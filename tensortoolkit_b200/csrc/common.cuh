@@ -103,8 +103,8 @@ cudaError_t LaunchPermute(int dtype, const PermBlk *blks, const uint32_t *tile_b
 cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, int num_sms, cudaStream_t stream);     // writes c_out[0] only
 cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, int num_sms, cudaStream_t stream);
 cudaError_t ConfigureKernels();   // one-time cudaFuncSetAttribute calls
-// warp-specialised complex kernel (gemm_ws.cu), CTA tile kWsBM x kWsBN
-cudaError_t LaunchGemmWsCplx(const GemmParams &p, int num_sms, cudaStream_t stream);
+// warp-specialised complex kernel (gemm_ws.cu), CTA tile kWsBM x kWsBN (4M arithmetic) or kWsBM x kWs3mBN (3M)
+cudaError_t LaunchGemmWsCplx(const GemmParams &p, bool three_m, int num_sms, cudaStream_t stream);
 cudaError_t ConfigureWsKernel();
 // warp-specialised real-double kernel (gemm_ws_real.cu), CTA tile kWsRealBM x kWsRealBN
 cudaError_t LaunchGemmWsReal(const GemmParams &p, int num_sms, cudaStream_t stream);
@@ -113,7 +113,7 @@ cudaError_t ConfigureWsRealKernel();
 // tile shapes of the DMMA kernel, needed by the host-side tiler
 constexpr int kRealBM = 128, kRealBN = 128, kRealBK = 16;
 constexpr int kCplxBM = 64, kCplxBN = 128, kCplxBK = 8;   // legacy cp.async kernel
-constexpr int kWsBM = 32, kWsBN = 128;                     // warp-specialised complex kernel
+constexpr int kWsBM = 32, kWsBN = 128, kWs3mBN = 96;       // warp-specialised complex kernel (4M / 3M tile width)
 constexpr int kWsRealBM = 64, kWsRealBN = 128;             // warp-specialised real kernel
 constexpr int kWsBK = 8, kWsRealBK = 16;                   // k extent of one pipeline stage
 constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyThreads = 256, kSkinnyPerThread = 8;

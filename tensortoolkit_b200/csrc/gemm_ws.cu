@@ -22,28 +22,49 @@
 //   * Ragged tiles cost what they use: a warp owns the n8 column groups {q, q+4, q+8, q+12} of the
 //     tile (interleaved, so valid columns spread evenly over the four sub-partitions) and skips the
 //     MMAs of m8 row groups / n8 column groups that lie outside the output block.
+//   * Two arithmetic schemes (template parameter CFG).  Cfg4M is the textbook product: four real DMMAs
+//     per complex 8x8x4 step, CTA tile 32 x 128.  Cfg3M (default) is the Gauss / Karatsuba product
+//         P1 += Ar Br,   P2 += Ai Bi,   P3 += (Ar + Ai) (Br + Bi);   Cr = P1 - P2,  Ci = P3 - P1 - P2
+//     -- three real DMMAs per step (the form with the fewest operand pre-additions: one per A and one
+//     per B fragment; they run on the same FP64 datapath as DMMA and cost ~5 pipe cycles each).  The kernel sits at ~90 % DMMA-pipe utilisation (ncu), so the only
+//     way to go faster is to issue fewer DMMAs: 3M cuts them by 25 %.  The three running sums need 3/2
+//     the accumulator registers, hence the narrower 32 x 96 CTA tile (a warp owns 3 n8 groups); the
+//     operand sums cost 7 DADDs per 36 DMMAs.  Deterministic like 4M; normwise error bound of the same
+//     order (the parity bar is a relative Frobenius error <= 1e-12, tests/test_parity_gpu.py).
 #include "common.cuh"
 #include "ws_common.cuh"
+
+#ifndef QLB200_EXP
+#define QLB200_EXP 0
+#endif
 
 namespace qlb200 {
 
 namespace {
 
-constexpr int WBM = kWsBM, WBN = kWsBN, WBK = kWsBK;
+constexpr int WBM = kWsBM, WBK = kWsBK;
+struct Cfg4M { static constexpr int BN = kWsBN, NT = kWsBN / 32, NACC = 2; static constexpr bool k3M = false; };
+struct Cfg3M { static constexpr int BN = kWs3mBN, NT = kWs3mBN / 32, NACC = 3; static constexpr bool k3M = true; };
 // Shared-memory tile layouts (units: complex elements = one 16-byte bank group); every fragment load
 // of a quarter-warp (lanes g4 in {2p, 2p+1}, t4 in 0..3) hits 8 distinct bank groups:
 //   A row-major   [32 m][12]      (12*g4 + t4)  mod 8 distinct
 //   A transposed  [8 k][34]       (34*t4 + g4)  mod 8 = 2*t4 + g4 distinct
-//   B row-major   [8 k][130]      (130*t4 + g4) mod 8 = 2*t4 + g4 distinct
-//   B transposed  [128 n][8] with the k4 halves of odd rows swapped (k ^ 4*(n&1)): 4*(g4&1) + t4 distinct
+//   B row-major   [8 k][BN + 2]   ((BN+2)*t4 + g4) mod 8 = 2*t4 + g4 distinct   (BN = 128 or 96)
+//   B transposed  [BN n][8] with the k4 halves of odd rows swapped (k ^ 4*(n&1)): 4*(g4&1) + t4 distinct
 constexpr int WLDA = WBK + 4, WLDAT = WBM + 2;
-constexpr int WLDB = WBN + 2;
-constexpr int A_ELEMS = WBM * WLDA, B_ELEMS = WBK * WLDB, STAGE_ELEMS = A_ELEMS + B_ELEMS;
-static_assert(WBK * WLDAT <= A_ELEMS && WBN * WBK <= B_ELEMS, "transposed tiles must fit the stage");
+constexpr int A_ELEMS = WBM * WLDA;
+static_assert(WBK * WLDAT <= A_ELEMS, "transposed A tile must fit the stage");
 
-template<int STAGES>
+template<class CFG>
+struct Lay {
+  static constexpr int WBN = CFG::BN, WLDB = WBN + 2, B_ELEMS = WBK * WLDB, STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  static_assert(WBN * WBK <= B_ELEMS, "transposed B tile must fit the stage");
+  static_assert(WLDB % 8 == 2, "bank-group spread of the B fragment loads");
+};
+
+template<class CFG, int STAGES>
 struct WsSmem {
-  static constexpr size_t kBytes = size_t(STAGES) * STAGE_ELEMS * sizeof(double2) + 2 * STAGES * sizeof(uint64_t) +
+  static constexpr size_t kBytes = size_t(STAGES) * Lay<CFG>::STAGE_ELEMS * sizeof(double2) + 2 * STAGES * sizeof(uint64_t) +
                                    STAGES * sizeof(StageMeta);
 };
 
@@ -56,68 +77,107 @@ struct FragAddr {
 
 // One k-stage (WBK = 8 -> two k4 steps) of a warp's sub-tile: MT valid m8 row groups x NT valid n8 column
 // groups.  Specialised at compile time so that skipped MMAs are not even issued.
-template<int MT, int NT>
-__device__ __forceinline__ void ComputeStage(double (&cr)[4][4][2], double (&ci)[4][4][2], const FragAddr &f, uint32_t smask) {
+// acc[0] / acc[1] = real / imaginary sums (4M);  acc[0..2] = P1, P2, P3 (3M).
+template<class CFG, int MT, int NT>
+__device__ __forceinline__ void ComputeStage(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f, uint32_t smask) {
 #pragma unroll
   for (int ks = 0; ks < WBK / 4; ++ks) {
-    double ax[MT], ay[MT], nay[MT];
-    double2 b[NT];
     const double2 *pa = f.a + (ks ? f.a_k1 : 0u);
     const double2 *pb = f.b + (ks ? f.b_k1 : f.b_k0);
+    if constexpr (CFG::k3M) {
+      double as[MT], ai[MT], ar[MT];
+      double br[NT], bs[NT], bi[NT];
 #pragma unroll
-    for (int i = 0; i < MT; ++i) {
-      const double2 a = pa[i * f.a_i];
-      ax[i] = FlipSign(a.x, smask);
-      ay[i] = FlipSign(a.y, smask);
-      nay[i] = FlipSign(a.y, smask ^ 0x80000000u);
+      for (int i = 0; i < MT; ++i) {
+        const double2 a = pa[i * f.a_i];
+        as[i] = FlipSign(a.x + a.y, smask);
+        ai[i] = FlipSign(a.y, smask);
+        ar[i] = FlipSign(a.x, smask);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const double2 b = pb[j * f.b_j];
+        br[j] = b.x; bi[j] = b.y; bs[j] = b.x + b.y;
+      }
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) DmmaNv(acc[0][i][j][0], acc[0][i][j][1], ar[i], br[j]);
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) DmmaNv(acc[1][i][j][0], acc[1][i][j][1], ai[i], bi[j]);
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) DmmaNv(acc[2][i][j][0], acc[2][i][j][1], as[i], bs[j]);
+    } else {
+      double ax[MT], ay[MT], nay[MT];
+      double2 b[NT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const double2 a = pa[i * f.a_i];
+        ax[i] = FlipSign(a.x, smask);
+        ay[i] = FlipSign(a.y, smask);
+        nay[i] = FlipSign(a.y, smask ^ 0x80000000u);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) b[j] = pb[j * f.b_j];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          DmmaNv(acc[0][i][j][0], acc[0][i][j][1], ax[i], b[j].x);
+          DmmaNv(acc[1][i][j][0], acc[1][i][j][1], ax[i], b[j].y);
+        }
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          DmmaNv(acc[0][i][j][0], acc[0][i][j][1], nay[i], b[j].y);
+          DmmaNv(acc[1][i][j][0], acc[1][i][j][1], ay[i], b[j].x);
+        }
     }
-#pragma unroll
-    for (int j = 0; j < NT; ++j) b[j] = pb[j * f.b_j];
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        DmmaNv(cr[i][j][0], cr[i][j][1], ax[i], b[j].x);
-        DmmaNv(ci[i][j][0], ci[i][j][1], ax[i], b[j].y);
-      }
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        DmmaNv(cr[i][j][0], cr[i][j][1], nay[i], b[j].y);
-        DmmaNv(ci[i][j][0], ci[i][j][1], ay[i], b[j].x);
-      }
   }
 }
 
-template<int MT>
-__device__ __forceinline__ void ComputeStageN(double (&cr)[4][4][2], double (&ci)[4][4][2], const FragAddr &f, uint32_t smask, int nt) {
+template<class CFG, int MT>
+__device__ __forceinline__ void ComputeStageN(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f, uint32_t smask, int nt) {
+  if constexpr (CFG::NT >= 4) { if (nt == 4) { ComputeStage<CFG, MT, 4>(acc, f, smask); return; } }
   switch (nt) {
-    case 4: ComputeStage<MT, 4>(cr, ci, f, smask); break;
-    case 3: ComputeStage<MT, 3>(cr, ci, f, smask); break;
-    case 2: ComputeStage<MT, 2>(cr, ci, f, smask); break;
-    case 1: ComputeStage<MT, 1>(cr, ci, f, smask); break;
+    case 3: ComputeStage<CFG, MT, 3>(acc, f, smask); break;
+    case 2: ComputeStage<CFG, MT, 2>(acc, f, smask); break;
+    case 1: ComputeStage<CFG, MT, 1>(acc, f, smask); break;
     default: break;
   }
+}
+
+// complex value of accumulator element (i, j, e)
+template<class CFG>
+__device__ __forceinline__ double2 AccValue(const double (&acc)[CFG::NACC][4][CFG::NT][2], int i, int j, int e) {
+  if constexpr (CFG::k3M) return make_double2(acc[0][i][j][e] - acc[1][i][j][e], (acc[2][i][j][e] - acc[0][i][j][e]) - acc[1][i][j][e]);
+  else return make_double2(acc[0][i][j][e], acc[1][i][j][e]);
 }
 
 // Split-K fix-up, run by the unit that arrived last: add the tile's partial tiles in slot order (a fixed
 // order, whichever unit happens to be last) one m8 row group at a time and write C.  Kept out of line:
 // it needs only a handful of registers and must not disturb the register allocation of the main loop.
+template<class CFG>
 __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile, const GemmGroup &g, int q, int g4, int t4) {
+  constexpr int WBN = CFG::BN, NT = CFG::NT;
   __threadfence();
   const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * WBM, col0 = uint32_t(tile.tn) * WBN;
   const double2 *src0 = static_cast<const double2 *>(p.partials) + (unsigned long long) tile.part_base * (WBM * WBN) +
                         g4 * WBN + q * 8 + 2 * t4;
 #pragma unroll 1
   for (int i = 0; i < 4; ++i) {
-    double2 sum[4][2];
+    double2 sum[NT][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sum[j][0] = sum[j][1] = make_double2(0.0, 0.0);
+    for (int j = 0; j < NT; ++j) sum[j][0] = sum[j][1] = make_double2(0.0, 0.0);
     const double2 *src = src0 + i * 8 * WBN;
     for (uint32_t sp = 0; sp < tile.nsplit; ++sp, src += WBM * WBN) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NT; ++j) {
         const double2 v0 = __ldcg(src + j * 32), v1 = __ldcg(src + j * 32 + 1);
         sum[j][0].x += v0.x; sum[j][0].y += v0.y; sum[j][1].x += v1.x; sum[j][1].y += v1.y;
       }
@@ -127,7 +187,7 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
       for (uint32_t d = 0; d < p.n_out; ++d) {
         double2 *Cg = static_cast<double2 *>(p.c_out[d]) + g.c_off + (unsigned long long) row * g.n;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NT; ++j) {
           const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
           if (col < g.n) Cg[col] = sum[j][0];
           if (col + 1 < g.n) Cg[col + 1] = sum[j][1];
@@ -138,9 +198,10 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
   if (q == 0 && g4 == 0 && t4 == 0) p.counters[2 + tile.ctr] = 0;
 }
 
-template<int STAGES>
+template<class CFG, int STAGES>
 __global__ void __launch_bounds__(kWsThreads, 2)
 GemmWsCplx(const __grid_constant__ GemmParams p) {
+  constexpr int WBN = CFG::BN, WLDB = Lay<CFG>::WLDB, STAGE_ELEMS = Lay<CFG>::STAGE_ELEMS, NTMAX = CFG::NT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2 *stages = reinterpret_cast<double2 *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + size_t(STAGES) * STAGE_ELEMS * sizeof(double2));
@@ -218,7 +279,7 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
               const bool rok = k0 + kr < task.k;
               const double2 *src = bBase + (unsigned long long) (k0 + kr) * g.n + col0 + lane;
 #pragma unroll
-              for (uint32_t c = 0; c < 4; ++c) {
+              for (uint32_t c = 0; c < uint32_t(WBN / 32); ++c) {
                 const uint32_t col = lane + 32u * c;
                 const bool ok = rok && col < cols;
                 CpAsync16Z(sB + (kr * WLDB + col) * 16u, ok ? src + 32u * c : bBase, ok);
@@ -229,8 +290,8 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
             const bool kok = kk < task.k;
             const double2 *src = bBase + (unsigned long long) (col0 + a_r) * task.k + kk;
 #pragma unroll
-            for (uint32_t rr = 0; rr < 8; ++rr) {
-              const uint32_t r = 8u * pw + rr, nl = a_r + 4u * r;
+            for (uint32_t rr = 0; rr < uint32_t(WBN / 16); ++rr) {
+              const uint32_t r = uint32_t(WBN / 16) * pw + rr, nl = a_r + 4u * r;
               const bool ok = kok && nl < cols;
               CpAsync16Z(sB + (nl * WBK + (a_kc ^ ((nl & 1u) << 2))) * 16u, ok ? src + (unsigned long long) (4u * r) * task.k : bBase, ok);
             }
@@ -265,7 +326,7 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
   // warp q owns all 32 rows and the n8 column groups {q, q+4, q+8, q+12} of the CTA tile
   const int q = warp;
   const int g4 = lane >> 2, t4 = lane & 3;
-  double cr[4][4][2], ci[4][4][2];
+  double acc[CFG::NACC][4][NTMAX][2];
   uint32_t s = 0, ph = 0;     // ring position and phase parity
   for (;; ph ^= (++s == uint32_t(STAGES)) ? 1u : 0u, s = (s == uint32_t(STAGES)) ? 0u : s) {
     MbarWait(&full[s], ph);
@@ -273,9 +334,11 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
     if (sm.tile == kSentinel) break;
     if (sm.flags & kFlagFirst) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int a = 0; a < CFG::NACC; ++a)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < NTMAX; ++j) acc[a][i][j][0] = acc[a][i][j][1] = 0.0;
     }
     const int mt = int((sm.flags >> 8) & 0xfu);
     const int n8 = int((sm.flags >> 16) & 0x1fu);
@@ -288,14 +351,14 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
     if (sm.flags & kFlagBTrans) { f.b = tileB + (q * 8 + g4) * WBK + t4; f.b_j = 32 * WBK; f.b_k0 = (g4 & 1) << 2; f.b_k1 = f.b_k0 ^ 4u; }
     else { f.b = tileB + t4 * WLDB + q * 8 + g4; f.b_j = 32; f.b_k0 = 0; f.b_k1 = 4 * WLDB; }
     const uint32_t smask = (sm.flags & kFlagNeg) ? 0x80000000u : 0u;
-    if (mt == 4 && nt == 4) {
-      ComputeStage<4, 4>(cr, ci, f, smask);
+    if (mt == 4 && nt == NTMAX) {
+      ComputeStage<CFG, 4, NTMAX>(acc, f, smask);
     } else {
       switch (mt) {
-        case 4: ComputeStageN<4>(cr, ci, f, smask, nt); break;
-        case 3: ComputeStageN<3>(cr, ci, f, smask, nt); break;
-        case 2: ComputeStageN<2>(cr, ci, f, smask, nt); break;
-        default: ComputeStageN<1>(cr, ci, f, smask, nt); break;
+        case 4: ComputeStageN<CFG, 4>(acc, f, smask, nt); break;
+        case 3: ComputeStageN<CFG, 3>(acc, f, smask, nt); break;
+        case 2: ComputeStageN<CFG, 2>(acc, f, smask, nt); break;
+        default: ComputeStageN<CFG, 1>(acc, f, smask, nt); break;
       }
     }
     __syncwarp();
@@ -312,16 +375,16 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            mine[i * 8 * WBN + j * 32] = make_double2(cr[i][j][0], ci[i][j][0]);
-            mine[i * 8 * WBN + j * 32 + 1] = make_double2(cr[i][j][1], ci[i][j][1]);
+          for (int j = 0; j < NTMAX; ++j) {
+            mine[i * 8 * WBN + j * 32] = AccValue<CFG>(acc, i, j, 0);
+            mine[i * 8 * WBN + j * 32 + 1] = AccValue<CFG>(acc, i, j, 1);
           }
         __threadfence();
         ConsumerBarrier();
         if (warp == 0 && lane == 0) s_last = atomicAdd(&p.counters[2 + tile.ctr], 1u) == uint32_t(tile.nsplit) - 1u ? 1u : 0u;
         ConsumerBarrier();
         write_c = false;
-        if (s_last != 0) FixupTile(p, tile, g, q, g4, t4);
+        if (s_last != 0) FixupTile<CFG>(p, tile, g, q, g4, t4);
       }
       if (write_c) {
         for (uint32_t d = 0; d < p.n_out; ++d) {     // n_out > 1: fused exchange, the same tile goes to every NVLink peer
@@ -331,11 +394,11 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
             const uint32_t row = row0 + i * 8 + g4;
             if (row >= g.row_end) continue;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NTMAX; ++j) {
               const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
               double2 *dst = Cg + (unsigned long long) row * g.n + col;
-              if (col < g.n) dst[0] = make_double2(cr[i][j][0], ci[i][j][0]);
-              if (col + 1 < g.n) dst[1] = make_double2(cr[i][j][1], ci[i][j][1]);
+              if (col < g.n) dst[0] = AccValue<CFG>(acc, i, j, 0);
+              if (col + 1 < g.n) dst[1] = AccValue<CFG>(acc, i, j, 1);
             }
           }
         }
@@ -344,21 +407,36 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
   }
 }
 
+#if QLB200_EXP == 2
+constexpr int kWsStages = 6;
+#elif QLB200_EXP == 3
+constexpr int kWsStages = 4;
+#else
 constexpr int kWsStages = 5;
+#endif
+
+template<class CFG>
+cudaError_t Launch(const GemmParams &p, int num_sms, cudaStream_t stream) {
+  constexpr size_t smem = WsSmem<CFG, kWsStages>::kBytes;
+  const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
+  const uint32_t grid = p.ntiles < cap ? p.ntiles : cap;
+  GemmWsCplx<CFG, kWsStages><<<grid, kWsThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
 
 }  // namespace
 
 cudaError_t ConfigureWsKernel() {
-  return cudaFuncSetAttribute(GemmWsCplx<kWsStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WsSmem<kWsStages>::kBytes));
+  cudaError_t e = cudaFuncSetAttribute(GemmWsCplx<Cfg4M, kWsStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(WsSmem<Cfg4M, kWsStages>::kBytes));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(GemmWsCplx<Cfg3M, kWsStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              int(WsSmem<Cfg3M, kWsStages>::kBytes));
 }
 
-cudaError_t LaunchGemmWsCplx(const GemmParams &p, int num_sms, cudaStream_t stream) {
+cudaError_t LaunchGemmWsCplx(const GemmParams &p, bool three_m, int num_sms, cudaStream_t stream) {
   if (p.ntiles == 0) return cudaSuccess;
-  constexpr size_t smem = WsSmem<kWsStages>::kBytes;
-  const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
-  const uint32_t grid = p.ntiles < cap ? p.ntiles : cap;
-  GemmWsCplx<kWsStages><<<grid, kWsThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  return three_m ? Launch<Cfg3M>(p, num_sms, stream) : Launch<Cfg4M>(p, num_sms, stream);
 }
 
 }  // namespace qlb200

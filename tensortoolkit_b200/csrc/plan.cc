@@ -279,7 +279,8 @@ std::string BuildTiles(PlanHost *h) {
   h->n_split_ctrs = 0; h->n_part_slots = 0;
   const bool legacy = (h->flags & QLB200_PLAN_LEGACY_GEMM) != 0;
   int BM, BN, BK;
-  if (h->dtype == QLB200_C64) { BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : kWsBN; BK = legacy ? kCplxBK : kWsBK; }
+  const bool four_m = (h->flags & QLB200_PLAN_CPLX_4M) != 0;
+  if (h->dtype == QLB200_C64) { BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : (four_m ? kWsBN : kWs3mBN); BK = legacy ? kCplxBK : kWsBK; }
   else { BM = legacy ? kRealBM : kWsRealBM; BN = legacy ? kRealBN : kWsRealBN; BK = legacy ? kRealBK : kWsRealBK; }
   h->part_slot_elems = uint64_t(BM) * BN;
 
@@ -309,12 +310,12 @@ std::string BuildTiles(PlanHost *h) {
   // round trip through L2/HBM), so the cut length is chosen by simulating the greedy schedule for a
   // few candidates and keeping the shortest modelled makespan.
   const uint64_t slots = uint64_t(std::max(1, h->num_sms)) * 2;
-  const int mt_full = BM / 8;
+  const int mt_full = BM / 8, nt_full = BN / 32;
   auto tile_weight = [&](const GInfo &d, uint32_t i, uint32_t j) {
     const GemmGroup &g = h->part_groups[d.gi];
     const uint32_t rows = std::min<uint32_t>(BM, g.row_end - g.row_begin - i * BM), cols = std::min<uint32_t>(BN, g.n - j * BN);
     const uint32_t mt = (rows + 7) / 8, nt = ((cols + 7) / 8 + 3) / 4;
-    return double(mt * nt) / double(mt_full * 4);
+    return double(mt * nt) / double(mt_full * nt_full);
   };
   constexpr double kSplitOverheadStages = 4.0;   // pipeline refill + partial-tile round trip, in stage units
   auto split_of = [](uint32_t stages, uint64_t chunk, uint32_t *len) {

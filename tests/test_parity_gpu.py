@@ -279,12 +279,13 @@ def test_full_size_properties_heff_d4096_complex(ctx):
 
 
 @pytest.mark.parametrize("dtype", [np.complex128, np.float64])
-@pytest.mark.parametrize("variant", ["ws", "legacy", "ws_permute_all", "legacy_permute_all"])
+@pytest.mark.parametrize("variant", ["ws", "ws_4m", "legacy", "ws_permute_all", "ws_4m_permute_all", "legacy_permute_all"])
 def test_gemm_kernel_variants(ref, ctx, variant, dtype):
     """The warp-specialised kernels (blocks read in place or through the permute kernel) and the
     cp.async kernels against the reference on a fermionic chain with ragged K tails, ragged tile
     edges, -1 exchange signs and several pairs per block."""
     flags = {"legacy": _lib.PLAN_LEGACY_GEMM, "ws": 0, "ws_permute_all": _lib.PLAN_PERMUTE_ALL,
+             "ws_4m": _lib.PLAN_CPLX_4M, "ws_4m_permute_all": _lib.PLAN_CPLX_4M | _lib.PLAN_PERMUTE_ALL,
              "legacy_permute_all": _lib.PLAN_LEGACY_GEMM | _lib.PLAN_PERMUTE_ALL}[variant]
     flags |= _lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY
     ti = wl.heff_tensor_indexes(wl.hubbard_indexes(150))
@@ -323,6 +324,7 @@ def test_transposed_operand_modes_vs_numpy(ctx, dtype):
     A = np.concatenate(a_data).astype(dtype); B = np.concatenate(b_data).astype(dtype)
     Cw = np.concatenate([w.ravel() for w in want]).astype(dtype)
     for flags in (_lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY, _lib.PLAN_DETERMINISTIC,
+                  _lib.PLAN_DETERMINISTIC | _lib.PLAN_CPLX_4M | _lib.PLAN_NO_SKINNY,
                   _lib.PLAN_DETERMINISTIC | _lib.PLAN_PERMUTE_ALL | _lib.PLAN_NO_SKINNY):
         plan = tk.RawPlan(ctx, dtype, 2, [1, 0], a_shape, a_off, 2, [1, 0], b_shape, b_off, tasks, co, flags)
         Cg = np.zeros(co, dtype)
