@@ -116,6 +116,11 @@ constexpr int kCplxBM = 64, kCplxBN = 128, kCplxBK = 8;   // legacy cp.async ker
 constexpr int kWsBM = 32, kWsBN = 128, kWs3mBN = 96;       // warp-specialised complex kernel (4M / 3M tile width)
 constexpr int kWsRealBM = 64, kWsRealBN = 128;             // warp-specialised real kernel
 constexpr int kWsBK = 8, kWsRealBK = 16;                   // k extent of one pipeline stage
+#ifndef QLB200_3M_BK
+#define QLB200_3M_BK 16
+#endif
+constexpr int kWs3mBK = QLB200_3M_BK;                      // 3M kernel: two half-stages share one barrier round trip
+constexpr int kWs3mStages = kWs3mBK == 16 ? 3 : 5;
 constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyThreads = 256, kSkinnyPerThread = 8;
 constexpr int kSkinnyElems = kSkinnyThreads * kSkinnyPerThread;   // output elements per work item
 

@@ -42,24 +42,24 @@ namespace qlb200 {
 
 namespace {
 
-constexpr int WBM = kWsBM, WBK = kWsBK;
-struct Cfg4M { static constexpr int BN = kWsBN, NT = kWsBN / 32, NACC = 2; static constexpr bool k3M = false; };
-struct Cfg3M { static constexpr int BN = kWs3mBN, NT = kWs3mBN / 32, NACC = 3; static constexpr bool k3M = true; };
+constexpr int WBM = kWsBM;
+struct Cfg4M { static constexpr int BN = kWsBN, BK = kWsBK, NT = kWsBN / 32, NACC = 2, STAGES = 5; static constexpr bool k3M = false; };
+struct Cfg3M { static constexpr int BN = kWs3mBN, BK = kWs3mBK, NT = kWs3mBN / 32, NACC = 3, STAGES = kWs3mStages; static constexpr bool k3M = true; };
 // Shared-memory tile layouts (units: complex elements = one 16-byte bank group); every fragment load
 // of a quarter-warp (lanes g4 in {2p, 2p+1}, t4 in 0..3) hits 8 distinct bank groups:
-//   A row-major   [32 m][12]      (12*g4 + t4)  mod 8 distinct
-//   A transposed  [8 k][34]       (34*t4 + g4)  mod 8 = 2*t4 + g4 distinct
-//   B row-major   [8 k][BN + 2]   ((BN+2)*t4 + g4) mod 8 = 2*t4 + g4 distinct   (BN = 128 or 96)
-//   B transposed  [BN n][8] with the k4 halves of odd rows swapped (k ^ 4*(n&1)): 4*(g4&1) + t4 distinct
-constexpr int WLDA = WBK + 4, WLDAT = WBM + 2;
-constexpr int A_ELEMS = WBM * WLDA;
-static_assert(WBK * WLDAT <= A_ELEMS, "transposed A tile must fit the stage");
+//   A row-major   [32 m][BK + 4]  ((BK+4)*g4 + t4) mod 8 = 4*(g4&1) + t4 distinct   (BK = 8 or 16)
+//   A transposed  [BK k][34]      (34*t4 + g4)  mod 8 = 2*t4 + g4 distinct
+//   B row-major   [BK k][BN + 2]  ((BN+2)*t4 + g4) mod 8 = 2*t4 + g4 distinct   (BN = 128 or 96)
+//   B transposed  [BN n][BK] with adjacent k4 groups of odd rows swapped (k ^ 4*(n&1)): 4*(g4&1) + t4 distinct
+constexpr int WLDAT = WBM + 2;
 
 template<class CFG>
 struct Lay {
-  static constexpr int WBN = CFG::BN, WLDB = WBN + 2, B_ELEMS = WBK * WLDB, STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  static constexpr int WBN = CFG::BN, WBK = CFG::BK, WLDA = WBK + 4, WLDB = WBN + 2;
+  static constexpr int A_ELEMS = WBM * WLDA, B_ELEMS = WBK * WLDB, STAGE_ELEMS = A_ELEMS + B_ELEMS;
+  static_assert(WBK * WLDAT <= A_ELEMS, "transposed A tile must fit the stage");
   static_assert(WBN * WBK <= B_ELEMS, "transposed B tile must fit the stage");
-  static_assert(WLDB % 8 == 2, "bank-group spread of the B fragment loads");
+  static_assert(WLDB % 8 == 2 && WLDA % 8 == 4, "bank-group spread of the fragment loads");
 };
 
 template<class CFG, int STAGES>
@@ -71,19 +71,20 @@ struct WsSmem {
 // Fragment addressing of one stage (element units, relative to the stage's A / B regions).
 struct FragAddr {
   const double2 *a, *b;     // lane's base inside the A / B tile
-  uint32_t a_i, a_k1;       // A: + i * a_i (m8 group)  + ks * a_k1 (second k4 step)
-  uint32_t b_j, b_k0, b_k1; // B: + j * b_j (owned n8 group) + b_k0 / b_k1 (first / second k4 step)
+  uint32_t a_i, a_ks;       // A: + i * a_i (m8 group) + ks * a_ks (k4 step)
+  uint32_t b_j, b_ks;       // B: + j * b_j (owned n8 group) + ks * b_ks  (row-major B; b_sw = 0)
+  uint32_t b_sw, b_x;       //    + ((ks ^ b_x) * b_sw)                   (transposed B: swizzled k4 groups; b_ks = 0)
 };
 
-// One k-stage (WBK = 8 -> two k4 steps) of a warp's sub-tile: MT valid m8 row groups x NT valid n8 column
-// groups.  Specialised at compile time so that skipped MMAs are not even issued.
+// Two k4 steps (k4 groups KS0, KS0+1 of the stage) of a warp's sub-tile: MT valid m8 row groups x NT valid
+// n8 column groups.  Specialised at compile time so that skipped MMAs are not even issued.
 // acc[0] / acc[1] = real / imaginary sums (4M);  acc[0..2] = P1, P2, P3 (3M).
-template<class CFG, int MT, int NT>
+template<class CFG, int MT, int NT, int KS0>
 __device__ __forceinline__ void ComputeStage(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f, uint32_t smask) {
 #pragma unroll
-  for (int ks = 0; ks < WBK / 4; ++ks) {
-    const double2 *pa = f.a + (ks ? f.a_k1 : 0u);
-    const double2 *pb = f.b + (ks ? f.b_k1 : f.b_k0);
+  for (int ks = KS0; ks < KS0 + 2; ++ks) {
+    const double2 *pa = f.a + ks * f.a_ks;
+    const double2 *pb = f.b + ks * f.b_ks + ((uint32_t(ks) ^ f.b_x) * f.b_sw);
     if constexpr (CFG::k3M) {
       double as[MT], ai[MT], ar[MT];
       double br[NT], bs[NT], bi[NT];
@@ -141,14 +142,28 @@ __device__ __forceinline__ void ComputeStage(double (&acc)[CFG::NACC][4][CFG::NT
   }
 }
 
-template<class CFG, int MT>
+template<class CFG, int MT, int KS0>
 __device__ __forceinline__ void ComputeStageN(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f, uint32_t smask, int nt) {
-  if constexpr (CFG::NT >= 4) { if (nt == 4) { ComputeStage<CFG, MT, 4>(acc, f, smask); return; } }
+  if constexpr (CFG::NT >= 4) { if (nt == 4) { ComputeStage<CFG, MT, 4, KS0>(acc, f, smask); return; } }
   switch (nt) {
-    case 3: ComputeStage<CFG, MT, 3>(acc, f, smask); break;
-    case 2: ComputeStage<CFG, MT, 2>(acc, f, smask); break;
-    case 1: ComputeStage<CFG, MT, 1>(acc, f, smask); break;
+    case 3: ComputeStage<CFG, MT, 3, KS0>(acc, f, smask); break;
+    case 2: ComputeStage<CFG, MT, 2, KS0>(acc, f, smask); break;
+    case 1: ComputeStage<CFG, MT, 1, KS0>(acc, f, smask); break;
     default: break;
+  }
+}
+
+template<class CFG, int KS0>
+__device__ __forceinline__ void ComputeHalf(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f, uint32_t smask, int mt, int nt) {
+  if (mt == 4 && nt == CFG::NT) {
+    ComputeStage<CFG, 4, CFG::NT, KS0>(acc, f, smask);
+  } else {
+    switch (mt) {
+      case 4: ComputeStageN<CFG, 4, KS0>(acc, f, smask, nt); break;
+      case 3: ComputeStageN<CFG, 3, KS0>(acc, f, smask, nt); break;
+      case 2: ComputeStageN<CFG, 2, KS0>(acc, f, smask, nt); break;
+      default: ComputeStageN<CFG, 1, KS0>(acc, f, smask, nt); break;
+    }
   }
 }
 
@@ -201,7 +216,9 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
 template<class CFG, int STAGES>
 __global__ void __launch_bounds__(kWsThreads, 2)
 GemmWsCplx(const __grid_constant__ GemmParams p) {
-  constexpr int WBN = CFG::BN, WLDB = Lay<CFG>::WLDB, STAGE_ELEMS = Lay<CFG>::STAGE_ELEMS, NTMAX = CFG::NT;
+  constexpr int WBN = CFG::BN, WBK = CFG::BK, WLDA = Lay<CFG>::WLDA, WLDB = Lay<CFG>::WLDB, A_ELEMS = Lay<CFG>::A_ELEMS,
+                STAGE_ELEMS = Lay<CFG>::STAGE_ELEMS, NTMAX = CFG::NT;
+  constexpr uint32_t RP = 32 / WBK;      // rows of a [rows][WBK] tile one warp pass covers (a lane copies one element)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2 *stages = reinterpret_cast<double2 *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + size_t(STAGES) * STAGE_ELEMS * sizeof(double2));
@@ -223,7 +240,7 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     // the four producer warps walk the same tile / stage sequence and each issue a quarter of a stage's copies
     const uint32_t pw = warp - kConsumerWarps;
-    const uint32_t a_kc = lane & 7, a_r = lane >> 3;
+    const uint32_t a_kc = lane % WBK, a_r = lane / WBK;
     uint32_t it = 0, tcount = 0;
     for (;; ++tcount) {
       if (pw == 0 && lane == 0) s_tile[tcount & 1u] = atomicAdd(&p.counters[0], 1u);
@@ -252,30 +269,30 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
           MbarWait(&empty[s], ph ^ 1u);
           const uint32_t sA = SmemAddr(stages + size_t(s) * STAGE_ELEMS);
           const uint32_t sB = sA + A_ELEMS * 16u;
-          if (!ta) {   // A row-major m x k: a lane copies element (a_r + 4r, a_kc) of the 32 x 8 tile
+          if (!ta) {   // A row-major m x k: a lane copies element (a_r + RP*r, a_kc) of the 32 x WBK tile
             const uint32_t kk = k0 + a_kc;
             const bool kok = kk < task.k;
             const double2 *src = aBase + (unsigned long long) (row0 + a_r) * task.k + kk;
 #pragma unroll
-            for (uint32_t rr = 0; rr < 2; ++rr) {
-              const uint32_t r = 2u * pw + rr, row = a_r + 4u * r;
+            for (uint32_t rr = 0; rr < WBM / RP / 4; ++rr) {
+              const uint32_t r = (WBM / RP / 4) * pw + rr, row = a_r + RP * r;
               const bool ok = kok && row < rows;
-              CpAsync16Z(sA + (row * WLDA + a_kc) * 16u, ok ? src + (unsigned long long) (4u * r) * task.k : aBase, ok);
+              CpAsync16Z(sA + (row * WLDA + a_kc) * 16u, ok ? src + (unsigned long long) (RP * r) * task.k : aBase, ok);
             }
-          } else {     // A stored k x m: 8 k-rows of 32 contiguous elements
+          } else {     // A stored k x m: WBK k-rows of 32 contiguous elements
             const double2 *src = aBase + (unsigned long long) k0 * g.m + row0 + lane;
             const bool mok = uint32_t(lane) < rows;
 #pragma unroll
-            for (uint32_t rr = 0; rr < 2; ++rr) {
-              const uint32_t kr = 2u * pw + rr;
+            for (uint32_t rr = 0; rr < WBK / 4; ++rr) {
+              const uint32_t kr = (WBK / 4) * pw + rr;
               const bool ok = mok && k0 + kr < task.k;
               CpAsync16Z(sA + (kr * WLDAT + lane) * 16u, ok ? src + (unsigned long long) kr * g.m : aBase, ok);
             }
           }
-          if (!tb) {   // B row-major k x n: 8 k-rows x 128 columns, 512 contiguous bytes per copy
+          if (!tb) {   // B row-major k x n: WBK k-rows x WBN columns, 512 contiguous bytes per copy
 #pragma unroll
-            for (uint32_t rr = 0; rr < 2; ++rr) {
-              const uint32_t kr = 2u * pw + rr;
+            for (uint32_t rr = 0; rr < WBK / 4; ++rr) {
+              const uint32_t kr = (WBK / 4) * pw + rr;
               const bool rok = k0 + kr < task.k;
               const double2 *src = bBase + (unsigned long long) (k0 + kr) * g.n + col0 + lane;
 #pragma unroll
@@ -285,20 +302,20 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
                 CpAsync16Z(sB + (kr * WLDB + col) * 16u, ok ? src + 32u * c : bBase, ok);
               }
             }
-          } else {     // B stored n x k: a lane copies element (a_r + 4r, a_kc) of the 128 x 8 tile
+          } else {     // B stored n x k: a lane copies element (a_r + RP*r, a_kc) of the WBN x WBK tile
             const uint32_t kk = k0 + a_kc;
             const bool kok = kk < task.k;
             const double2 *src = bBase + (unsigned long long) (col0 + a_r) * task.k + kk;
 #pragma unroll
-            for (uint32_t rr = 0; rr < uint32_t(WBN / 16); ++rr) {
-              const uint32_t r = uint32_t(WBN / 16) * pw + rr, nl = a_r + 4u * r;
+            for (uint32_t rr = 0; rr < WBN / RP / 4; ++rr) {
+              const uint32_t r = (WBN / RP / 4) * pw + rr, nl = a_r + RP * r;
               const bool ok = kok && nl < cols;
-              CpAsync16Z(sB + (nl * WBK + (a_kc ^ ((nl & 1u) << 2))) * 16u, ok ? src + (unsigned long long) (4u * r) * task.k : bBase, ok);
+              CpAsync16Z(sB + (nl * WBK + (a_kc ^ ((nl & 1u) << 2))) * 16u, ok ? src + (unsigned long long) (RP * r) * task.k : bBase, ok);
             }
           }
           CpAsyncMbarArrive(&full[s]);
           if (pw == 0 && lane == 0) {
-            uint32_t fl = tflags;
+            uint32_t fl = tflags | (min(uint32_t(WBK / 4), (task.k - k0 + 3u) >> 2) << 24);
             if (st == tile.s_begin) fl |= kFlagFirst;
             if (st + 1 == tile.s_end) fl |= kFlagLast;
             meta[s].tile = tile_id; meta[s].flags = fl;
@@ -346,20 +363,14 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
     const double2 *tileA = stages + size_t(s) * STAGE_ELEMS;
     const double2 *tileB = tileA + A_ELEMS;
     FragAddr f;
-    if (sm.flags & kFlagATrans) { f.a = tileA + t4 * WLDAT + g4; f.a_i = 8; f.a_k1 = 4 * WLDAT; }
-    else { f.a = tileA + g4 * WLDA + t4; f.a_i = 8 * WLDA; f.a_k1 = 4; }
-    if (sm.flags & kFlagBTrans) { f.b = tileB + (q * 8 + g4) * WBK + t4; f.b_j = 32 * WBK; f.b_k0 = (g4 & 1) << 2; f.b_k1 = f.b_k0 ^ 4u; }
-    else { f.b = tileB + t4 * WLDB + q * 8 + g4; f.b_j = 32; f.b_k0 = 0; f.b_k1 = 4 * WLDB; }
+    if (sm.flags & kFlagATrans) { f.a = tileA + t4 * WLDAT + g4; f.a_i = 8; f.a_ks = 4 * WLDAT; }
+    else { f.a = tileA + g4 * WLDA + t4; f.a_i = 8 * WLDA; f.a_ks = 4; }
+    if (sm.flags & kFlagBTrans) { f.b = tileB + (q * 8 + g4) * WBK + t4; f.b_j = 32 * WBK; f.b_ks = 0; f.b_sw = 4; f.b_x = g4 & 1; }
+    else { f.b = tileB + t4 * WLDB + q * 8 + g4; f.b_j = 32; f.b_ks = 4 * WLDB; f.b_sw = 0; f.b_x = 0; }
     const uint32_t smask = (sm.flags & kFlagNeg) ? 0x80000000u : 0u;
-    if (mt == 4 && nt == NTMAX) {
-      ComputeStage<CFG, 4, NTMAX>(acc, f, smask);
-    } else {
-      switch (mt) {
-        case 4: ComputeStageN<CFG, 4>(acc, f, smask, nt); break;
-        case 3: ComputeStageN<CFG, 3>(acc, f, smask, nt); break;
-        case 2: ComputeStageN<CFG, 2>(acc, f, smask, nt); break;
-        default: ComputeStageN<CFG, 1>(acc, f, smask, nt); break;
-      }
+    ComputeHalf<CFG, 0>(acc, f, smask, mt, nt);
+    if constexpr (WBK == 16) {
+      if (((sm.flags >> 24) & 7u) > 2u) ComputeHalf<CFG, 2>(acc, f, smask, mt, nt);   // K tail: skip an all-zero half stage
     }
     __syncwarp();
     if (lane == 0) MbarArrive(&empty[s]);
@@ -407,31 +418,23 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
   }
 }
 
-#if QLB200_EXP == 2
-constexpr int kWsStages = 6;
-#elif QLB200_EXP == 3
-constexpr int kWsStages = 4;
-#else
-constexpr int kWsStages = 5;
-#endif
-
 template<class CFG>
 cudaError_t Launch(const GemmParams &p, int num_sms, cudaStream_t stream) {
-  constexpr size_t smem = WsSmem<CFG, kWsStages>::kBytes;
+  constexpr size_t smem = WsSmem<CFG, CFG::STAGES>::kBytes;
   const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
   const uint32_t grid = p.ntiles < cap ? p.ntiles : cap;
-  GemmWsCplx<CFG, kWsStages><<<grid, kWsThreads, smem, stream>>>(p);
+  GemmWsCplx<CFG, CFG::STAGES><<<grid, kWsThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t ConfigureWsKernel() {
-  cudaError_t e = cudaFuncSetAttribute(GemmWsCplx<Cfg4M, kWsStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(WsSmem<Cfg4M, kWsStages>::kBytes));
+  cudaError_t e = cudaFuncSetAttribute(GemmWsCplx<Cfg4M, Cfg4M::STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(WsSmem<Cfg4M, Cfg4M::STAGES>::kBytes));
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(GemmWsCplx<Cfg3M, kWsStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              int(WsSmem<Cfg3M, kWsStages>::kBytes));
+  return cudaFuncSetAttribute(GemmWsCplx<Cfg3M, Cfg3M::STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              int(WsSmem<Cfg3M, Cfg3M::STAGES>::kBytes));
 }
 
 cudaError_t LaunchGemmWsCplx(const GemmParams &p, bool three_m, int num_sms, cudaStream_t stream) {

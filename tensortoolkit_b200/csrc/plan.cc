@@ -280,7 +280,7 @@ std::string BuildTiles(PlanHost *h) {
   const bool legacy = (h->flags & QLB200_PLAN_LEGACY_GEMM) != 0;
   int BM, BN, BK;
   const bool four_m = (h->flags & QLB200_PLAN_CPLX_4M) != 0;
-  if (h->dtype == QLB200_C64) { BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : (four_m ? kWsBN : kWs3mBN); BK = legacy ? kCplxBK : kWsBK; }
+  if (h->dtype == QLB200_C64) { BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : (four_m ? kWsBN : kWs3mBN); BK = legacy ? kCplxBK : (four_m ? kWsBK : kWs3mBK); }
   else { BM = legacy ? kRealBM : kWsRealBM; BN = legacy ? kRealBN : kWsRealBN; BK = legacy ? kRealBK : kWsRealBK; }
   h->part_slot_elems = uint64_t(BM) * BN;
 
