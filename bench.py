@@ -38,8 +38,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--plan-flags", type=int, default=1, help="qlb200_plan_create flags (kernel A/B testing; 1 = default)")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "allgather"],
-                    help="N>1: output exchange fused into the last GEMM's epilogue (peer stores over NVLink) or NCCL all-gather + unpack")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "multicast", "fused", "allgather"],
+                    help="N>1: output exchange fused into the last GEMM's epilogue -- multimem.st through the NVSwitch multicast mapping "
+                         "(multicast; auto picks it when the fabric offers it) or unicast peer stores (fused) -- or NCCL all-gather + unpack")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of an apply from the host instead of replaying one CUDA graph")
     ap.add_argument("--shard-of", default="", help="W:r -- time rank r's share of a W-GPU run on one GPU, no collective (tuning aid)")
     return ap.parse_args()
 
@@ -252,6 +254,12 @@ def run_ours(args):
         if not verified <= 1e-12:
             raise SystemExit(f"rank {rank}: sharded apply differs from the unsharded one, rel err {verified:.3e}")
         del want, got
+    graph = None
+    if not args.no_graph:
+        # one apply = one CUDA graph launch (kernels, and for N>1 the exchange barrier): no per-kernel host launch cost
+        with torch.cuda.stream(stream):
+            graph = (sharded if sharded is not None else chain).capture()
+        apply_eager, apply_fn = apply_fn, graph.launch
     stats = chain.stats()
     flops_local = chain.flops()
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -289,7 +297,7 @@ def run_ours(args):
                 plan.execute_permute(chain.buf[lhs].ptr, chain.buf[rhs].ptr)
                 a1.record(stream)
                 # a fused-exchange plan addresses its output in the full result layout
-                fused_last = sharded is not None and sharded.exchange == "fused" and si == len(chain.plans) - 1
+                fused_last = sharded is not None and sharded.exchange in ("fused", "multicast") and si == len(chain.plans) - 1
                 plan.execute_gemm(chain.buf[lhs].ptr, chain.buf[rhs].ptr, sharded.full_ptr if fused_last else chain.buf[out].ptr)
                 a2.record(stream)
                 torch.cuda.synchronize()
@@ -308,6 +316,24 @@ def run_ours(args):
                 kern.append({"step": si + 1, "kernel": kname, "ms": float(np.mean(tg)), "bound": "hbm", "alg_bytes": byts,
                              "achieved": byts / (np.mean(tg) * 1e-3) / 1e9, "unit": "GB/s"})
         sampler.stop()
+        # ---- N>1: where one apply's time goes on every rank (local steps vs exchange + waiting for the slowest rank) ----
+        rank_phase = None
+        if world > 1:
+            comp, exch = [], []
+            for _ in range(5):
+                flush.zero_()
+                torch.distributed.barrier()
+                marks = {}
+                e0 = torch.cuda.Event(enable_timing=True); e0.record(stream)
+                def mark(label):
+                    ev = torch.cuda.Event(enable_timing=True); ev.record(stream); marks[label] = ev
+                sharded.apply(mark)
+                torch.cuda.synchronize()
+                comp.append(e0.elapsed_time(marks["compute"])); exch.append(marks["compute"].elapsed_time(marks["exchange"]))
+            mine = torch.tensor([float(np.mean(comp[1:])), float(np.mean(exch[1:]))], device="cuda", dtype=torch.float64)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            torch.distributed.all_gather(allr, mine)
+            rank_phase = [{"rank": r, "local_steps_ms": float(x[0]), "exchange_and_wait_ms": float(x[1])} for r, x in enumerate(allr)]
         # ---- e2e: psi in pinned host memory, H2D + 4 steps + D2H per step ----
         psi_host = tensors["psi"].data
         out_host = np.empty(sharded.info.full_elems if sharded is not None else chain.shells["out"].data.size, np_dtype(dtype))
@@ -318,7 +344,7 @@ def run_ours(args):
                 chain.apply_host("psi", psi_host, "out", out_host)
             else:   # psi H2D on every rank, local steps + all-gather + unpack, full result D2H on every rank
                 chain.buf["psi"].upload(psi_host)
-                sharded.apply()
+                apply_fn()
                 sharded.download_full(out_host)
                 ctx.sync()
         for _ in range(2):
@@ -352,14 +378,27 @@ def run_ours(args):
         hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    # DRAM traffic per launch of each kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json), else null
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"D{args.D}_{dtype}", {})
+    except Exception:
+        traffic = {}
+    # the default complex kernel multiplies with three real DMMAs per complex step (Karatsuba / "3M") instead of four:
+    # `achieved` stays ALGORITHMIC flops (the reference's cost model, 8*m*k*n) / time, so it may exceed the 4-product
+    # cuBLAS ZGEMM rate used as `peak`; `executed_ratio` says how many of those flops the tensor pipe really issues
+    three_m = dtype == "c128" and not (args.plan_flags & (4 | 32))
     if dom["bound"] == "tensor":
         roof = {"bound": "tensor", "kernel": f"step{dom['step']}:{dom['kernel']}", "achieved": dom["achieved"], "peak": peak_burst,
-                "unit": "TFLOP/s", "frac": dom["achieved"] / peak_burst, "traffic": None,
+                "unit": "TFLOP/s", "frac": dom["achieved"] / peak_burst, "traffic": traffic.get(f"step{dom['step']}:{dom['kernel']}"),
+                "executed_ratio": 0.75 if three_m else 1.0,
+                "pipe_frac": dom["achieved"] * (0.75 if three_m else 1.0) / peak_burst,
+                "arithmetic": "3M complex product: 3 real DMMA.8x8x4 per complex 8x8x4 step (6*m*k*n executed flops for 8*m*k*n algorithmic)"
+                              if three_m else "4 real DMMA.8x8x4 per complex 8x8x4 step" if dtype == "c128" else "DMMA.8x8x4",
                 "peak_source": f"FP64 GEMM peak measured in this run: {peak_how}; burst {peak_burst:.2f} / sustained {peak_sust:.2f} TFLOP/s "
                                "(MEASURED_PEAKS.json has no FP64 entry; tcgen05 has no FP64 kind, DMMA via mma.sync is the FP64 tensor path)"}
     else:
         roof = {"bound": "hbm", "kernel": f"step{dom['step']}:{dom['kernel']}", "achieved": dom["achieved"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": dom["achieved"] / hbm_peak, "traffic": None, "peak_source": hbm_src}
+                "frac": dom["achieved"] / hbm_peak, "traffic": traffic.get(f"step{dom['step']}:{dom['kernel']}"), "peak_source": hbm_src}
     for k in kern:
         k["frac"] = k["achieved"] / (peak_burst if k["bound"] == "tensor" else hbm_peak)
 
@@ -379,8 +418,9 @@ def run_ours(args):
         "warmup": max(3, args.warmup), "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
         "vs_baseline": None, "dtype": "c64(f64 pairs)" if dtype == "c128" else "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.D, dtype), "l2": "512 MiB flush written between timed applies; operands+intermediates (>1 GB) exceed the 126 MB L2",
-                   "parallelism": (f"output-sector/row-slab x{world}, exchange={args.exchange}" + (" (peer stores over NVLink from the GEMM epilogue)" if args.exchange == "fused" else " (NCCL)")) if world > 1 else "single GPU", "flops_per_step": flops_total,
-                   "tasks_per_step": int(sum(s.ntask for s in stats))},
+                   "parallelism": (f"output-sector/row-slab x{world}, exchange={sharded.exchange}" + {"fused": " (unicast peer stores over NVLink from the GEMM epilogue)", "multicast": " (multimem.st from the GEMM epilogue, replicated by the NVSwitch)"}.get(sharded.exchange, " (NCCL)")) if world > 1 else "single GPU", "flops_per_step": flops_total,
+                   "tasks_per_step": int(sum(s.ntask for s in stats)),
+                   "launch": "one CUDA graph replay per apply" if graph is not None else "one host launch per kernel"},
         "pct_fp64_peak": 100.0 * value / 1e3 / peak_burst / world, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sust, "how": peak_how},
         "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
         "e2e": {"value": flops_total / e2e_max / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_max * 1e3,
@@ -389,7 +429,11 @@ def run_ours(args):
     }
     if verified is not None:
         line["sharded_vs_unsharded_rel_err"] = verified
+    if rank_phase is not None:
+        line["rank_phases"] = rank_phase
     if args.breakdown:
+        for rp in rank_phase or []:
+            print(f"  rank {rp['rank']}: local steps {rp['local_steps_ms']:.3f} ms, exchange + wait {rp['exchange_and_wait_ms']:.3f} ms", file=sys.stderr)
         for k in kern:
             print(f"  step {k['step']} {k['kernel']:22s} {k['ms']:8.3f} ms  {k['achieved']:9.2f} {k['unit']:8s} frac {k['frac']:.3f}", file=sys.stderr)
     print(json.dumps(line))

@@ -190,6 +190,12 @@ int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const vo
  * barrier before the result is read.  Device pointers only; npeers <= 8. */
 int qlb200_execute_bcast(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *const *C_peers,
                          int32_t npeers);
+/* Same exchange through the NVSwitch: `C_multicast` is a multicast (NVLS) mapping of the full result buffer of
+ * every GPU (cuMulticastCreate / cuMulticastBindMem, or torch.distributed._symmetric_memory's multicast_ptr).
+ * Each output tile leaves the GPU once as multimem.st stores and the switch writes it into every replica, the
+ * caller's own included -- 1/npeers of the NVLink traffic of qlb200_execute_bcast.  A barrier is still needed
+ * before the result is read. */
+int qlb200_execute_mcast(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C_multicast);
 /* Rebase output blocks: the block the plan would write at element offset from_off[i] is written at
  * to_off[i] instead (a rank's packed row slabs -> their place in the full result layout). */
 int qlb200_plan_remap_output(qlb200_plan *p, uint64_t n, const uint64_t *from_off, const uint64_t *to_off);
@@ -198,6 +204,17 @@ int qlb200_plan_remap_output(qlb200_plan *p, uint64_t n, const uint64_t *from_of
 int qlb200_ipc_export(qlb200_ctx *ctx, const void *dev_ptr, unsigned char *handle64);
 int qlb200_ipc_open(qlb200_ctx *ctx, const unsigned char *handle64, void **peer_ptr);
 int qlb200_ipc_close(qlb200_ctx *ctx, void *peer_ptr);
+
+/* ---- CUDA graphs: replay a fixed sequence of executes (one Lanczos mat-vec) with one launch ---- */
+/* Everything enqueued on the context's stream between begin and end -- this library's kernels and foreign work
+ * such as an NCCL collective or a symmetric-memory barrier -- is captured (relaxed mode) instead of executed;
+ * qlb200_graph_launch replays it.  Device-pointer executes only; run the sequence once before capturing so that
+ * the workspace arena has its final size. */
+typedef struct qlb200_graph qlb200_graph;
+int qlb200_graph_begin(qlb200_ctx *ctx);
+int qlb200_graph_end(qlb200_ctx *ctx, qlb200_graph **out);
+int qlb200_graph_launch(qlb200_ctx *ctx, qlb200_graph *g);
+void qlb200_graph_destroy(qlb200_graph *g);
 
 /* number of kernel launches the last execute on this ctx issued */
 uint64_t qlb200_ctx_launch_count(const qlb200_ctx *ctx);

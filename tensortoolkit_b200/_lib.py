@@ -102,6 +102,11 @@ SYMBOLS = {
     "qlb200_execute_permute": (C.c_int, [_P, _P, _P, _P]),
     "qlb200_execute_gemm": (C.c_int, [_P, _P, _P, _P, _P]),
     "qlb200_execute_bcast": (C.c_int, [_P, _P, _P, _P, _PP, C.c_int32]),
+    "qlb200_execute_mcast": (C.c_int, [_P, _P, _P, _P, _P]),
+    "qlb200_graph_begin": (C.c_int, [_P]),
+    "qlb200_graph_end": (C.c_int, [_P, _PP]),
+    "qlb200_graph_launch": (C.c_int, [_P, _P]),
+    "qlb200_graph_destroy": (None, [_P]),
     "qlb200_plan_remap_output": (C.c_int, [_P, C.c_uint64, _U64P, _U64P]),
     "qlb200_ipc_export": (C.c_int, [_P, _P, C.c_char_p]),
     "qlb200_ipc_open": (C.c_int, [_P, C.c_char_p, _PP]),

@@ -174,6 +174,11 @@ class ContractionPlan:
         check(lib.qlb200_execute(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(c_ptr), _lib.MEM_DEVICE),
               "qlb200_execute")
 
+    def execute_mcast(self, a_ptr: int, b_ptr: int, c_multicast_ptr: int):
+        """Permute + GEMM with the output stored through an NVSwitch multicast mapping of the result (multimem.st)."""
+        check(lib.qlb200_execute_mcast(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(c_multicast_ptr)),
+              "qlb200_execute_mcast")
+
     def execute_bcast(self, a_ptr: int, b_ptr: int, c_ptrs):
         """Device-resident execute whose output tiles are stored to every buffer of `c_ptrs` (this GPU's and
         its NVLink peers') from inside the GEMM epilogue."""

@@ -78,11 +78,12 @@ int FinishPlan(qlb200_ctx *ctx, qlb200_plan *p) {
 }
 
 GemmParams MakeParams(const qlb200_plan *p, const void *A, const void *B, const void *wsA, const void *wsB, void *partials,
-                      void *const *c_out, uint32_t n_out) {
+                      void *const *c_out, uint32_t n_out, uint32_t mcast = 0) {
   GemmParams gp;
   gp.a_src = A; gp.b_src = B; gp.a_ws = wsA; gp.b_ws = wsB; gp.partials = partials;
   for (uint32_t d = 0; d < uint32_t(kMaxOut); ++d) gp.c_out[d] = d < n_out ? c_out[d] : nullptr;
   gp.n_out = n_out;
+  gp.mcast = mcast;
   gp.tasks = p->d.tasks; gp.groups = p->d.groups; gp.tiles = p->d.tiles; gp.items = p->d.items;
   gp.ntiles = static_cast<uint32_t>(p->h.tiles.size());
   gp.nitems = static_cast<uint32_t>(p->h.items.size());
@@ -377,16 +378,17 @@ int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const
   return QLB200_OK;
 }
 
-static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *const *c_out, uint32_t n_out) {
+static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *const *c_out, uint32_t n_out,
+                       uint32_t mcast = 0) {
   QL_CUDA(cudaSetDevice(ctx->device));
   void *wa, *wb, *parts;
   int rc = ResolveWorkspace(ctx, p, &wa, &wb, &parts);
   if (rc != QLB200_OK) return rc;
   ctx->launches = 0;
-  GemmParams gp = MakeParams(p, A, B, wa, wb, parts, c_out, n_out);
+  GemmParams gp = MakeParams(p, A, B, wa, wb, parts, c_out, n_out, mcast);
   if (gp.ntiles > 0) {
     if (p->h.flags & QLB200_PLAN_LEGACY_GEMM) {
-      if (n_out != 1) return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels cannot broadcast their output");
+      if (n_out != 1 || mcast) return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels cannot broadcast their output");
       QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, ctx->num_sms, ctx->stream));
     } else if (p->h.dtype == QLB200_C64) {
       QL_CUDA(LaunchGemmWsCplx(gp, !(p->h.flags & QLB200_PLAN_CPLX_4M), ctx->num_sms, ctx->stream));
@@ -422,6 +424,19 @@ int qlb200_execute_bcast(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const v
   return QLB200_OK;
 }
 
+int qlb200_execute_mcast(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C_multicast) {
+  if (!ctx || !p || !A || !B || !C_multicast) return Fail(QLB200_ERR_ARG, "null argument");
+  if (p->ctx != ctx) return Fail(QLB200_ERR_ARG, "plan belongs to another context");
+  int rc = qlb200_execute_permute(ctx, p, A, B);
+  if (rc != QLB200_OK) return rc;
+  const uint64_t l0 = ctx->launches;
+  void *out[1] = {C_multicast};
+  rc = ExecuteGemm(ctx, p, A, B, out, 1, 1);
+  if (rc != QLB200_OK) return rc;
+  ctx->launches += l0;
+  return QLB200_OK;
+}
+
 int qlb200_plan_remap_output(qlb200_plan *p, uint64_t n, const uint64_t *from_off, const uint64_t *to_off) {
   if (!p || (n && (!from_off || !to_off))) return Fail(QLB200_ERR_ARG, "null argument");
   std::vector<std::pair<uint64_t, uint64_t>> map(n);
@@ -437,6 +452,42 @@ int qlb200_plan_remap_output(qlb200_plan *p, uint64_t n, const uint64_t *from_of
   if (!p->ctx) return QLB200_OK;
   QL_CUDA(cudaSetDevice(p->ctx->device));
   return UploadGemmTables(p);
+}
+
+struct qlb200_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+};
+
+int qlb200_graph_begin(qlb200_ctx *ctx) {
+  if (!ctx) return Fail(QLB200_ERR_ARG, "null argument");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  QL_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+  return QLB200_OK;
+}
+int qlb200_graph_end(qlb200_ctx *ctx, qlb200_graph **out) {
+  if (!ctx || !out) return Fail(QLB200_ERR_ARG, "null argument");
+  cudaGraph_t graph = nullptr;
+  QL_CUDA(cudaStreamEndCapture(ctx->stream, &graph));
+  if (!graph) return Fail(QLB200_ERR_CUDA, "stream capture produced no graph");
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  if (e != cudaSuccess) { cudaGraphDestroy(graph); return Fail(QLB200_ERR_CUDA, CudaErr("cudaGraphInstantiate", e)); }
+  qlb200_graph *g = new qlb200_graph;
+  g->graph = graph; g->exec = exec;
+  *out = g;
+  return QLB200_OK;
+}
+int qlb200_graph_launch(qlb200_ctx *ctx, qlb200_graph *g) {
+  if (!ctx || !g || !g->exec) return Fail(QLB200_ERR_ARG, "null argument");
+  QL_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+  return QLB200_OK;
+}
+void qlb200_graph_destroy(qlb200_graph *g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
 }
 
 int qlb200_ipc_export(qlb200_ctx *ctx, const void *dev_ptr, unsigned char *handle64) {

@@ -83,6 +83,7 @@ struct GemmParams {
   const void *a_src, *a_ws, *b_src, *b_ws;   // caller's raw buffers / permuted workspace (set per launch)
   void *c_out[kMaxOut];                      // every output element is stored to c_out[0 .. n_out): the caller's C and,
   uint32_t n_out;                            // for a fused multi-GPU exchange, the same buffer on each NVLink peer
+  uint32_t mcast;                            // c_out[0] is an NVSwitch multicast address: one multimem.st reaches every GPU
   const GemmTask *tasks;
   const GemmGroup *groups;
   const GemmTile *tiles;
@@ -91,6 +92,25 @@ struct GemmParams {
   unsigned int *counters;           // [0] next tile, [1] finished CTAs, [2 + ctr] split-K arrivals (all self-resetting)
   void *partials;                   // split-K partial tiles, slot = BM x BN elements
 };
+
+#ifdef __CUDACC__
+// Output stores.  With `mcast` the address is a multicast mapping of the result buffer (NVLS): the store leaves the
+// GPU once and the NVSwitch replicates it into every GPU's copy -- multimem.st is the only legal access to such memory.
+__device__ __forceinline__ void StoreOut(double2 *dst, double2 v, uint32_t mcast) {
+  if (mcast) {   // 16 bytes as four 32-bit lanes (multimem.st has no .v2.f64 form); SASS: one STG.E.128
+    asm volatile(
+        "{\n .reg .b32 q0, q1, q2, q3;\n mov.b64 {q0, q1}, %1;\n mov.b64 {q2, q3}, %2;\n"
+        " multimem.st.weak.global.v4.f32 [%0], {q0, q1, q2, q3};\n}" ::"l"(dst), "d"(v.x), "d"(v.y)
+        : "memory");
+  } else {
+    *dst = v;
+  }
+}
+__device__ __forceinline__ void StoreOut(double *dst, double v, uint32_t mcast) {
+  if (mcast) asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(dst), "d"(v) : "memory");
+  else *dst = v;
+}
+#endif
 
 inline std::string CudaErr(const char *what, cudaError_t e) {
   return std::string(what) + ": " + cudaGetErrorString(e);

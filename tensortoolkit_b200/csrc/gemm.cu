@@ -420,7 +420,7 @@ GemmSkinny(GemmParams p) {
 #pragma unroll
       for (int u = 0; u < kSkinnyPerThread; ++u) {
         const uint32_t e = tid + u * kSkinnyThreads;
-        if (e < total) cb[e] = acc[u];
+        if (e < total) StoreOut(cb + e, acc[u], p.mcast);
       }
     }
   }

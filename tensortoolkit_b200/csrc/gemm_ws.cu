@@ -177,7 +177,7 @@ __device__ __forceinline__ double2 AccValue(const double (&acc)[CFG::NACC][4][CF
 // Split-K fix-up, run by the unit that arrived last: add the tile's partial tiles in slot order (a fixed
 // order, whichever unit happens to be last) one m8 row group at a time and write C.  Kept out of line:
 // it needs only a handful of registers and must not disturb the register allocation of the main loop.
-template<class CFG>
+template<class CFG, bool MCAST>
 __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile, const GemmGroup &g, int q, int g4, int t4) {
   constexpr int WBN = CFG::BN, NT = CFG::NT;
   __threadfence();
@@ -204,8 +204,8 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-          if (col < g.n) Cg[col] = sum[j][0];
-          if (col + 1 < g.n) Cg[col + 1] = sum[j][1];
+          if (col < g.n) StoreOut(Cg + col, sum[j][0], MCAST);
+          if (col + 1 < g.n) StoreOut(Cg + col + 1, sum[j][1], MCAST);
         }
       }
     }
@@ -213,7 +213,9 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
   if (q == 0 && g4 == 0 && t4 == 0) p.counters[2 + tile.ctr] = 0;
 }
 
-template<class CFG, int STAGES>
+// MCAST: the output address is an NVSwitch multicast mapping (multimem.st); a compile-time switch, because a
+// run-time branch around every store of the unrolled epilogue costs registers the main loop cannot spare.
+template<class CFG, int STAGES, bool MCAST>
 __global__ void __launch_bounds__(kWsThreads, 2)
 GemmWsCplx(const __grid_constant__ GemmParams p) {
   constexpr int WBN = CFG::BN, WBK = CFG::BK, WLDA = Lay<CFG>::WLDA, WLDB = Lay<CFG>::WLDB, A_ELEMS = Lay<CFG>::A_ELEMS,
@@ -395,7 +397,7 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
         if (warp == 0 && lane == 0) s_last = atomicAdd(&p.counters[2 + tile.ctr], 1u) == uint32_t(tile.nsplit) - 1u ? 1u : 0u;
         ConsumerBarrier();
         write_c = false;
-        if (s_last != 0) FixupTile<CFG>(p, tile, g, q, g4, t4);
+        if (s_last != 0) FixupTile<CFG, MCAST>(p, tile, g, q, g4, t4);
       }
       if (write_c) {
         for (uint32_t d = 0; d < p.n_out; ++d) {     // n_out > 1: fused exchange, the same tile goes to every NVLink peer
@@ -408,8 +410,8 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < NTMAX; ++j) {
               const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
               double2 *dst = Cg + (unsigned long long) row * g.n + col;
-              if (col < g.n) dst[0] = AccValue<CFG>(acc, i, j, 0);
-              if (col + 1 < g.n) dst[1] = AccValue<CFG>(acc, i, j, 1);
+              if (col < g.n) StoreOut(dst, AccValue<CFG>(acc, i, j, 0), MCAST);
+              if (col + 1 < g.n) StoreOut(dst + 1, AccValue<CFG>(acc, i, j, 1), MCAST);
             }
           }
         }
@@ -423,18 +425,25 @@ cudaError_t Launch(const GemmParams &p, int num_sms, cudaStream_t stream) {
   constexpr size_t smem = WsSmem<CFG, CFG::STAGES>::kBytes;
   const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
   const uint32_t grid = p.ntiles < cap ? p.ntiles : cap;
-  GemmWsCplx<CFG, CFG::STAGES><<<grid, kWsThreads, smem, stream>>>(p);
+  if (p.mcast) GemmWsCplx<CFG, CFG::STAGES, true><<<grid, kWsThreads, smem, stream>>>(p);
+  else GemmWsCplx<CFG, CFG::STAGES, false><<<grid, kWsThreads, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+template<class CFG>
+cudaError_t Configure() {
+  constexpr int smem = int(WsSmem<CFG, CFG::STAGES>::kBytes);
+  cudaError_t e = cudaFuncSetAttribute(GemmWsCplx<CFG, CFG::STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(GemmWsCplx<CFG, CFG::STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 }  // namespace
 
 cudaError_t ConfigureWsKernel() {
-  cudaError_t e = cudaFuncSetAttribute(GemmWsCplx<Cfg4M, Cfg4M::STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(WsSmem<Cfg4M, Cfg4M::STAGES>::kBytes));
+  cudaError_t e = Configure<Cfg4M>();
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(GemmWsCplx<Cfg3M, Cfg3M::STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              int(WsSmem<Cfg3M, Cfg3M::STAGES>::kBytes));
+  return Configure<Cfg3M>();
 }
 
 cudaError_t LaunchGemmWsCplx(const GemmParams &p, bool three_m, int num_sms, cudaStream_t stream) {

@@ -88,8 +88,8 @@ __device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &til
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-          if (col < g.n) Cg[col] = sum[j].x;
-          if (col + 1 < g.n) Cg[col + 1] = sum[j].y;
+          if (col < g.n) StoreOut(Cg + col, sum[j].x, p.mcast);
+          if (col + 1 < g.n) StoreOut(Cg + col + 1, sum[j].y, p.mcast);
         }
       }
     }
@@ -291,8 +291,8 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
             for (int j = 0; j < 4; ++j) {
               const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
               double *dst = Cg + (unsigned long long) row * g.n + col;
-              if (col < g.n) dst[0] = acc[i][j][0];
-              if (col + 1 < g.n) dst[1] = acc[i][j][1];
+              if (col < g.n) StoreOut(dst, acc[i][j][0], p.mcast);
+              if (col + 1 < g.n) StoreOut(dst + 1, acc[i][j][1], p.mcast);
             }
           }
         }

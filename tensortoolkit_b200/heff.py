@@ -48,6 +48,32 @@ class ExternalBuffer(DeviceBuffer):
         self.ptr = None
 
 
+class CapturedGraph:
+    """A CUDA graph of everything `fn` enqueued on the context's stream (qlb200_graph_*): one launch per replay."""
+
+    def __init__(self, ctx: Context, fn):
+        self.ctx = ctx
+        fn()                      # run once eagerly: arenas reach their final size, lazy initialisation is done
+        ctx.sync()
+        check(lib.qlb200_graph_begin(ctx.h), "qlb200_graph_begin")
+        try:
+            self.launches = fn()
+        finally:
+            h = C.c_void_p()
+            rc = lib.qlb200_graph_end(ctx.h, C.byref(h))
+        check(rc, "qlb200_graph_end")
+        self.h = h
+
+    def launch(self):
+        check(lib.qlb200_graph_launch(self.ctx.h, self.h), "qlb200_graph_launch")
+        return self.launches
+
+    def close(self):
+        if self.h:
+            lib.qlb200_graph_destroy(self.h)
+            self.h = None
+
+
 class ContractionChain:
     """steps: list of (lhs name, rhs name, axes, out name); `tensors` holds the host operands."""
 
@@ -91,6 +117,10 @@ class ContractionChain:
         self.launches_per_apply = n
         return n
 
+    def capture(self) -> CapturedGraph:
+        """The whole chain as one CUDA graph (replay with .launch())."""
+        return CapturedGraph(self.ctx, self.apply_device)
+
     def apply_host(self, in_name: str, host_in: np.ndarray, out_name: str, host_out: np.ndarray):
         """End-to-end apply: input H2D, all steps, result D2H, synchronise."""
         self.buf[in_name].upload(host_in)
@@ -127,12 +157,17 @@ class ShardedChain:
         into the full result buffer of EVERY rank -- its own and, through CUDA-IPC-mapped NVLink peer
         pointers, the others' -- from inside the kernel epilogue (qlb200_execute_bcast); the only collective
         left is a one-element all-reduce that acts as the barrier before the result is read.
+    exchange="multicast": as "fused", but the result buffer is symmetric memory (torch.distributed._symmetric_memory)
+        with an NVSwitch multicast mapping: every output tile leaves the GPU ONCE as multimem.st stores and the
+        switch replicates it into all replicas (qlb200_execute_mcast) -- 1/world of the NVLink traffic of the
+        unicast peer stores; the barrier is symmetric memory's signal-pad barrier (no NCCL call per apply).
+    exchange="auto": "multicast" when the fabric offers it, else "fused".
     exchange="allgather": local steps -> NCCL all-gather of the packed row slabs -> one batched-copy launch
         that scatters every rank's slabs into the full raw-buffer layout (the library-collective baseline).
     exchange=None: no exchange at all (time one rank's share on a single GPU)."""
 
     def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, dtype,
-                 world: int, rank: int, group=None, flags: int = _lib.PLAN_DETERMINISTIC, exchange="fused", peers=None):
+                 world: int, rank: int, group=None, flags: int = _lib.PLAN_DETERMINISTIC, exchange="auto", peers=None):
         import torch
         from .sharding import shard_chain
         self.torch, self.group = torch, group
@@ -148,7 +183,29 @@ class ShardedChain:
         self.cplan, self.full_buf, self.peer_ptrs, self.opened = None, None, None, []
         self.chain = ContractionChain(ctx, mine, steps, dtype, flags, external={self.out_name: self.local.data_ptr()})
         full_bytes = max(self.info.full_elems, 1) * self.dtype.itemsize
-        if exchange == "fused":
+        self.symm = None
+        if exchange in ("auto", "multicast") and world > 1 and peers is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else torch.distributed.group.WORLD
+            with torch.cuda.device(dev):
+                self.symm_buf = symm_mem.empty(max(self.info.full_elems, 1), dtype=tdt, device=dev)
+                self.symm = symm_mem.rendezvous(self.symm_buf, grp)
+            if not int(self.symm.multicast_ptr):
+                if exchange == "multicast":
+                    raise RuntimeError("exchange='multicast': this NVLink domain offers no multicast (NVLS) mapping")
+                self.symm, self.symm_buf, exchange = None, None, "fused"
+            else:
+                exchange = "multicast"
+                self.full_ptr = int(self.symm_buf.data_ptr())
+                self.mc_ptr = int(self.symm.multicast_ptr)
+                my = self.info.slabs[rank]
+                self.chain.plans[-1].remap_output([s.local_offset for s in my], [s.full_offset for s in my])
+        elif exchange == "auto":
+            exchange = "fused"
+        self.exchange = exchange
+        if exchange == "multicast":
+            pass
+        elif exchange == "fused":
             # the full result lives in a cudaMalloc'ed buffer of its own so that it can be exported over CUDA IPC
             self.full_buf = DeviceBuffer(ctx, full_bytes)
             self.full_ptr = self.full_buf.ptr
@@ -190,9 +247,23 @@ class ShardedChain:
     def flops_local(self) -> float:
         return self.chain.flops()
 
-    def apply(self) -> int:
-        """All steps of this rank plus the exchange, enqueued on the current torch stream (== ctx stream)."""
+    def apply(self, mark=None) -> int:
+        """All steps of this rank plus the exchange, enqueued on the current torch stream (== ctx stream).
+        `mark(label)` (optional) is called after the local steps and after the exchange (timing hooks)."""
         ch = self.chain
+        mark = mark or (lambda label: None)
+        if self.exchange == "multicast":
+            n = 0
+            for (lhs, rhs, _, out), plan in zip(ch.steps[:-1], ch.plans[:-1]):
+                plan.execute_device(ch.buf[lhs].ptr, ch.buf[rhs].ptr, ch.buf[out].ptr)
+                n += self.ctx.launch_count()
+            lhs, rhs, _, _ = ch.steps[-1]
+            ch.plans[-1].execute_mcast(ch.buf[lhs].ptr, ch.buf[rhs].ptr, self.mc_ptr)
+            n += self.ctx.launch_count()
+            mark("compute")
+            self.symm.barrier()      # every rank's tiles have landed in every replica
+            mark("exchange")
+            return n
         if self.exchange == "fused":
             n = 0
             for (lhs, rhs, _, out), plan in zip(ch.steps[:-1], ch.plans[:-1]):
@@ -201,10 +272,13 @@ class ShardedChain:
             lhs, rhs, _, _ = ch.steps[-1]
             ch.plans[-1].execute_bcast(ch.buf[lhs].ptr, ch.buf[rhs].ptr, self.peer_ptrs)
             n += self.ctx.launch_count()
+            mark("compute")
             if self.world > 1 and self.opened:
                 self.torch.distributed.all_reduce(self.flag, group=self.group)    # barrier: every peer's tiles have landed
+            mark("exchange")
             return n
         n = ch.apply_device()
+        mark("compute")
         if self.exchange is None:
             return n
         if self.world > 1:
@@ -213,7 +287,12 @@ class ShardedChain:
             self.gathered.copy_(self.local)
         check(lib.qlb200_copy_execute(self.ctx.h, self.cplan, C.c_void_p(self.gathered.data_ptr()), C.c_void_p(self.full_ptr)),
               "qlb200_copy_execute")
+        mark("exchange")
         return n + 1
+
+    def capture(self) -> CapturedGraph:
+        """Local steps + exchange + barrier as one CUDA graph (the torch stream must be the context's stream)."""
+        return CapturedGraph(self.ctx, self.apply)
 
     def download_full(self, host: np.ndarray):
         check(lib.qlb200_memcpy_d2h(self.ctx.h, host.ctypes.data, C.c_void_p(self.full_ptr), host.nbytes), "qlb200_memcpy_d2h")

@@ -331,3 +331,25 @@ def test_transposed_operand_modes_vs_numpy(ctx, dtype):
         plan.execute_host(A, B, Cg)
         plan.close()
         assert util.rel_fro(Cg, Cw) <= TOL
+
+
+def test_chain_graph_replay_matches_eager(ctx):
+    """qlb200_graph_*: the H_eff chain captured as one CUDA graph replays to bit-identical results, also after
+    the input changed (the graph holds pointers, not data)."""
+    from tensortoolkit_b200.heff import ContractionChain
+    rng = np.random.default_rng(31)
+    ti = wl.heff_tensor_indexes(wl.u1_heisenberg_indexes(120))
+    t = {name: tk.BlockSparseTensor(idxs, np.complex128).random((0,), rng) for name, idxs in ti.items()}
+    chain = ContractionChain(ctx, t, wl.HEFF_STEPS, np.complex128)
+    chain.apply_device()
+    eager = chain.result("out").data.copy()
+    g = chain.capture()
+    assert g.launches == chain.launches_per_apply and g.launches > 0
+    g.launch()
+    assert np.array_equal(chain.result("out").data, eager)
+    psi2 = t["psi"].data * (0.25 - 1.5j)
+    chain.upload("psi", psi2)
+    g.launch()
+    got = chain.result("out").data
+    assert util.rel_fro(got, eager * (0.25 - 1.5j)) <= TOL
+    g.close(); chain.close()
