@@ -141,7 +141,10 @@ constexpr int kWsBK = 8, kWsRealBK = 16;                   // k extent of one pi
 #endif
 constexpr int kWs3mBK = QLB200_3M_BK;                      // 3M kernel: two half-stages share one barrier round trip
 constexpr int kWs3mStages = kWs3mBK == 16 ? 3 : 5;
-constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyThreads = 256, kSkinnyPerThread = 8;
+// narrow-pair kernel: 4 outputs per thread keep it at 64 registers -> 4 CTAs (32 warps) per SM; the kernel is
+// latency-bound, so resident warps (loads in flight) matter more than per-thread reuse (measured: 8 per thread /
+// 2 CTAs 0.83 ms, 4 / 4 CTAs 0.69 ms, 2 / 6 CTAs 0.99 ms for the two MPO steps of the D=4096 apply)
+constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyThreads = 256, kSkinnyPerThread = 4, kSkinnyMinCtas = 4;
 constexpr int kSkinnyElems = kSkinnyThreads * kSkinnyPerThread;   // output elements per work item
 
 }  // namespace qlb200

@@ -330,7 +330,7 @@ GemmDmmaCplx(GemmParams p) {
 // thread owns up to kSkinnyPerThread of them (element e = tid + 256*u: consecutive threads write
 // consecutive elements of C).  The (pair, kk) terms of the block are first flattened into a small
 // shared-memory table {A pointer, A row stride, B coefficients with the sign folded in}; the main
-// loop then issues one A load per owned element per term -- up to 8 independent loads in flight per
+// loop then issues one A load per owned element per term -- kSkinnyPerThread independent loads in flight per
 // thread -- and multiplies by coefficients broadcast from shared memory.  A and B blocks are read in
 // place: row-major, or 2-D transposed in the caller's buffer (kTask?Trans).
 // ================================================================================================
@@ -354,7 +354,7 @@ template<> struct Elem<true> {
 constexpr int kSkinnyTermChunk = 64;
 
 template<bool CPLX>
-__global__ void __launch_bounds__(kSkinnyThreads)
+__global__ void __launch_bounds__(kSkinnyThreads, kSkinnyMinCtas)
 GemmSkinny(GemmParams p) {
   using E = Elem<CPLX>;
   using T = typename E::T;
@@ -402,6 +402,7 @@ GemmSkinny(GemmParams p) {
       }
       t = tt; kk0 = kk;
       __syncthreads();
+#pragma unroll 1
       for (uint32_t x = 0; x < nterm; ++x) {
         const T *ap = s_ap[x];
         const unsigned long long as = s_as[x];

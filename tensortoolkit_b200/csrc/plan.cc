@@ -2,6 +2,8 @@
 // tile lists, multi-GPU row partition).  No reference counterpart: the reference walks tasks one
 // by one (global_operations.h:919-982); here the whole contraction is flattened into tables once.
 #include "plan.h"
+#include <cstdio>
+#include <cstdlib>
 
 #include <algorithm>
 #include <cstring>
@@ -360,6 +362,19 @@ std::string BuildTiles(PlanHost *h) {
       if (cand == kMinChunk) break;
     }
   }
+  if (const char *ov = std::getenv("QLB200_SPLIT_CHUNK")) {      // tuning aid: force the split-K cut length (stages)
+    const long long v = std::atoll(ov);
+    if (v > 0 && !legacy) chunk = uint64_t(v);
+  }
+  if (std::getenv("QLB200_DEBUG_TILES") && !dm.empty()) {
+    double wsum = 0;
+    for (const GInfo &d : dm)
+      for (uint32_t i = 0; i < d.tm; ++i)
+        for (uint32_t j = 0; j < d.tn; ++j) wsum += tile_weight(d, i, j) * d.stages;
+    std::fprintf(stderr, "[qlb200 tiles] groups %zu stage-tiles %llu weighted %.0f ideal/slot %.1f chunk %lld makespan(nosplit) %.1f makespan(chosen) %.1f\n",
+                 dm.size(), (unsigned long long) total_stage_tiles, wsum, wsum / double(slots), chunk == ~0ull ? -1ll : (long long) chunk,
+                 makespan(~0ull), makespan(chunk));
+  }
   for (const GInfo &d : dm) {
     uint32_t len;
     const uint32_t nsplit = split_of(d.stages, chunk, &len);
@@ -381,9 +396,21 @@ std::string BuildTiles(PlanHost *h) {
       }
   }
   if (h->n_part_slots >= (1ull << 32)) return "too many split-K slots";
-  // longest units first: persistent CTAs then finish with the short ones (LPT)
-  std::stable_sort(h->tiles.begin(), h->tiles.end(),
-                   [](const GemmTile &x, const GemmTile &y) { return x.s_end - x.s_begin > y.s_end - y.s_begin; });
+  // costliest units first: persistent CTAs then finish with the cheap ones (LPT).  Cost = k-loop length x the
+  // fraction of the tile's MMAs that are issued (ragged edge tiles skip the groups outside the block).
+  {
+    std::vector<uint32_t> gi_to_dm(h->part_groups.size(), 0);
+    for (uint32_t x = 0; x < dm.size(); ++x) gi_to_dm[dm[x].gi] = x;
+    std::vector<std::pair<double, uint32_t>> key(h->tiles.size());
+    for (uint32_t x = 0; x < h->tiles.size(); ++x) {
+      const GemmTile &t = h->tiles[x];
+      key[x] = {-double(t.s_end - t.s_begin) * tile_weight(dm[gi_to_dm[t.group]], t.tm, t.tn), x};
+    }
+    std::stable_sort(key.begin(), key.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+    std::vector<GemmTile> sorted(h->tiles.size());
+    for (uint32_t x = 0; x < key.size(); ++x) sorted[x] = h->tiles[key[x].second];
+    h->tiles.swap(sorted);
+  }
   if (h->tiles.size() >= (1ull << 32) || h->items.size() >= (1ull << 32)) return "too many tiles";
   return "";
 }
