@@ -405,11 +405,14 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            threads = pick_threads()
-            sec, fl = cpu_reference_apply(args.cpu_sample_D, dtype, 2, threads)
-            cpu = {"value": fl / sec / 1e9, "unit": "GFLOP/s", "cores": threads, "kind": "reference",
-                   "sample": f"one H_eff apply at D={args.cpu_sample_D} {dtype} ({fl / 1e9:.1f} GFLOP, {sec:.2f} s best of 2) with the reference's own "
-                             "CPU path (TensorToolkit Contract + HPTT + OpenBLAS 0.3.15), Contract calls only"}
+            # a clean child process (no torch / CUDA runtime threads competing with HPTT's and OpenBLAS's pools):
+            # exactly what `bench.py --impl reference` measures
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                                  "--D", str(args.D), "--dtype", dtype, "--cpu-sample-D", str(args.cpu_sample_D)],
+                                 capture_output=True, text=True, timeout=900, env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+            ref_line = json.loads(out.stdout.strip().splitlines()[-1])
+            cpu = dict(ref_line["cpu_baseline"])
+            cpu["sample"] += f"; reference's own CPU path (TensorToolkit Contract + HPTT + OpenBLAS 0.3.15), mean of {ref_line['steps']} applies, {ref_line['ms_per_step']:.0f} ms each"
         except Exception as e:   # the oracle library is test infrastructure; never fatal for the product bench
             cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 

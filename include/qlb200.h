@@ -144,6 +144,9 @@ int qlb200_host_unregister(void *p);
 #define QLB200_PLAN_LEGACY_GEMM 4u     /* use the cp.async kernels instead of the warp-specialised ones */
 #define QLB200_PLAN_CPLX_4M 32u       /* complex GEMM: four real DMMAs per complex step instead of the default three
                                          (Gauss / 3M product: 25 % fewer tensor-pipe instructions, same error order) */
+#define QLB200_PLAN_STAGGER_OUTPUT 64u /* cut every long k loop into ~4 units queued back to back, so that output tiles complete
+                                         throughout the launch instead of all at its end: lets a fused multi-GPU exchange
+                                         (execute_bcast / execute_mcast) overlap the NVLink transfer with the remaining math */
 #define QLB200_PLAN_NO_SPLIT_K 16u     /* never cut a tile's k loop into several units (testing / tuning) */
 #define QLB200_PLAN_PERMUTE_ALL 8u     /* send every block of a transposed operand through the permute kernel
                                           (default: blocks whose permutation is trivial or one 2-D transposition

@@ -14,7 +14,7 @@ OK = 0
 F64, C64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 DIR_IN, DIR_OUT = -1, 1
-PLAN_DETERMINISTIC, PLAN_NO_SKINNY, PLAN_LEGACY_GEMM, PLAN_PERMUTE_ALL, PLAN_NO_SPLIT_K, PLAN_CPLX_4M = 1, 2, 4, 8, 16, 32
+PLAN_DETERMINISTIC, PLAN_NO_SKINNY, PLAN_LEGACY_GEMM, PLAN_PERMUTE_ALL, PLAN_NO_SPLIT_K, PLAN_CPLX_4M, PLAN_STAGGER_OUTPUT = 1, 2, 4, 8, 16, 32, 64
 
 
 class Shell(C.Structure):

@@ -362,6 +362,11 @@ std::string BuildTiles(PlanHost *h) {
       if (cand == kMinChunk) break;
     }
   }
+  if (!legacy && !dm.empty() && (h->flags & QLB200_PLAN_STAGGER_OUTPUT) && !(h->flags & QLB200_PLAN_NO_SPLIT_K)) {
+    uint32_t longest = 0;
+    for (const GInfo &d : dm) longest = std::max(longest, d.stages);
+    chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(8, (longest + 3) / 4));
+  }
   if (const char *ov = std::getenv("QLB200_SPLIT_CHUNK")) {      // tuning aid: force the split-K cut length (stages)
     const long long v = std::atoll(ov);
     if (v > 0 && !legacy) chunk = uint64_t(v);

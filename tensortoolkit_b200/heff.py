@@ -6,6 +6,7 @@ across iterations, so matches, descriptor tables and buffers are built once here
 only enqueues kernels on the context's stream (no host round trips between steps).
 """
 import ctypes as C
+import os
 from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
@@ -78,7 +79,7 @@ class ContractionChain:
     """steps: list of (lhs name, rhs name, axes, out name); `tensors` holds the host operands."""
 
     def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps: Sequence[Tuple[str, str, tuple, str]],
-                 dtype, flags: int = _lib.PLAN_DETERMINISTIC, external: Dict[str, int] = None):
+                 dtype, flags: int = _lib.PLAN_DETERMINISTIC, external: Dict[str, int] = None, last_flags: int = 0):
         self.ctx, self.dtype, self.steps = ctx, np.dtype(dtype), list(steps)
         self.shells: Dict[str, BlockSparseTensor] = dict(tensors)
         self.matches: List[Match] = []
@@ -87,7 +88,8 @@ class ContractionChain:
             m = Match(self.shells[lhs], self.shells[rhs], axes)
             self.matches.append(m)
             self.shells[out] = m.result_shell(self.dtype)
-            self.plans.append(ContractionPlan(ctx, m, self.dtype, flags))
+            last = len(self.plans) == len(self.steps) - 1
+            self.plans.append(ContractionPlan(ctx, m, self.dtype, flags | (last_flags if last else 0)))
         self.buf: Dict[str, DeviceBuffer] = {}
         for name, t in self.shells.items():
             if external and name in external:      # caller-owned device memory (e.g. a torch tensor)
@@ -181,7 +183,12 @@ class ShardedChain:
         self.local = torch.zeros(self.stride, dtype=tdt, device=dev)
         self.out_name = steps[-1][3]
         self.cplan, self.full_buf, self.peer_ptrs, self.opened = None, None, None, []
-        self.chain = ContractionChain(ctx, mine, steps, dtype, flags, external={self.out_name: self.local.data_ptr()})
+        # exchanged result: let the last step's output tiles complete throughout its launch, so that the NVLink
+        # transfer (every GPU has to RECEIVE the whole result) overlaps the remaining math
+        stagger = _lib.PLAN_STAGGER_OUTPUT if (world > 1 and exchange in ("auto", "multicast", "fused")
+                                               and os.environ.get("QLB200_STAGGER", "1") != "0") else 0
+        self.chain = ContractionChain(ctx, mine, steps, dtype, flags, external={self.out_name: self.local.data_ptr()},
+                                      last_flags=stagger)
         full_bytes = max(self.info.full_elems, 1) * self.dtype.itemsize
         self.symm = None
         if exchange in ("auto", "multicast") and world > 1 and peers is None:
