@@ -235,7 +235,7 @@ class RawPlan(ContractionPlan):
         h = C.c_void_p()
         u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
         check(lib.qlb200_plan_create_raw(
-            ctx.h, _dtype_code(dtype), flags, a_rank, (C.c_int32 * a_rank)(*a_perm), len(aof), ash.ctypes.data_as(u32p),
+            ctx.h if ctx is not None else None, _dtype_code(dtype), flags, a_rank, (C.c_int32 * a_rank)(*a_perm), len(aof), ash.ctypes.data_as(u32p),
             aof.ctypes.data_as(u64p), b_rank, (C.c_int32 * b_rank)(*b_perm), len(bof), bsh.ctypes.data_as(u32p),
             bof.ctypes.data_as(u64p), nt, tarr, int(c_elems), C.byref(h)), "qlb200_plan_create_raw")
         self.h = h

@@ -267,7 +267,7 @@ int qlb200_plan_create_raw(qlb200_ctx *ctx, int dtype, uint32_t flags, int32_t a
                            uint64_t na, const uint32_t *a_shape, const uint64_t *a_off, int32_t b_rank,
                            const int32_t *b_perm, uint64_t nb, const uint32_t *b_shape, const uint64_t *b_off,
                            uint64_t ntask, const qlb200_task *tasks, uint64_t c_elems, qlb200_plan **out) {
-  if (!ctx || !out || !a_shape || !b_shape || !a_off || !b_off || (ntask && !tasks)) return Fail(QLB200_ERR_ARG, "null argument");
+  if (!out || !a_shape || !b_shape || !a_off || !b_off || (ntask && !tasks)) return Fail(QLB200_ERR_ARG, "null argument");
   if (dtype != QLB200_F64 && dtype != QLB200_C64) return Fail(QLB200_ERR_ARG, "bad dtype");
   if (a_rank < 1 || a_rank > QLB200_MAX_RANK || b_rank < 1 || b_rank > QLB200_MAX_RANK) return Fail(QLB200_ERR_ARG, "bad rank");
   auto total = [](int rank, uint64_t n, const uint32_t *shape, const uint64_t *off) {
@@ -296,8 +296,10 @@ int qlb200_plan_create_raw(qlb200_ctx *ctx, int dtype, uint32_t flags, int32_t a
   std::string err = BuildPlanHost(dtype, flags, 0, a_rank, a_perm, na, a_shape, a_off, total(a_rank, na, a_shape, a_off),
                                   b_rank, b_perm, nb, b_shape, b_off, total(b_rank, nb, b_shape, b_off), st, c_elems, &p->h);
   if (!err.empty()) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, err); }
-  int rc = FinishPlan(ctx, p);
-  if (rc != QLB200_OK) { p->d.Free(); delete p; return rc; }
+  if (ctx != nullptr) {   // ctx == NULL: host-only plan (stats / partition queries, no device tables)
+    int rc = FinishPlan(ctx, p);
+    if (rc != QLB200_OK) { p->d.Free(); delete p; return rc; }
+  }
   *out = p;
   return QLB200_OK;
 }

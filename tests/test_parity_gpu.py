@@ -279,13 +279,15 @@ def test_full_size_properties_heff_d4096_complex(ctx):
 
 
 @pytest.mark.parametrize("dtype", [np.complex128, np.float64])
-@pytest.mark.parametrize("variant", ["ws", "ws_4m", "legacy", "ws_permute_all", "ws_4m_permute_all", "legacy_permute_all"])
+@pytest.mark.parametrize("variant", ["ws", "ws_4m", "ws_stagger", "ws_4m_stagger", "legacy", "ws_permute_all", "ws_4m_permute_all",
+                                     "legacy_permute_all"])
 def test_gemm_kernel_variants(ref, ctx, variant, dtype):
     """The warp-specialised kernels (blocks read in place or through the permute kernel) and the
     cp.async kernels against the reference on a fermionic chain with ragged K tails, ragged tile
     edges, -1 exchange signs and several pairs per block."""
     flags = {"legacy": _lib.PLAN_LEGACY_GEMM, "ws": 0, "ws_permute_all": _lib.PLAN_PERMUTE_ALL,
              "ws_4m": _lib.PLAN_CPLX_4M, "ws_4m_permute_all": _lib.PLAN_CPLX_4M | _lib.PLAN_PERMUTE_ALL,
+             "ws_stagger": _lib.PLAN_STAGGER_OUTPUT, "ws_4m_stagger": _lib.PLAN_CPLX_4M | _lib.PLAN_STAGGER_OUTPUT,
              "legacy_permute_all": _lib.PLAN_LEGACY_GEMM | _lib.PLAN_PERMUTE_ALL}[variant]
     flags |= _lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY
     ti = wl.heff_tensor_indexes(wl.hubbard_indexes(150))
@@ -353,3 +355,43 @@ def test_chain_graph_replay_matches_eager(ctx):
     got = chain.result("out").data
     assert util.rel_fro(got, eager * (0.25 - 1.5j)) <= TOL
     g.close(); chain.close()
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
+@pytest.mark.parametrize("extra", [0, _lib.PLAN_STAGGER_OUTPUT, _lib.PLAN_CPLX_4M, _lib.PLAN_NO_SPLIT_K])
+def test_split_k_long_contractions_vs_numpy(ctx, dtype, extra):
+    """Few output blocks with very long k loops: the tiler cuts them along k (deterministic split-K: partial tiles
+    + fix-up by the last arriver in slot order).  Ragged edges, several pairs per block, a -1 sign, identity and
+    transposed operand storage; against numpy, and bit-identical when repeated."""
+    rng = np.random.default_rng(77)
+    cplx = dtype == np.complex128
+    blocks = [(33, 100, [1500, 700]), (64, 200, [2100]), (20, 97, [900, 33, 1000])]
+    a_shape, b_shape, a_off, b_off, tasks, want = [], [], [], [], [], []
+    a_data, b_data = [], []
+    ao = bo = co = 0
+    for ci, (m, n, ks) in enumerate(blocks):
+        acc = np.zeros((m, n), dtype)
+        for pi, k in enumerate(ks):
+            a = rng.standard_normal((m, k)) + (1j * rng.standard_normal((m, k)) if cplx else 0)
+            b = rng.standard_normal((k, n)) + (1j * rng.standard_normal((k, n)) if cplx else 0)
+            sign = -1 if (ci + pi) % 3 == 1 else 1
+            acc += sign * (a @ b)
+            tasks.append(dict(a_ord=len(a_off), b_ord=len(b_off), c_ord=ci, a_off=ao, b_off=bo, c_off=co, m=m, k=k, n=n,
+                              sign=sign, first=1 if pi == 0 else 0))
+            a_shape += [m, k]; b_shape += [k, n]; a_off.append(ao); b_off.append(bo)
+            a_data.append(a.ravel()); b_data.append(b.ravel())
+            ao += a.size; bo += b.size
+        want.append(acc.ravel()); co += m * n
+    A = np.concatenate(a_data).astype(dtype); B = np.concatenate(b_data).astype(dtype)
+    Cw = np.concatenate(want).astype(dtype)
+    flags = _lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY | extra
+    plan = tk.RawPlan(ctx, dtype, 2, [0, 1], a_shape, a_off, 2, [0, 1], b_shape, b_off, tasks, co, flags)
+    full_tiles = sum(-(-m // 32) * -(-n // 96) for m, n, _ in blocks)     # at least this many even with the widest tile
+    if not (extra & _lib.PLAN_NO_SPLIT_K):
+        assert plan.stats().ntile_dmma > 2 * full_tiles, "the k loops of this plan are expected to be cut"
+    C1 = np.zeros(co, dtype); C2 = np.zeros(co, dtype)
+    plan.execute_host(A, B, C1)
+    plan.execute_host(A, B, C2)
+    plan.close()
+    assert util.rel_fro(C1, Cw) <= TOL
+    assert np.array_equal(C1, C2)
