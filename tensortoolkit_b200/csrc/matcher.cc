@@ -9,7 +9,7 @@
 // Design differences (B200-first host side, not a port):
 //  * the reference scans all N_A x N_B block pairs comparing 64-bit hashes of the contracted
 //    coordinates (never verifying them); here B blocks are bucketed by the EXACT mixed-radix key of
-//    their contracted coordinates, so matching is O(N_A + N_B + pairs) and collision-free.  Buckets
+//    their contracted coordinates, so matching is O(N_A + N_B log N_B + pairs) and collision-free (dense key / block-index tables when the sector spaces are small).  Buckets
 //    keep ascending block order, so the discovery order (and therefore which pair is "first" for a
 //    C block) is the reference's.
 //  * everything is flat arrays; no per-hit std::map lookups or vector allocations.
@@ -179,30 +179,52 @@ std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrc
   std::vector<std::pair<uint64_t, uint32_t>> b_keys(B.nblk);
   for (uint64_t j = 0; j < B.nblk; ++j) b_keys[j] = {key_of(B, j, m.b_ctrct, A, m.a_ctrct), static_cast<uint32_t>(j)};
   std::sort(b_keys.begin(), b_keys.end());
-  std::unordered_map<uint64_t, std::pair<uint32_t, uint32_t>> bucket;  // key -> [begin, end) in b_keys
-  bucket.reserve(B.nblk * 2 + 1);
-  for (uint32_t j = 0; j < b_keys.size();) {
-    uint32_t e = j;
-    while (e < b_keys.size() && b_keys[e].first == b_keys[j].first) ++e;
-    bucket.emplace(b_keys[j].first, std::make_pair(j, e));
-    j = e;
+  // key -> [begin, end) in b_keys: a dense table over the contracted sector space when that is small (the usual
+  // case: a few bond sectors per contracted index), else binary search in the sorted key list
+  uint64_t key_span = 1;
+  for (int ax : m.a_ctrct) key_span *= A.nsct[ax];
+  constexpr uint64_t kDenseLimit = 1u << 22;
+  const bool dense_keys = key_span <= kDenseLimit;
+  std::vector<uint32_t> bucket_begin;      // [key_span + 1] when dense
+  if (dense_keys) {
+    bucket_begin.assign(key_span + 1, 0);
+    for (const auto &kv : b_keys) ++bucket_begin[kv.first + 1];
+    for (uint64_t k = 0; k < key_span; ++k) bucket_begin[k + 1] += bucket_begin[k];
   }
+  auto find_bucket = [&](uint64_t key, uint32_t *lo, uint32_t *hi) {
+    if (dense_keys) { *lo = bucket_begin[key]; *hi = bucket_begin[key + 1]; return *hi > *lo; }
+    auto first = std::lower_bound(b_keys.begin(), b_keys.end(), std::make_pair(key, uint32_t(0)));
+    auto last = first;
+    while (last != b_keys.end() && last->first == key) ++last;
+    *lo = uint32_t(first - b_keys.begin()); *hi = uint32_t(last - b_keys.begin());
+    return *hi > *lo;
+  };
 
-  std::unordered_map<uint64_t, uint32_t> c_seen;  // c_blk_idx -> slot in c_unsorted
+  // c_blk_idx -> "already created": a bitmap over C's block-index space when that is small, else a hash set
+  unsigned __int128 c_span128 = 1;
+  for (uint32_t n : m.c_nsct) c_span128 *= n;
+  const bool dense_c = c_span128 <= (static_cast<unsigned __int128>(1) << 27);
+  std::vector<uint64_t> c_bitmap(dense_c ? (static_cast<uint64_t>(c_span128) + 63) / 64 : 0, 0);
+  std::unordered_map<uint64_t, uint32_t> c_seen;
   std::vector<CBlock> c_unsorted;
   uint8_t a_par[QLB200_MAX_RANK], b_par[QLB200_MAX_RANK];
   const bool fermi = A.fermionic();
+  // fermion exchange sign depends only on the two blocks' leg-parity patterns: memoise per (mask_a, mask_b)
+  std::vector<int8_t> sign_cache;
+  if (fermi) sign_cache.assign(size_t(1) << (A.rank + B.rank), 0);
+  m.tasks.reserve(A.nblk + B.nblk);
   for (uint64_t i = 0; i < A.nblk; ++i) {
     const uint32_t *ac = &A.coors[i * A.rank];
     if (sel_axis >= 0 && ac[sel_axis] != sel_sector) continue;
-    auto it = bucket.find(key_of(A, i, m.a_ctrct, A, m.a_ctrct));
-    if (it == bucket.end()) continue;
+    uint32_t q_lo, q_hi;
+    if (!find_bucket(key_of(A, i, m.a_ctrct, A, m.a_ctrct), &q_lo, &q_hi)) continue;
     const uint32_t *ash = &A.shape[i * A.rank];
     uint64_t mm = 1, kk = 1;
     for (int ax : m.a_saved) mm *= ash[ax];
     for (int ax : m.a_ctrct) kk *= ash[ax];
-    if (fermi) for (int r = 0; r < A.rank; ++r) a_par[r] = A.parity[A.sct_base[r] + ac[r]];
-    for (uint32_t q = it->second.first; q < it->second.second; ++q) {
+    uint32_t a_mask = 0;
+    if (fermi) for (int r = 0; r < A.rank; ++r) { a_par[r] = A.parity[A.sct_base[r] + ac[r]]; a_mask |= uint32_t(a_par[r] != 0) << r; }
+    for (uint32_t q = q_lo; q < q_hi; ++q) {
       const uint64_t j = b_keys[q].second;
       const uint32_t *bc = &B.coors[j * B.rank];
       const uint32_t *bsh = &B.shape[j * B.rank];
@@ -231,12 +253,23 @@ std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrc
         for (int ax : m.b_saved) { cb.coors[r] = bc[ax]; cb.shape[r] = bsh[ax]; cidx = cidx * m.c_nsct[r] + bc[ax]; csz *= bsh[ax]; ++r; }
         cb.blk_idx = cidx; cb.size = csz;
         t.c_blk_idx = cidx;
-        auto ins = c_seen.emplace(cidx, static_cast<uint32_t>(c_unsorted.size()));
-        if (ins.second) { c_unsorted.push_back(cb); t.first = 1; } else { t.first = 0; }
+        bool fresh;
+        if (dense_c) {
+          uint64_t &w = c_bitmap[cidx >> 6];
+          const uint64_t bit = uint64_t(1) << (cidx & 63);
+          fresh = !(w & bit);
+          w |= bit;
+        } else {
+          fresh = c_seen.emplace(cidx, static_cast<uint32_t>(c_unsorted.size())).second;
+        }
+        if (fresh) { c_unsorted.push_back(cb); t.first = 1; } else { t.first = 0; }
       }
       if (fermi) {
-        for (int r = 0; r < B.rank; ++r) b_par[r] = B.parity[B.sct_base[r] + bc[r]];
-        t.sign = static_cast<int8_t>(FermionCtrctSign(a_par, A.rank, b_par, B.rank, m.a_ctrct, m.b_ctrct, A.dir.data()));
+        uint32_t b_mask = 0;
+        for (int r = 0; r < B.rank; ++r) { b_par[r] = B.parity[B.sct_base[r] + bc[r]]; b_mask |= uint32_t(b_par[r] != 0) << r; }
+        int8_t &sg = sign_cache[(size_t(b_mask) << A.rank) | a_mask];
+        if (sg == 0) sg = static_cast<int8_t>(FermionCtrctSign(a_par, A.rank, b_par, B.rank, m.a_ctrct, m.b_ctrct, A.dir.data()));
+        t.sign = sg;
       }
       m.tasks.push_back(t);
       if (m.scalar) break;
@@ -250,17 +283,27 @@ std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrc
   // offsets by prefix sum in ascending blk_idx order (DataBlksOffsetRefresh)
   std::sort(c_unsorted.begin(), c_unsorted.end(), [](const CBlock &x, const CBlock &y) { return x.blk_idx < y.blk_idx; });
   uint64_t off = 0;
-  std::unordered_map<uint64_t, uint32_t> c_ord;
-  c_ord.reserve(c_unsorted.size() * 2 + 1);
   for (size_t i = 0; i < c_unsorted.size(); ++i) {
     c_unsorted[i].offset = off;
     off += c_unsorted[i].size;
-    c_ord.emplace(c_unsorted[i].blk_idx, static_cast<uint32_t>(i));
   }
   m.c_blocks = std::move(c_unsorted);
   m.c_elems = off;
+  // ordinal of a C block = its rank among the created blocks: popcount prefix over the bitmap, or binary search
+  std::vector<uint32_t> word_rank;
+  if (dense_c) {
+    word_rank.resize(c_bitmap.size() + 1, 0);
+    for (size_t w = 0; w < c_bitmap.size(); ++w) word_rank[w + 1] = word_rank[w] + uint32_t(__builtin_popcountll(c_bitmap[w]));
+  }
   for (auto &t : m.tasks) {
-    t.c_ord = c_ord[t.c_blk_idx];
+    if (dense_c) {
+      const uint64_t w = t.c_blk_idx >> 6, bit = t.c_blk_idx & 63;
+      t.c_ord = word_rank[w] + uint32_t(__builtin_popcountll(c_bitmap[w] & ((uint64_t(1) << bit) - 1)));
+    } else {
+      auto it = std::lower_bound(m.c_blocks.begin(), m.c_blocks.end(), t.c_blk_idx,
+                                 [](const CBlock &cb, uint64_t v) { return cb.blk_idx < v; });
+      t.c_ord = uint32_t(it - m.c_blocks.begin());
+    }
     t.c_off = m.c_blocks[t.c_ord].offset;
   }
   return "";
