@@ -195,6 +195,10 @@ int qlb200_ctx_create(int device, qlb200_ctx **out) {
   c->num_sms = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete c; return Fail(QLB200_ERR_CUDA, CudaErr("cudaStreamCreate", e)); }
+  e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return Fail(QLB200_ERR_CUDA, CudaErr("side stream / events", e)); }
   e = ConfigureKernels();
   if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return Fail(QLB200_ERR_CUDA, CudaErr("cudaFuncSetAttribute", e)); }
   *out = c;
@@ -204,8 +208,12 @@ void qlb200_ctx_destroy(qlb200_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->side) cudaStreamSynchronize(ctx->side);
   cudaFree(ctx->ws); cudaFree(ctx->stage);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
 }
 int qlb200_ctx_sync(qlb200_ctx *ctx) { QL_CUDA(cudaStreamSynchronize(ctx->stream)); return QLB200_OK; }
@@ -388,9 +396,23 @@ static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const voi
   if (rc != QLB200_OK) return rc;
   ctx->launches = 0;
   GemmParams gp = MakeParams(p, A, B, wa, wb, parts, c_out, n_out, mcast);
+  // A plan that has both DMMA tiles and a handful of narrow-pair items (the small sectors of a GEMM-shaped step):
+  // the narrow kernel is a 10-15 us latency-bound launch on a few SMs.  It is forked onto the side stream FIRST, so the
+  // persistent DMMA CTAs fill the remaining SMs at once and the narrow kernel costs no time of its own (two in-order
+  // launches on one stream would serialise).  The two kernels write disjoint output blocks.  Fork / join by events is
+  // legal under stream capture (qlb200_graph_*).
+  if (gp.ntiles > 0 && (p->h.flags & QLB200_PLAN_LEGACY_GEMM) && (n_out != 1 || mcast))
+    return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels cannot broadcast their output");
+  const bool beside = gp.ntiles > 0 && gp.nitems > 0 && gp.nitems <= uint32_t(ctx->num_sms) && ctx->side != nullptr;
+  if (beside) {
+    QL_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    QL_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    QL_CUDA(LaunchGemmSkinny(p->h.dtype, gp, ctx->num_sms, ctx->side));
+    QL_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+    ctx->launches += 1; ctx->total_launches += 1;
+  }
   if (gp.ntiles > 0) {
     if (p->h.flags & QLB200_PLAN_LEGACY_GEMM) {
-      if (n_out != 1 || mcast) return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels cannot broadcast their output");
       QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, ctx->num_sms, ctx->stream));
     } else if (p->h.dtype == QLB200_C64) {
       QL_CUDA(LaunchGemmWsCplx(gp, !(p->h.flags & QLB200_PLAN_CPLX_4M), ctx->num_sms, ctx->stream));
@@ -399,7 +421,9 @@ static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const voi
     }
     ctx->launches += 1; ctx->total_launches += 1;
   }
-  if (gp.nitems > 0) {
+  if (beside) {
+    QL_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  } else if (gp.nitems > 0) {
     QL_CUDA(LaunchGemmSkinny(p->h.dtype, gp, ctx->num_sms, ctx->stream));
     ctx->launches += 1; ctx->total_launches += 1;
   }

@@ -14,6 +14,9 @@ struct qlb200_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  // a contraction's few narrow-pair work items run beside its DMMA kernel: forked onto `side`, joined before returning
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // grow-only arenas: `ws` holds the permuted operands, `stage` the device copies of host tensors
   void *ws = nullptr; size_t ws_bytes = 0;
   void *stage = nullptr; size_t stage_bytes = 0;
