@@ -107,6 +107,18 @@ void qlb200_match_destroy(qlb200_match *m);
 int qlb200_match_create_1sector(const qlb200_shell *a, int32_t axis, uint32_t sector,
                                 const qlb200_shell *b, int32_t nctrct, const int32_t *a_axes,
                                 const int32_t *b_axes, qlb200_match **out);
+/* Contiguous-axes contraction: the block pairing, result layout and fermion signs of
+ * qlten::ContractContiguousAxes / MatrixBasedTensorContractionExecutor
+ * (tensor_manipulation/contract_contiguous_axes.h:205-331, 333-364, 849-873).  The contracted axes are
+ * (a_start + i) % rank_a and (b_start + i) % rank_b, i < size; the free axes of each operand enter the result in
+ * CYCLIC order starting behind the contracted range.  The plan built from this match reads every operand block
+ * in place -- a cyclic rotation is one 2-D transposition of the block, absorbed by the GEMM's operand loads --
+ * so the reference's OutOfPlaceMatrixTransposeForSelectedDataBlk pass has no counterpart here.  The result is the
+ * same for every CtrctSide pair (they are performance hints in the reference). */
+int qlb200_match_create_contiguous(const qlb200_shell *a, const qlb200_shell *b, int32_t a_start, int32_t b_start,
+                                   int32_t size, qlb200_match **out);
+/* the free axes of A (which = 0) / B (1) in result order; returns how many */
+int32_t qlb200_match_saved_axes(const qlb200_match *m, int which, int32_t *axes_out);
 int32_t qlb200_match_c_rank(const qlb200_match *m);
 uint64_t qlb200_match_c_nblk(const qlb200_match *m);
 uint64_t qlb200_match_c_elems(const qlb200_match *m);            /* raw_data_size_ of C */

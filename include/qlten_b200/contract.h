@@ -7,6 +7,8 @@
 //       qlten::dmrg::Contract1Sector (tensor_manipulation/dmrg/contract_1sector.h:211-228)
 //   qlten::b200::Transpose(pt, order)                          as QLTensor::Transpose
 //       (qltensor/qltensor_impl.h:449-464)
+//   qlten::b200::ContractContiguousAxes<T, QNT, ASide, BSide>(a, b, a_start, b_start, size, c)  as
+//       qlten::ContractContiguousAxes (tensor_manipulation/contract_contiguous_axes.h:849-873)
 //
 // Only PUBLIC reference API is used (GetBlkSparDataTen, GetBlkIdxDataBlkMap, GetActualRawDataPtr,
 // DataBlksInsert, TenCtrctGenSavedAxesSet, TenCtrctInitResTen), so the reference tree stays
@@ -25,6 +27,7 @@
 #include "qlb200.h"
 #include "qlten/qltensor_all.h"
 #include "qlten/tensor_manipulation/ten_ctrct.h"
+#include "qlten/tensor_manipulation/contract_contiguous_axes.h"
 
 namespace qlten {
 namespace b200 {
@@ -209,6 +212,40 @@ void Contract1Sector(const QLTensor<TenElemT, QNT> *pa, const size_t idx_a, cons
                                             static_cast<int32_t>(aa.size()), aa.data(), ba.data(), &match.m),
                 "match_create_1sector");
   detail::RunMatched(pa, pb, sa, sb, match.m, pc, ctx);
+}
+
+/// Same signature and result as qlten::ContractContiguousAxes.  ASide / BSide only tell the reference which operand
+/// to transpose physically; here every block is read in place by the grouped GEMM whatever the sides are, so they
+/// are accepted and ignored.  The accumulate variants (alpha / beta, output-topology union) are not provided.
+template<typename TenElemT, typename QNT, CtrctSide ASide = CtrctSide::Tail, CtrctSide BSide = CtrctSide::Head>
+void ContractContiguousAxes(const QLTensor<TenElemT, QNT> &a, const QLTensor<TenElemT, QNT> &b,
+                            const size_t a_ctrct_axes_start, const size_t b_ctrct_axes_start,
+                            const size_t ctrct_axes_size, QLTensor<TenElemT, QNT> &c, qlb200_ctx *ctx = nullptr) {
+  const size_t ra = a.Rank(), rb = b.Rank();
+  if (ra == 0 || rb == 0 || a_ctrct_axes_start >= ra || b_ctrct_axes_start >= rb || ctrct_axes_size > ra ||
+      ctrct_axes_size > rb) {
+    throw std::invalid_argument("b200::ContractContiguousAxes: bad axis range");
+  }
+  std::vector<std::vector<size_t>> axes_set(2), saved_axes_set(2);
+  for (size_t i = 0; i < ctrct_axes_size; ++i) {
+    axes_set[0].push_back((a_ctrct_axes_start + i) % ra);
+    axes_set[1].push_back((b_ctrct_axes_start + i) % rb);
+  }
+  for (size_t i = 0; i < ra - ctrct_axes_size; ++i) { saved_axes_set[0].push_back((a_ctrct_axes_start + ctrct_axes_size + i) % ra); }
+  for (size_t i = 0; i < rb - ctrct_axes_size; ++i) { saved_axes_set[1].push_back((b_ctrct_axes_start + ctrct_axes_size + i) % rb); }
+  c = QLTensor<TenElemT, QNT>();     // the reference re-initialises the output (TenCtrctInitResTen on whatever c held)
+  detail::CheckPreconditions(&a, &b, axes_set, &c);
+  if (ctx == nullptr) { ctx = detail::DefaultCtx(); }
+  TenCtrctInitResTen(&a, &b, saved_axes_set, &c);
+  detail::ShellHolder sa, sb;
+  detail::FillShell(a, sa);
+  detail::FillShell(b, sb);
+  detail::MatchGuard match;
+  detail::Check(qlb200_match_create_contiguous(&sa.shell, &sb.shell, static_cast<int32_t>(a_ctrct_axes_start),
+                                               static_cast<int32_t>(b_ctrct_axes_start),
+                                               static_cast<int32_t>(ctrct_axes_size), &match.m),
+                "match_create_contiguous");
+  detail::RunMatched(&a, &b, sa, sb, match.m, &c, ctx);
 }
 
 template<typename TenElemT, typename QNT>

@@ -72,11 +72,13 @@ def _blk_parities(t: BlockSparseTensor, b: int):
     return [k.parity(t.indexes[i].sectors[int(c)].qn) for i, c in enumerate(t.blk_coors[b])]
 
 
-def match_tasks(a: BlockSparseTensor, b: BlockSparseTensor, axes):
+def match_tasks(a: BlockSparseTensor, b: BlockSparseTensor, axes, saved=None):
     """DataBlkGenForTenCtrct -- data_blk_operations.h:411-578: scan every (a, b) block pair in
     ascending blk_idx order, keep those whose coordinates agree on the contracted axes.
+    `saved` overrides the order of the free axes in the result (the contiguous-axes executor passes a
+    cyclic order, contract_contiguous_axes.h:346-352).
     Returns (tasks in discovery order, c_coors sorted by blk_idx, c_offsets)."""
-    sa, sb = saved_axes(a.rank, b.rank, axes)
+    sa, sb = saved if saved is not None else saved_axes(a.rank, b.rank, axes)
     c_nsct = [a.indexes[i].nsct for i in sa] + [b.indexes[i].nsct for i in sb]
     scalar = len(c_nsct) == 0
     fermi = a.kind.fermionic
@@ -138,6 +140,57 @@ def contract_np(a: BlockSparseTensor, b: BlockSparseTensor, axes) -> BlockSparse
         bm = np.transpose(b.block(t["b"]), pb).reshape(t["k"], t["n"])
         out = c.data[t["c_off"]:t["c_off"] + t["m"] * t["n"]].reshape(t["m"], t["n"])
         prod = t["sign"] * (am.astype(dt) @ bm.astype(dt))
+        if t["beta"] == 0.0:
+            out[...] = prod
+        else:
+            out += prod
+    return c
+
+
+def residue_fermion_sign(parities, saved, trans_critical_axe):
+    """CountResidueFermionSignForMatBasedCtrct -- data_blk_operations.h:579-611, for one block."""
+    first = [ax for ax in saved if ax < trans_critical_axe]
+    second = [ax for ax in saved if ax >= trans_critical_axe]
+    if not first or not second:
+        return 1
+    n1 = sum(parities[:len(first)])
+    n2 = sum(parities[second[0]:])
+    return -1 if (n1 & 1) and (n2 & 1) else 1
+
+
+def contract_contiguous_np(a: BlockSparseTensor, b: BlockSparseTensor, a_start: int, b_start: int, size: int) -> BlockSparseTensor:
+    """ContractContiguousAxes<Tail, Head> -- tensor_manipulation/contract_contiguous_axes.h:849-873 ->
+    MatrixBasedTensorContractionExecutor: GenerateDataBlk_ (:333-364: contracted axes (start + i) % rank, free axes in
+    cyclic order from the end of the contracted range), TransposePrepare_ (:473-534: the blocks are rotated as
+    matrices about the critical axis -- Tail: end of A's range, Head: start of B's -- and fermionic blocks pick up the
+    residue sign), then C = sign * A' B' per task (CtrctAccordingTask)."""
+    ra, rb = a.rank, b.rank
+    axes = ([(a_start + i) % ra for i in range(size)], [(b_start + i) % rb for i in range(size)])
+    a_end, b_end = (a_start + size) % ra, (b_start + size) % rb
+    sa = [(a_end + i) % ra for i in range(ra - size)]
+    sb = [(b_end + i) % rb for i in range(rb - size)]
+    a_crit, b_crit = a_end, b_start                     # <Tail, Head>, :325-326
+    tasks, c_coors, c_elems = match_tasks(a, b, axes, saved=(sa, sb))
+    dt = np.result_type(a.dtype, b.dtype)
+    c = BlockSparseTensor([a.indexes[i] for i in sa] + [b.indexes[i] for i in sb], dt)
+    if c.rank:
+        c.set_blocks(c_coors)
+    c.data = np.zeros(c_elems, dtype=dt)
+    fermi = a.kind.fermionic
+    # matrix rotation about the critical axis: axes [crit, rank) come first, then [0, crit)
+    rot_a = list(range(a_crit, ra)) + list(range(a_crit))
+    rot_b = list(range(b_crit, rb)) + list(range(b_crit))
+    for t in sorted(tasks, key=lambda t: (t["c_idx"], t["beta"])):
+        am = np.transpose(a.block(t["a"]), rot_a).reshape(t["m"], t["k"])
+        bm = np.transpose(b.block(t["b"]), rot_b).reshape(t["k"], t["n"])
+        sign = t["sign"]
+        if fermi:
+            if a_crit > 0:
+                sign *= residue_fermion_sign(_blk_parities(a, t["a"]), sa, a_crit)
+            if b_crit > 0:
+                sign *= residue_fermion_sign(_blk_parities(b, t["b"]), sb, b_crit)
+        out = c.data[t["c_off"]:t["c_off"] + t["m"] * t["n"]].reshape(t["m"], t["n"])
+        prod = sign * (am.astype(dt) @ bm.astype(dt))
         if t["beta"] == 0.0:
             out[...] = prod
         else:

@@ -19,6 +19,7 @@
 #include "qlten/tensor_manipulation/ten_ctrct.h"
 #include "qlten/tensor_manipulation/tensor_op_cost.h"
 #include "qlten/tensor_manipulation/dmrg/contract_1sector.h"
+#include "qlten/tensor_manipulation/contract_contiguous_axes.h"
 
 #include "qlten_b200/contract.h"
 
@@ -80,6 +81,9 @@ struct TenBase {
   virtual TenBase *contract_1sector(int64_t axis, int64_t sct, const TenBase *b, int n, const int64_t *aa, const int64_t *ba) const = 0;
   virtual TenBase *contract_1sector_b200(int64_t axis, int64_t sct, const TenBase *b, int n, const int64_t *aa, const int64_t *ba, void *ctx) const = 0;
   virtual void transpose_b200(const int64_t *perm, void *ctx) = 0;
+  // side: 0 = <Tail, Head> (default), 1 = <Head, Head>, 2 = <Tail, Tail>, 3 = <Head, Tail>
+  virtual TenBase *contract_contiguous(const TenBase *b, int64_t a_start, int64_t b_start, int64_t size, int side) const = 0;
+  virtual TenBase *contract_contiguous_b200(const TenBase *b, int64_t a_start, int64_t b_start, int64_t size, int side, void *ctx) const = 0;
   virtual std::vector<TaskRec> tasks(const TenBase *b, int n, const int64_t *aa, const int64_t *ba, bool sorted) const = 0;
   virtual void cost(const TenBase *b, int n, const int64_t *aa, const int64_t *ba, double *out8) const = 0;
 };
@@ -150,6 +154,28 @@ struct TenBox : TenBase {
   }
   TenBase *contract_1sector_b200(int64_t axis, int64_t sct, const TenBase *b, int n, const int64_t *aa, const int64_t *ba, void *ctx) const override {
     Ten c; qlten::b200::Contract1Sector(&t, (size_t) axis, (size_t) sct, &cast(b)->t, MakeAxes(n, aa, ba), &c, (qlb200_ctx *) ctx); return wrap(std::move(c));
+  }
+  TenBase *contract_contiguous(const TenBase *b, int64_t a_start, int64_t b_start, int64_t size, int side) const override {
+    Ten c;
+    const Ten &tb = cast(b)->t;
+    switch (side) {
+      case 1: ContractContiguousAxes<ElemT, QNT, CtrctSide::Head, CtrctSide::Head>(t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c); break;
+      case 2: ContractContiguousAxes<ElemT, QNT, CtrctSide::Tail, CtrctSide::Tail>(t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c); break;
+      case 3: ContractContiguousAxes<ElemT, QNT, CtrctSide::Head, CtrctSide::Tail>(t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c); break;
+      default: ContractContiguousAxes<ElemT, QNT, CtrctSide::Tail, CtrctSide::Head>(t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c); break;
+    }
+    return wrap(std::move(c));
+  }
+  TenBase *contract_contiguous_b200(const TenBase *b, int64_t a_start, int64_t b_start, int64_t size, int side, void *ctx) const override {
+    Ten c;
+    const Ten &tb = cast(b)->t;
+    switch (side) {
+      case 1: qlten::b200::ContractContiguousAxes<ElemT, QNT, CtrctSide::Head, CtrctSide::Head>(t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c, (qlb200_ctx *) ctx); break;
+      case 2: qlten::b200::ContractContiguousAxes<ElemT, QNT, CtrctSide::Tail, CtrctSide::Tail>(t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c, (qlb200_ctx *) ctx); break;
+      case 3: qlten::b200::ContractContiguousAxes<ElemT, QNT, CtrctSide::Head, CtrctSide::Tail>(t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c, (qlb200_ctx *) ctx); break;
+      default: qlten::b200::ContractContiguousAxes<ElemT, QNT, CtrctSide::Tail, CtrctSide::Head>(t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c, (qlb200_ctx *) ctx); break;
+    }
+    return wrap(std::move(c));
   }
   std::vector<TaskRec> tasks(const TenBase *b, int n, const int64_t *aa, const int64_t *ba, bool sorted) const override {
     auto axes = MakeAxes(n, aa, ba);
@@ -283,6 +309,14 @@ void *qlref_b200_contract_1sector(const void *a, int64_t axis, int64_t sct, cons
   try {
     return static_cast<const TenBase *>(a)->contract_1sector_b200(axis, sct, static_cast<const TenBase *>(b), n, aa, ba, ctx);
   } catch (const std::exception &e) { std::fprintf(stderr, "qlref_b200_contract_1sector: %s\n", e.what()); return nullptr; }
+}
+void *qlref_contract_contiguous(const void *a, const void *b, int64_t a_start, int64_t b_start, int64_t size, int side) {
+  return static_cast<const TenBase *>(a)->contract_contiguous(static_cast<const TenBase *>(b), a_start, b_start, size, side);
+}
+void *qlref_b200_contract_contiguous(const void *a, const void *b, int64_t a_start, int64_t b_start, int64_t size, int side, void *ctx) {
+  try {
+    return static_cast<const TenBase *>(a)->contract_contiguous_b200(static_cast<const TenBase *>(b), a_start, b_start, size, side, ctx);
+  } catch (const std::exception &e) { std::fprintf(stderr, "qlref_b200_contract_contiguous: %s\n", e.what()); return nullptr; }
 }
 int qlref_b200_transpose(void *t, const int64_t *perm, void *ctx) {
   try { static_cast<TenBase *>(t)->transpose_b200(perm, ctx); return 0; }

@@ -60,6 +60,8 @@ def lib():
             "qlref_b200_contract": (_P, [_P, _P, C.c_int, _I64P, _I64P, _P]),
             "qlref_b200_contract_1sector": (_P, [_P, C.c_int64, C.c_int64, _P, C.c_int, _I64P, _I64P, _P]),
             "qlref_b200_transpose": (C.c_int, [_P, _I64P, _P]),
+            "qlref_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+            "qlref_b200_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -218,6 +220,33 @@ def b200_contract_1sector(a: RefTensor, axis, sct, b: RefTensor, axes, ctx_handl
     if not h:
         raise RuntimeError("qlten::b200::Contract1Sector failed")
     return RefTensor(h, _c_indexes(a, b, axes), a.dtype)
+
+
+def _c_indexes_cyclic(a: RefTensor, b: RefTensor, a_start, b_start, size):
+    ra, rb = len(a.indexes), len(b.indexes)
+    sa = [(a_start + size + i) % ra for i in range(ra - size)]
+    sb = [(b_start + size + i) % rb for i in range(rb - size)]
+    return [a.indexes[i] for i in sa] + [b.indexes[i] for i in sb]
+
+
+SIDES = {("tail", "head"): 0, ("head", "head"): 1, ("tail", "tail"): 2, ("head", "tail"): 3}
+
+
+def contract_contiguous(a: RefTensor, b: RefTensor, a_start: int, b_start: int, size: int, sides=("tail", "head")) -> RefTensor:
+    """The reference's qlten::ContractContiguousAxes<ASide, BSide> (contract_contiguous_axes.h:849-873)."""
+    L = lib()
+    h = L.qlref_contract_contiguous(a.h, b.h, int(a_start), int(b_start), int(size), SIDES[tuple(sides)])
+    return RefTensor(h, _c_indexes_cyclic(a, b, a_start, b_start, size), a.dtype)
+
+
+def b200_contract_contiguous(a: RefTensor, b: RefTensor, a_start: int, b_start: int, size: int, sides=("tail", "head"),
+                             ctx_handle=None) -> RefTensor:
+    """qlten::b200::ContractContiguousAxes on reference tensors (the drop-in adapter over the C ABI)."""
+    L = lib()
+    h = L.qlref_b200_contract_contiguous(a.h, b.h, int(a_start), int(b_start), int(size), SIDES[tuple(sides)], ctx_handle)
+    if not h:
+        raise RuntimeError("qlref_b200_contract_contiguous failed (see stderr)")
+    return RefTensor(h, _c_indexes_cyclic(a, b, a_start, b_start, size), a.dtype)
 
 
 def contract_tasks(a: RefTensor, b: RefTensor, axes, sorted_by_c=False):

@@ -2,7 +2,9 @@
 (the qlten::Contract hot path of QuantumLiquids/TensorToolkit), behind the C ABI in include/qlb200.h.
 """
 from .tensor import (IN, OUT, QNKind, QNSector, Index, BlockSparseTensor, U1, fU1, U1U1, fU1U1, Z2, fZ2)
-from .contract import (Context, Match, ContractionPlan, RawPlan, contract, contract_1sector, transpose, default_context)
+from .contract import (Context, Match, ContractionPlan, RawPlan, contract, contract_1sector, contract_contiguous_axes, transpose,
+                       default_context)
 
 __all__ = ["IN", "OUT", "QNKind", "QNSector", "Index", "BlockSparseTensor", "U1", "fU1", "U1U1", "fU1U1", "Z2", "fZ2",
-           "Context", "Match", "ContractionPlan", "RawPlan", "contract", "contract_1sector", "transpose", "default_context"]
+           "Context", "Match", "ContractionPlan", "RawPlan", "contract", "contract_1sector", "contract_contiguous_axes",
+           "transpose", "default_context"]

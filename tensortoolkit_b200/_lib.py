@@ -69,6 +69,8 @@ SYMBOLS = {
     "qlb200_match_create": (C.c_int, [_SH, _SH, C.c_int32, _I32P, _I32P, _PP]),
     "qlb200_match_destroy": (None, [_P]),
     "qlb200_match_create_1sector": (C.c_int, [_SH, C.c_int32, C.c_uint32, _SH, C.c_int32, _I32P, _I32P, _PP]),
+    "qlb200_match_create_contiguous": (C.c_int, [_SH, _SH, C.c_int32, C.c_int32, C.c_int32, _PP]),
+    "qlb200_match_saved_axes": (C.c_int32, [_P, C.c_int, _I32P]),
     "qlb200_match_c_rank": (C.c_int32, [_P]),
     "qlb200_match_c_nblk": (C.c_uint64, [_P]),
     "qlb200_match_c_elems": (C.c_uint64, [_P]),

@@ -67,7 +67,14 @@ def _i32(v):
 class Match:
     """Result of the host sector matcher (qlb200_match)."""
 
-    def __init__(self, a: BlockSparseTensor, b: BlockSparseTensor, axes, one_sector=None):
+    def __init__(self, a: BlockSparseTensor, b: BlockSparseTensor, axes, one_sector=None, contiguous=None):
+        """axes = (a axes, b axes) for the general contraction; contiguous = (a_start, b_start, size) selects the
+        block pairing / result layout of qlten::ContractContiguousAxes instead (axes is then ignored)."""
+        if contiguous is not None:
+            a_start, b_start, size = (int(x) for x in contiguous)
+            if not (0 <= a_start < a.rank and 0 <= b_start < b.rank and 0 <= size <= min(a.rank, b.rank)):
+                raise ValueError("bad contiguous axis range")
+            axes = ([(a_start + i) % a.rank for i in range(size)], [(b_start + i) % b.rank for i in range(size)])
         axes_a, axes_b = list(axes[0]), list(axes[1])
         if len(axes_a) != len(axes_b):
             raise ValueError("axes_set must pair axes of A with axes of B")
@@ -78,7 +85,9 @@ class Match:
         self.axes = (axes_a, axes_b)
         self.sa, self.sb = a.shell(), b.shell()
         h = C.c_void_p()
-        if one_sector is None:
+        if contiguous is not None:
+            rc = lib.qlb200_match_create_contiguous(self.sa.ptr(), self.sb.ptr(), a_start, b_start, size, C.byref(h))
+        elif one_sector is None:
             rc = lib.qlb200_match_create(self.sa.ptr(), self.sb.ptr(), len(axes_a), _i32(axes_a), _i32(axes_b), C.byref(h))
         else:
             rc = lib.qlb200_match_create_1sector(self.sa.ptr(), int(one_sector[0]), int(one_sector[1]), self.sb.ptr(),
@@ -90,8 +99,10 @@ class Match:
         self.c_elems = int(lib.qlb200_match_c_elems(h))
         self.ntask = int(lib.qlb200_match_ntask(h))
         self.is_scalar = bool(lib.qlb200_match_is_scalar(h))
-        saved_a = [i for i in range(a.rank) if i not in axes_a]
-        saved_b = [i for i in range(b.rank) if i not in axes_b]
+        buf = (C.c_int32 * _lib.QLB200_MAX_RANK)()
+        saved_a = [int(buf[i]) for i in range(lib.qlb200_match_saved_axes(h, 0, buf))]
+        saved_b = [int(buf[i]) for i in range(lib.qlb200_match_saved_axes(h, 1, buf))]
+        self.saved_axes = (saved_a, saved_b)
         self.c_indexes = [a.indexes[i] for i in saved_a] + [b.indexes[i] for i in saved_b]
 
     def perm(self, which: int):
@@ -263,6 +274,19 @@ def _run(a, b, match, ctx):
 def contract(a: BlockSparseTensor, b: BlockSparseTensor, axes: Sequence[Sequence[int]], ctx: Context = None) -> BlockSparseTensor:
     """C = Contract(A, B, {{a axes}, {b axes}}): C's indexes are A's free indexes then B's free indexes."""
     m = Match(a, b, axes)
+    try:
+        return _run(a, b, m, ctx)
+    finally:
+        m.close()
+
+
+def contract_contiguous_axes(a: BlockSparseTensor, b: BlockSparseTensor, a_ctrct_axes_start: int, b_ctrct_axes_start: int,
+                             ctrct_axes_size: int, ctx: Context = None) -> BlockSparseTensor:
+    """qlten::ContractContiguousAxes (tensor_manipulation/contract_contiguous_axes.h:849-873): contract axes
+    (a_start + i) % rank_a of A with (b_start + i) % rank_b of B; the result's indexes are A's free indexes in cyclic
+    order starting behind the contracted range, then B's likewise.  Every block is read in place by the grouped GEMM
+    (a cyclic rotation is a 2-D transposition of the block), so no transpose pass runs."""
+    m = Match(a, b, None, contiguous=(a_ctrct_axes_start, b_ctrct_axes_start, ctrct_axes_size))
     try:
         return _run(a, b, m, ctx)
     finally:

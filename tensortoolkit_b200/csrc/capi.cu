@@ -138,6 +138,30 @@ int qlb200_match_create_1sector(const qlb200_shell *a, int32_t axis, uint32_t se
   if (axis < 0) return Fail(QLB200_ERR_ARG, "negative 1-sector axis");
   return MatchCreate(a, b, nctrct, a_axes, b_axes, axis, sector, out);
 }
+int qlb200_match_create_contiguous(const qlb200_shell *a, const qlb200_shell *b, int32_t a_start, int32_t b_start,
+                                   int32_t size, qlb200_match **out) {
+  if (!a || !b || !out) return Fail(QLB200_ERR_ARG, "null argument");
+  const int32_t ra = a->rank, rb = b->rank;
+  if (ra < 1 || rb < 1 || ra > QLB200_MAX_RANK || rb > QLB200_MAX_RANK) return Fail(QLB200_ERR_ARG, "rank out of range");
+  if (size < 0 || size > ra || size > rb || a_start < 0 || a_start >= ra || b_start < 0 || b_start >= rb)
+    return Fail(QLB200_ERR_ARG, "bad contiguous axis range");
+  int32_t a_axes[QLB200_MAX_RANK], b_axes[QLB200_MAX_RANK], a_saved[QLB200_MAX_RANK], b_saved[QLB200_MAX_RANK];
+  for (int32_t i = 0; i < size; ++i) { a_axes[i] = (a_start + i) % ra; b_axes[i] = (b_start + i) % rb; }
+  const int32_t a_end = (a_start + size) % ra, b_end = (b_start + size) % rb;
+  for (int32_t i = 0; i < ra - size; ++i) a_saved[i] = (a_end + i) % ra;
+  for (int32_t i = 0; i < rb - size; ++i) b_saved[i] = (b_end + i) % rb;
+  qlb200_match *m = new (std::nothrow) qlb200_match();
+  if (!m) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  std::string err = BuildMatch(a, b, size, a_axes, b_axes, -1, 0, &m->m, a_saved, b_saved, true);
+  if (!err.empty()) { delete m; return Fail(QLB200_ERR_ARG, err); }
+  *out = m;
+  return QLB200_OK;
+}
+int32_t qlb200_match_saved_axes(const qlb200_match *m, int which, int32_t *axes_out) {
+  const std::vector<int> &v = which == 0 ? m->m.a_saved : m->m.b_saved;
+  if (axes_out) for (size_t i = 0; i < v.size(); ++i) axes_out[i] = v[i];
+  return static_cast<int32_t>(v.size());
+}
 void qlb200_match_destroy(qlb200_match *m) { delete m; }
 int32_t qlb200_match_c_rank(const qlb200_match *m) { return m->m.c_rank; }
 uint64_t qlb200_match_c_nblk(const qlb200_match *m) { return m->m.c_blocks.size(); }

@@ -122,8 +122,25 @@ std::vector<qlb200_task> Match::SortedTasks() const {
   return t;
 }
 
+namespace {
+
+// Sign the contiguous-axes executor applies per operand block (reference: data_blk_operations.h:579-611,
+// CountResidueFermionSignForMatBasedCtrct): the free legs of the block fall into the group in front of the
+// contracted range and the group behind it; bringing the rear group to the front (the cyclic order of the
+// result) costs a sign when both groups hold an odd number of odd-parity legs.
+int ResidueSign(const uint8_t *par, const std::vector<int> &saved, const std::vector<int> &ctrct) {
+  if (ctrct.empty()) return 1;
+  const int first_ctrct = ctrct.front();
+  int n_front = 0, n_rear = 0;
+  for (int ax : saved) (ax < first_ctrct ? n_front : n_rear) += par[ax] ? 1 : 0;
+  return ((n_front & 1) && (n_rear & 1)) ? -1 : 1;
+}
+
+}  // namespace
+
 std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrct, const int32_t *a_axes,
-                       const int32_t *b_axes, int sel_axis, uint32_t sel_sector, Match *out) {
+                       const int32_t *b_axes, int sel_axis, uint32_t sel_sector, Match *out,
+                       const int32_t *a_saved_order, const int32_t *b_saved_order, bool mat_based_residue) {
   Match &m = *out;
   std::string err = m.a.Load(sa);
   if (!err.empty()) return "A: " + err;
@@ -150,8 +167,26 @@ std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrc
     if (sel_axis >= A.rank || a_used[sel_axis]) return "1-sector axis must be a free axis of A";
     if (sel_sector >= A.nsct[sel_axis]) return "1-sector index out of range";
   }
-  for (int i = 0; i < A.rank; ++i) if (!a_used[i]) m.a_saved.push_back(i);
-  for (int i = 0; i < B.rank; ++i) if (!b_used[i]) m.b_saved.push_back(i);
+  auto fill_saved = [](int rank, const std::vector<char> &used, const int32_t *order, std::vector<int> *saved) -> std::string {
+    if (order == nullptr) {
+      for (int i = 0; i < rank; ++i) if (!used[i]) saved->push_back(i);
+      return "";
+    }
+    std::vector<char> seen(rank, 0);
+    int nfree = 0;
+    for (int i = 0; i < rank; ++i) nfree += used[i] ? 0 : 1;
+    for (int i = 0; i < nfree; ++i) {
+      const int ax = order[i];
+      if (ax < 0 || ax >= rank || used[ax] || seen[ax]) return "saved-axes order must list every free axis exactly once";
+      seen[ax] = 1;
+      saved->push_back(ax);
+    }
+    return "";
+  };
+  err = fill_saved(A.rank, a_used, a_saved_order, &m.a_saved);
+  if (!err.empty()) return "A: " + err;
+  err = fill_saved(B.rank, b_used, b_saved_order, &m.b_saved);
+  if (!err.empty()) return "B: " + err;
   m.a_perm = m.a_saved; m.a_perm.insert(m.a_perm.end(), m.a_ctrct.begin(), m.a_ctrct.end());
   m.b_perm = m.b_ctrct; m.b_perm.insert(m.b_perm.end(), m.b_saved.begin(), m.b_saved.end());
   m.a_need_trans = !std::is_sorted(m.a_perm.begin(), m.a_perm.end());
@@ -268,7 +303,11 @@ std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrc
         uint32_t b_mask = 0;
         for (int r = 0; r < B.rank; ++r) { b_par[r] = B.parity[B.sct_base[r] + bc[r]]; b_mask |= uint32_t(b_par[r] != 0) << r; }
         int8_t &sg = sign_cache[(size_t(b_mask) << A.rank) | a_mask];
-        if (sg == 0) sg = static_cast<int8_t>(FermionCtrctSign(a_par, A.rank, b_par, B.rank, m.a_ctrct, m.b_ctrct, A.dir.data()));
+        if (sg == 0) {
+          int v = FermionCtrctSign(a_par, A.rank, b_par, B.rank, m.a_ctrct, m.b_ctrct, A.dir.data());
+          if (mat_based_residue) v *= ResidueSign(a_par, m.a_saved, m.a_ctrct) * ResidueSign(b_par, m.b_saved, m.b_ctrct);
+          sg = static_cast<int8_t>(v);
+        }
         t.sign = sg;
       }
       m.tasks.push_back(t);

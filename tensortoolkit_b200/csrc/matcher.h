@@ -56,8 +56,13 @@ struct Match {
 };
 
 /// sel_axis < 0: all A blocks; otherwise only A blocks with coors[sel_axis] == sel_sector.
+/// a_saved_order / b_saved_order (optional): the order in which the free axes of A / B appear in the result;
+/// default is ascending (qlten::Contract).  mat_based_residue: multiply every task by the per-block signs of
+/// BlockSparseDataTensor::CountResidueFermionSignForMatBasedCtrct (the contiguous-axes executor).
 std::string BuildMatch(const qlb200_shell *a, const qlb200_shell *b, int nctrct, const int32_t *a_axes,
-                       const int32_t *b_axes, int sel_axis, uint32_t sel_sector, Match *out);
+                       const int32_t *b_axes, int sel_axis, uint32_t sel_sector, Match *out,
+                       const int32_t *a_saved_order = nullptr, const int32_t *b_saved_order = nullptr,
+                       bool mat_based_residue = false);
 
 /// Fermion exchange sign of one block pair (reference: data_blk_operations.h:351-401).
 int FermionCtrctSign(const uint8_t *a_par, int a_rank, const uint8_t *b_par, int b_rank,
