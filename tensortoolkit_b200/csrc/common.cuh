@@ -15,7 +15,7 @@ namespace qlb200 {
 // The tile of a block spans TI elements of the source-fastest axis (`jin`, source stride 1) and TO
 // elements of the output-fastest axis (nd-1); all remaining axes enumerate tiles.  When the two
 // axes coincide (jin == nd-1) the block is a batch of contiguous runs ("row copy") and TO
-// enumerates the next-outer output axis instead.
+// enumerates the next-outer output axis instead -- unless the runs are short, see PermBlk::vec.
 // ------------------------------------------------------------------------------------------------
 constexpr int kPermMaxDims = 8;
 constexpr int kPermTileElems = 2048;   // elements staged in shared memory per tile
@@ -33,7 +33,10 @@ struct PermBlk {
   uint32_t txi_log2, txo_log2;          // log2 of the thread-row width used in the load / store phase
   uint32_t src_sel;                     // 0 = operand A buffer, 1 = operand B buffer
   float scale;                          // +1 / -1 (fermionic whole-tensor transpose), applied on the fly
-  uint32_t pad_;
+  uint32_t vec;                         // 0, or V = ext[nd-1]: "run" mode -- the fastest axis is the same on both sides but
+                                        // short (V elements); the tile is then a 2-D transposition of V-element runs:
+                                        // jin = source-next-fastest axis (source stride V, tiled by TI), jout = nd-2
+                                        // (destination stride V, tiled by TO); loads read TI*V, stores write TO*V contiguous
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -59,16 +59,17 @@ PermuteKernel(const PermBlk *__restrict__ blks, const uint32_t *__restrict__ til
     __syncthreads();
 
     uint32_t lt = tile - tile_base[b];
-    const uint32_t nd = sd.nd, jin = sd.jin, jout = sd.jout;
+    const uint32_t nd = sd.nd, jin = sd.jin, jout = sd.jout, V = sd.vec;
     const uint32_t ti0 = (lt % sd.nti) * sd.TI; lt /= sd.nti;
     const uint32_t to0 = (lt % sd.nto) * sd.TO; lt /= sd.nto;
-    unsigned long long so = sd.src_off + ti0, dofs = sd.dst_off + (unsigned long long) ti0 * sd.dstr[jin];
+    // sstr[jin] is 1 except in run mode, where jin is the axis behind the run in the source (stride V)
+    unsigned long long so = sd.src_off + (unsigned long long) ti0 * sd.sstr[jin], dofs = sd.dst_off + (unsigned long long) ti0 * sd.dstr[jin];
     if (jout != jin) {
       so += (unsigned long long) to0 * sd.sstr[jout];
       dofs += (unsigned long long) to0 * sd.dstr[jout];
     }
     for (int j = int(nd) - 1; j >= 0; --j) {
-      if (uint32_t(j) == jin || uint32_t(j) == jout) continue;
+      if (uint32_t(j) == jin || uint32_t(j) == jout || (V != 0u && uint32_t(j) == nd - 1)) continue;
       const uint32_t e = sd.ext[j];
       const uint32_t c = lt % e; lt /= e;
       so += (unsigned long long) c * sd.sstr[j];
@@ -81,7 +82,20 @@ PermuteKernel(const PermBlk *__restrict__ blks, const uint32_t *__restrict__ til
     const float scale = sd.scale;
     const uint32_t s_out = sd.sstr[jout], d_in = sd.dstr[jin], d_out = sd.dstr[jout];
 
-    if (jin == nd - 1) {
+    if (V != 0u) {
+      // run mode: TOa pieces of TIa*V contiguous source elements in, TIa pieces of TOa*V contiguous destination elements out
+      const uint32_t L = TIa * V, P = sd.TI * V + 1u, M = TOa * V;
+      for (uint32_t idx = tid; idx < TOa * L; idx += kPermThreads) {
+        const uint32_t to = idx / L, x = idx - to * L;
+        s[to * P + x] = src[(unsigned long long) to * s_out + x];
+      }
+      __syncthreads();
+      for (uint32_t idx = tid; idx < TIa * M; idx += kPermThreads) {
+        const uint32_t ti = idx / M, y = idx - ti * M;
+        const uint32_t to = y / V, v = y - to * V;
+        dst[(unsigned long long) ti * d_in + y] = ScaleBy(s[to * P + ti * V + v], scale);
+      }
+    } else if (jin == nd - 1) {
       // source-fastest axis is also destination-fastest: contiguous runs, no staging needed
       const uint32_t tx = tid & ((1u << sd.txi_log2) - 1u), ty = tid >> sd.txi_log2;
       const uint32_t TX = 1u << sd.txi_log2, RY = kPermThreads >> sd.txi_log2;

@@ -46,6 +46,36 @@ PermBlk MakePermBlk(int rank, const uint32_t *shape, const int32_t *perm, uint64
   uint32_t jin = nd - 1;
   for (int j = 0; j < nd; ++j) if (sst[j] == 1) jin = j;
   d.jin = jin;
+  constexpr uint32_t kVecMaxRun = 64;       // runs shorter than this are moved in groups (run mode)
+  if (jin == uint32_t(nd - 1) && nd >= 3 && d.ext[nd - 1] < kVecMaxRun) {
+    // Short runs shared by source and destination, e.g. (n1, k, n2) -> (k, n1, n2) with small n2: a tile of single runs
+    // would move a few hundred bytes per CTA iteration.  Transpose RUNS instead: js = the axis that follows the run in
+    // the source (stride V), jd = nd-2 follows it in the destination (stride V); a TI x TO tile of runs is read as TO
+    // contiguous pieces of TI*V elements and written as TI contiguous pieces of TO*V elements.
+    const uint32_t V = d.ext[nd - 1];
+    uint32_t js = 0;
+    for (int j = 0; j < nd - 1; ++j) if (sst[j] < sst[js]) js = uint32_t(j);
+    const uint32_t jd = uint32_t(nd - 2);
+    // js != jd: otherwise the two axes would have been merged above (dense block: the stride that follows V is V itself)
+    if (js != jd && sst[js] == V) {
+      d.vec = V; d.jin = js; d.jout = jd;
+      const uint32_t ei = d.ext[js], eo = d.ext[jd];
+      uint32_t side = 1;
+      while ((side + 1) * (side + 1) * V + (side + 1) <= kSmemCap) ++side;      // square-ish tile of runs
+      uint32_t TI = std::min(ei, side), TO = std::min(eo, side);
+      // a short axis leaves room for more of the other one
+      if (TI < side) TO = std::min<uint32_t>(eo, kSmemCap / (TI * V + 1));
+      else if (TO < side) TI = std::min<uint32_t>(ei, (kSmemCap / TO - 1) / V);
+      while ((TI * V + 1) * TO > kSmemCap) { if (TO > 1) --TO; else --TI; }
+      d.TI = TI; d.TO = TO;
+      d.nti = (ei + TI - 1) / TI; d.nto = (eo + TO - 1) / TO;
+      d.txi_log2 = d.txo_log2 = 0;
+      uint64_t nt = uint64_t(d.nti) * d.nto;
+      for (int j = 0; j < nd - 1; ++j) if (uint32_t(j) != js && uint32_t(j) != jd) nt *= d.ext[j];
+      *ntiles_out = nt;
+      return d;
+    }
+  }
   if (jin == uint32_t(nd - 1)) {            // contiguous runs on both sides
     d.jout = nd >= 2 ? nd - 2 : jin;
     d.TI = std::min<uint32_t>(d.ext[jin], 2048);
