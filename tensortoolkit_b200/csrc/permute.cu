@@ -34,6 +34,7 @@ PermuteKernel(const PermBlk *__restrict__ blks, const uint32_t *__restrict__ til
   T *s = reinterpret_cast<T *>(smem_raw);
   __shared__ PermBlk sd;
   __shared__ uint32_t s_blk;
+  __shared__ uint16_t s_off[kPermSmemElems];   // run mode: shared-memory offset of every element of a destination piece
   const int tid = threadIdx.x;
   uint32_t cur_blk = 0xffffffffu;
 
@@ -85,15 +86,27 @@ PermuteKernel(const PermBlk *__restrict__ blks, const uint32_t *__restrict__ til
     if (V != 0u) {
       // run mode: TOa pieces of TIa*V contiguous source elements in, TIa pieces of TOa*V contiguous destination elements out
       const uint32_t L = TIa * V, P = sd.TI * V + 1u, M = TOa * V;
-      for (uint32_t idx = tid; idx < TOa * L; idx += kPermThreads) {
-        const uint32_t to = idx / L, x = idx - to * L;
-        s[to * P + x] = src[(unsigned long long) to * s_out + x];
+      // index arithmetic without a division per element: each thread advances its (piece, offset) pair by the block
+      // size; the (to, v) decomposition of a destination offset comes from a small shared table
+      for (uint32_t y = tid; y < M; y += kPermThreads) { const uint32_t to = y / V; s_off[y] = uint16_t(to * P + (y - to * V)); }
+      {
+        const uint32_t q = kPermThreads / L, r = kPermThreads - q * L, total = TOa * L;
+        uint32_t to = tid / L, x = tid - to * L;
+        for (uint32_t idx = tid; idx < total; idx += kPermThreads) {
+          s[to * P + x] = src[(unsigned long long) to * s_out + x];
+          to += q; x += r;
+          if (x >= L) { x -= L; ++to; }
+        }
       }
       __syncthreads();
-      for (uint32_t idx = tid; idx < TIa * M; idx += kPermThreads) {
-        const uint32_t ti = idx / M, y = idx - ti * M;
-        const uint32_t to = y / V, v = y - to * V;
-        dst[(unsigned long long) ti * d_in + y] = ScaleBy(s[to * P + ti * V + v], scale);
+      {
+        const uint32_t q = kPermThreads / M, r = kPermThreads - q * M, total = TIa * M;
+        uint32_t ti = tid / M, y = tid - ti * M;
+        for (uint32_t idx = tid; idx < total; idx += kPermThreads) {
+          dst[(unsigned long long) ti * d_in + y] = ScaleBy(s[s_off[y] + ti * V], scale);
+          ti += q; y += r;
+          if (y >= M) { y -= M; ++ti; }
+        }
       }
     } else if (jin == nd - 1) {
       // source-fastest axis is also destination-fastest: contiguous runs, no staging needed
