@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--exchange", default="auto", choices=["auto", "multicast", "fused", "allgather"],
                     help="N>1: output exchange fused into the last GEMM's epilogue -- multimem.st through the NVSwitch multicast mapping "
                          "(multicast; auto picks it when the fabric offers it) or unicast peer stores (fused) -- or NCCL all-gather + unpack")
+    ap.add_argument("--tensors", default="", help="directory with lenv.qlten, psi.qlten, mpo1.qlten, mpo2.qlten, renv.qlten written by a "
+                                                  "TensorToolkit program (operator<<): run the H_eff apply on those tensors instead of synthetic ones")
+    ap.add_argument("--qn", default="U1QN", choices=["U1QN", "fU1QN", "U1U1QN", "fU1U1QN", "Z2QN", "fZ2QN"], help="quantum-number type of --tensors files")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel of an apply from the host instead of replaying one CUDA graph")
     ap.add_argument("--shard-of", default="", help="W:r -- time rank r's share of a W-GPU run on one GPU, no collective (tuning aid)")
     args = ap.parse_args()
@@ -115,6 +118,14 @@ class ClockSampler:
         pw = [v for v in (num(s[2]) for s in self.samples) if v is not None]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": num(self.samples[0][1]),
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+def load_tensors(directory, qn_name, dtype):
+    """Real tensors in the reference's file format (tensortoolkit_b200/qlten_io.py); indexes must chain like workloads.HEFF_STEPS."""
+    import tensortoolkit_b200 as tk
+    from tensortoolkit_b200 import qlten_io
+    kind = {k.name: k for k in (tk.U1, tk.fU1, tk.U1U1, tk.fU1U1, tk.Z2, tk.fZ2)}[qn_name]
+    return {name: qlten_io.load(os.path.join(directory, name + ".qlten"), kind, np_dtype(dtype)) for name in ("lenv", "psi", "mpo1", "mpo2", "renv")}
 
 
 def build_tensors(D, dtype, rng, workload="heff_u1"):
@@ -236,7 +247,7 @@ def run_ours(args):
     dtype = args.dtype
     es = 16 if dtype == "c128" else 8
     rng = np.random.default_rng(workload_seed(args.workload, dtype))
-    tensors = build_tensors(args.D, dtype, rng, args.workload)
+    tensors = load_tensors(args.tensors, args.qn, dtype) if args.tensors else build_tensors(args.D, dtype, rng, args.workload)
     sharded = None
     if args.shard_of:
         from tensortoolkit_b200.heff import ShardedChain
@@ -423,7 +434,7 @@ def run_ours(args):
         k["frac"] = k["achieved"] / (peak_burst if k["bound"] == "tensor" else hbm_peak)
 
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not args.tensors:
         try:
             # a clean child process (no torch / CUDA runtime threads competing with HPTT's and OpenBLAS's pools):
             # exactly what `bench.py --impl reference` measures
@@ -439,8 +450,8 @@ def run_ours(args):
     line = {
         "metric": "block-sparse contraction useful FP64 GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-        "vs_baseline": None, "dtype": "c64(f64 pairs)" if dtype == "c128" else "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.D, dtype, args.workload), "l2": "512 MiB flush written between timed applies; operands+intermediates (>1 GB) exceed the 126 MB L2",
+        "vs_baseline": None, "dtype": "c64(f64 pairs)" if dtype == "c128" else "f64", "data": "files" if args.tensors else "synthetic",
+        "config": {"workload": (f"H_eff apply on tensors read from {args.tensors} ({args.qn})" if args.tensors else workload_name(args.D, dtype, args.workload)), "l2": "512 MiB flush written between timed applies; operands+intermediates (>1 GB) exceed the 126 MB L2",
                    "parallelism": (f"output-sector/row-slab x{world}, exchange={sharded.exchange}" + {"fused": " (unicast peer stores over NVLink from the GEMM epilogue)", "multicast": " (multimem.st from the GEMM epilogue, replicated by the NVSwitch)"}.get(sharded.exchange, " (NCCL)")) if world > 1 else "single GPU", "flops_per_step": flops_total,
                    "tasks_per_step": int(sum(s.ntask for s in stats)),
                    "launch": "one CUDA graph replay per apply" if graph is not None else "one host launch per kernel"},

@@ -10,6 +10,7 @@
 // like a TensorToolkit user would (qlten::b200::Contract(&A, &B, axes, &C)).
 #include <cstdint>
 #include <cstring>
+#include <fstream>
 #include <chrono>
 #include <memory>
 #include <string>
@@ -81,6 +82,8 @@ struct TenBase {
   virtual TenBase *contract_1sector(int64_t axis, int64_t sct, const TenBase *b, int n, const int64_t *aa, const int64_t *ba) const = 0;
   virtual TenBase *contract_1sector_b200(int64_t axis, int64_t sct, const TenBase *b, int n, const int64_t *aa, const int64_t *ba, void *ctx) const = 0;
   virtual void transpose_b200(const int64_t *perm, void *ctx) = 0;
+  virtual int write_file(const char *path) const = 0;
+  virtual int read_file(const char *path) = 0;
   // side: 0 = <Tail, Head> (default), 1 = <Head, Head>, 2 = <Tail, Tail>, 3 = <Head, Tail>
   virtual TenBase *contract_contiguous(const TenBase *b, int64_t a_start, int64_t b_start, int64_t size, int side) const = 0;
   virtual TenBase *contract_contiguous_b200(const TenBase *b, int64_t a_start, int64_t b_start, int64_t size, int side, void *ctx) const = 0;
@@ -141,6 +144,19 @@ struct TenBox : TenBase {
     qlten::b200::Transpose(&t, o, (qlb200_ctx *) ctx);
   }
   double norm2() const override { return (double) t.Get2Norm(); }
+  int write_file(const char *path) const override {          // the reference's own stream format (operator<<)
+    std::ofstream ofs(path, std::ofstream::binary);
+    if (!ofs) return -1;
+    ofs << t;
+    return ofs ? 0 : -1;
+  }
+  int read_file(const char *path) override {                 // operator>> into a default tensor
+    std::ifstream ifs(path, std::ifstream::binary);
+    if (!ifs) return -1;
+    t = Ten();
+    ifs >> t;
+    return ifs ? 0 : -1;
+  }
   bool indexes_equal(const TenBase *o) const override { return t.GetIndexes() == cast(o)->t.GetIndexes(); }
   TenBase *wrap(Ten &&c) const { auto *p = new TenBox(); p->kind = kind; p->dtype = dtype; p->t = std::move(c); return p; }
   TenBase *contract(const TenBase *b, int n, const int64_t *aa, const int64_t *ba) const override {
@@ -310,6 +326,8 @@ void *qlref_b200_contract_1sector(const void *a, int64_t axis, int64_t sct, cons
     return static_cast<const TenBase *>(a)->contract_1sector_b200(axis, sct, static_cast<const TenBase *>(b), n, aa, ba, ctx);
   } catch (const std::exception &e) { std::fprintf(stderr, "qlref_b200_contract_1sector: %s\n", e.what()); return nullptr; }
 }
+int qlref_tensor_write(const void *t, const char *path) { return static_cast<const TenBase *>(t)->write_file(path); }
+int qlref_tensor_read(void *t, const char *path) { return static_cast<TenBase *>(t)->read_file(path); }
 void *qlref_contract_contiguous(const void *a, const void *b, int64_t a_start, int64_t b_start, int64_t size, int side) {
   return static_cast<const TenBase *>(a)->contract_contiguous(static_cast<const TenBase *>(b), a_start, b_start, size, side);
 }

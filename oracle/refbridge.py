@@ -60,6 +60,8 @@ def lib():
             "qlref_b200_contract": (_P, [_P, _P, C.c_int, _I64P, _I64P, _P]),
             "qlref_b200_contract_1sector": (_P, [_P, C.c_int64, C.c_int64, _P, C.c_int, _I64P, _I64P, _P]),
             "qlref_b200_transpose": (C.c_int, [_P, _I64P, _P]),
+            "qlref_tensor_write": (C.c_int, [_P, C.c_char_p]),
+            "qlref_tensor_read": (C.c_int, [_P, C.c_char_p]),
             "qlref_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
             "qlref_b200_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P]),
         }
@@ -112,6 +114,21 @@ class RefTensor:
 
     def clone(self) -> "RefTensor":
         return RefTensor(lib().qlref_tensor_clone(self.h), self.indexes, self.dtype)
+
+    def write_file(self, path: str):
+        """`ofstream << tensor`: the reference's stream format (qltensor_impl.h:823-833)."""
+        if lib().qlref_tensor_write(self.h, str(path).encode()) != 0:
+            raise RuntimeError("reference could not write " + str(path))
+
+    def read_file(self, path: str) -> "RefTensor":
+        """`ifstream >> tensor` into this handle (same QN kind / element type); the caller's index list is kept as the
+        expectation to compare against."""
+        if lib().qlref_tensor_read(self.h, str(path).encode()) != 0:
+            raise RuntimeError("reference could not read " + str(path))
+        return self
+
+    def indexes_equal(self, other: "RefTensor") -> bool:
+        return bool(lib().qlref_tensor_indexes_equal(self.h, other.h))
 
     def transpose(self, perm):
         lib().qlref_tensor_transpose(self.h, _i64(perm))

@@ -2,9 +2,10 @@
 (the qlten::Contract hot path of QuantumLiquids/TensorToolkit), behind the C ABI in include/qlb200.h.
 """
 from .tensor import (IN, OUT, QNKind, QNSector, Index, BlockSparseTensor, U1, fU1, U1U1, fU1U1, Z2, fZ2)
+from . import qlten_io
 from .contract import (Context, Match, ContractionPlan, RawPlan, contract, contract_1sector, contract_contiguous_axes, transpose,
                        default_context)
 
 __all__ = ["IN", "OUT", "QNKind", "QNSector", "Index", "BlockSparseTensor", "U1", "fU1", "U1U1", "fU1U1", "Z2", "fZ2",
            "Context", "Match", "ContractionPlan", "RawPlan", "contract", "contract_1sector", "contract_contiguous_axes",
-           "transpose", "default_context"]
+           "transpose", "default_context", "qlten_io"]
