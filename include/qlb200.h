@@ -188,6 +188,18 @@ typedef struct qlb200_plan_stats {
   uint64_t gemm_read_bytes, gemm_write_bytes;  /* (mk+kn)*s per task, mn*s per C block */
 } qlb200_plan_stats;
 int qlb200_plan_get_stats(const qlb200_plan *p, qlb200_plan_stats *out);
+/* The DMMA work-unit list in launch order (introspection for tests / tuning): a unit is the k-stage range
+ * [s_begin, s_end) of output tile (tm, tn) of one output block; a tile cut along k has nsplit units (split = its slot).
+ * Geometry of the plan's kernel: tile rows x cols and k elements per stage.  Returns the number of units; fills at
+ * most `cap` entries. */
+typedef struct qlb200_unit {
+  uint32_t group, tm, tn;          /* output block (ordinal among the plan's output blocks), tile coordinates */
+  uint32_t s_begin, s_end;         /* k-stage range */
+  uint32_t split, nsplit;
+  uint32_t rows, cols;             /* valid extent of the tile inside the (partitioned) block */
+} qlb200_unit;
+uint64_t qlb200_plan_units(const qlb200_plan *p, uint64_t cap, qlb200_unit *out, uint32_t *tile_rows, uint32_t *tile_cols,
+                           uint32_t *stage_k);
 
 /* C = contract(A, B).  C must hold c_elems elements (uninitialised is fine).  With
  * QLB200_MEM_HOST the call stages A, B through device memory and copies C back, then

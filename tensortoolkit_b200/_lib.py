@@ -55,6 +55,11 @@ class PlanStats(C.Structure):
     ]
 
 
+class Unit(C.Structure):
+    _fields_ = [("group", C.c_uint32), ("tm", C.c_uint32), ("tn", C.c_uint32), ("s_begin", C.c_uint32), ("s_end", C.c_uint32),
+                ("split", C.c_uint32), ("nsplit", C.c_uint32), ("rows", C.c_uint32), ("cols", C.c_uint32)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/qlb200.h
 _P = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
@@ -100,6 +105,7 @@ SYMBOLS = {
     "qlb200_plan_c_range_count": (C.c_uint64, [_P]),
     "qlb200_plan_c_ranges": (C.c_int, [_P, _U64P, _U64P]),
     "qlb200_plan_get_stats": (C.c_int, [_P, C.POINTER(PlanStats)]),
+    "qlb200_plan_units": (C.c_uint64, [_P, C.c_uint64, C.POINTER(Unit), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "qlb200_execute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "qlb200_execute_permute": (C.c_int, [_P, _P, _P, _P]),
     "qlb200_execute_gemm": (C.c_int, [_P, _P, _P, _P, _P]),

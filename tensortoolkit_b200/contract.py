@@ -181,6 +181,14 @@ class ContractionPlan:
     def execute_host(self, a: np.ndarray, b: np.ndarray, c: np.ndarray):
         check(lib.qlb200_execute(self.ctx.h, self.h, a.ctypes.data, b.ctypes.data, c.ctypes.data, _lib.MEM_HOST), "qlb200_execute")
 
+    def units(self):
+        """(list of work units in launch order, (tile rows, tile cols, k per stage)) -- qlb200_plan_units."""
+        n = int(lib.qlb200_plan_units(self.h, 0, None, None, None, None))
+        arr = (_lib.Unit * max(n, 1))()
+        bm, bn, bk = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        lib.qlb200_plan_units(self.h, n, arr, C.byref(bm), C.byref(bn), C.byref(bk))
+        return [arr[i] for i in range(n)], (bm.value, bn.value, bk.value)
+
     def execute_device(self, a_ptr: int, b_ptr: int, c_ptr: int):
         check(lib.qlb200_execute(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(c_ptr), _lib.MEM_DEVICE),
               "qlb200_execute")

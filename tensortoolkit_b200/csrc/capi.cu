@@ -385,6 +385,28 @@ int qlb200_plan_get_stats(const qlb200_plan *p, qlb200_plan_stats *out) {
   return QLB200_OK;
 }
 
+uint64_t qlb200_plan_units(const qlb200_plan *p, uint64_t cap, qlb200_unit *out, uint32_t *tile_rows, uint32_t *tile_cols,
+                           uint32_t *stage_k) {
+  if (!p) return 0;
+  const bool legacy = (p->h.flags & QLB200_PLAN_LEGACY_GEMM) != 0, four_m = (p->h.flags & QLB200_PLAN_CPLX_4M) != 0;
+  uint32_t BM, BN, BK;
+  if (p->h.dtype == QLB200_C64) { BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : (four_m ? kWsBN : kWs3mBN); BK = legacy ? kCplxBK : (four_m ? kWsBK : kWs3mBK); }
+  else { BM = legacy ? kRealBM : kWsRealBM; BN = legacy ? kRealBN : kWsRealBN; BK = legacy ? kRealBK : kWsRealBK; }
+  if (tile_rows) *tile_rows = BM;
+  if (tile_cols) *tile_cols = BN;
+  if (stage_k) *stage_k = BK;
+  const uint64_t n = p->h.tiles.size();
+  for (uint64_t i = 0; i < n && i < cap && out; ++i) {
+    const GemmTile &t = p->h.tiles[i];
+    const GemmGroup &g = p->h.part_groups[t.group];
+    qlb200_unit &u = out[i];
+    u.group = t.group; u.tm = t.tm; u.tn = t.tn; u.s_begin = t.s_begin; u.s_end = t.s_end; u.split = t.split; u.nsplit = t.nsplit;
+    u.rows = std::min<uint32_t>(BM, g.row_end - g.row_begin - uint32_t(t.tm) * BM);
+    u.cols = std::min<uint32_t>(BN, g.n - uint32_t(t.tn) * BN);
+  }
+  return n;
+}
+
 // ---- execution ---------------------------------------------------------------------------------
 static int ResolveWorkspace(qlb200_ctx *ctx, qlb200_plan *p, void **wsA, void **wsB, void **partials = nullptr) {
   const size_t es = ElemSize(p->h.dtype);

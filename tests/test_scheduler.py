@@ -1,0 +1,113 @@
+"""Work-unit lists of the grouped GEMM (host side, no GPU): whatever the tiler does -- LPT order, split-K chosen by the
+simulated schedule, forced cuts for staggered output, row-slab partitions -- every output element must be produced by
+exactly one tile, every tile's k loop covered exactly once by its units in slot order, and the launch order must be
+costliest first.  (The kernels that consume these lists are covered by the GPU parity tests.)"""
+import numpy as np
+import pytest
+
+import tensortoolkit_b200 as tk
+from tensortoolkit_b200 import _lib, workloads as wl
+
+
+def heff_matches(ix, dtype):
+    rng = np.random.default_rng(2)
+    ti = wl.heff_tensor_indexes(ix)
+    div = (0,) * ti["psi"][0].kind.nvals
+    shells = {n: tk.BlockSparseTensor(i, dtype).random(div, rng) for n, i in ti.items()}
+    out = []
+    for lhs, rhs, axes, res in wl.HEFF_STEPS:
+        m = tk.Match(shells[lhs], shells[rhs], axes)
+        shells[res] = m.result_shell(dtype)
+        out.append(m)
+    return out
+
+
+def check_units(plan, match, dtype):
+    units, (bm, bn, bk) = plan.units()
+    if not units:
+        return 0
+    tasks = match.tasks(sorted_by_c=True)
+    stages, shape = {}, {}
+    for t in tasks:                               # k loop of an output block = its pairs' k loops back to back, in stages of bk
+        stages[t.c_ord] = stages.get(t.c_ord, 0) + -(-int(t.k) // bk)
+        shape[t.c_ord] = (int(t.m), int(t.n))
+    # groups are numbered like the output blocks that have DMMA work; map through (rows, cols) coverage instead of ids
+    by_tile = {}
+    for u in units:
+        by_tile.setdefault((u.group, u.tm, u.tn), []).append(u)
+    cover = {}
+    for (g, tm, tn), us in by_tile.items():
+        us = sorted(us, key=lambda u: u.split)
+        assert [u.split for u in us] == list(range(len(us))) and all(u.nsplit == len(us) for u in us)
+        assert us[0].s_begin == 0
+        for a, b in zip(us, us[1:]):
+            assert a.s_end == b.s_begin and a.s_end > a.s_begin      # contiguous, non-empty, slot order == k order
+        assert us[-1].s_end > us[-1].s_begin
+        assert 1 <= us[0].rows <= bm and 1 <= us[0].cols <= bn
+        cover.setdefault(g, {"stages": us[-1].s_end, "tiles": set(), "elems": 0})
+        assert cover[g]["stages"] == us[-1].s_end                    # every tile of a block walks the same k loop
+        assert (tm, tn) not in cover[g]["tiles"]
+        cover[g]["tiles"].add((tm, tn))
+        cover[g]["elems"] += us[0].rows * us[0].cols
+    # launch order: costliest first (k-loop length x issued share of the tile), ties keep generation order
+    def cost(u):
+        mt, nt = -(-u.rows // 8), -(-(-(-u.cols // 8)) // 4)
+        return (u.s_end - u.s_begin) * mt * nt
+    costs = [cost(u) for u in units]
+    assert all(a >= b for a, b in zip(costs, costs[1:]))
+    return sum(c["elems"] for c in cover.values())
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
+@pytest.mark.parametrize("flags", [0, _lib.PLAN_STAGGER_OUTPUT, _lib.PLAN_NO_SPLIT_K, _lib.PLAN_CPLX_4M, _lib.PLAN_NO_SKINNY | _lib.PLAN_STAGGER_OUTPUT])
+@pytest.mark.parametrize("workload", ["u1_300", "u1_1500", "hubbard_200"])
+def test_units_cover_every_tile_once(workload, flags, dtype):
+    ix = {"u1_300": lambda: wl.u1_heisenberg_indexes(300), "u1_1500": lambda: wl.u1_heisenberg_indexes(1500),
+          "hubbard_200": lambda: wl.hubbard_indexes(200)}[workload]()
+    for m in heff_matches(ix, dtype):
+        plan = tk.ContractionPlan(None, m, dtype, _lib.PLAN_DETERMINISTIC | flags)
+        st = plan.stats()
+        covered = check_units(plan, m, dtype)
+        if st.nrow_skinny == 0 and st.ntile_dmma:
+            assert covered == m.c_elems                              # all of C comes from DMMA tiles
+        plan.close(); m.close()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_partitioned_units_tile_the_rank_slabs(world):
+    """Row-slab partitions (multi-GPU): the ranks' tiles cover disjoint rows that add up to the whole result."""
+    (m, *rest) = heff_matches(wl.u1_heisenberg_indexes(1200), np.complex128)
+    total = 0
+    for rank in range(world):
+        plan = tk.ContractionPlan(None, m, np.complex128, _lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY | _lib.PLAN_STAGGER_OUTPUT)
+        plan.partition(world, rank)
+        total += check_units(plan, m, np.complex128)
+        off, ln = plan.c_ranges()
+        assert sum(int(x) for x in ln) > 0 or world > 4
+        plan.close()
+    assert total == m.c_elems
+    for x in [m] + rest:
+        x.close()
+
+
+def test_stagger_cuts_long_loops_and_keeps_a_tile_together():
+    """QLB200_PLAN_STAGGER_OUTPUT: long k loops are cut into about four units, queued back to back."""
+    (*rest, m) = heff_matches(wl.u1_heisenberg_indexes(2048), np.complex128)      # the last step: k runs over (wb, vb)
+    plain = tk.ContractionPlan(None, m, np.complex128, _lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SPLIT_K)
+    stag = tk.ContractionPlan(None, m, np.complex128, _lib.PLAN_DETERMINISTIC | _lib.PLAN_STAGGER_OUTPUT)
+    up, _ = plain.units()
+    us, _ = stag.units()
+    longest = max(u.s_end for u in up)
+    assert all(u.nsplit == 1 for u in up)
+    assert longest > 32
+    assert max(u.nsplit for u in us) >= 4 and max(u.s_end - u.s_begin for u in us) <= max(8, -(-longest // 4)) + 1
+    pos = {}
+    for i, u in enumerate(us):
+        pos.setdefault((u.group, u.tm, u.tn), []).append(i)
+    for idxs in pos.values():                                       # equal-cost units of one tile stay adjacent (stable order)
+        lens = {us[i].s_end - us[i].s_begin for i in idxs}
+        if len(lens) == 1:
+            assert idxs == list(range(idxs[0], idxs[0] + len(idxs)))
+    plain.close(); stag.close()
+    for x in [m] + rest:
+        x.close()
