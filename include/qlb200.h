@@ -159,6 +159,12 @@ int qlb200_host_unregister(void *p);
 #define QLB200_PLAN_STAGGER_OUTPUT 64u /* cut every long k loop into ~4 units queued back to back, so that output tiles complete
                                          throughout the launch instead of all at its end: lets a fused multi-GPU exchange
                                          (execute_bcast / execute_mcast) overlap the NVLink transfer with the remaining math */
+#define QLB200_PLAN_STREAM_K 128u      /* stream-K schedule: the tiles' k loops, laid end to end, are cut into one equal-cost
+                                         segment per resident CTA (static assignment); a tile that straddles a cut is split
+                                         and finished by the deterministic split-K fix-up.  Opt-in experiment: balances to within 2 % on paper
+                                         but measured SLOWER than the default weighted-LPT list on the 8-way shards of the headline
+                                         workload (0.60 / 0.63 ms vs 0.54 / 0.57 ms per GEMM step): ~2 partial tiles per CTA cost
+                                         more than the imbalance they remove. */
 #define QLB200_PLAN_NO_SPLIT_K 16u     /* never cut a tile's k loop into several units (testing / tuning) */
 #define QLB200_PLAN_PERMUTE_ALL 8u     /* send every block of a transposed operand through the permute kernel
                                           (default: blocks whose permutation is trivial or one 2-D transposition
@@ -200,6 +206,9 @@ typedef struct qlb200_unit {
 } qlb200_unit;
 uint64_t qlb200_plan_units(const qlb200_plan *p, uint64_t cap, qlb200_unit *out, uint32_t *tile_rows, uint32_t *tile_cols,
                            uint32_t *stage_k);
+/* QLB200_PLAN_STREAM_K plans: CTA b runs units [seg[b], seg[b+1]).  Returns the number of table entries (CTAs + 1; 0 for
+ * plans whose units are pulled dynamically); fills at most `cap`. */
+uint64_t qlb200_plan_segments(const qlb200_plan *p, uint64_t cap, uint32_t *seg_out);
 
 /* C = contract(A, B).  C must hold c_elems elements (uninitialised is fine).  With
  * QLB200_MEM_HOST the call stages A, B through device memory and copies C back, then

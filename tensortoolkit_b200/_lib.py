@@ -14,7 +14,7 @@ OK = 0
 F64, C64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 DIR_IN, DIR_OUT = -1, 1
-PLAN_DETERMINISTIC, PLAN_NO_SKINNY, PLAN_LEGACY_GEMM, PLAN_PERMUTE_ALL, PLAN_NO_SPLIT_K, PLAN_CPLX_4M, PLAN_STAGGER_OUTPUT = 1, 2, 4, 8, 16, 32, 64
+PLAN_DETERMINISTIC, PLAN_NO_SKINNY, PLAN_LEGACY_GEMM, PLAN_PERMUTE_ALL, PLAN_NO_SPLIT_K, PLAN_CPLX_4M, PLAN_STAGGER_OUTPUT, PLAN_STREAM_K = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 class Shell(C.Structure):
@@ -106,6 +106,7 @@ SYMBOLS = {
     "qlb200_plan_c_ranges": (C.c_int, [_P, _U64P, _U64P]),
     "qlb200_plan_get_stats": (C.c_int, [_P, C.POINTER(PlanStats)]),
     "qlb200_plan_units": (C.c_uint64, [_P, C.c_uint64, C.POINTER(Unit), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "qlb200_plan_segments": (C.c_uint64, [_P, C.c_uint64, C.POINTER(C.c_uint32)]),
     "qlb200_execute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "qlb200_execute_permute": (C.c_int, [_P, _P, _P, _P]),
     "qlb200_execute_gemm": (C.c_int, [_P, _P, _P, _P, _P]),

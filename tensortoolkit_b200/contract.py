@@ -189,6 +189,13 @@ class ContractionPlan:
         lib.qlb200_plan_units(self.h, n, arr, C.byref(bm), C.byref(bn), C.byref(bk))
         return [arr[i] for i in range(n)], (bm.value, bn.value, bk.value)
 
+    def segments(self):
+        """Stream-K plans: unit range boundaries per CTA (qlb200_plan_segments); [] for dynamically scheduled plans."""
+        n = int(lib.qlb200_plan_segments(self.h, 0, None))
+        arr = (C.c_uint32 * max(n, 1))()
+        lib.qlb200_plan_segments(self.h, n, arr)
+        return [int(arr[i]) for i in range(n)]
+
     def execute_device(self, a_ptr: int, b_ptr: int, c_ptr: int):
         check(lib.qlb200_execute(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(c_ptr), _lib.MEM_DEVICE),
               "qlb200_execute")

@@ -56,6 +56,8 @@ int UploadGemmTables(qlb200_plan *p) {
   if (p->d.groups) { cudaFree(p->d.groups); p->d.groups = nullptr; }
   if (p->d.tiles) { cudaFree(p->d.tiles); p->d.tiles = nullptr; }
   if (p->d.items) { cudaFree(p->d.items); p->d.items = nullptr; }
+  if (p->d.seg) { cudaFree(p->d.seg); p->d.seg = nullptr; }
+  if ((rc = Upload(p->h.seg, &p->d.seg, s)) != QLB200_OK) return rc;
   if ((rc = Upload(p->h.part_groups, &p->d.groups, s)) != QLB200_OK) return rc;
   if ((rc = Upload(p->h.tiles, &p->d.tiles, s)) != QLB200_OK) return rc;
   if ((rc = Upload(p->h.items, &p->d.items, s)) != QLB200_OK) return rc;
@@ -87,6 +89,8 @@ GemmParams MakeParams(const qlb200_plan *p, const void *A, const void *B, const 
   gp.tasks = p->d.tasks; gp.groups = p->d.groups; gp.tiles = p->d.tiles; gp.items = p->d.items;
   gp.ntiles = static_cast<uint32_t>(p->h.tiles.size());
   gp.nitems = static_cast<uint32_t>(p->h.items.size());
+  gp.seg = p->h.seg.empty() ? nullptr : p->d.seg;
+  gp.nseg = p->h.seg.empty() ? 0u : static_cast<uint32_t>(p->h.seg.size() - 1);
   gp.counters = p->d.counters;
   return gp;
 }
@@ -105,9 +109,9 @@ size_t WsBytes(const qlb200_plan *p) {
 
 void qlb200::DeviceTables::Free() {
   cudaFree(perm_blks); cudaFree(perm_tile_base); cudaFree(tasks); cudaFree(groups); cudaFree(tiles);
-  cudaFree(items); cudaFree(counters);
+  cudaFree(items); cudaFree(counters); cudaFree(seg);
   perm_blks = nullptr; perm_tile_base = nullptr; tasks = nullptr; groups = nullptr; tiles = nullptr;
-  items = nullptr; counters = nullptr;
+  items = nullptr; counters = nullptr; seg = nullptr;
 }
 
 extern "C" {
@@ -405,6 +409,12 @@ uint64_t qlb200_plan_units(const qlb200_plan *p, uint64_t cap, qlb200_unit *out,
     u.cols = std::min<uint32_t>(BN, g.n - uint32_t(t.tn) * BN);
   }
   return n;
+}
+
+uint64_t qlb200_plan_segments(const qlb200_plan *p, uint64_t cap, uint32_t *seg_out) {
+  if (!p) return 0;
+  for (uint64_t i = 0; i < p->h.seg.size() && i < cap && seg_out; ++i) seg_out[i] = p->h.seg[i];
+  return p->h.seg.size();
 }
 
 // ---- execution ---------------------------------------------------------------------------------

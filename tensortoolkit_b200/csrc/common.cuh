@@ -92,6 +92,8 @@ struct GemmParams {
   const GemmTile *tiles;
   const SkinnyItem *items;
   uint32_t ntiles, nitems;
+  const uint32_t *seg;              // stream-K: CTA b runs units [seg[b], seg[b+1]) (nullptr: units are pulled from counters[0])
+  uint32_t nseg;
   unsigned int *counters;           // [0] next tile, [1] finished CTAs, [2 + ctr] split-K arrivals (all self-resetting)
   void *partials;                   // split-K partial tiles, slot = BM x BN elements
 };

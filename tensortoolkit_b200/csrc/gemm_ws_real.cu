@@ -122,7 +122,16 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
     const uint32_t a_kc = lane & 15, a_r = lane >> 4;
     uint32_t it = 0, tcount = 0;
     for (;; ++tcount) {
-      if (pw == 0 && lane == 0) s_tile[tcount & 1u] = atomicAdd(&p.counters[0], 1u);
+      if (pw == 0 && lane == 0) {
+        uint32_t id;
+        if (p.seg != nullptr) {      // stream-K: this CTA owns the units [seg[b], seg[b+1])
+          const uint32_t u = p.seg[blockIdx.x] + tcount;
+          id = u < p.seg[blockIdx.x + 1] ? u : p.ntiles;
+        } else {
+          id = atomicAdd(&p.counters[0], 1u);
+        }
+        s_tile[tcount & 1u] = id;
+      }
       ProducerBarrier();
       const uint32_t tile_id = s_tile[tcount & 1u];
       if (tile_id >= p.ntiles) break;
@@ -310,7 +319,7 @@ cudaError_t ConfigureWsRealKernel() {
 cudaError_t LaunchGemmWsReal(const GemmParams &p, int num_sms, cudaStream_t stream) {
   if (p.ntiles == 0) return cudaSuccess;
   const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
-  const uint32_t grid = p.ntiles < cap ? p.ntiles : cap;
+  const uint32_t grid = p.seg != nullptr ? p.nseg : (p.ntiles < cap ? p.ntiles : cap);
   GemmWsReal<<<grid, kWsThreads, kRealWsSmem, stream>>>(p);
   return cudaGetLastError();
 }

@@ -2,6 +2,7 @@
 // tile lists, multi-GPU row partition).  No reference counterpart: the reference walks tasks one
 // by one (global_operations.h:919-982); here the whole contraction is flattened into tables once.
 #include "plan.h"
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -307,7 +308,7 @@ GroupClass Classify(const PlanHost *h, const GemmGroup &g, int bk) {
 }  // namespace
 
 std::string BuildTiles(PlanHost *h) {
-  h->tiles.clear(); h->items.clear();
+  h->tiles.clear(); h->items.clear(); h->seg.clear();
   h->n_split_ctrs = 0; h->n_part_slots = 0;
   const bool legacy = (h->flags & QLB200_PLAN_LEGACY_GEMM) != 0;
   int BM, BN, BK;
@@ -396,6 +397,86 @@ std::string BuildTiles(PlanHost *h) {
     uint32_t longest = 0;
     for (const GInfo &d : dm) longest = std::max(longest, d.stages);
     chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(8, (longest + 3) / 4));
+  }
+  if (!legacy && !dm.empty() && (h->flags & QLB200_PLAN_STREAM_K) && !(h->flags & QLB200_PLAN_NO_SPLIT_K)) {
+    // Stream-K.  Tiles in block order (neighbours share operand panels in L2), their k loops laid end to end and weighted
+    // by the share of MMA groups a tile issues; the line is cut into one equal-cost segment per resident CTA and CTA b runs
+    // segment b (GemmParams::seg).  A tile that straddles a cut becomes 2+ units finished by the split-K fix-up; cuts that
+    // would leave a piece shorter than kMinPiece stages snap to the tile boundary instead.
+    constexpr uint32_t kMinPiece = 4;
+    struct TileRef { uint32_t dm_idx, i, j; double w; };
+    std::vector<TileRef> order;
+    double W = 0;
+    for (uint32_t x = 0; x < dm.size(); ++x)
+      for (uint32_t i = 0; i < dm[x].tm; ++i)
+        for (uint32_t j = 0; j < dm[x].tn; ++j) {
+          const double w = tile_weight(dm[x], i, j);
+          order.push_back({x, i, j, w});
+          W += w * dm[x].stages;
+        }
+    // one segment per resident CTA, fewer only when the whole launch is tiny
+    const uint32_t nseg = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(slots, uint64_t(W / (2.0 * kMinPiece)))));
+    double share = W / nseg, placed = 0;     // the share is re-derived from what is left whenever a segment closes
+    h->seg.assign(1, 0u);
+    double acc = 0;                 // cost already placed in the open segment
+    uint32_t closed = 0;            // segments closed so far (the last one takes whatever is left)
+    struct Piece { uint32_t end; bool closes; };
+    std::vector<Piece> pieces;
+    for (const TileRef &tr : order) {
+      const GInfo &d = dm[tr.dm_idx];
+      pieces.clear();
+      uint32_t pos = 0;
+      while (pos < d.stages) {
+        const bool final_seg = closed + 1 >= nseg;
+        const uint32_t rest = d.stages - pos;
+        uint32_t take = rest;
+        if (!final_seg) {
+          const double room = share - acc;
+          const double want = room > 0 ? std::floor(room / tr.w + 0.5) : 0.0;
+          if (want < double(rest)) {
+            take = uint32_t(want);
+            if (take < kMinPiece) {
+              if (pos == 0 && acc > 0) {              // the open segment is (almost) full: the tile starts the next one
+                h->seg.push_back(uint32_t(h->tiles.size()));
+                ++closed; acc = 0;
+                share = (W - placed) / double(nseg - closed);
+                continue;
+              }
+              take = std::min(kMinPiece, rest);
+            }
+            if (rest - take < kMinPiece) take = rest;  // no tiny tail piece either
+          }
+        }
+        pos += take;
+        acc += tr.w * take;
+        placed += tr.w * take;
+        const bool closes = !final_seg && acc + 0.5 * tr.w >= share;
+        pieces.push_back({pos, closes});
+        if (closes) { ++closed; acc = 0; share = (W - placed) / double(nseg - closed); }
+      }
+      const uint32_t nsplit = uint32_t(pieces.size());
+      if (nsplit > 0xffffu) return "k loop cut into too many units";
+      GemmTile t;
+      std::memset(&t, 0, sizeof(t));
+      t.group = d.gi; t.tm = uint16_t(tr.i); t.tn = uint16_t(tr.j); t.nsplit = uint16_t(nsplit);
+      if (nsplit > 1) {
+        t.ctr = h->n_split_ctrs++;
+        t.part_base = static_cast<uint32_t>(h->n_part_slots);
+        h->n_part_slots += nsplit;
+      }
+      uint32_t begin = 0;
+      for (uint32_t sp = 0; sp < nsplit; ++sp) {
+        t.split = uint16_t(sp);
+        t.s_begin = begin; t.s_end = pieces[sp].end;
+        begin = pieces[sp].end;
+        h->tiles.push_back(t);
+        if (pieces[sp].closes) h->seg.push_back(uint32_t(h->tiles.size()));
+      }
+    }
+    if (h->seg.back() != h->tiles.size()) h->seg.push_back(uint32_t(h->tiles.size()));
+    if (h->n_part_slots >= (1ull << 32)) return "too many split-K slots";
+    if (h->tiles.size() >= (1ull << 32) || h->items.size() >= (1ull << 32)) return "too many tiles";
+    return "";
   }
   if (const char *ov = std::getenv("QLB200_SPLIT_CHUNK")) {      // tuning aid: force the split-K cut length (stages)
     const long long v = std::atoll(ov);

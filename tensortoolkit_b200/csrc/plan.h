@@ -33,6 +33,7 @@ struct DeviceTables {
   GemmGroup *groups = nullptr;
   GemmTile *tiles = nullptr;
   SkinnyItem *items = nullptr;
+  uint32_t *seg = nullptr;
   unsigned int *counters = nullptr;
   void Free();
 };
@@ -51,6 +52,7 @@ struct PlanHost {
   std::vector<uint64_t> group_ksum;
   std::vector<GemmGroup> part_groups;                  // row ranges after partitioning
   std::vector<GemmTile> tiles;
+  std::vector<uint32_t> seg;                           // stream-K: unit range of every CTA ([nseg + 1]); empty = dynamic
   uint32_t n_split_ctrs = 0;                           // split-K tiles (one arrival counter each)
   uint64_t n_part_slots = 0;                           // split-K partial-tile slots
   uint64_t part_slot_elems = 0;                        // elements per slot (BM x BN)

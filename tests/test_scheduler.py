@@ -22,7 +22,7 @@ def heff_matches(ix, dtype):
     return out
 
 
-def check_units(plan, match, dtype):
+def check_units(plan, match, dtype, stream_k=False):
     units, (bm, bn, bk) = plan.units()
     if not units:
         return 0
@@ -49,6 +49,8 @@ def check_units(plan, match, dtype):
         assert (tm, tn) not in cover[g]["tiles"]
         cover[g]["tiles"].add((tm, tn))
         cover[g]["elems"] += us[0].rows * us[0].cols
+    if stream_k:
+        return sum(c["elems"] for c in cover.values())
     # launch order: costliest first (k-loop length x issued share of the tile), ties keep generation order
     def cost(u):
         mt, nt = -(-u.rows // 8), -(-(-(-u.cols // 8)) // 4)
@@ -59,7 +61,8 @@ def check_units(plan, match, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.complex128, np.float64])
-@pytest.mark.parametrize("flags", [0, _lib.PLAN_STAGGER_OUTPUT, _lib.PLAN_NO_SPLIT_K, _lib.PLAN_CPLX_4M, _lib.PLAN_NO_SKINNY | _lib.PLAN_STAGGER_OUTPUT])
+@pytest.mark.parametrize("flags", [0, _lib.PLAN_STAGGER_OUTPUT, _lib.PLAN_NO_SPLIT_K, _lib.PLAN_CPLX_4M, _lib.PLAN_NO_SKINNY | _lib.PLAN_STAGGER_OUTPUT,
+                                   _lib.PLAN_STREAM_K, _lib.PLAN_STREAM_K | _lib.PLAN_CPLX_4M | _lib.PLAN_NO_SKINNY])
 @pytest.mark.parametrize("workload", ["u1_300", "u1_1500", "hubbard_200"])
 def test_units_cover_every_tile_once(workload, flags, dtype):
     ix = {"u1_300": lambda: wl.u1_heisenberg_indexes(300), "u1_1500": lambda: wl.u1_heisenberg_indexes(1500),
@@ -67,7 +70,7 @@ def test_units_cover_every_tile_once(workload, flags, dtype):
     for m in heff_matches(ix, dtype):
         plan = tk.ContractionPlan(None, m, dtype, _lib.PLAN_DETERMINISTIC | flags)
         st = plan.stats()
-        covered = check_units(plan, m, dtype)
+        covered = check_units(plan, m, dtype, stream_k=bool(flags & _lib.PLAN_STREAM_K))
         if st.nrow_skinny == 0 and st.ntile_dmma:
             assert covered == m.c_elems                              # all of C comes from DMMA tiles
         plan.close(); m.close()
@@ -111,3 +114,40 @@ def test_stagger_cuts_long_loops_and_keeps_a_tile_together():
     plain.close(); stag.close()
     for x in [m] + rest:
         x.close()
+
+
+def unit_cost(u):
+    mt, nt = -(-u.rows // 8), -(-(-(-u.cols // 8)) // 4)
+    return (u.s_end - u.s_begin) * mt * nt
+
+
+@pytest.mark.parametrize("world,rank", [(1, 0), (8, 1), (8, 4)])
+def test_stream_k_segments_are_balanced(world, rank):
+    """QLB200_PLAN_STREAM_K: one contiguous unit range per resident CTA, in order, covering every unit; the costliest
+    segment stays within a few percent of the mean, where the default LPT list of whole tiles cannot when there are
+    about as many equal tiles as CTA slots (the 8-GPU shards of the headline workload)."""
+    from tensortoolkit_b200.sharding import shard_chain
+    rng = np.random.default_rng(5)
+    ti = wl.heff_tensor_indexes(wl.u1_heisenberg_indexes(4096))
+    t = {n: tk.BlockSparseTensor(i, np.complex128) for n, i in ti.items()}
+    for n in t:                                            # structure only: block lists without touching 100 MB of data
+        t[n].set_blocks(t[n].div_blocks((0,)))
+    if world > 1:
+        t, _ = shard_chain(t, wl.HEFF_STEPS, "lenv", 2, world, rank, np.complex128)
+    shells = dict(t)
+    for step, (lhs, rhs, axes, res) in enumerate(wl.HEFF_STEPS):
+        m = tk.Match(shells[lhs], shells[rhs], axes)
+        shells[res] = m.result_shell(np.complex128)
+        if step in (0, 3):
+            sk = tk.ContractionPlan(None, m, np.complex128, _lib.PLAN_DETERMINISTIC | _lib.PLAN_STREAM_K)
+            units, _ = sk.units()
+            seg = sk.segments()
+            assert seg[0] == 0 and seg[-1] == len(units) and all(a < b for a, b in zip(seg, seg[1:]))
+            assert len(seg) - 1 <= 296
+            costs = [sum(unit_cost(u) for u in units[a:b]) for a, b in zip(seg, seg[1:])]
+            mean = sum(costs) / 296.0
+            assert max(costs) <= 1.06 * mean, (step, max(costs) / mean)
+            # at most two cut tiles per segment boundary: the fix-up traffic stays small
+            assert sum(1 for u in units if u.nsplit > 1) <= 3 * len(costs)
+            sk.close()
+        m.close()
