@@ -16,6 +16,7 @@
 #include "matcher.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <unordered_map>
 
@@ -219,7 +220,9 @@ std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrc
   uint64_t key_span = 1;
   for (int ax : m.a_ctrct) key_span *= A.nsct[ax];
   constexpr uint64_t kDenseLimit = 1u << 22;
-  const bool dense_keys = key_span <= kDenseLimit;
+  // QLB200_MATCH_NO_DENSE=1 forces the large-sector-space code paths (tests)
+  const bool allow_dense = std::getenv("QLB200_MATCH_NO_DENSE") == nullptr;
+  const bool dense_keys = allow_dense && key_span <= kDenseLimit;
   std::vector<uint32_t> bucket_begin;      // [key_span + 1] when dense
   if (dense_keys) {
     bucket_begin.assign(key_span + 1, 0);
@@ -238,7 +241,7 @@ std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrc
   // c_blk_idx -> "already created": a bitmap over C's block-index space when that is small, else a hash set
   unsigned __int128 c_span128 = 1;
   for (uint32_t n : m.c_nsct) c_span128 *= n;
-  const bool dense_c = c_span128 <= (static_cast<unsigned __int128>(1) << 27);
+  const bool dense_c = allow_dense && c_span128 <= (static_cast<unsigned __int128>(1) << 27);
   std::vector<uint64_t> c_bitmap(dense_c ? (static_cast<uint64_t>(c_span128) + 63) / 64 : 0, 0);
   std::unordered_map<uint64_t, uint32_t> c_seen;
   std::vector<CBlock> c_unsorted;

@@ -137,3 +137,39 @@ def test_empty_operand_gives_no_tasks():
     B = tk.BlockSparseTensor([i_in, i_in.inverse()]); B.set_blocks(B.div_blocks((0,)))
     m = tk.Match(A, B, ([1], [0]))
     assert m.ntask == 0 and m.c_nblk == 0 and m.c_elems == 0
+
+
+def _task_rows(m):
+    return [(x.a_blk_idx, x.b_blk_idx, x.c_blk_idx, x.a_off, x.b_off, x.c_off, x.a_ord, x.b_ord, x.c_ord, x.m, x.k, x.n, x.sign, x.first)
+            for x in m.tasks()]
+
+
+def test_large_sector_space_paths_agree_with_dense_tables(monkeypatch):
+    """The matcher keeps dense tables (contracted-key buckets, C block bitmap) when the sector spaces are small and
+    falls back to binary search / hashing otherwise; QLB200_MATCH_NO_DENSE forces the fallbacks.  Same tasks, same C
+    blocks, on random cases of every symmetry (general and contiguous-axes matching) and on the fermionic H_eff chain."""
+    from tensortoolkit_b200 import workloads as wl
+    rng = np.random.default_rng(99)
+    pairs = []
+    for kind_name in util.KINDS:
+        for _ in range(6):
+            idx_a, idx_b, axes, div_a, div_b = util.random_case(kind_name, rng)
+            A = tk.BlockSparseTensor(idx_a, np.float64).random(div_a, rng)
+            B = tk.BlockSparseTensor(idx_b, np.float64).random(div_b, rng)
+            pairs.append((A, B, axes))
+    ti = wl.heff_tensor_indexes(wl.hubbard_indexes(60))
+    t = {n: tk.BlockSparseTensor(ix, np.float64).random((0, 0), rng) for n, ix in ti.items()}
+    for lhs, rhs, axes, out in wl.HEFF_STEPS:
+        pairs.append((t[lhs], t[rhs], axes))
+        m = tk.Match(t[lhs], t[rhs], axes); t[out] = m.result_shell(np.float64); m.close()
+    for A, B, axes in pairs:
+        monkeypatch.delenv("QLB200_MATCH_NO_DENSE", raising=False)
+        dense = tk.Match(A, B, axes)
+        monkeypatch.setenv("QLB200_MATCH_NO_DENSE", "1")
+        sparse = tk.Match(A, B, axes)
+        assert _task_rows(dense) == _task_rows(sparse)
+        assert dense.c_elems == sparse.c_elems and dense.c_nblk == sparse.c_nblk
+        if dense.c_rank:
+            assert all(np.array_equal(x, y) for x, y in zip(dense.c_blocks(), sparse.c_blocks()))
+        dense.close(); sparse.close()
+    monkeypatch.delenv("QLB200_MATCH_NO_DENSE", raising=False)
