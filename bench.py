@@ -78,13 +78,43 @@ def workload_seed(workload, dtype):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region
-    (B200_PROFILING.md recipe: start before, stop after)."""
+    """SM clock, power and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md recipe).
+    In-process NVML thread, one sample every 20 ms, so that even a 30 ms multi-GPU timed region is covered; falls back
+    to an `nvidia-smi -lms 100` child process when NVML cannot be initialised."""
+    _REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.index, self.proc, self.samples = index, None, []
+        self.index, self.proc, self.samples = index, None, []      # samples: (sm_mhz, sm_max_mhz, power_w, reason bitmask)
+        self.thread, self.stop_flag, self.nvml = None, None, None
+
+    def _nvml_loop(self):
+        n = self.nvml
+        try:
+            h = n.nvmlDeviceGetHandleByIndex(self.index)
+            smax = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            while True:
+                try:
+                    pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = None
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), smax, pw, int(reasons_fn(h))))
+                if self.stop_flag.wait(0.02):
+                    break
+        except Exception:
+            pass
 
     def start(self):
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.stop_flag = pynvml, threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = self.thread = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -94,6 +124,12 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            time.sleep(0.03)
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            self.thread = None
+            return
         if self.proc is None:
             return
         time.sleep(0.15)
@@ -103,20 +139,20 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
+        num = lambda x: float(x) if x.replace(".", "", 1).isdigit() else None
         for ln in out.splitlines():
             f = [x.strip() for x in ln.split(",")]
             if len(f) >= 7:
-                self.samples.append(f)
+                mask = sum(bit for (bit, _), v in zip(self._REASONS, f[3:7]) if v.lower().startswith("active"))
+                self.samples.append((num(f[0]), num(f[1]), num(f[2]), mask))
 
     def summary(self):
-        num = lambda x: float(x) if x.replace(".", "", 1).isdigit() else None
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(v for v in (num(s[0]) for s in self.samples) if v is not None)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        pw = [v for v in (num(s[2]) for s in self.samples) if v is not None]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": num(self.samples[0][1]),
+        sm = sorted(s[0] for s in self.samples if s[0] is not None)
+        pw = [s[2] for s in self.samples if s[2] is not None]
+        reasons = [name for bit, name in self._REASONS if any(s[3] & bit for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.samples[0][1],
                 "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(self.samples)}
 
 
