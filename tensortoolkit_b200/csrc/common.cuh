@@ -141,10 +141,7 @@ constexpr int kCplxBM = 64, kCplxBN = 128, kCplxBK = 8;   // legacy cp.async ker
 constexpr int kWsBM = 32, kWsBN = 128, kWs3mBN = 96;       // warp-specialised complex kernel (4M / 3M tile width)
 constexpr int kWsRealBM = 64, kWsRealBN = 128;             // warp-specialised real kernel
 constexpr int kWsBK = 8, kWsRealBK = 16;                   // k extent of one pipeline stage
-#ifndef QLB200_3M_BK
-#define QLB200_3M_BK 16
-#endif
-constexpr int kWs3mBK = QLB200_3M_BK;                      // 3M kernel: two half-stages share one barrier round trip
+constexpr int kWs3mBK = 16;                                // 3M kernel: two half-stages share one barrier round trip
 constexpr int kWs3mStages = kWs3mBK == 16 ? 3 : 5;
 // narrow-pair kernel: 4 outputs per thread keep it at 64 registers -> 4 CTAs (32 warps) per SM; the kernel is
 // latency-bound, so resident warps (loads in flight) matter more than per-thread reuse (measured: 8 per thread /

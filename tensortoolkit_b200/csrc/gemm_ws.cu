@@ -34,9 +34,6 @@
 #include "common.cuh"
 #include "ws_common.cuh"
 
-#ifndef QLB200_EXP
-#define QLB200_EXP 0
-#endif
 
 namespace qlb200 {
 
