@@ -1,9 +1,13 @@
 """Sector matcher: ours (hash join, qlb200_match_create) vs the reference's DataBlkGenForTenCtrct
 (O(N_A*N_B) scan) on the block structure of config 4 (fermionic Hubbard H_eff chain; the structure does not
-depend on D because every sector keeps degeneracy >= 1).  Host-only, no GPU."""
-import sys, time
+depend on D because every sector keeps degeneracy >= 1).  Host-only, no GPU.
+
+    python tests/matcher_vs_reference.py [D]      (output kept in profiles/r1_matcher_cpu.txt)
+
+Test infrastructure: it calls the oracle (the reference compiled into oracle/_ref) as the thing to compare against."""
+import os, sys, time
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import tensortoolkit_b200 as tk
 from tensortoolkit_b200 import workloads as wl
 from oracle import refbridge as ref
