@@ -185,3 +185,42 @@ def test_dropin_adapter_contiguous(ref, ctx, case):
         assert all(np.array_equal(x, y) for x, y in zip(got.blocks(), want.blocks()))
         if want.raw().size:
             assert util.rel_fro(got.raw(), want.raw()) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+import glob
+import os
+
+from tests.golden import io as gio
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "contig_*.npz")))
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 4
+
+
+@pytest.mark.parametrize("path", GOLDEN)
+def test_oracle_matches_golden(path):
+    """Fixtures dumped from the reference's ContractContiguousAxes (tests/golden/make_golden.py); no reference needed."""
+    g = gio.load_case(path)
+    a0, b0, n = g["meta"]["contiguous"]
+    c = onp.contract_contiguous_np(g["A"], g["B"], a0, b0, n)
+    assert c.indexes == g["C"].indexes
+    assert np.array_equal(c.blk_coors, g["C"].blk_coors) and np.array_equal(c.blk_offset, g["C"].blk_offset)
+    assert util.rel_fro(c.data, g["C"].data) <= 1e-13
+    m = tk.Match(g["A"], g["B"], None, contiguous=(a0, b0, n))
+    assert m.c_indexes == g["C"].indexes and m.c_elems == g["C"].data.size
+    _, coors, _, off = m.c_blocks()
+    assert np.array_equal(coors, g["C"].blk_coors) and np.array_equal(off, g["C"].blk_offset)
+    m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN)
+def test_gpu_matches_golden(ctx, path):
+    g = gio.load_case(path)
+    a0, b0, n = g["meta"]["contiguous"]
+    c = tk.contract_contiguous_axes(g["A"], g["B"], a0, b0, n, ctx)
+    assert c.same_structure(g["C"]) and c.indexes == g["C"].indexes
+    assert util.rel_fro(c.data, g["C"].data) <= TOL

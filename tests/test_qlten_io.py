@@ -79,3 +79,27 @@ def test_bench_loads_a_chain_from_files(tmp_path):
         shells[out] = m.result_shell(np.float64)
         m.close()
     assert shells["out"].indexes == got["psi"].indexes
+
+
+import glob
+import os
+
+from tests.golden import io as gio
+
+FILES = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "file_*.qlten")))
+
+
+def test_golden_files_present():
+    assert len(FILES) >= 3
+
+
+@pytest.mark.parametrize("path", FILES)
+def test_golden_files(path):
+    """Files written by the reference (tests/golden/make_golden.py) and the tensors they hold: read back exactly,
+    re-written byte for byte -- without the reference library."""
+    g = gio.load_case(path[:-len(".qlten")] + ".npz")
+    want = g["A"]
+    got = qlten_io.load(path, want.indexes[0].kind, want.dtype)
+    assert got.indexes == want.indexes and got.same_structure(want) and np.array_equal(got.data, want.data)
+    with open(path, "rb") as f:
+        assert qlten_io.dumps(want) == f.read()
