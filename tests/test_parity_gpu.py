@@ -23,7 +23,8 @@ TOL = 1e-12
 CASES = util.case_list(n_per_kind=6)
 BIG = util.case_list(n_per_kind=3, seed=99, big=True)
 FIXED = util.fixed_cases()
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith(("contig_", "file_")))     # those belong to test_contiguous / test_qlten_io
 
 
 @pytest.mark.parametrize("case", range(len(CASES)))
