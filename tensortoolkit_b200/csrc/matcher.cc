@@ -251,25 +251,43 @@ std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrc
   std::vector<int8_t> sign_cache;
   if (fermi) sign_cache.assign(size_t(1) << (A.rank + B.rank), 0);
   m.tasks.reserve(A.nblk + B.nblk);
+  // per-B-block quantities that do not depend on the partner: n, the B part of the C block index, the parity mask
+  const size_t n_a_saved = m.a_saved.size();
+  uint64_t b_radix = 1;                         // product of the sector counts of B's free axes
+  for (int ax : m.b_saved) b_radix *= B.nsct[ax];
+  std::vector<uint64_t> b_nn(B.nblk), b_cpart(B.nblk);
+  std::vector<uint32_t> b_masks(fermi ? B.nblk : 0);
+  for (uint64_t j = 0; j < B.nblk; ++j) {
+    const uint32_t *bc = &B.coors[j * B.rank];
+    const uint32_t *bsh = &B.shape[j * B.rank];
+    uint64_t nn = 1, part = 0;
+    for (int ax : m.b_saved) { nn *= bsh[ax]; part = part * B.nsct[ax] + bc[ax]; }
+    b_nn[j] = nn; b_cpart[j] = part;
+    if (fermi) {
+      uint32_t mask = 0;
+      for (int r = 0; r < B.rank; ++r) mask |= uint32_t(B.parity[B.sct_base[r] + bc[r]] != 0) << r;
+      b_masks[j] = mask;
+    }
+  }
   for (uint64_t i = 0; i < A.nblk; ++i) {
     const uint32_t *ac = &A.coors[i * A.rank];
     if (sel_axis >= 0 && ac[sel_axis] != sel_sector) continue;
     uint32_t q_lo, q_hi;
     if (!find_bucket(key_of(A, i, m.a_ctrct, A, m.a_ctrct), &q_lo, &q_hi)) continue;
     const uint32_t *ash = &A.shape[i * A.rank];
-    uint64_t mm = 1, kk = 1;
-    for (int ax : m.a_saved) mm *= ash[ax];
+    uint64_t mm = 1, kk = 1, a_cpart = 0;
+    for (int ax : m.a_saved) { mm *= ash[ax]; a_cpart = a_cpart * A.nsct[ax] + ac[ax]; }
     for (int ax : m.a_ctrct) kk *= ash[ax];
+    if (mm > UINT32_MAX || kk > UINT32_MAX) return "block dimension exceeds 2^32";
+    a_cpart *= b_radix;
     uint32_t a_mask = 0;
     if (fermi) for (int r = 0; r < A.rank; ++r) { a_par[r] = A.parity[A.sct_base[r] + ac[r]]; a_mask |= uint32_t(a_par[r] != 0) << r; }
     for (uint32_t q = q_lo; q < q_hi; ++q) {
       const uint64_t j = b_keys[q].second;
-      const uint32_t *bc = &B.coors[j * B.rank];
-      const uint32_t *bsh = &B.shape[j * B.rank];
-      uint64_t nn = 1;
-      for (int ax : m.b_saved) nn *= bsh[ax];
-      if (mm > UINT32_MAX || kk > UINT32_MAX || nn > UINT32_MAX) return "block dimension exceeds 2^32";
-      qlb200_task t;
+      const uint64_t nn = b_nn[j];
+      if (nn > UINT32_MAX) return "block dimension exceeds 2^32";
+      m.tasks.emplace_back();
+      qlb200_task &t = m.tasks.back();
       std::memset(&t, 0, sizeof(t));
       t.a_blk_idx = A.blk_idx[i]; t.b_blk_idx = B.blk_idx[j];
       t.a_off = A.offset[i]; t.b_off = B.offset[j];
@@ -280,16 +298,10 @@ std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrc
         // all axes contracted: one B block can match; C is the size-1 raw buffer
         t.m = t.n = 1;
         t.c_blk_idx = 0; t.c_ord = 0;
-        t.first = m.tasks.empty() ? 1 : 0;
+        t.first = m.tasks.size() == 1 ? 1 : 0;
       } else {
         t.m = static_cast<uint32_t>(mm); t.n = static_cast<uint32_t>(nn);
-        CBlock cb;
-        std::memset(&cb, 0, sizeof(cb));
-        int r = 0;
-        uint64_t cidx = 0, csz = 1;
-        for (int ax : m.a_saved) { cb.coors[r] = ac[ax]; cb.shape[r] = ash[ax]; cidx = cidx * m.c_nsct[r] + ac[ax]; csz *= ash[ax]; ++r; }
-        for (int ax : m.b_saved) { cb.coors[r] = bc[ax]; cb.shape[r] = bsh[ax]; cidx = cidx * m.c_nsct[r] + bc[ax]; csz *= bsh[ax]; ++r; }
-        cb.blk_idx = cidx; cb.size = csz;
+        const uint64_t cidx = a_cpart + b_cpart[j];
         t.c_blk_idx = cidx;
         bool fresh;
         if (dense_c) {
@@ -300,20 +312,31 @@ std::string BuildMatch(const qlb200_shell *sa, const qlb200_shell *sb, int nctrc
         } else {
           fresh = c_seen.emplace(cidx, static_cast<uint32_t>(c_unsorted.size())).second;
         }
-        if (fresh) { c_unsorted.push_back(cb); t.first = 1; } else { t.first = 0; }
+        t.first = fresh ? 1 : 0;
+        if (fresh) {
+          const uint32_t *bc = &B.coors[j * B.rank];
+          const uint32_t *bsh = &B.shape[j * B.rank];
+          c_unsorted.emplace_back();
+          CBlock &cb = c_unsorted.back();
+          std::memset(&cb, 0, sizeof(cb));
+          size_t r = 0;
+          for (int ax : m.a_saved) { cb.coors[r] = ac[ax]; cb.shape[r] = ash[ax]; ++r; }
+          for (int ax : m.b_saved) { cb.coors[r] = bc[ax]; cb.shape[r] = bsh[ax]; ++r; }
+          (void) n_a_saved;
+          cb.blk_idx = cidx; cb.size = mm * nn;
+        }
       }
       if (fermi) {
-        uint32_t b_mask = 0;
-        for (int r = 0; r < B.rank; ++r) { b_par[r] = B.parity[B.sct_base[r] + bc[r]]; b_mask |= uint32_t(b_par[r] != 0) << r; }
-        int8_t &sg = sign_cache[(size_t(b_mask) << A.rank) | a_mask];
+        int8_t &sg = sign_cache[(size_t(b_masks[j]) << A.rank) | a_mask];
         if (sg == 0) {
+          const uint32_t *bc = &B.coors[j * B.rank];
+          for (int r = 0; r < B.rank; ++r) b_par[r] = B.parity[B.sct_base[r] + bc[r]];
           int v = FermionCtrctSign(a_par, A.rank, b_par, B.rank, m.a_ctrct, m.b_ctrct, A.dir.data());
           if (mat_based_residue) v *= ResidueSign(a_par, m.a_saved, m.a_ctrct) * ResidueSign(b_par, m.b_saved, m.b_ctrct);
           sg = static_cast<int8_t>(v);
         }
         t.sign = sg;
       }
-      m.tasks.push_back(t);
       if (m.scalar) break;
     }
   }
