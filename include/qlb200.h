@@ -223,7 +223,11 @@ int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const vo
  * a row range) can write them straight into the full result on EVERY GPU of the NVLink domain: the
  * output tiles of the grouped GEMM are stored to all `npeers` buffers (the caller's own and its peers',
  * mapped with qlb200_ipc_open) from inside the kernel, so no separate all-gather is needed -- only a
- * barrier before the result is read.  Device pointers only; npeers <= 8. */
+ * barrier before the result is read.  Device pointers only; npeers <= 8.
+ * ORDERING IN A LOOP: the barrier that follows the stores orders them before the peers' reads of THIS result; nothing
+ * orders the NEXT call's stores after a slower peer's reads.  When the result of call j is the input of call j+1
+ * (Lanczos), alternate between two result buffers (call j writes buffer j & 1, as tensortoolkit_b200.ShardedChain and
+ * qlten::b200 do) or put a second barrier in front of the storing call. */
 int qlb200_execute_bcast(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *const *C_peers,
                          int32_t npeers);
 /* Same exchange through the NVSwitch: `C_multicast` is a multicast (NVLS) mapping of the full result buffer of
@@ -245,7 +249,10 @@ int qlb200_ipc_close(qlb200_ctx *ctx, void *peer_ptr);
 /* Everything enqueued on the context's stream between begin and end -- this library's kernels and foreign work
  * such as an NCCL collective or a symmetric-memory barrier -- is captured (relaxed mode) instead of executed;
  * qlb200_graph_launch replays it.  Device-pointer executes only; run the sequence once before capturing so that
- * the workspace arena has its final size. */
+ * the workspace arena has its final size (an execute that would have to grow it during capture fails with
+ * QLB200_ERR_UNSUPPORTED).  A graph keeps the arena addresses it was captured with: while any graph of a context is
+ * alive, arenas outgrown by later plans are kept allocated (retired) instead of freed, so replay stays valid.  Destroy a
+ * context's graphs before the context. */
 typedef struct qlb200_graph qlb200_graph;
 int qlb200_graph_begin(qlb200_ctx *ctx);
 int qlb200_graph_end(qlb200_ctx *ctx, qlb200_graph **out);

@@ -1,0 +1,105 @@
+// oracle/adapter_driver.cc -- TEST INFRASTRUCTURE ONLY (never linked into the product library).
+//
+// The drop-in adapter (include/qlten_b200/contract.h) instantiated on the reference's own QLTensor types, behind a C
+// ABI: this is how the parity tests call the CUDA path exactly like a TensorToolkit user would
+// (qlten::b200::Contract(&A, &B, axes, &C)).  Handles are the TenBase* objects of oracle/ref_handles.h, created by
+// libqlref.so.  Built by oracle/Makefile into oracle/_ref/libqladapter.so; links tensortoolkit_b200/libqlb200.so.
+#include "ref_handles.h"
+
+#include "qlten_b200/contract.h"
+
+using namespace qlref;
+
+namespace {
+
+// Calls f(const TenBox<ElemT, QNT>*) for the element / quantum-number type the handle was created with; every
+// instantiation of the generic lambda returns the same type R.
+template<typename R, typename F>
+R Dispatch(const TenBase *t, F &&f) {
+#define QLREF_CASE(K, QN)                                                                   \
+  case K:                                                                                   \
+    if (t->dtype == D_F64) return f(static_cast<const TenBox<QLTEN_Double, QN> *>(t));      \
+    return f(static_cast<const TenBox<QLTEN_Complex, QN> *>(t));
+  switch (t->kind) {
+    QLREF_CASE(K_U1, U1QN)
+    QLREF_CASE(K_FU1, fU1QN)
+    QLREF_CASE(K_U1U1, U1U1QN)
+    QLREF_CASE(K_FU1U1, fU1U1QN)
+    QLREF_CASE(K_Z2, Z2QN)
+    QLREF_CASE(K_FZ2, fZ2QN)
+    default: break;
+  }
+#undef QLREF_CASE
+  throw std::invalid_argument("unknown quantum-number kind in handle");
+}
+
+template<typename Box> const Box *Same(const Box *, const TenBase *o) { return static_cast<const Box *>(o); }
+
+template<typename Fn>
+void *Guard(const char *what, Fn &&fn) {
+  try { return fn(); }
+  catch (const std::exception &e) { std::fprintf(stderr, "%s: %s\n", what, e.what()); return nullptr; }
+}
+
+}  // namespace
+
+extern "C" {
+
+void *qlref_b200_contract(const void *a, const void *b, int n, const int64_t *aa, const int64_t *ba, void *ctx) {
+  return Guard("qlref_b200_contract", [&]() -> void * {
+    return Dispatch<TenBase *>(static_cast<const TenBase *>(a), [&](auto *A) -> TenBase * {
+      typename std::remove_pointer_t<decltype(A)>::Ten c;
+      qlten::b200::Contract(&A->t, &Same(A, static_cast<const TenBase *>(b))->t, MakeAxes(n, aa, ba), &c, (qlb200_ctx *) ctx);
+      return A->wrap(std::move(c));
+    });
+  });
+}
+
+void *qlref_b200_contract_1sector(const void *a, int64_t axis, int64_t sct, const void *b, int n, const int64_t *aa,
+                                  const int64_t *ba, void *ctx) {
+  return Guard("qlref_b200_contract_1sector", [&]() -> void * {
+    return Dispatch<TenBase *>(static_cast<const TenBase *>(a), [&](auto *A) -> TenBase * {
+      typename std::remove_pointer_t<decltype(A)>::Ten c;
+      qlten::b200::Contract1Sector(&A->t, (size_t) axis, (size_t) sct, &Same(A, static_cast<const TenBase *>(b))->t,
+                                   MakeAxes(n, aa, ba), &c, (qlb200_ctx *) ctx);
+      return A->wrap(std::move(c));
+    });
+  });
+}
+
+// side: 0 = <Tail, Head> (default), 1 = <Head, Head>, 2 = <Tail, Tail>, 3 = <Head, Tail>
+void *qlref_b200_contract_contiguous(const void *a, const void *b, int64_t a_start, int64_t b_start, int64_t size, int side,
+                                     void *ctx) {
+  return Guard("qlref_b200_contract_contiguous", [&]() -> void * {
+    return Dispatch<TenBase *>(static_cast<const TenBase *>(a), [&](auto *A) -> TenBase * {
+      using Box = std::remove_pointer_t<decltype(A)>;
+      using E = typename Box::Elem;
+      using Q = typename Box::QN;
+      typename Box::Ten c;
+      const auto &tb = Same(A, static_cast<const TenBase *>(b))->t;
+      qlb200_ctx *cx = (qlb200_ctx *) ctx;
+      switch (side) {
+        case 1: qlten::b200::ContractContiguousAxes<E, Q, CtrctSide::Head, CtrctSide::Head>(A->t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c, cx); break;
+        case 2: qlten::b200::ContractContiguousAxes<E, Q, CtrctSide::Tail, CtrctSide::Tail>(A->t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c, cx); break;
+        case 3: qlten::b200::ContractContiguousAxes<E, Q, CtrctSide::Head, CtrctSide::Tail>(A->t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c, cx); break;
+        default: qlten::b200::ContractContiguousAxes<E, Q, CtrctSide::Tail, CtrctSide::Head>(A->t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c, cx); break;
+      }
+      return A->wrap(std::move(c));
+    });
+  });
+}
+
+int qlref_b200_transpose(void *t, const int64_t *perm, void *ctx) {
+  try {
+    return Dispatch<int>(static_cast<const TenBase *>(t), [&](auto *A) -> int {
+      using Box = std::remove_pointer_t<decltype(A)>;
+      auto &ten = const_cast<typename std::remove_const_t<Box> &>(*A).t;
+      std::vector<size_t> o(ten.Rank());
+      for (size_t i = 0; i < ten.Rank(); ++i) o[i] = (size_t) perm[i];
+      qlten::b200::Transpose(&ten, o, (qlb200_ctx *) ctx);
+      return 0;
+    });
+  } catch (const std::exception &e) { std::fprintf(stderr, "qlref_b200_transpose: %s\n", e.what()); return -1; }
+}
+
+}  // extern "C"

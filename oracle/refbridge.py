@@ -12,7 +12,8 @@ import numpy as np
 from tensortoolkit_b200.tensor import BlockSparseTensor, Index, KIND_ORDINAL
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REF_LIB = os.path.join(_HERE, "_ref", "libqlref.so")
+REF_LIB = os.path.join(_HERE, "_ref", "libqlref.so")          # the unmodified reference, nothing else
+ADAPTER_LIB = os.path.join(_HERE, "_ref", "libqladapter.so")  # include/qlten_b200/*.h instantiated on reference tensors (links libqlb200.so)
 
 _I64P = C.POINTER(C.c_int64)
 _P = C.c_void_p
@@ -29,7 +30,7 @@ def lib():
     global _lib
     if _lib is None:
         os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # see BASELINE.md: active spin-wait oversubscribes
-        L = C.CDLL(REF_LIB)
+        L = C.CDLL(REF_LIB, mode=C.RTLD_GLOBAL)
         sig = {
             "qlref_set_seed": (None, [C.c_uint64]),
             "qlref_set_threads": (None, [C.c_int]),
@@ -57,19 +58,38 @@ def lib():
             "qlref_contract_1sector": (_P, [_P, C.c_int64, C.c_int64, _P, C.c_int, _I64P, _I64P]),
             "qlref_contract_tasks": (C.c_uint64, [_P, _P, C.c_int, _I64P, _I64P, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
             "qlref_contract_cost": (None, [_P, _P, C.c_int, _I64P, _I64P, C.POINTER(C.c_double)]),
-            "qlref_b200_contract": (_P, [_P, _P, C.c_int, _I64P, _I64P, _P]),
-            "qlref_b200_contract_1sector": (_P, [_P, C.c_int64, C.c_int64, _P, C.c_int, _I64P, _I64P, _P]),
-            "qlref_b200_transpose": (C.c_int, [_P, _I64P, _P]),
             "qlref_tensor_write": (C.c_int, [_P, C.c_char_p]),
             "qlref_tensor_read": (C.c_int, [_P, C.c_char_p]),
             "qlref_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
-            "qlref_b200_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
+
+
+_adapter = None
+
+
+def adapter():
+    """The drop-in adapter library (qlref_b200_*): loaded only by tests that call the CUDA path through the C++ adapter,
+    never by the reference arm / cpu_baseline leg of bench.py."""
+    global _adapter
+    if _adapter is None:
+        lib()                                   # reference symbols first (the adapter library links against them)
+        L = C.CDLL(ADAPTER_LIB, mode=C.RTLD_GLOBAL)
+        sig = {
+            "qlref_b200_contract": (_P, [_P, _P, C.c_int, _I64P, _I64P, _P]),
+            "qlref_b200_contract_1sector": (_P, [_P, C.c_int64, C.c_int64, _P, C.c_int, _I64P, _I64P, _P]),
+            "qlref_b200_transpose": (C.c_int, [_P, _I64P, _P]),
+            "qlref_b200_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _adapter = L
+    return _adapter
 
 
 def _i64(v):
@@ -136,7 +156,7 @@ class RefTensor:
         return self
 
     def b200_transpose(self, perm, ctx_handle=None):
-        rc = lib().qlref_b200_transpose(self.h, _i64(perm), ctx_handle)
+        rc = adapter().qlref_b200_transpose(self.h, _i64(perm), ctx_handle)
         if rc != 0:
             raise RuntimeError("qlten::b200::Transpose failed")
         self.indexes = [self.indexes[i] for i in perm]
@@ -226,14 +246,14 @@ def contract_1sector(a: RefTensor, axis, sct, b: RefTensor, axes) -> RefTensor:
 
 def b200_contract(a: RefTensor, b: RefTensor, axes, ctx_handle=None) -> RefTensor:
     """qlten::b200::Contract on reference QLTensors (the drop-in adapter, CUDA path)."""
-    h = lib().qlref_b200_contract(a.h, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), ctx_handle)
+    h = adapter().qlref_b200_contract(a.h, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), ctx_handle)
     if not h:
         raise RuntimeError("qlten::b200::Contract failed")
     return RefTensor(h, _c_indexes(a, b, axes), a.dtype)
 
 
 def b200_contract_1sector(a: RefTensor, axis, sct, b: RefTensor, axes, ctx_handle=None) -> RefTensor:
-    h = lib().qlref_b200_contract_1sector(a.h, axis, sct, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), ctx_handle)
+    h = adapter().qlref_b200_contract_1sector(a.h, axis, sct, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), ctx_handle)
     if not h:
         raise RuntimeError("qlten::b200::Contract1Sector failed")
     return RefTensor(h, _c_indexes(a, b, axes), a.dtype)
@@ -259,7 +279,7 @@ def contract_contiguous(a: RefTensor, b: RefTensor, a_start: int, b_start: int, 
 def b200_contract_contiguous(a: RefTensor, b: RefTensor, a_start: int, b_start: int, size: int, sides=("tail", "head"),
                              ctx_handle=None) -> RefTensor:
     """qlten::b200::ContractContiguousAxes on reference tensors (the drop-in adapter over the C ABI)."""
-    L = lib()
+    L = adapter()
     h = L.qlref_b200_contract_contiguous(a.h, b.h, int(a_start), int(b_start), int(size), SIDES[tuple(sides)], ctx_handle)
     if not h:
         raise RuntimeError("qlref_b200_contract_contiguous failed (see stderr)")

@@ -34,10 +34,21 @@ int Upload(const std::vector<T> &v, T **dst, cudaStream_t s) {
   return QLB200_OK;
 }
 
-int EnsureArena(void **p, size_t *cap, size_t need, cudaStream_t s) {
+// Grow-only arenas.  A captured CUDA graph bakes arena addresses into its kernel nodes, so an arena that a live graph
+// may reference is never freed when a later plan needs more room: it is retired (kept allocated until the context's last
+// graph is destroyed, or the context itself) and a new, larger one takes its place.  Growth is impossible while the
+// stream is capturing (cudaMalloc / synchronise are illegal there): the caller must run the sequence once eagerly first.
+int EnsureArena(qlb200_ctx *ctx, void **p, size_t *cap, size_t need) {
   if (need <= *cap) return QLB200_OK;
-  QL_CUDA(cudaStreamSynchronize(s));
-  if (*p) { QL_CUDA(cudaFree(*p)); *p = nullptr; *cap = 0; }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(ctx->stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+    return Fail(QLB200_ERR_UNSUPPORTED, "workspace arena must grow while the stream is being captured: run the sequence once before qlb200_graph_begin");
+  QL_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (*p) {
+    if (ctx->graphs_alive > 0) ctx->retired.push_back(*p);
+    else QL_CUDA(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+  }
   size_t want = need + need / 8 + 256;
   QL_CUDA(cudaMalloc(p, want));
   *cap = want;
@@ -162,23 +173,26 @@ int qlb200_match_create_contiguous(const qlb200_shell *a, const qlb200_shell *b,
   return QLB200_OK;
 }
 int32_t qlb200_match_saved_axes(const qlb200_match *m, int which, int32_t *axes_out) {
+  if (!m) return 0;
   const std::vector<int> &v = which == 0 ? m->m.a_saved : m->m.b_saved;
   if (axes_out) for (size_t i = 0; i < v.size(); ++i) axes_out[i] = v[i];
   return static_cast<int32_t>(v.size());
 }
 void qlb200_match_destroy(qlb200_match *m) { delete m; }
-int32_t qlb200_match_c_rank(const qlb200_match *m) { return m->m.c_rank; }
-uint64_t qlb200_match_c_nblk(const qlb200_match *m) { return m->m.c_blocks.size(); }
-uint64_t qlb200_match_c_elems(const qlb200_match *m) { return m->m.c_elems; }
-uint64_t qlb200_match_ntask(const qlb200_match *m) { return m->m.tasks.size(); }
-int qlb200_match_is_scalar(const qlb200_match *m) { return m->m.scalar ? 1 : 0; }
+int32_t qlb200_match_c_rank(const qlb200_match *m) { return m ? m->m.c_rank : 0; }
+uint64_t qlb200_match_c_nblk(const qlb200_match *m) { return m ? m->m.c_blocks.size() : 0; }
+uint64_t qlb200_match_c_elems(const qlb200_match *m) { return m ? m->m.c_elems : 0; }
+uint64_t qlb200_match_ntask(const qlb200_match *m) { return m ? m->m.tasks.size() : 0; }
+int qlb200_match_is_scalar(const qlb200_match *m) { return m && m->m.scalar ? 1 : 0; }
 int qlb200_match_perm(const qlb200_match *m, int which, int32_t *perm_out) {
+  if (!m || !perm_out) return Fail(QLB200_ERR_ARG, "null argument");
   const std::vector<int> &p = which == 0 ? m->m.a_perm : m->m.b_perm;
   for (size_t i = 0; i < p.size(); ++i) perm_out[i] = p[i];
   return which == 0 ? (m->m.a_need_trans ? 1 : 0) : (m->m.b_need_trans ? 1 : 0);
 }
 int qlb200_match_c_blocks(const qlb200_match *m, uint64_t *blk_idx, uint32_t *blk_coors, uint32_t *shape,
                           uint64_t *offset) {
+  if (!m) return Fail(QLB200_ERR_ARG, "null argument");
   const int r = m->m.c_rank;
   for (size_t b = 0; b < m->m.c_blocks.size(); ++b) {
     const CBlock &cb = m->m.c_blocks[b];
@@ -192,6 +206,7 @@ int qlb200_match_c_blocks(const qlb200_match *m, uint64_t *blk_idx, uint32_t *bl
   return QLB200_OK;
 }
 int qlb200_match_tasks(const qlb200_match *m, int order, qlb200_task *tasks_out) {
+  if (!m || (!tasks_out && !m->m.tasks.empty())) return Fail(QLB200_ERR_ARG, "null argument");
   if (order == 0) {
     std::memcpy(tasks_out, m->m.tasks.data(), m->m.tasks.size() * sizeof(qlb200_task));
   } else {
@@ -238,6 +253,7 @@ void qlb200_ctx_destroy(qlb200_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->side) cudaStreamSynchronize(ctx->side);
   cudaFree(ctx->ws); cudaFree(ctx->stage);
+  for (void *r : ctx->retired) cudaFree(r);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -418,9 +434,18 @@ uint64_t qlb200_plan_segments(const qlb200_plan *p, uint64_t cap, uint32_t *seg_
 }
 
 // ---- execution ---------------------------------------------------------------------------------
+// Checks shared by every execute entry point: a host-only plan has no device tables, a plan of another context
+// lives on another device / stream.
+static int CheckExec(const qlb200_ctx *ctx, const qlb200_plan *p, const void *A, const void *B) {
+  if (!ctx || !p || !A || !B) return Fail(QLB200_ERR_ARG, "null argument");
+  if (p->ctx == nullptr) return Fail(QLB200_ERR_ARG, "host-only plan (created without a context) cannot execute");
+  if (p->ctx != ctx) return Fail(QLB200_ERR_ARG, "plan belongs to another context");
+  return QLB200_OK;
+}
+
 static int ResolveWorkspace(qlb200_ctx *ctx, qlb200_plan *p, void **wsA, void **wsB, void **partials = nullptr) {
   const size_t es = ElemSize(p->h.dtype);
-  int rc = EnsureArena(&ctx->ws, &ctx->ws_bytes, WsBytes(p), ctx->stream);
+  int rc = EnsureArena(ctx, &ctx->ws, &ctx->ws_bytes, WsBytes(p));
   if (rc != QLB200_OK) return rc;
   *wsA = ctx->ws;
   *wsB = static_cast<char *>(ctx->ws) + Align256(p->h.ws_a_elems * es);
@@ -429,7 +454,8 @@ static int ResolveWorkspace(qlb200_ctx *ctx, qlb200_plan *p, void **wsA, void **
 }
 
 int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B) {
-  if (!ctx || !p) return Fail(QLB200_ERR_ARG, "null argument");
+  int ok = CheckExec(ctx, p, A, B);
+  if (ok != QLB200_OK) return ok;
   QL_CUDA(cudaSetDevice(ctx->device));
   void *wa, *wb;
   int rc = ResolveWorkspace(ctx, p, &wa, &wb);
@@ -446,6 +472,10 @@ int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const
 
 static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *const *c_out, uint32_t n_out,
                        uint32_t mcast = 0) {
+  int ok = CheckExec(ctx, p, A, B);
+  if (ok != QLB200_OK) return ok;
+  if (!c_out || n_out < 1 || n_out > uint32_t(kMaxOut)) return Fail(QLB200_ERR_ARG, "bad output list");
+  for (uint32_t d = 0; d < n_out; ++d) if (!c_out[d]) return Fail(QLB200_ERR_ARG, "null output pointer");
   QL_CUDA(cudaSetDevice(ctx->device));
   void *wa, *wb, *parts;
   int rc = ResolveWorkspace(ctx, p, &wa, &wb, &parts);
@@ -487,7 +517,6 @@ static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const voi
 }
 
 int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C) {
-  if (!ctx || !p) return Fail(QLB200_ERR_ARG, "null argument");
   void *outs[1] = {C};
   return ExecuteGemm(ctx, p, A, B, outs, 1);
 }
@@ -537,6 +566,7 @@ int qlb200_plan_remap_output(qlb200_plan *p, uint64_t n, const uint64_t *from_of
 }
 
 struct qlb200_graph {
+  qlb200_ctx *ctx = nullptr;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
 };
@@ -556,12 +586,14 @@ int qlb200_graph_end(qlb200_ctx *ctx, qlb200_graph **out) {
   cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
   if (e != cudaSuccess) { cudaGraphDestroy(graph); return Fail(QLB200_ERR_CUDA, CudaErr("cudaGraphInstantiate", e)); }
   qlb200_graph *g = new qlb200_graph;
-  g->graph = graph; g->exec = exec;
+  g->ctx = ctx; g->graph = graph; g->exec = exec;
+  ++ctx->graphs_alive;
   *out = g;
   return QLB200_OK;
 }
 int qlb200_graph_launch(qlb200_ctx *ctx, qlb200_graph *g) {
   if (!ctx || !g || !g->exec) return Fail(QLB200_ERR_ARG, "null argument");
+  if (g->ctx != ctx) return Fail(QLB200_ERR_ARG, "graph was captured on another context");
   QL_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
   return QLB200_OK;
 }
@@ -569,6 +601,12 @@ void qlb200_graph_destroy(qlb200_graph *g) {
   if (!g) return;
   if (g->exec) cudaGraphExecDestroy(g->exec);
   if (g->graph) cudaGraphDestroy(g->graph);
+  if (g->ctx && --g->ctx->graphs_alive == 0) {      // nothing can replay into the outgrown arenas any more
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    for (void *r : g->ctx->retired) cudaFree(r);
+    g->ctx->retired.clear();
+  }
   delete g;
 }
 
@@ -606,7 +644,7 @@ int qlb200_execute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B
   void *dC = C;
   if (mem_kind == QLB200_MEM_HOST) {
     const size_t ab = Align256(p->h.a_elems * es), bb = Align256(p->h.b_elems * es), cb = Align256(p->h.c_elems * es);
-    int rc = EnsureArena(&ctx->stage, &ctx->stage_bytes, ab + bb + cb, ctx->stream);
+    int rc = EnsureArena(ctx, &ctx->stage, &ctx->stage_bytes, ab + bb + cb);
     if (rc != QLB200_OK) return rc;
     char *base = static_cast<char *>(ctx->stage);
     QL_CUDA(cudaMemcpyAsync(base, A, p->h.a_elems * es, cudaMemcpyHostToDevice, ctx->stream));
@@ -723,7 +761,7 @@ int qlb200_transpose_execute(qlb200_ctx *ctx, qlb200_tplan *p, const void *src, 
   const void *ds = src; void *dd = dst;
   const size_t bytes = p->elems * es;
   if (mem_kind == QLB200_MEM_HOST) {
-    int rc = EnsureArena(&ctx->stage, &ctx->stage_bytes, 2 * Align256(bytes), ctx->stream);
+    int rc = EnsureArena(ctx, &ctx->stage, &ctx->stage_bytes, 2 * Align256(bytes));
     if (rc != QLB200_OK) return rc;
     char *base = static_cast<char *>(ctx->stage);
     QL_CUDA(cudaMemcpyAsync(base, src, bytes, cudaMemcpyHostToDevice, ctx->stream));

@@ -26,6 +26,8 @@ std::string Shell::Load(const qlb200_shell *s) {
   if (s == nullptr) return "null shell";
   if (s->rank < 0 || s->rank > QLB200_MAX_RANK) return "rank out of range";
   rank = s->rank;
+  if (rank > 0 && (s->nsct == nullptr || s->deg == nullptr)) return "shell without sector tables";
+  if (s->nblk > 0 && rank > 0 && s->blk_coors == nullptr) return "shell with blocks but no block coordinates";
   nsct.assign(s->nsct, s->nsct + rank);
   sct_base.resize(rank + 1);
   uint32_t tot = 0;

@@ -22,6 +22,9 @@ struct qlb200_ctx {
   void *stage = nullptr; size_t stage_bytes = 0;
   uint64_t launches = 0;          // kernels launched by the last execute call
   uint64_t total_launches = 0;
+  // captured graphs hold arena addresses: while any is alive, outgrown arenas are retired instead of freed
+  int graphs_alive = 0;
+  std::vector<void *> retired;
 };
 
 namespace qlb200 {

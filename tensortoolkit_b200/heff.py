@@ -151,6 +151,44 @@ class ContractionChain:
         self.plans, self.matches, self.buf = [], [], {}
 
 
+class _IdleChain:
+    """Stand-in for a rank whose share of the split index is empty (world larger than the number of cuttable row
+    groups): no plans, no launches -- the rank still takes part in the exchange barrier."""
+
+    def __init__(self, steps):
+        self.steps, self.plans, self.matches, self.buf, self.shells = list(steps), [], [], {}, {}
+        self.launches_per_apply = 0
+
+    def stats(self):
+        return []
+
+    def flops(self) -> float:
+        return 0.0
+
+    def apply_device(self):
+        return 0
+
+    def close(self):
+        pass
+
+
+class _AlternatingGraphs:
+    """The two captured applies of a ShardedChain (one per result replica), launched in turn."""
+
+    def __init__(self, owner, graphs):
+        self.owner, self.graphs = owner, graphs
+        self.launches = graphs[0].launches
+
+    def launch(self):
+        g = self.graphs[self.owner.parity]
+        self.owner.parity ^= 1
+        return g.launch()
+
+    def close(self):
+        for g in self.graphs:
+            g.close()
+
+
 class ShardedChain:
     """One rank's share of a contraction chain plus the exchange that rebuilds the full result on
     every GPU.  Ranks own disjoint output rows (see sharding.py), so no reduction is needed.
@@ -166,7 +204,15 @@ class ShardedChain:
     exchange="auto": "multicast" when the fabric offers it, else "fused".
     exchange="allgather": local steps -> NCCL all-gather of the packed row slabs -> one batched-copy launch
         that scatters every rank's slabs into the full raw-buffer layout (the library-collective baseline).
-    exchange=None: no exchange at all (time one rank's share on a single GPU)."""
+    exchange=None: no exchange at all (time one rank's share on a single GPU).
+
+    Iterative use (Lanczos: the result of apply j is the input of apply j+1).  The fused exchanges store into the
+    replicas of PEERS, and the only ordering point is the barrier that ends an apply.  With a single result buffer a fast
+    rank could reach the exchanged step of apply j+1 and overwrite a slower peer's replica while that peer is still
+    reading result j as its input.  The full result is therefore DOUBLE-BUFFERED: apply j writes replica j & 1 on every
+    GPU, so the stores of apply j+1 never touch what anybody reads during apply j+1 (result j), and the replica they do
+    touch (result j-1) was last read before the barrier that ended apply j.  `full_ptr` is the replica the last apply
+    wrote; pass it as the next input."""
 
     def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, dtype,
                  world: int, rank: int, group=None, flags: int = _lib.PLAN_DETERMINISTIC, exchange="auto", peers=None):
@@ -187,15 +233,24 @@ class ShardedChain:
         # transfer (every GPU has to RECEIVE the whole result) overlaps the remaining math
         stagger = _lib.PLAN_STAGGER_OUTPUT if (world > 1 and exchange in ("auto", "multicast", "fused")
                                                and os.environ.get("QLB200_STAGGER", "1") != "0") else 0
-        self.chain = ContractionChain(ctx, mine, steps, dtype, flags, external={self.out_name: self.local.data_ptr()},
-                                      last_flags=stagger)
+        # a rank can end up with no rows at all (cuts are snapped to row groups; world may exceed what can be cut):
+        # it builds no plans but joins every rendezvous, exchange and barrier below like its peers
+        self.idle = self.info.local_elems[rank] == 0
+        if self.idle:
+            self.chain = _IdleChain(steps)
+        else:
+            self.chain = ContractionChain(ctx, mine, steps, dtype, flags, external={self.out_name: self.local.data_ptr()},
+                                          last_flags=stagger)
         full_bytes = max(self.info.full_elems, 1) * self.dtype.itemsize
+        self.full_bytes = (full_bytes + 255) & ~255          # replica stride (keeps both halves 256-byte aligned)
+        self.parity = 0                                      # replica the NEXT apply writes
+        self.full_base = None
         self.symm = None
         if exchange in ("auto", "multicast") and world > 1 and peers is None:
             import torch.distributed._symmetric_memory as symm_mem
             grp = group if group is not None else torch.distributed.group.WORLD
             with torch.cuda.device(dev):
-                self.symm_buf = symm_mem.empty(max(self.info.full_elems, 1), dtype=tdt, device=dev)
+                self.symm_buf = symm_mem.empty(2 * self.full_bytes // self.dtype.itemsize, dtype=tdt, device=dev)
                 self.symm = symm_mem.rendezvous(self.symm_buf, grp)
             if not int(self.symm.multicast_ptr):
                 if exchange == "multicast":
@@ -203,10 +258,11 @@ class ShardedChain:
                 self.symm, self.symm_buf, exchange = None, None, "fused"
             else:
                 exchange = "multicast"
-                self.full_ptr = int(self.symm_buf.data_ptr())
-                self.mc_ptr = int(self.symm.multicast_ptr)
+                self.full_base = int(self.symm_buf.data_ptr())
+                self.mc_base = int(self.symm.multicast_ptr)
                 my = self.info.slabs[rank]
-                self.chain.plans[-1].remap_output([s.local_offset for s in my], [s.full_offset for s in my])
+                if not self.idle:
+                    self.chain.plans[-1].remap_output([s.local_offset for s in my], [s.full_offset for s in my])
         elif exchange == "auto":
             exchange = "fused"
         self.exchange = exchange
@@ -214,18 +270,19 @@ class ShardedChain:
             pass
         elif exchange == "fused":
             # the full result lives in a cudaMalloc'ed buffer of its own so that it can be exported over CUDA IPC
-            self.full_buf = DeviceBuffer(ctx, full_bytes)
-            self.full_ptr = self.full_buf.ptr
+            self.full_buf = DeviceBuffer(ctx, 2 * self.full_bytes)
+            self.full_base = self.full_buf.ptr
             my = self.info.slabs[rank]
-            self.chain.plans[-1].remap_output([s.local_offset for s in my], [s.full_offset for s in my])
+            if not self.idle:
+                self.chain.plans[-1].remap_output([s.local_offset for s in my], [s.full_offset for s in my])
             if peers is not None:                       # caller-supplied replicas (single-process tests)
-                self.peer_ptrs = [self.full_ptr] + [int(x) for x in peers]
+                self.peer_ptrs = [self.full_base] + [int(x) for x in peers]      # each 2 * full_bytes long
             elif world > 1:
                 handle = C.create_string_buffer(64)
-                check(lib.qlb200_ipc_export(ctx.h, C.c_void_p(self.full_ptr), handle), "qlb200_ipc_export")
+                check(lib.qlb200_ipc_export(ctx.h, C.c_void_p(self.full_base), handle), "qlb200_ipc_export")
                 handles = [None] * world
                 torch.distributed.all_gather_object(handles, bytes(handle.raw), group=group)
-                self.peer_ptrs = [self.full_ptr]
+                self.peer_ptrs = [self.full_base]
                 for r in range(world):
                     if r == rank:
                         continue
@@ -234,12 +291,12 @@ class ShardedChain:
                     self.opened.append(pp.value)
                     self.peer_ptrs.append(pp.value)
             else:
-                self.peer_ptrs = [self.full_ptr]
+                self.peer_ptrs = [self.full_base]
             self.flag = torch.zeros(1, dtype=torch.float32, device=dev)
         else:
             self.gathered = torch.zeros(world * self.stride, dtype=tdt, device=dev)
-            self.full = torch.zeros(max(self.info.full_elems, 1), dtype=tdt, device=dev)
-            self.full_ptr = self.full.data_ptr()
+            self.full2 = torch.zeros(2 * self.full_bytes // self.dtype.itemsize, dtype=tdt, device=dev)
+            self.full_base = self.full2.data_ptr()
             src, dst, ln = [], [], []
             for r in range(world):
                 for s in self.info.slabs[r]:
@@ -259,14 +316,17 @@ class ShardedChain:
         `mark(label)` (optional) is called after the local steps and after the exchange (timing hooks)."""
         ch = self.chain
         mark = mark or (lambda label: None)
+        off = self.parity * self.full_bytes       # this apply's replica
+        self.parity ^= 1
         if self.exchange == "multicast":
             n = 0
             for (lhs, rhs, _, out), plan in zip(ch.steps[:-1], ch.plans[:-1]):
                 plan.execute_device(ch.buf[lhs].ptr, ch.buf[rhs].ptr, ch.buf[out].ptr)
                 n += self.ctx.launch_count()
-            lhs, rhs, _, _ = ch.steps[-1]
-            ch.plans[-1].execute_mcast(ch.buf[lhs].ptr, ch.buf[rhs].ptr, self.mc_ptr)
-            n += self.ctx.launch_count()
+            if not self.idle:
+                lhs, rhs, _, _ = ch.steps[-1]
+                ch.plans[-1].execute_mcast(ch.buf[lhs].ptr, ch.buf[rhs].ptr, self.mc_base + off)
+                n += self.ctx.launch_count()
             mark("compute")
             self.symm.barrier()      # every rank's tiles have landed in every replica
             mark("exchange")
@@ -276,9 +336,10 @@ class ShardedChain:
             for (lhs, rhs, _, out), plan in zip(ch.steps[:-1], ch.plans[:-1]):
                 plan.execute_device(ch.buf[lhs].ptr, ch.buf[rhs].ptr, ch.buf[out].ptr)
                 n += self.ctx.launch_count()
-            lhs, rhs, _, _ = ch.steps[-1]
-            ch.plans[-1].execute_bcast(ch.buf[lhs].ptr, ch.buf[rhs].ptr, self.peer_ptrs)
-            n += self.ctx.launch_count()
+            if not self.idle:
+                lhs, rhs, _, _ = ch.steps[-1]
+                ch.plans[-1].execute_bcast(ch.buf[lhs].ptr, ch.buf[rhs].ptr, [p + off for p in self.peer_ptrs])
+                n += self.ctx.launch_count()
             mark("compute")
             if self.world > 1 and self.opened:
                 self.torch.distributed.all_reduce(self.flag, group=self.group)    # barrier: every peer's tiles have landed
@@ -292,14 +353,34 @@ class ShardedChain:
             self.torch.distributed.all_gather_into_tensor(self.gathered, self.local, group=self.group)
         else:
             self.gathered.copy_(self.local)
-        check(lib.qlb200_copy_execute(self.ctx.h, self.cplan, C.c_void_p(self.gathered.data_ptr()), C.c_void_p(self.full_ptr)),
+        check(lib.qlb200_copy_execute(self.ctx.h, self.cplan, C.c_void_p(self.gathered.data_ptr()), C.c_void_p(self.full_base + off)),
               "qlb200_copy_execute")
         mark("exchange")
         return n + 1
 
-    def capture(self) -> CapturedGraph:
-        """Local steps + exchange + barrier as one CUDA graph (the torch stream must be the context's stream)."""
-        return CapturedGraph(self.ctx, self.apply)
+    @property
+    def full_ptr(self) -> int:
+        """Device address of the full result the LAST apply produced (before the first apply: replica 0)."""
+        return self.full_base + (self.parity ^ 1) * self.full_bytes if self.full_base else 0
+
+    @property
+    def full(self):
+        """torch view of the full result the last apply produced (exchange='allgather' only)."""
+        n = max(self.info.full_elems, 1)
+        o = (self.parity ^ 1) * self.full_bytes // self.dtype.itemsize
+        return self.full2[o:o + n]
+
+    def capture(self):
+        """Local steps + exchange + barrier as CUDA graphs, one per result replica, replayed alternately (the torch
+        stream must be the context's stream)."""
+        graphs = []
+        for par in (0, 1):
+            def fn(par=par):
+                self.parity = par
+                return self.apply()
+            graphs.append(CapturedGraph(self.ctx, fn))
+        self.parity = 0
+        return _AlternatingGraphs(self, graphs)
 
     def download_full(self, host: np.ndarray):
         check(lib.qlb200_memcpy_d2h(self.ctx.h, host.ctypes.data, C.c_void_p(self.full_ptr), host.nbytes), "qlb200_memcpy_d2h")

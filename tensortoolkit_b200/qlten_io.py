@@ -70,7 +70,9 @@ def dumps(t: BlockSparseTensor) -> bytes:
         for s in ix.sectors:
             w(*s.qn, qn_hash(ix.kind, s.qn), s.dgnc, sector_hash(ix.kind, s))
         w(ix.dir, ix.dim, index_hash(ix))
-    w(t.nblk if t.rank else (1 if t.data.size else 0))
+    # block count = blk_idx_data_blk_map_.size() (blk_spar_data_ten.h:790-796); a scalar never inserts a block, so a
+    # rank-0 tensor writes 0 whether or not it holds a value -- only the payload differs
+    w(t.nblk if t.rank else 0)
     if t.rank:
         for b in range(t.nblk):
             w(*[int(c) for c in t.blk_coors[b]])

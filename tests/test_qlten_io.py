@@ -35,9 +35,16 @@ def test_round_trip_through_the_reference(ref, tmp_path, case):
 
 def test_contraction_result_files(ref, tmp_path):
     """A result of the reference's Contract (incl. a rank-0 scalar) survives the trip through our reader / writer."""
-    for kind_name, dtype, (idx_a, idx_b, axes, div_a, div_b) in CASES[::5]:
+    # every rank-0 result of the case list (empty and non-empty scalars) plus a sample of the others, and the
+    # reference's own full-trace fixtures (test_ten_ctrct.cc "2d_trace" / "3d_3axes": non-empty scalars)
+    picked = [c for i, c in enumerate(CASES) if i % 5 == 0 or len(c[2][0]) == len(c[2][1]) == len(c[2][2][0])]
+    picked += [(k, dt, (ia, ib, ax, da, db)) for (k, name, ia, ib, ax, da, db) in util.fixed_cases()
+               if name in ("1d", "2d_trace", "3d_3axes") for dt in (np.float64, np.complex128)]
+    n_scalar_full = 0
+    for kind_name, dtype, (idx_a, idx_b, axes, div_a, div_b) in picked:
         a, b = util.make_ref_pair(ref, idx_a, idx_b, dtype, div_a, div_b, 77)
         c = ref.contract(a, b, axes)
+        n_scalar_full += int(c.rank == 0 and c.raw().size == 1)
         f = tmp_path / "c.qlten"
         c.write_file(f)
         got = qlten_io.load(str(f), util.KINDS[kind_name], dtype)
@@ -50,6 +57,7 @@ def test_contraction_result_files(ref, tmp_path):
         if C.rank:
             assert got.same_structure(C)
         assert qlten_io.dumps(C) == f.read_bytes()
+    assert n_scalar_full >= 4, "the non-empty rank-0 case must be exercised"
 
 
 def test_hash_known_answers():

@@ -36,6 +36,33 @@ def test_slabs_tile_the_result(world):
         assert max(infos[0].cost_share) * world < 1.25       # balanced well beyond whole-sector LPT (~1.36 at 8)
 
 
+@pytest.mark.parametrize("D,world", [(17, 8), (20, 8), (24, 8), (40, 8), (40, 5), (64, 8), (8, 4)])
+def test_small_bonds_leave_idle_ranks_not_crashes(D, world):
+    """world may exceed what the snapped cuts can separate: an empty share is legal (the rank idles), every non-empty
+    share still matches through the whole chain, and the slabs of all ranks tile the result exactly."""
+    ts = make_tensors(D, np.float64, 4)
+    cov = None
+    n_idle = 0
+    for r in range(world):
+        mine, info = sh.shard_heff_tensors(ts, world, r)
+        if cov is None:
+            cov = np.zeros(info.full_elems, np.int32)
+        if info.local_elems[r] == 0:
+            n_idle += 1
+            assert info.slabs[r] == []
+            continue
+        shells = dict(mine)
+        for lhs, rhs, axes, out in wl.HEFF_STEPS:              # the host matcher accepts every restricted operand
+            m = tk.Match(shells[lhs], shells[rhs], axes)
+            shells[out] = m.result_shell(np.float64)
+            m.close()
+        assert shells["out"].data.size == info.local_elems[r]
+        for s in info.slabs[r]:
+            cov[s.full_offset:s.full_offset + s.length] += 1
+    assert np.all(cov == 1)
+    assert n_idle < world
+
+
 def test_restricted_operand_is_a_row_slice():
     ts = make_tensors(64, np.complex128, 2)
     mine, info = sh.shard_heff_tensors(ts, 4, 1)
@@ -162,26 +189,61 @@ def test_fused_exchange_writes_every_replica(ctx, dtype):
     full_chain.close()
     world = 3
     nbytes = want.nbytes
-    replicas = [DeviceBuffer(ctx, nbytes) for _ in range(2)]
+    stride = (nbytes + 255) & ~255
+    replicas = [DeviceBuffer(ctx, 2 * stride) for _ in range(2)]      # double-buffered result: two halves per replica
     chains = []
     for r in range(world):
         sc = ShardedChain(ctx, ts, wl.HEFF_STEPS, "lenv", 2, dtype, world, r, exchange="fused", peers=[b.ptr for b in replicas])
         chains.append(sc)
     # rank 0's own buffer is the third replica: make ranks 1, 2 write into it as well
     for sc in chains[1:]:
-        sc.peer_ptrs.append(chains[0].full_ptr)
-    for sc in chains:
-        sc.apply()
-    ctx.sync()
-    for ptr in [chains[0].full_ptr] + [b.ptr for b in replicas]:
-        got = np.empty_like(want)
-        tk._lib.check(tk._lib.lib.qlb200_memcpy_d2h(ctx.h, got.ctypes.data, ptr, got.nbytes), "d2h")
+        sc.peer_ptrs.append(chains[0].full_base)
+    for half in (0, 1, 0):                 # consecutive applies alternate between the two halves of every replica
+        for b in replicas + [chains[0].full_buf]:
+            zero = np.zeros(stride // 8, np.float64)
+            tk._lib.check(tk._lib.lib.qlb200_memcpy_h2d(ctx.h, b.ptr + half * stride, zero.ctypes.data, zero.nbytes), "h2d")
         ctx.sync()
-        assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-12
+        for sc in chains:
+            assert sc.parity == half
+            sc.apply()
+        ctx.sync()
+        assert chains[0].full_ptr == chains[0].full_base + half * stride
+        for ptr in [chains[0].full_ptr] + [b.ptr + half * stride for b in replicas]:
+            got = np.empty_like(want)
+            tk._lib.check(tk._lib.lib.qlb200_memcpy_d2h(ctx.h, got.ctypes.data, ptr, got.nbytes), "d2h")
+            ctx.sync()
+            assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-12
     for sc in chains:
         sc.close()
     for b in replicas:
         b.free()
+
+
+@pytest.mark.gpu
+def test_sharded_chain_with_idle_ranks(ctx):
+    """D=40 over 8 ranks leaves some ranks without rows: they build no plans, launch nothing, and the others still
+    rebuild the full result (all ranks store into one buffer here)."""
+    from tensortoolkit_b200.heff import ContractionChain, ShardedChain
+    ts = make_tensors(40, np.float64, 10)
+    full_chain = ContractionChain(ctx, ts, wl.HEFF_STEPS, np.float64)
+    full_chain.apply_device()
+    want = full_chain.result("out").data
+    full_chain.close()
+    world = 8
+    chains = [ShardedChain(ctx, ts, wl.HEFF_STEPS, "lenv", 2, np.float64, world, r, exchange="fused", peers=[]) for r in range(world)]
+    assert any(sc.idle for sc in chains) and not all(sc.idle for sc in chains)
+    for sc in chains[1:]:
+        sc.peer_ptrs = [chains[0].full_base]
+    for sc in chains:
+        n = sc.apply()
+        assert (n == 0) == sc.idle
+    ctx.sync()
+    got = np.empty_like(want)
+    tk._lib.check(tk._lib.lib.qlb200_memcpy_d2h(ctx.h, got.ctypes.data, chains[0].full_ptr, got.nbytes), "d2h")
+    ctx.sync()
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= 1e-12
+    for sc in chains:
+        sc.close()
 
 
 def test_plan_reads_heff_blocks_in_place():
