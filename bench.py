@@ -37,7 +37,12 @@ def parse():
                          "Hubbard H_eff apply, default D=8192 double); ragged: configs[4] (10^4 random blocks, permute + grouped GEMM)")
     ap.add_argument("--D", type=int, default=None, help="bond dimension (default 4096; 8192 for heff_hubbard)")
     ap.add_argument("--dtype", default=None, choices=["c128", "f64"], help="default c128; f64 for heff_hubbard and ragged")
-    ap.add_argument("--cpu-sample-D", type=int, default=2048)
+    ap.add_argument("--cpu-sample-D", type=int, default=0, help="reference arm / cpu_baseline: bond dimension of the CPU run (0 = the workload's own D, i.e. the same configuration)")
+    ap.add_argument("--cpu-time-cap", type=float, default=150.0, help="reference arm: stop adding timed applies after this many seconds (steps actually run are reported)")
+    ap.add_argument("--sweep-D", type=int, default=2048, help="reference arm: bond dimension of the thread sweep")
+    ap.add_argument("--no-thread-sweep", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="GPU arm: timed applies of the cpu_baseline child")
+    ap.add_argument("--write-out", default="", help="reference arm: write the result tensor of the apply to this file (the reference's stream format)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--plan-flags", type=int, default=1, help="qlb200_plan_create flags (kernel A/B testing; 1 = default)")
@@ -173,28 +178,39 @@ def build_tensors(D, dtype, rng, workload="heff_u1"):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_apply(D, dtype, reps, threads, workload="heff_u1"):
-    """The reference's own CPU path (oracle/_ref: TensorToolkit + HPTT + OpenBLAS) on one H_eff apply.
-    Returns (best seconds per apply, flops per apply)."""
-    from oracle import refbridge as ref
-    from tensortoolkit_b200 import workloads as wl
-    ref.lib()
-    ref.set_threads(threads)
-    ref.set_seed(workload_seed(workload, dtype))
-    ti = wl.heff_tensor_indexes(workload_indexes(workload, D))
-    div = (0,) * ti["psi"][0].kind.nvals
-    r = {name: ref.RefTensor.new(idxs, np_dtype(dtype)).random(div) for name, idxs in ti.items()}
-    flops = 0.0
-    for lhs, rhs, axes, out in wl.HEFF_STEPS:          # warm-up pass, also builds the intermediates
-        flops += ref.contract_cost(r[lhs], r[rhs], axes)["flops"]
-        r[out] = ref.contract(r[lhs], r[rhs], axes)
-    best = float("inf")
-    for _ in range(reps):
-        t = 0.0
-        for lhs, rhs, axes, out in wl.HEFF_STEPS:
-            t += ref.contract_time(r[lhs], r[rhs], axes, 1)
-        best = min(best, t)
-    return best, flops
+class RefApply:
+    """The reference's own CPU path (oracle/_ref/libqlref.so: TensorToolkit + HPTT + OpenBLAS) on one H_eff apply:
+    operands built once (the reference's seeded Random, or files written in its stream format), every apply = the four
+    chained qlten::Contract calls of workloads.HEFF_STEPS, Contract calls only inside the timed region."""
+
+    def __init__(self, D, dtype, workload="heff_u1", tensors_dir="", qn="U1QN"):
+        from oracle import refbridge as ref
+        from tensortoolkit_b200 import workloads as wl
+        self.ref, self.wl = ref, wl
+        ref.lib()
+        ti = wl.heff_tensor_indexes(workload_indexes(workload, D))
+        if tensors_dir:
+            import tensortoolkit_b200 as tk
+            from tensortoolkit_b200 import qlten_io
+            kind = {k.name: k for k in (tk.U1, tk.fU1, tk.U1U1, tk.fU1U1, tk.Z2, tk.fZ2)}[qn]
+            self.r = {}
+            for name in ("lenv", "psi", "mpo1", "mpo2", "renv"):
+                path = os.path.join(tensors_dir, name + ".qlten")
+                idxs = qlten_io.load(path, kind, np_dtype(dtype)).indexes       # our reader: indexes only (to type the handle)
+                self.r[name] = ref.RefTensor.new(idxs, np_dtype(dtype)).read_file(path)   # the reference's own reader
+        else:
+            ref.set_seed(workload_seed(workload, dtype))
+            div = (0,) * ti["psi"][0].kind.nvals
+            self.r = {name: ref.RefTensor.new(idxs, np_dtype(dtype)).random(div) for name, idxs in ti.items()}
+        self.flops = 0.0
+        for lhs, rhs, axes, out in wl.HEFF_STEPS:       # builds the intermediates; doubles as the warm-up pass
+            self.flops += ref.contract_cost(self.r[lhs], self.r[rhs], axes)["flops"]
+            self.r[out] = ref.contract(self.r[lhs], self.r[rhs], axes)
+
+    def apply(self, threads):
+        """Seconds of one apply (sum of the four Contract calls)."""
+        self.ref.set_threads(threads)
+        return sum(self.ref.contract_time(self.r[lhs], self.r[rhs], axes, 1) for lhs, rhs, axes, _ in self.wl.HEFF_STEPS)
 
 
 def pick_threads():
@@ -210,27 +226,65 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun injects OMP_NUM_THREADS=1; the reference arm uses every host core it can (set before the BLAS / OpenMP
+    # runtimes are loaded, and again explicitly through the reference's own SetTensorManipulationThreads)
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "GOTO_NUM_THREADS"):
+        os.environ.pop(k, None)
     threads = pick_threads()
-    D = args.cpu_sample_D
+    D = args.cpu_sample_D or args.D          # default: the SAME configuration as the GPU arm
+    t_setup = time.perf_counter()
+    ra = RefApply(D, args.dtype, args.workload, args.tensors, args.qn)
     times = []
-    flops = None
-    for _ in range(max(1, args.warmup)):
-        cpu_reference_apply(D, args.dtype, 1, threads, args.workload)
+    # calibration (doubles as warm-up): all host threads vs half of them -- HPTT's OpenMP pool and OpenBLAS's pthread pool
+    # oversubscribe on some boxes; the timed run uses whichever is faster, `cores` says which
+    all_threads = threads
+    if threads >= 4:
+        cal = {t: ra.apply(t) for t in (threads, threads // 2)}
+        threads = min(cal, key=cal.get)
+    for _ in range(max(0, args.warmup - 2)):          # RefApply's constructor already ran one full apply
+        ra.apply(threads)
+        if time.perf_counter() - t_setup > args.cpu_time_cap / 2:
+            break
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sec, flops = cpu_reference_apply(D, args.dtype, 1, threads, args.workload)
-        times.append(sec)
-        if time.perf_counter() - t0 > 240:
+    for _ in range(max(1, args.steps)):
+        times.append(ra.apply(threads))
+        if time.perf_counter() - t0 > args.cpu_time_cap:       # bounded sample: report the steps actually run
             break
     sec = float(np.mean(times))
-    val = flops / sec / 1e9
-    sample = f"one H_eff apply at D={D} ({flops / 1e9:.1f} GFLOP; the D={args.D} workload is {(args.D / D) ** 3:.0f}x the flops), Contract calls only"
+    val = ra.flops / sec / 1e9
+    if args.write_out:
+        ra.r["out"].write_file(args.write_out)             # the reference's result, in its own stream format (parity check)
+    # thread sweep: best-t vs all-cores, on a smaller bond dimension so that t = 1 stays bounded
+    sweep = None
+    if not args.no_thread_sweep:
+        Ds = min(D, args.sweep_D)
+        rs = ra if (Ds == D and not args.tensors) else RefApply(Ds, args.dtype, args.workload)
+        sweep = {"D": Ds, "gflops_by_threads": {}}
+        t = 1
+        cand = []
+        while t < all_threads:
+            cand.append(t); t *= 2
+        cand.append(all_threads)
+        budget = time.perf_counter() + args.cpu_time_cap / 2
+        for t in reversed(cand):                  # most threads first; stop when the budget is gone
+            if time.perf_counter() > budget:
+                break
+            best = min(rs.apply(t) for _ in range(2))
+            sweep["gflops_by_threads"][str(t)] = rs.flops / best / 1e9
+        bt = max(sweep["gflops_by_threads"], key=lambda k: sweep["gflops_by_threads"][k])
+        sweep["best_threads"], sweep["best_gflops"] = int(bt), sweep["gflops_by_threads"][bt]
+    same = D == args.D
+    sample = (f"{len(times)} H_eff applies at D={D} ({ra.flops / 1e9:.1f} GFLOP each"
+              + ("" if same else f"; the D={args.D} workload is {(args.D / D) ** 3:.0f}x the flops") + "), Contract calls only, "
+              f"{threads} of {all_threads} host threads (the faster of all / half, OMP_WAIT_POLICY=passive)")
     line = {
         "impl": "reference", "metric": "block-sparse contraction useful FP64 GFLOP/s", "value": val, "unit": "GFLOP/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "c64(f64 pairs)" if args.dtype == "c128" else "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.D, args.dtype, args.workload), "bounded_sample": sample},
-        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": "reference", "sample": sample},
+        "scaling": "strong", "vs_baseline": None, "dtype": "c64(f64 pairs)" if args.dtype == "c128" else "f64",
+        "data": "files" if args.tensors else "synthetic",
+        "config": {"workload": workload_name(args.D, args.dtype, args.workload), "bounded_sample": sample, "same_config": same,
+                   "steps_requested": args.steps},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": "reference", "sample": sample, "thread_sweep": sweep},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -469,30 +523,60 @@ def run_ours(args):
     for k in kern:
         k["frac"] = k["achieved"] / (peak_burst if k["bound"] == "tensor" else hbm_peak)
 
-    cpu = None
-    if not args.no_cpu_baseline and world == 1 and not args.tensors:
+    cpu, parity = None, None
+    if not args.no_cpu_baseline and world == 1:
+        import shutil
+        import tempfile
+        from tensortoolkit_b200 import qlten_io
+        tmp = tempfile.mkdtemp(prefix="qlb200_bench_")
         try:
-            # a clean child process (no torch / CUDA runtime threads competing with HPTT's and OpenBLAS's pools):
-            # exactly what `bench.py --impl reference` measures
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                                  "--D", str(args.D), "--dtype", dtype, "--cpu-sample-D", str(args.cpu_sample_D), "--workload", args.workload],
-                                 capture_output=True, text=True, timeout=900, env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+            # The reference's CPU path on THIS input, in a clean child process (no torch / CUDA runtime threads competing
+            # with HPTT's and OpenBLAS's pools) -- exactly what `bench.py --impl reference` measures.  The operands travel
+            # in the reference's own tensor file format; its result comes back the same way and is compared with ours.
+            cD = args.cpu_sample_D or args.D
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(args.cpu_steps), "--warmup", "1",
+                   "--D", str(args.D), "--dtype", dtype, "--cpu-sample-D", str(cD), "--workload", args.workload,
+                   "--cpu-time-cap", str(args.cpu_time_cap)]
+            same = cD == args.D and not args.shard_of
+            if same:
+                qn = args.qn if args.tensors else ("fU1U1QN" if args.workload == "heff_hubbard" else "U1QN")
+                for name in ("lenv", "psi", "mpo1", "mpo2", "renv"):
+                    qlten_io.save(tensors[name], os.path.join(tmp, name + ".qlten"))
+                cmd += ["--tensors", tmp, "--qn", qn, "--write-out", os.path.join(tmp, "out_ref.qlten")]
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=1500,
+                                 env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
             ref_line = json.loads(out.stdout.strip().splitlines()[-1])
             cpu = dict(ref_line["cpu_baseline"])
-            cpu["sample"] += f"; reference's own CPU path (TensorToolkit Contract + HPTT + OpenBLAS 0.3.15), mean of {ref_line['steps']} applies, {ref_line['ms_per_step']:.0f} ms each"
+            cpu["sample"] += f"; reference's own CPU path (TensorToolkit Contract + HPTT + OpenBLAS 0.3.15), mean {ref_line['ms_per_step']:.0f} ms per apply"
+            if same:
+                kind = tensors["psi"].indexes[0].kind
+                want = qlten_io.load(os.path.join(tmp, "out_ref.qlten"), kind, np_dtype(dtype))
+                with torch.cuda.stream(stream):
+                    chain.upload("psi", tensors["psi"].data)
+                    chain.apply_device()
+                    got = chain.result("out")
+                parity = {"rel_fro_vs_reference": float(np.linalg.norm(got.data - want.data) / np.linalg.norm(want.data)),
+                          "same_block_structure": bool(got.same_structure(want)), "tolerance": 1e-12,
+                          "how": "result of this apply vs the reference's qlten::Contract chain on the same operands (exchanged as .qlten files)"}
+                if not (parity["same_block_structure"] and parity["rel_fro_vs_reference"] <= 1e-12):
+                    raise SystemExit(f"parity against the reference FAILED: {parity}")
+        except SystemExit:
+            raise
         except Exception as e:   # the oracle library is test infrastructure; never fatal for the product bench
-            cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+            cpu = cpu or {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
 
     line = {
         "metric": "block-sparse contraction useful FP64 GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "warmup": max(3, args.warmup), "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "c64(f64 pairs)" if dtype == "c128" else "f64", "data": "files" if args.tensors else "synthetic",
         "config": {"workload": (f"H_eff apply on tensors read from {args.tensors} ({args.qn})" if args.tensors else workload_name(args.D, dtype, args.workload)), "l2": "512 MiB flush written between timed applies; operands+intermediates (>1 GB) exceed the 126 MB L2",
                    "parallelism": (f"output-sector/row-slab x{world}, exchange={sharded.exchange}" + {"fused": " (unicast peer stores over NVLink from the GEMM epilogue)", "multicast": " (multimem.st from the GEMM epilogue, replicated by the NVSwitch)"}.get(sharded.exchange, " (NCCL)")) if world > 1 else "single GPU", "flops_per_step": flops_total,
                    "tasks_per_step": int(sum(s.ntask for s in stats)),
                    "launch": "one CUDA graph replay per apply" if graph is not None else "one host launch per kernel"},
         "pct_fp64_peak": 100.0 * value / 1e3 / peak_burst / world, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sust, "how": peak_how},
-        "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
+        "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "parity": parity,
         "e2e": {"value": flops_total / e2e_max / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_max * 1e3,
                 "h2d_bytes_per_step": int(psi_host.nbytes), "d2h_bytes_per_step": int(out_host.nbytes)},
         "gpu_launches": int(launches) * args.steps, "clocks": sampler.summary(),
@@ -511,54 +595,7 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def ragged_tables(nC=2500, pairs=4, lo=8, hi=2048, seed=20260005):
-    """BASELINE configs[4] (SURVEY.md 8d, config 5): descriptor table built directly, no QLTensor.  SplitMix64 stream;
-    every C block has (m, n) log-uniform in [lo, hi] and `pairs` contributing pairs with k log-uniform in [lo, hi];
-    A blocks stored rank-3 (k, m1, m2) with m1 the largest divisor of m <= sqrt(m), permutation {1,2,0};
-    B blocks stored (n1, k, n2), permutation {1,0,2}."""
-    state = [seed & 0xFFFFFFFFFFFFFFFF]
-
-    def splitmix():
-        state[0] = (state[0] + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
-        z = state[0]
-        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
-        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
-        return z ^ (z >> 31)
-
-    def loguniform():
-        u = (splitmix() >> 11) * (1.0 / (1 << 53))
-        return int(min(hi, max(lo, round(float(np.exp(np.log(lo) + u * (np.log(hi) - np.log(lo))))))))
-
-    def split(x):
-        d = int(x ** 0.5)
-        while x % d:
-            d -= 1
-        return d, x // d
-
-    a_shape, b_shape, a_off, b_off = [], [], [], []
-    tasks = np.zeros(nC * pairs, dtype=np.dtype([("a_blk_idx", "<u8"), ("b_blk_idx", "<u8"), ("c_blk_idx", "<u8"), ("a_off", "<u8"), ("b_off", "<u8"),
-                                                 ("c_off", "<u8"), ("a_ord", "<u4"), ("b_ord", "<u4"), ("c_ord", "<u4"), ("m", "<u4"), ("k", "<u4"),
-                                                 ("n", "<u4"), ("sign", "i1"), ("first", "u1"), ("pad_", "u1", (2,))], align=True))
-    ao = bo = co = 0
-    flops = 0.0
-    ti = 0
-    for c in range(nC):
-        m, n = loguniform(), loguniform()
-        m1, m2 = split(m)
-        n1, n2 = split(n)
-        for p in range(pairs):
-            k = loguniform()
-            t = tasks[ti]
-            t["a_blk_idx"] = t["a_ord"] = ti; t["b_blk_idx"] = t["b_ord"] = ti; t["c_blk_idx"] = t["c_ord"] = c
-            t["a_off"], t["b_off"], t["c_off"] = ao, bo, co
-            t["m"], t["k"], t["n"], t["sign"], t["first"] = m, k, n, 1, 1 if p == 0 else 0
-            a_shape.append((k, m1, m2)); b_shape.append((n1, k, n2)); a_off.append(ao); b_off.append(bo)
-            ao += m * k; bo += k * n
-            flops += 2.0 * m * k * n
-            ti += 1
-        co += m * n
-    return dict(a_shape=np.array(a_shape, np.uint32), b_shape=np.array(b_shape, np.uint32), a_off=np.array(a_off, np.uint64),
-                b_off=np.array(b_off, np.uint64), tasks=tasks, a_elems=ao, b_elems=bo, c_elems=co, flops=flops)
+from tensortoolkit_b200.workloads import ragged_tables  # noqa: E402  (BASELINE configs[4] descriptor table)
 
 
 def run_ragged(args):

@@ -47,7 +47,9 @@ enum {
   QLB200_ERR_ARG = -1,      /* precondition violated (the reference only assert()s these) */
   QLB200_ERR_CUDA = -2,     /* CUDA runtime error / no device */
   QLB200_ERR_NOMEM = -3,
-  QLB200_ERR_UNSUPPORTED = -4
+  QLB200_ERR_UNSUPPORTED = -4,
+  QLB200_ERR_LAYOUT = -5    /* accumulate form: the existing output cannot take the result (the reference's
+                               detail::ContractAccumulateLayoutMismatch; Try... returns false on it) */
 };
 
 enum { QLB200_F64 = 0, QLB200_C64 = 1 };               /* double, complex double (interleaved re,im) */
@@ -194,6 +196,15 @@ typedef struct qlb200_plan_stats {
   uint64_t gemm_read_bytes, gemm_write_bytes;  /* (mk+kn)*s per task, mn*s per C block */
 } qlb200_plan_stats;
 int qlb200_plan_get_stats(const qlb200_plan *p, qlb200_plan_stats *out);
+/* Where the GEMM reads block `ord` of operand `which` (0 = A, 1 = B): returns 0 when it is read in place from the
+ * caller's buffer (identity or one 2-D transposition), 1 when it goes through the batched permute kernel -- *ws_off is
+ * then the element offset of its permuted (row-major m x k / k x n) copy inside that operand's workspace region --
+ * or a negative error code. */
+int qlb200_plan_operand_block(const qlb200_plan *p, int which, uint64_t ord, uint64_t *ws_off);
+/* Copy `elems` elements at `elem_off` of operand `which`'s permuted workspace to host memory (after
+ * qlb200_execute_permute or qlb200_execute; synchronises).  Lets a test compare the permute kernel's output bit for bit
+ * with the reference's per-block hp_numeric::TensorTranspose (ten_trans.h:94-114). */
+int qlb200_plan_read_workspace(qlb200_ctx *ctx, qlb200_plan *p, int which, uint64_t elem_off, uint64_t elems, void *dst_host);
 /* The DMMA work-unit list in launch order (introspection for tests / tuning): a unit is the k-stage range
  * [s_begin, s_end) of output tile (tm, tn) of one output block; a tile cut along k has nsplit units (split = its slot).
  * Geometry of the plan's kernel: tile rows x cols and k elements per stage.  Returns the number of units; fills at
@@ -218,6 +229,41 @@ int qlb200_execute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B
 /* the two phases separately (device pointers only) -- used by the benchmark to time each kernel */
 int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B);
 int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C);
+/* ---- accumulate form: C = beta * C + alpha * contract(A, B) ------------------------------------ */
+/* Replaces the accumulate mode of MatrixBasedTensorContractionExecutor behind qlten::ContractTailHeadContiguousAccumulate /
+ * TryContractTailHeadContiguousAccumulate (tensor_manipulation/contract_contiguous_axes.h:954-1041; executor :333-475,
+ * :567-782).  The existing output may hold MORE blocks than the contraction produces (they are only scaled by beta) or
+ * FEWER (allow_expand: the output is rebuilt on the union topology; new blocks get a first-task beta of zero).  Everything
+ * the reference does with per-block VectorCopy / VectorScale / GEMM-with-beta calls happens in at most three launches:
+ * batched permute (if any block needs it), one scale-copy launch over the untouched blocks, and the grouped GEMM whose
+ * epilogue reads the old block once and writes  beta * C_old + alpha * sum(pairs)  at the block's new place. */
+typedef struct qlb200_accum_stats {   /* the ContiguousContractStats counters (contract_contiguous_axes.h:55-80) this path defines */
+  uint64_t raw_data_contract_tasks, gemm_calls, accumulate_calls, accumulate_gemm_calls;
+  uint64_t output_tensor_rebuilds, temporary_output_bytes_avoided;
+  uint64_t output_topology_expansions, output_expand_copy_bytes, output_expand_new_blocks, output_untouched_scale_bytes;
+} qlb200_accum_stats;
+typedef struct qlb200_accum qlb200_accum;   /* resulting output topology of one accumulate call (host only) */
+/* c_old: shell of the existing output, NULL for a default tensor (then beta must be 0: QLB200_ERR_ARG otherwise).
+ * c_old_has_data: its raw buffer is allocated.  alpha / beta: (re, im); im ignored for QLB200_F64.
+ * Returns QLB200_ERR_LAYOUT when the indexes / block shapes are incompatible or blocks are missing and !allow_expand. */
+int qlb200_accum_create(const qlb200_match *m, const qlb200_shell *c_old, int c_old_has_data, int allow_expand, int dtype,
+                        const double *alpha2, const double *beta2, qlb200_accum **out);
+void qlb200_accum_destroy(qlb200_accum *a);
+uint64_t qlb200_accum_nblk(const qlb200_accum *a);
+uint64_t qlb200_accum_elems(const qlb200_accum *a);        /* raw size of the resulting output */
+int qlb200_accum_expanded(const qlb200_accum *a);          /* 1: the output must be rebuilt on the union topology */
+/* resulting blocks in ascending blk_idx order; old_offset = ~0 for blocks the contraction adds; touched = the contraction writes it */
+int qlb200_accum_blocks(const qlb200_accum *a, uint64_t *blk_idx, uint32_t *blk_coors, uint32_t *shape, uint64_t *offset,
+                        uint64_t *old_offset, uint8_t *touched);
+int qlb200_accum_get_stats(const qlb200_accum *a, qlb200_accum_stats *out);
+int qlb200_plan_create_accum(qlb200_ctx *ctx, const qlb200_match *m, const qlb200_accum *a, int dtype, uint32_t flags,
+                             qlb200_plan **out);
+/* C_new = beta * C_old + alpha * contract(A, B) on the resulting topology.  C_old may be NULL when beta == 0 or the output
+ * was default.  Device pointers: same topology (qlb200_accum_expanded == 0) runs IN PLACE, C_old == C_new; an expanded
+ * topology needs a new buffer of qlb200_accum_elems elements, C_new != C_old.  Host pointers: any combination. */
+int qlb200_execute_accum(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, const void *C_old, void *C_new,
+                         int mem_kind);
+
 /* ---- multi-GPU: exchange fused into the GEMM epilogue ---------------------------------------- */
 /* Ranks that own disjoint row slabs of one result (qlb200_plan_partition, or operands restricted to
  * a row range) can write them straight into the full result on EVERY GPU of the NVLink domain: the

@@ -11,6 +11,83 @@
 
 using namespace qlref;
 
+namespace {
+
+// ---- tensors built from the product's host mirror (same blocks, same raw data) ----------------
+// Inserts the listed blocks (DataBlksInsert, allocating) and copies `raw` (blocks in ascending blk_idx order, the
+// reference's own layout) into the tensor.  Returns 0, or -1 when the sizes disagree.
+template<typename Box>
+int FillBlocks(Box *bx, uint64_t nblk, const uint32_t *coors, const void *raw, uint64_t nelem) {
+  auto &t = bx->t;
+  const size_t r = t.Rank();
+  auto &bsdt = t.GetBlkSparDataTen();
+  if (r == 0) {                                   // scalar: ElemSet creates the size-1 raw buffer
+    if (nelem != 1) return -1;
+    t.SetElem({}, *static_cast<const typename Box::Elem *>(raw));
+    return 0;
+  }
+  std::vector<CoorsT> cs(nblk, CoorsT(r));
+  std::vector<size_t> idxs(nblk);
+  for (uint64_t b = 0; b < nblk; ++b) {
+    for (size_t i = 0; i < r; ++i) cs[b][i] = coors[b * r + i];
+    idxs[b] = bsdt.BlkCoorsToBlkIdx(cs[b]);
+  }
+  bsdt.DataBlksInsert(idxs, cs, true, false);
+  if (bsdt.GetActualRawDataSize() != nelem) return -1;
+  std::memcpy(bsdt.GetActualRawDataPtr(), raw, nelem * sizeof(typename Box::Elem));
+  return 0;
+}
+
+// ---- the executor loop on bare descriptor tables (BASELINE configs[4], the ragged stress test) --
+// Exactly the reference's CtrctTwoBSDTAndAssignIn (global_operations.h:895-992) without the QLTensor shells: tasks
+// sorted by (c, beta); every distinct A / B block transposed once with hp_numeric::TensorTranspose (HPTT) into its own
+// buffer; one hp_numeric::MatMultiply (CBLAS) per task with alpha = sign and beta = 0 for the first task of an output
+// block, 1 for the rest.  tu = [ntask][8] {a_ord, b_ord, a_off, b_off, c_off, m, k, n}; ts = [ntask][2] {sign, beta}.
+// If a_t / b_t are given, the transposed copy of block b is also stored at a_t + a_off[b] (bit-exact permute oracle).
+template<typename ElemT>
+void RawContract(int a_rank, const int32_t *a_perm, const uint32_t *a_shape, const uint64_t *a_off, int b_rank,
+                        const int32_t *b_perm, const uint32_t *b_shape, const uint64_t *b_off, uint64_t ntask, const uint64_t *tu,
+                        const double *ts, const ElemT *A, const ElemT *B, ElemT *C, ElemT *a_t, ElemT *b_t) {
+  std::vector<uint64_t> order(ntask);
+  for (uint64_t i = 0; i < ntask; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) {
+    if (tu[8 * x + 4] != tu[8 * y + 4]) return tu[8 * x + 4] < tu[8 * y + 4];
+    return ts[2 * x + 1] < ts[2 * y + 1];
+  });
+  auto transposed = [](int rank, const int32_t *perm, const uint32_t *shape, const ElemT *src, ElemT *keep) {
+    std::vector<int> ord(perm, perm + rank);
+    std::vector<size_t> shp(shape, shape + rank);
+    std::vector<int> tshape(rank);
+    size_t size = 1;
+    for (int i = 0; i < rank; ++i) { tshape[i] = (int) shape[perm[i]]; size *= shape[i]; }
+    ElemT *out = (ElemT *) qlten::QLMalloc(size * sizeof(ElemT));
+    hp_numeric::TensorTranspose(ord, (size_t) rank, const_cast<ElemT *>(src), shp, out, tshape, 1.0);
+    if (keep) std::memcpy(keep, out, size * sizeof(ElemT));
+    return out;
+  };
+  std::unordered_map<uint64_t, ElemT *> ta, tb;
+  for (uint64_t oi = 0; oi < ntask; ++oi) {
+    const uint64_t *u = tu + 8 * order[oi];
+    const double sign = ts[2 * order[oi]], beta = ts[2 * order[oi] + 1];
+    const ElemT *a = A + u[2], *b = B + u[3];
+    if (a_perm) {
+      auto it = ta.find(u[0]);
+      if (it == ta.end()) it = ta.emplace(u[0], transposed(a_rank, a_perm, a_shape + u[0] * a_rank, a, a_t ? a_t + a_off[u[0]] : nullptr)).first;
+      a = it->second;
+    }
+    if (b_perm) {
+      auto it = tb.find(u[1]);
+      if (it == tb.end()) it = tb.emplace(u[1], transposed(b_rank, b_perm, b_shape + u[1] * b_rank, b, b_t ? b_t + b_off[u[1]] : nullptr)).first;
+      b = it->second;
+    }
+    hp_numeric::MatMultiply(sign, a, b, (size_t) u[5], (size_t) u[6], (size_t) u[7], ElemT(beta), C + u[4]);
+  }
+  for (auto &kv : ta) qlten::QLFree(kv.second);
+  for (auto &kv : tb) qlten::QLFree(kv.second);
+}
+
+}  // namespace
+
 extern "C" {
 
 void qlref_set_seed(uint64_t seed) { SetRandomSeed((size_t) seed); }
@@ -84,6 +161,33 @@ int qlref_tensor_write(const void *t, const char *path) { return static_cast<con
 int qlref_tensor_read(void *t, const char *path) { return static_cast<TenBase *>(t)->read_file(path); }
 void *qlref_contract_contiguous(const void *a, const void *b, int64_t a_start, int64_t b_start, int64_t size, int side) {
   return static_cast<const TenBase *>(a)->contract_contiguous(static_cast<const TenBase *>(b), a_start, b_start, size, side);
+}
+
+int qlref_tensor_fill(void *t, uint64_t nblk, const uint32_t *coors, const void *raw, uint64_t nelem) {
+  TenBase *tb = static_cast<TenBase *>(t);
+#define QLREF_FILL(K, QN)                                                                                           \
+  case K:                                                                                                           \
+    if (tb->dtype == D_F64) return FillBlocks(static_cast<TenBox<QLTEN_Double, QN> *>(tb), nblk, coors, raw, nelem); \
+    return FillBlocks(static_cast<TenBox<QLTEN_Complex, QN> *>(tb), nblk, coors, raw, nelem);
+  switch (tb->kind) {
+    QLREF_FILL(K_U1, U1QN) QLREF_FILL(K_FU1, fU1QN) QLREF_FILL(K_U1U1, U1U1QN)
+    QLREF_FILL(K_FU1U1, fU1U1QN) QLREF_FILL(K_Z2, Z2QN) QLREF_FILL(K_FZ2, fZ2QN)
+    default: return -1;
+  }
+#undef QLREF_FILL
+}
+
+double qlref_raw_contract(int dtype, int a_rank, const int32_t *a_perm, const uint32_t *a_shape, const uint64_t *a_off, int b_rank,
+                          const int32_t *b_perm, const uint32_t *b_shape, const uint64_t *b_off, uint64_t ntask, const uint64_t *tu,
+                          const double *ts, const void *A, const void *B, void *C, void *a_t, void *b_t) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (dtype == D_F64)
+    RawContract<QLTEN_Double>(a_rank, a_perm, a_shape, a_off, b_rank, b_perm, b_shape, b_off, ntask, tu, ts, (const QLTEN_Double *) A,
+                              (const QLTEN_Double *) B, (QLTEN_Double *) C, (QLTEN_Double *) a_t, (QLTEN_Double *) b_t);
+  else
+    RawContract<QLTEN_Complex>(a_rank, a_perm, a_shape, a_off, b_rank, b_perm, b_shape, b_off, ntask, tu, ts, (const QLTEN_Complex *) A,
+                               (const QLTEN_Complex *) B, (QLTEN_Complex *) C, (QLTEN_Complex *) a_t, (QLTEN_Complex *) b_t);
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // extern "C"

@@ -12,7 +12,9 @@
 #include <cstring>
 #include <fstream>
 #include <chrono>
+#include <algorithm>
 #include <memory>
+#include <unordered_map>
 #include <string>
 #include <vector>
 

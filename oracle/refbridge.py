@@ -61,6 +61,10 @@ def lib():
             "qlref_tensor_write": (C.c_int, [_P, C.c_char_p]),
             "qlref_tensor_read": (C.c_int, [_P, C.c_char_p]),
             "qlref_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+            "qlref_tensor_fill": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_uint32), _P, C.c_uint64]),
+            "qlref_raw_contract": (C.c_double, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                                C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                                C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_double), _P, _P, _P, _P, _P]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -131,6 +135,18 @@ class RefTensor:
     def random(self, div):
         lib().qlref_tensor_random(self.h, _i64(list(div)))
         return self
+
+    @staticmethod
+    def from_bst(t: BlockSparseTensor) -> "RefTensor":
+        """A reference tensor with the same indexes, stored blocks and raw data as the product's host mirror."""
+        r = RefTensor.new(t.indexes, t.dtype)
+        coors = np.ascontiguousarray(t.blk_coors, dtype=np.uint32)
+        data = np.ascontiguousarray(t.data)
+        if data.size:
+            rc = lib().qlref_tensor_fill(r.h, t.nblk, coors.ctypes.data_as(C.POINTER(C.c_uint32)), data.ctypes.data, data.size)
+            if rc != 0:
+                raise RuntimeError("qlref_tensor_fill: block list and raw size disagree")
+        return r
 
     def clone(self) -> "RefTensor":
         return RefTensor(lib().qlref_tensor_clone(self.h), self.indexes, self.dtype)
@@ -284,6 +300,32 @@ def b200_contract_contiguous(a: RefTensor, b: RefTensor, a_start: int, b_start: 
     if not h:
         raise RuntimeError("qlref_b200_contract_contiguous failed (see stderr)")
     return RefTensor(h, _c_indexes_cyclic(a, b, a_start, b_start, size), a.dtype)
+
+
+def raw_contract(dtype, a_rank, a_perm, a_shape, a_off, b_rank, b_perm, b_shape, b_off, tasks, A, B, c_elems, keep_permuted=False):
+    """The reference's executor loop (CtrctTwoBSDTAndAssignIn, global_operations.h:895-992) on bare descriptor tables:
+    hp_numeric::TensorTranspose per distinct block + hp_numeric::MatMultiply per task.  `tasks`: structured array /
+    sequence with a_ord, b_ord, a_off, b_off, c_off, m, k, n, sign, first.  a_perm / b_perm None = no transpose.
+    Returns (C, seconds[, A_permuted, B_permuted]) -- permuted block b lies at a_off[b] of A_permuted."""
+    dtype = np.dtype(dtype)
+    n = len(tasks)
+    tu = np.zeros((n, 8), np.uint64); ts = np.zeros((n, 2), np.float64)
+    for i, t in enumerate(tasks):
+        tu[i] = (t["a_ord"], t["b_ord"], t["a_off"], t["b_off"], t["c_off"], t["m"], t["k"], t["n"])
+        ts[i] = (t["sign"], 0.0 if t["first"] else 1.0)
+    ash = np.ascontiguousarray(np.asarray(a_shape, np.uint32).reshape(-1)); bsh = np.ascontiguousarray(np.asarray(b_shape, np.uint32).reshape(-1))
+    aof = np.ascontiguousarray(np.asarray(a_off, np.uint64)); bof = np.ascontiguousarray(np.asarray(b_off, np.uint64))
+    A = np.ascontiguousarray(A, dtype=dtype); B = np.ascontiguousarray(B, dtype=dtype)
+    Cout = np.zeros(c_elems, dtype)
+    At = np.zeros_like(A) if keep_permuted and a_perm is not None else None
+    Bt = np.zeros_like(B) if keep_permuted and b_perm is not None else None
+    i32 = lambda v: (C.c_int32 * len(v))(*[int(x) for x in v]) if v is not None else None
+    u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    sec = lib().qlref_raw_contract(0 if dtype == np.float64 else 1, a_rank, i32(a_perm), ash.ctypes.data_as(u32p), aof.ctypes.data_as(u64p),
+                                   b_rank, i32(b_perm), bsh.ctypes.data_as(u32p), bof.ctypes.data_as(u64p), n,
+                                   tu.ctypes.data_as(u64p), ts.ctypes.data_as(C.POINTER(C.c_double)), A.ctypes.data, B.ctypes.data,
+                                   Cout.ctypes.data, At.ctypes.data if At is not None else None, Bt.ctypes.data if Bt is not None else None)
+    return (Cout, sec, At, Bt) if keep_permuted else (Cout, sec)
 
 
 def contract_tasks(a: RefTensor, b: RefTensor, axes, sorted_by_c=False):

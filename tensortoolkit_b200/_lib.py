@@ -105,6 +105,8 @@ SYMBOLS = {
     "qlb200_plan_c_range_count": (C.c_uint64, [_P]),
     "qlb200_plan_c_ranges": (C.c_int, [_P, _U64P, _U64P]),
     "qlb200_plan_get_stats": (C.c_int, [_P, C.POINTER(PlanStats)]),
+    "qlb200_plan_operand_block": (C.c_int, [_P, C.c_int, C.c_uint64, _U64P]),
+    "qlb200_plan_read_workspace": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, _P]),
     "qlb200_plan_units": (C.c_uint64, [_P, C.c_uint64, C.POINTER(Unit), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "qlb200_plan_segments": (C.c_uint64, [_P, C.c_uint64, C.POINTER(C.c_uint32)]),
     "qlb200_execute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),

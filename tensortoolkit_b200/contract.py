@@ -216,6 +216,20 @@ class ContractionPlan:
         check(lib.qlb200_plan_remap_output(self.h, len(f), f.ctypes.data_as(C.POINTER(C.c_uint64)), t.ctypes.data_as(C.POINTER(C.c_uint64))),
               "qlb200_plan_remap_output")
 
+    def operand_block(self, which: int, ord_: int):
+        """None when the GEMM reads block `ord_` of operand `which` in place, else its element offset in the permuted workspace."""
+        off = C.c_uint64()
+        rc = lib.qlb200_plan_operand_block(self.h, which, ord_, C.byref(off))
+        if rc < 0:
+            check(rc, "qlb200_plan_operand_block")
+        return int(off.value) if rc == 1 else None
+
+    def read_workspace(self, which: int, elem_off: int, elems: int) -> np.ndarray:
+        """Permuted copy of operand `which` (elements [elem_off, elem_off + elems) of its workspace region) after execute_permute."""
+        out = np.empty(elems, self.dtype)
+        check(lib.qlb200_plan_read_workspace(self.ctx.h, self.h, which, elem_off, elems, out.ctypes.data), "qlb200_plan_read_workspace")
+        return out
+
     def execute_permute(self, a_ptr: int, b_ptr: int):
         check(lib.qlb200_execute_permute(self.ctx.h, self.h, C.c_void_p(a_ptr), C.c_void_p(b_ptr)), "qlb200_execute_permute")
 

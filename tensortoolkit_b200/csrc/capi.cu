@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" surface declared in include/qlb200.h.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -103,12 +104,17 @@ GemmParams MakeParams(const qlb200_plan *p, const void *A, const void *B, const 
   gp.seg = p->h.seg.empty() ? nullptr : p->d.seg;
   gp.nseg = p->h.seg.empty() ? 0u : static_cast<uint32_t>(p->h.seg.size() - 1);
   gp.counters = p->d.counters;
+  gp.accum = 0; gp.c_in = nullptr;
+  gp.alpha_re = 1.0; gp.alpha_im = 0.0; gp.beta_re = 0.0; gp.beta_im = 0.0;
   return gp;
 }
 
-void SetPlanKnobs(const qlb200_ctx *ctx, uint32_t flags, PlanHost *h) {
+void SetPlanKnobs(const qlb200_ctx *ctx, uint32_t *flags, PlanHost *h) {
   h->num_sms = ctx ? ctx->num_sms : 148;
-  (void) flags;
+  // process-wide choice of the complex product: QLB200_COMPLEX_PRODUCT=4m plans every complex contraction with the
+  // four-product kernel (componentwise-accurate small parts; see DESIGN.md section 4 "Why 3M, and when not")
+  if (const char *cp = std::getenv("QLB200_COMPLEX_PRODUCT"))
+    if (cp[0] == '4') *flags |= QLB200_PLAN_CPLX_4M;
 }
 
 size_t WsBytes(const qlb200_plan *p) {
@@ -301,7 +307,7 @@ int qlb200_plan_create(qlb200_ctx *ctx, const qlb200_match *m, const qlb200_shel
   qlb200_plan *p = new (std::nothrow) qlb200_plan();
   if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
   p->ctx = ctx;
-  SetPlanKnobs(ctx, flags, &p->h);
+  SetPlanKnobs(ctx, &flags, &p->h);
   std::vector<int32_t> ap(mm.a_perm.begin(), mm.a_perm.end()), bp(mm.b_perm.begin(), mm.b_perm.end());
   std::string err = BuildPlanHost(dtype, flags, static_cast<int>(mm.a_ctrct.size()), mm.a.rank, ap.data(), mm.a.nblk,
                                   mm.a.shape.data(), mm.a.offset.data(), mm.a.elems, mm.b.rank, bp.data(), mm.b.nblk,
@@ -344,7 +350,7 @@ int qlb200_plan_create_raw(qlb200_ctx *ctx, int dtype, uint32_t flags, int32_t a
   qlb200_plan *p = new (std::nothrow) qlb200_plan();
   if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
   p->ctx = ctx;
-  SetPlanKnobs(ctx, flags, &p->h);
+  SetPlanKnobs(ctx, &flags, &p->h);
   std::string err = BuildPlanHost(dtype, flags, 0, a_rank, a_perm, na, a_shape, a_off, total(a_rank, na, a_shape, a_off),
                                   b_rank, b_perm, nb, b_shape, b_off, total(b_rank, nb, b_shape, b_off), st, c_elems, &p->h);
   if (!err.empty()) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, err); }
@@ -362,6 +368,7 @@ void qlb200_plan_destroy(qlb200_plan *p) {
   cudaSetDevice(p->ctx->device);
   cudaStreamSynchronize(p->ctx->stream);
   p->d.Free();
+  if (p->d_acc_ranges) cudaFree(p->d_acc_ranges);
   delete p;
 }
 
@@ -402,6 +409,29 @@ int qlb200_plan_get_stats(const qlb200_plan *p, qlb200_plan_stats *out) {
   out->workspace_bytes = WsBytes(p);
   out->gemm_read_bytes = p->h.gemm_read_bytes;
   out->gemm_write_bytes = p->h.gemm_write_bytes;
+  return QLB200_OK;
+}
+
+int qlb200_plan_operand_block(const qlb200_plan *p, int which, uint64_t ord, uint64_t *ws_off) {
+  if (!p || (which != 0 && which != 1)) return Fail(QLB200_ERR_ARG, "bad argument");
+  const std::vector<uint64_t> &v = which == 0 ? p->h.ws_off_a : p->h.ws_off_b;
+  if (ord >= v.size()) return Fail(QLB200_ERR_ARG, "block ordinal out of range");
+  if (v[ord] == ~0ull) return 0;
+  if (ws_off) *ws_off = v[ord];
+  return 1;
+}
+
+int qlb200_plan_read_workspace(qlb200_ctx *ctx, qlb200_plan *p, int which, uint64_t elem_off, uint64_t elems, void *dst_host) {
+  if (!ctx || !p || !dst_host || (which != 0 && which != 1)) return Fail(QLB200_ERR_ARG, "bad argument");
+  if (p->ctx != ctx) return Fail(QLB200_ERR_ARG, "plan belongs to another context");
+  const size_t es = ElemSize(p->h.dtype);
+  const uint64_t have = which == 0 ? p->h.ws_a_elems : p->h.ws_b_elems;
+  if (elem_off > have || elems > have - elem_off) return Fail(QLB200_ERR_ARG, "range outside the permuted workspace");
+  if (WsBytes(p) > ctx->ws_bytes) return Fail(QLB200_ERR_ARG, "workspace not populated: call qlb200_execute_permute first");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  const char *base = static_cast<const char *>(ctx->ws) + (which == 0 ? 0 : Align256(p->h.ws_a_elems * es));
+  QL_CUDA(cudaMemcpyAsync(dst_host, base + elem_off * es, elems * es, cudaMemcpyDeviceToHost, ctx->stream));
+  QL_CUDA(cudaStreamSynchronize(ctx->stream));
   return QLB200_OK;
 }
 
@@ -471,7 +501,7 @@ int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const
 }
 
 static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *const *c_out, uint32_t n_out,
-                       uint32_t mcast = 0) {
+                       uint32_t mcast = 0, const void *c_in = nullptr) {
   int ok = CheckExec(ctx, p, A, B);
   if (ok != QLB200_OK) return ok;
   if (!c_out || n_out < 1 || n_out > uint32_t(kMaxOut)) return Fail(QLB200_ERR_ARG, "bad output list");
@@ -482,6 +512,12 @@ static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const voi
   if (rc != QLB200_OK) return rc;
   ctx->launches = 0;
   GemmParams gp = MakeParams(p, A, B, wa, wb, parts, c_out, n_out, mcast);
+  if (p->accum) {
+    if (n_out != 1 || mcast) return Fail(QLB200_ERR_UNSUPPORTED, "an accumulate plan writes one local output (use qlb200_execute_accum)");
+    if (p->h.flags & QLB200_PLAN_LEGACY_GEMM) return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels have no accumulate epilogue");
+    gp.accum = 1; gp.c_in = c_in;
+    gp.alpha_re = p->alpha[0]; gp.alpha_im = p->alpha[1]; gp.beta_re = p->beta[0]; gp.beta_im = p->beta[1];
+  }
   // A plan that has both DMMA tiles and a handful of narrow-pair items (the small sectors of a GEMM-shaped step):
   // the narrow kernel is a 10-15 us latency-bound launch on a few SMs.  It is forked onto the side stream FIRST, so the
   // persistent DMMA CTAs fill the remaining SMs at once and the narrow kernel costs no time of its own (two in-order
@@ -673,6 +709,174 @@ int qlb200_execute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B
         QL_CUDA(cudaMemcpyAsync(static_cast<char *>(C) + o, static_cast<char *>(dC) + o, l, cudaMemcpyDeviceToHost, ctx->stream));
       }
     }
+    QL_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return QLB200_OK;
+}
+
+// ---- accumulate form ------------------------------------------------------------------------------
+struct qlb200_accum {
+  AccumLayout L;
+  int dtype = 0;
+  double alpha[2] = {1.0, 0.0}, beta[2] = {0.0, 0.0};
+};
+
+int qlb200_accum_create(const qlb200_match *m, const qlb200_shell *c_old, int c_old_has_data, int allow_expand, int dtype,
+                        const double *alpha2, const double *beta2, qlb200_accum **out) {
+  if (!m || !out || !alpha2 || !beta2) return Fail(QLB200_ERR_ARG, "null argument");
+  if (dtype != QLB200_F64 && dtype != QLB200_C64) return Fail(QLB200_ERR_ARG, "bad dtype");
+  const double bi = dtype == QLB200_C64 ? beta2[1] : 0.0, ai = dtype == QLB200_C64 ? alpha2[1] : 0.0;
+  const bool beta_zero = beta2[0] == 0.0 && bi == 0.0, beta_one = beta2[0] == 1.0 && bi == 0.0;
+  // the reference's argument checks (contract_contiguous_axes.h:376-380, :683-688): no existing values to scale
+  if (c_old == nullptr && !beta_zero) return Fail(QLB200_ERR_ARG, "accumulate into a default output requires beta == 0");
+  if (c_old != nullptr && !c_old_has_data && !beta_zero) return Fail(QLB200_ERR_ARG, "accumulate requires allocated output raw data unless beta == 0");
+  qlb200_accum *a = new (std::nothrow) qlb200_accum();
+  if (!a) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  a->dtype = dtype;
+  a->alpha[0] = alpha2[0]; a->alpha[1] = ai; a->beta[0] = beta2[0]; a->beta[1] = bi;
+  bool mismatch = false;
+  std::string err = BuildAccumLayout(m->m, c_old, c_old_has_data != 0, allow_expand != 0, dtype, beta_zero, beta_one, &a->L, &mismatch);
+  if (!err.empty()) { delete a; return Fail(mismatch ? QLB200_ERR_LAYOUT : QLB200_ERR_ARG, err); }
+  *out = a;
+  return QLB200_OK;
+}
+void qlb200_accum_destroy(qlb200_accum *a) { delete a; }
+uint64_t qlb200_accum_nblk(const qlb200_accum *a) { return a ? a->L.blocks.size() : 0; }
+uint64_t qlb200_accum_elems(const qlb200_accum *a) { return a ? a->L.elems : 0; }
+int qlb200_accum_expanded(const qlb200_accum *a) { return a && a->L.expanded ? 1 : 0; }
+int qlb200_accum_blocks(const qlb200_accum *a, uint64_t *blk_idx, uint32_t *blk_coors, uint32_t *shape, uint64_t *offset,
+                        uint64_t *old_offset, uint8_t *touched) {
+  if (!a) return Fail(QLB200_ERR_ARG, "null argument");
+  const int r = a->L.rank;
+  for (size_t b = 0; b < a->L.blocks.size(); ++b) {
+    const CBlock &cb = a->L.blocks[b];
+    if (blk_idx) blk_idx[b] = cb.blk_idx;
+    if (offset) offset[b] = cb.offset;
+    if (old_offset) old_offset[b] = a->L.old_off[b];
+    if (touched) touched[b] = a->L.touched[b];
+    for (int i = 0; i < r; ++i) {
+      if (blk_coors) blk_coors[b * r + i] = cb.coors[i];
+      if (shape) shape[b * r + i] = cb.shape[i];
+    }
+  }
+  return QLB200_OK;
+}
+int qlb200_accum_get_stats(const qlb200_accum *a, qlb200_accum_stats *out) {
+  if (!a || !out) return Fail(QLB200_ERR_ARG, "null argument");
+  *out = a->L.stats;
+  return QLB200_OK;
+}
+
+int qlb200_plan_create_accum(qlb200_ctx *ctx, const qlb200_match *m, const qlb200_accum *a, int dtype, uint32_t flags,
+                             qlb200_plan **out) {
+  if (!m || !a || !out) return Fail(QLB200_ERR_ARG, "null argument");
+  if (dtype != a->dtype) return Fail(QLB200_ERR_ARG, "dtype differs from the accumulate layout's");
+  if (flags & QLB200_PLAN_LEGACY_GEMM) return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels have no accumulate epilogue");
+  const Match &mm = m->m;
+  const AccumLayout &L = a->L;
+  const bool beta_zero = a->beta[0] == 0.0 && a->beta[1] == 0.0, beta_one = a->beta[0] == 1.0 && a->beta[1] == 0.0;
+  // tasks addressed in the RESULTING topology
+  std::vector<qlb200_task> st = mm.SortedTasks();
+  if (!mm.scalar) {
+    for (qlb200_task &t : st) {
+      const uint64_t u = L.req_to_union[t.c_ord];
+      t.c_off = L.blocks[u].offset;
+      t.c_ord = static_cast<uint32_t>(u);
+    }
+  }
+  qlb200_plan *p = new (std::nothrow) qlb200_plan();
+  if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  p->ctx = ctx;
+  SetPlanKnobs(ctx, &flags, &p->h);
+  std::vector<int32_t> ap(mm.a_perm.begin(), mm.a_perm.end()), bp(mm.b_perm.begin(), mm.b_perm.end());
+  std::string err = BuildPlanHost(dtype, flags, static_cast<int>(mm.a_ctrct.size()), mm.a.rank, ap.data(), mm.a.nblk,
+                                  mm.a.shape.data(), mm.a.offset.data(), mm.a.elems, mm.b.rank, bp.data(), mm.b.nblk,
+                                  mm.b.shape.data(), mm.b.offset.data(), mm.b.elems, st, mm.scalar ? 1 : L.elems, &p->h);
+  if (!err.empty()) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, err); }
+  p->accum = true;
+  p->alpha[0] = a->alpha[0]; p->alpha[1] = a->alpha[1]; p->beta[0] = a->beta[0]; p->beta[1] = a->beta[1];
+  p->c_old_elems = L.old_elems;
+  p->acc_expanded = L.expanded;
+  // every output block the contraction touches: where its old values lie (if any are to be read)
+  auto set_in = [&](GemmGroup &g) {
+    if (mm.scalar) { g.c_in_off = 0; g.beta_on = (!beta_zero && L.old_elems == 1) ? 1u : 0u; return; }
+    auto it = std::lower_bound(L.blocks.begin(), L.blocks.end(), g.c_off, [](const CBlock &b, uint64_t off) { return b.offset < off; });
+    const size_t u = size_t(it - L.blocks.begin());
+    const bool is_new = L.c_default || L.old_off[u] == ~0ull;
+    g.c_in_off = is_new ? 0 : L.old_off[u];
+    g.beta_on = (!is_new && !beta_zero) ? 1u : 0u;
+  };
+  for (GemmGroup &g : p->h.groups) set_in(g);
+  for (GemmGroup &g : p->h.part_groups) set_in(g);
+  // output blocks the contraction does not touch: scaled in place, or scale-copied to their new place after an expansion
+  if (mm.scalar) {
+    if (st.empty() && L.old_elems == 1 && !beta_one) { p->acc_ranges.insert(p->acc_ranges.end(), {0ull, 0ull, 1ull}); }
+  } else if (!L.c_default) {
+    for (size_t u = 0; u < L.blocks.size(); ++u) {
+      if (L.touched[u] || L.old_off[u] == ~0ull) continue;
+      if (!L.expanded && beta_one) continue;
+      p->acc_ranges.insert(p->acc_ranges.end(), {(unsigned long long) L.old_off[u], (unsigned long long) L.blocks[u].offset, (unsigned long long) L.blocks[u].size});
+    }
+  }
+  if (ctx != nullptr) {
+    int rc = FinishPlan(ctx, p);
+    if (rc == QLB200_OK && !p->acc_ranges.empty()) {
+      cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p->d_acc_ranges), p->acc_ranges.size() * sizeof(unsigned long long));
+      if (e == cudaSuccess) e = cudaMemcpy(p->d_acc_ranges, p->acc_ranges.data(), p->acc_ranges.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) rc = Fail(QLB200_ERR_CUDA, CudaErr("accumulate range table", e));
+    }
+    if (rc != QLB200_OK) { p->d.Free(); if (p->d_acc_ranges) cudaFree(p->d_acc_ranges); delete p; return rc; }
+  }
+  *out = p;
+  return QLB200_OK;
+}
+
+int qlb200_execute_accum(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, const void *C_old, void *C_new, int mem_kind) {
+  int ok = CheckExec(ctx, p, A, B);
+  if (ok != QLB200_OK) return ok;
+  if (!p->accum) return Fail(QLB200_ERR_ARG, "not an accumulate plan (qlb200_plan_create_accum)");
+  if (!C_new) return Fail(QLB200_ERR_ARG, "null output");
+  const bool beta_zero = p->beta[0] == 0.0 && p->beta[1] == 0.0;
+  const bool need_old = !beta_zero && p->c_old_elems > 0;
+  if (need_old && !C_old) return Fail(QLB200_ERR_ARG, "beta != 0 needs the existing output values");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  const size_t es = ElemSize(p->h.dtype);
+  const void *dA = A, *dB = B, *dCo = C_old;
+  void *dCn = C_new;
+  if (mem_kind == QLB200_MEM_HOST) {
+    const size_t ab = Align256(p->h.a_elems * es), bb = Align256(p->h.b_elems * es), cn = Align256(p->h.c_elems * es),
+                 co = need_old ? Align256(p->c_old_elems * es) : 0;
+    int rc = EnsureArena(ctx, &ctx->stage, &ctx->stage_bytes, ab + bb + cn + co);
+    if (rc != QLB200_OK) return rc;
+    char *base = static_cast<char *>(ctx->stage);
+    QL_CUDA(cudaMemcpyAsync(base, A, p->h.a_elems * es, cudaMemcpyHostToDevice, ctx->stream));
+    QL_CUDA(cudaMemcpyAsync(base + ab, B, p->h.b_elems * es, cudaMemcpyHostToDevice, ctx->stream));
+    // same topology: the old values are staged where the result is built (in place: untouched blocks with beta == 1 stay put)
+    char *old_at = p->acc_expanded ? base + ab + bb + cn : base + ab + bb;
+    if (need_old) QL_CUDA(cudaMemcpyAsync(old_at, C_old, p->c_old_elems * es, cudaMemcpyHostToDevice, ctx->stream));
+    dA = base; dB = base + ab; dCn = base + ab + bb; dCo = need_old ? old_at : nullptr;
+  } else if (mem_kind != QLB200_MEM_DEVICE) {
+    return Fail(QLB200_ERR_ARG, "bad mem_kind");
+  } else if (need_old && !p->acc_expanded && C_old != C_new) {
+    return Fail(QLB200_ERR_ARG, "same output topology: the accumulate runs in place, pass C_old == C_new");
+  } else if (need_old && p->acc_expanded && C_old == C_new) {
+    return Fail(QLB200_ERR_ARG, "expanded output topology: C_new must be a different buffer than C_old");
+  }
+  int rc = qlb200_execute_permute(ctx, p, dA, dB);
+  if (rc != QLB200_OK) return rc;
+  uint64_t launched = ctx->launches;
+  if (!p->acc_ranges.empty()) {
+    // beta == 0: the kernel stores zeros without reading, so dCo may be null
+    QL_CUDA(LaunchScaleCopyRanges(p->h.dtype, p->d_acc_ranges, static_cast<uint32_t>(p->acc_ranges.size() / 3), dCo ? dCo : dCn, dCn,
+                                  p->beta[0], p->beta[1], ctx->num_sms, ctx->stream));
+    ++launched; ++ctx->total_launches;
+  }
+  void *outs[1] = {dCn};
+  rc = ExecuteGemm(ctx, p, dA, dB, outs, 1, 0, dCo);
+  if (rc != QLB200_OK) return rc;
+  ctx->launches += launched;
+  if (mem_kind == QLB200_MEM_HOST) {
+    QL_CUDA(cudaMemcpyAsync(C_new, dCn, p->h.c_elems * es, cudaMemcpyDeviceToHost, ctx->stream));
     QL_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   return QLB200_OK;

@@ -59,6 +59,11 @@ struct GemmGroup {
   uint32_t m, n;
   uint32_t task_begin, task_end;
   uint32_t row_begin, row_end;      // rows of the block this plan computes (multi-GPU slabs)
+  // accumulate plans (C_out = beta * C_in + alpha * sum of pairs): where the block lies in the EXISTING output, and whether
+  // it is read at all (0 for blocks the contraction adds to the output topology: their first-task beta is zero)
+  unsigned long long c_in_off;
+  uint32_t beta_on;
+  uint32_t pad_;
 };
 
 // DMMA work unit: rows [tm*BM, ..) x cols [tn*BN, ..) of a group, k-stages [s_begin, s_end) of the
@@ -96,9 +101,30 @@ struct GemmParams {
   uint32_t nseg;
   unsigned int *counters;           // [0] next tile, [1] finished CTAs, [2 + ctr] split-K arrivals (all self-resetting)
   void *partials;                   // split-K partial tiles, slot = BM x BN elements
+  // accumulate form (qlb200_execute_accum): C_out = beta * C_in + alpha * (sum of the block's pairs); alpha / beta are
+  // (re, im), im ignored for real tensors.  accum == 0: plain contraction, C_in is never read.
+  uint32_t accum;
+  const void *c_in;
+  double alpha_re, alpha_im, beta_re, beta_im;
 };
 
 #ifdef __CUDACC__
+// Epilogue of the accumulate form: v <- alpha * v + (beta_on ? beta * C_in[idx] : 0).
+__device__ __forceinline__ double AxpbyOut(const GemmParams &p, double v, const double *cin, bool beta_on) {
+  double r = p.alpha_re * v;
+  if (beta_on) r = fma(p.beta_re, *cin, r);
+  return r;
+}
+__device__ __forceinline__ double2 AxpbyOut(const GemmParams &p, double2 v, const double2 *cin, bool beta_on) {
+  double2 r = make_double2(p.alpha_re * v.x - p.alpha_im * v.y, p.alpha_re * v.y + p.alpha_im * v.x);
+  if (beta_on) {
+    const double2 c = *cin;
+    r.x += p.beta_re * c.x - p.beta_im * c.y;
+    r.y += p.beta_re * c.y + p.beta_im * c.x;
+  }
+  return r;
+}
+
 // Output stores.  With `mcast` the address is a multicast mapping of the result buffer (NVLS): the store leaves the
 // GPU once and the NVSwitch replicates it into every GPU's copy -- multimem.st is the only legal access to such memory.
 __device__ __forceinline__ void StoreOut(double2 *dst, double2 v, uint32_t mcast) {
@@ -127,6 +153,11 @@ cudaError_t LaunchPermute(int dtype, const PermBlk *blks, const uint32_t *tile_b
                           int num_sms, cudaStream_t stream);
 cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, int num_sms, cudaStream_t stream);     // writes c_out[0] only
 cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, int num_sms, cudaStream_t stream);
+// dst[dst_off[i] + j] = beta * src[src_off[i] + j], j < len[i]: the output blocks of an accumulate call that the contraction
+// does not touch (ScaleUntouchedOutputBlocks_ / ExpandOutputTopology_, contract_contiguous_axes.h:567-671).  Ranges are
+// {src_off, dst_off, len} triples in elements.
+cudaError_t LaunchScaleCopyRanges(int dtype, const unsigned long long *ranges3, uint32_t nranges, const void *src, void *dst,
+                                  double beta_re, double beta_im, int num_sms, cudaStream_t stream);
 cudaError_t ConfigureKernels();   // one-time cudaFuncSetAttribute calls
 // warp-specialised complex kernel (gemm_ws.cu), CTA tile kWsBM x kWsBN (4M arithmetic) or kWsBM x kWs3mBN (3M)
 cudaError_t LaunchGemmWsCplx(const GemmParams &p, bool three_m, int num_sms, cudaStream_t stream);

@@ -353,7 +353,7 @@ template<> struct Elem<true> {
 
 constexpr int kSkinnyTermChunk = 64;
 
-template<bool CPLX>
+template<bool CPLX, bool ACC>
 __global__ void __launch_bounds__(kSkinnyThreads, kSkinnyMinCtas)
 GemmSkinny(GemmParams p) {
   using E = Elem<CPLX>;
@@ -418,10 +418,15 @@ GemmSkinny(GemmParams p) {
     const unsigned long long cbase = g.c_off + (unsigned long long) item.row0 * n;
     for (uint32_t d = 0; d < p.n_out; ++d) {
       T *cb = static_cast<T *>(p.c_out[d]) + cbase;
+      const T *ci = static_cast<const T *>(p.c_in) + g.c_in_off + (unsigned long long) item.row0 * n;
 #pragma unroll
       for (int u = 0; u < kSkinnyPerThread; ++u) {
         const uint32_t e = tid + u * kSkinnyThreads;
-        if (e < total) StoreOut(cb + e, acc[u], p.mcast);
+        if constexpr (ACC) {
+          if (e < total) StoreOut(cb + e, AxpbyOut(p, acc[u], ci + e, g.beta_on != 0), p.mcast);
+        } else {
+          if (e < total) StoreOut(cb + e, acc[u], p.mcast);
+        }
       }
     }
   }
@@ -451,8 +456,13 @@ cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, int num_sms, cudaSt
   if (p.nitems == 0) return cudaSuccess;
   const uint32_t cap = uint32_t(num_sms) * 8u;
   const uint32_t grid = p.nitems < cap ? p.nitems : cap;
-  if (dtype == 0) GemmSkinny<false><<<grid, kSkinnyThreads, 0, stream>>>(p);
-  else GemmSkinny<true><<<grid, kSkinnyThreads, 0, stream>>>(p);
+  if (p.accum) {
+    if (dtype == 0) GemmSkinny<false, true><<<grid, kSkinnyThreads, 0, stream>>>(p);
+    else GemmSkinny<true, true><<<grid, kSkinnyThreads, 0, stream>>>(p);
+  } else {
+    if (dtype == 0) GemmSkinny<false, false><<<grid, kSkinnyThreads, 0, stream>>>(p);
+    else GemmSkinny<true, false><<<grid, kSkinnyThreads, 0, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 

@@ -174,7 +174,7 @@ __device__ __forceinline__ double2 AccValue(const double (&acc)[CFG::NACC][4][CF
 // Split-K fix-up, run by the unit that arrived last: add the tile's partial tiles in slot order (a fixed
 // order, whichever unit happens to be last) one m8 row group at a time and write C.  Kept out of line:
 // it needs only a handful of registers and must not disturb the register allocation of the main loop.
-template<class CFG, bool MCAST>
+template<class CFG, bool MCAST, bool ACC>
 __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile, const GemmGroup &g, int q, int g4, int t4) {
   constexpr int WBN = CFG::BN, NT = CFG::NT;
   __threadfence();
@@ -198,9 +198,14 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
     if (row < g.row_end) {
       for (uint32_t d = 0; d < p.n_out; ++d) {
         double2 *Cg = static_cast<double2 *>(p.c_out[d]) + g.c_off + (unsigned long long) row * g.n;
+        const double2 *Ci = static_cast<const double2 *>(p.c_in) + g.c_in_off + (unsigned long long) row * g.n;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+          if constexpr (ACC) {
+            if (col < g.n) sum[j][0] = AxpbyOut(p, sum[j][0], Ci + col, g.beta_on != 0);
+            if (col + 1 < g.n) sum[j][1] = AxpbyOut(p, sum[j][1], Ci + col + 1, g.beta_on != 0);
+          }
           if (col < g.n) StoreOut(Cg + col, sum[j][0], MCAST);
           if (col + 1 < g.n) StoreOut(Cg + col + 1, sum[j][1], MCAST);
         }
@@ -212,7 +217,8 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
 
 // MCAST: the output address is an NVSwitch multicast mapping (multimem.st); a compile-time switch, because a
 // run-time branch around every store of the unrolled epilogue costs registers the main loop cannot spare.
-template<class CFG, int STAGES, bool MCAST>
+// ACC: accumulate form, the epilogue computes beta * C_in + alpha * (sum of pairs) (qlb200_execute_accum); also compile-time.
+template<class CFG, int STAGES, bool MCAST, bool ACC>
 __global__ void __launch_bounds__(kWsThreads, 2)
 GemmWsCplx(const __grid_constant__ GemmParams p) {
   constexpr int WBN = CFG::BN, WBK = CFG::BK, WLDA = Lay<CFG>::WLDA, WLDB = Lay<CFG>::WLDB, A_ELEMS = Lay<CFG>::A_ELEMS,
@@ -403,11 +409,12 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
         if (warp == 0 && lane == 0) s_last = atomicAdd(&p.counters[2 + tile.ctr], 1u) == uint32_t(tile.nsplit) - 1u ? 1u : 0u;
         ConsumerBarrier();
         write_c = false;
-        if (s_last != 0) FixupTile<CFG, MCAST>(p, tile, g, q, g4, t4);
+        if (s_last != 0) FixupTile<CFG, MCAST, ACC>(p, tile, g, q, g4, t4);
       }
       if (write_c) {
         for (uint32_t d = 0; d < p.n_out; ++d) {     // n_out > 1: fused exchange, the same tile goes to every NVLink peer
           double2 *Cg = static_cast<double2 *>(p.c_out[d]) + g.c_off;
+          const double2 *Ci = static_cast<const double2 *>(p.c_in) + g.c_in_off;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t row = row0 + i * 8 + g4;
@@ -415,9 +422,15 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < NTMAX; ++j) {
               const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-              double2 *dst = Cg + (unsigned long long) row * g.n + col;
-              if (col < g.n) StoreOut(dst, AccValue<CFG>(acc, i, j, 0), MCAST);
-              if (col + 1 < g.n) StoreOut(dst + 1, AccValue<CFG>(acc, i, j, 1), MCAST);
+              const unsigned long long at = (unsigned long long) row * g.n + col;
+              double2 *dst = Cg + at;
+              if constexpr (ACC) {
+                if (col < g.n) StoreOut(dst, AxpbyOut(p, AccValue<CFG>(acc, i, j, 0), Ci + at, g.beta_on != 0), MCAST);
+                if (col + 1 < g.n) StoreOut(dst + 1, AxpbyOut(p, AccValue<CFG>(acc, i, j, 1), Ci + at + 1, g.beta_on != 0), MCAST);
+              } else {
+                if (col < g.n) StoreOut(dst, AccValue<CFG>(acc, i, j, 0), MCAST);
+                if (col + 1 < g.n) StoreOut(dst + 1, AccValue<CFG>(acc, i, j, 1), MCAST);
+              }
             }
           }
         }
@@ -431,17 +444,20 @@ cudaError_t Launch(const GemmParams &p, int num_sms, cudaStream_t stream) {
   constexpr size_t smem = WsSmem<CFG, CFG::STAGES>::kBytes;
   const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
   const uint32_t grid = p.seg != nullptr ? p.nseg : (p.ntiles < cap ? p.ntiles : cap);
-  if (p.mcast) GemmWsCplx<CFG, CFG::STAGES, true><<<grid, kWsThreads, smem, stream>>>(p);
-  else GemmWsCplx<CFG, CFG::STAGES, false><<<grid, kWsThreads, smem, stream>>>(p);
+  if (p.accum) GemmWsCplx<CFG, CFG::STAGES, false, true><<<grid, kWsThreads, smem, stream>>>(p);    // never with mcast (checked by the caller)
+  else if (p.mcast) GemmWsCplx<CFG, CFG::STAGES, true, false><<<grid, kWsThreads, smem, stream>>>(p);
+  else GemmWsCplx<CFG, CFG::STAGES, false, false><<<grid, kWsThreads, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
 template<class CFG>
 cudaError_t Configure() {
   constexpr int smem = int(WsSmem<CFG, CFG::STAGES>::kBytes);
-  cudaError_t e = cudaFuncSetAttribute(GemmWsCplx<CFG, CFG::STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t e = cudaFuncSetAttribute(GemmWsCplx<CFG, CFG::STAGES, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(GemmWsCplx<CFG, CFG::STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  e = cudaFuncSetAttribute(GemmWsCplx<CFG, CFG::STAGES, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(GemmWsCplx<CFG, CFG::STAGES, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 }  // namespace

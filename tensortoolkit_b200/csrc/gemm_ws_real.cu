@@ -63,6 +63,7 @@ __device__ __forceinline__ void ComputeStageRN(double (&acc)[8][4][2], const Fra
 }
 
 // Split-K fix-up (see gemm_ws.cu FixupTile): out of line, sums the partial tiles in slot order, writes C.
+template<bool ACC>
 __device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &tile, const GemmGroup &g, int q, int g4, int t4) {
   __threadfence();
   const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * RBM, col0 = uint32_t(tile.tn) * RBN;
@@ -85,9 +86,14 @@ __device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &til
     if (row < g.row_end) {
       for (uint32_t d = 0; d < p.n_out; ++d) {
         double *Cg = static_cast<double *>(p.c_out[d]) + g.c_off + (unsigned long long) row * g.n;
+        const double *Ci = static_cast<const double *>(p.c_in) + g.c_in_off + (unsigned long long) row * g.n;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+          if constexpr (ACC) {
+            if (col < g.n) sum[j].x = AxpbyOut(p, sum[j].x, Ci + col, g.beta_on != 0);
+            if (col + 1 < g.n) sum[j].y = AxpbyOut(p, sum[j].y, Ci + col + 1, g.beta_on != 0);
+          }
           if (col < g.n) StoreOut(Cg + col, sum[j].x, p.mcast);
           if (col + 1 < g.n) StoreOut(Cg + col + 1, sum[j].y, p.mcast);
         }
@@ -97,6 +103,7 @@ __device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &til
   if (q == 0 && g4 == 0 && t4 == 0) p.counters[2 + tile.ctr] = 0;
 }
 
+template<bool ACC>
 __global__ void __launch_bounds__(kWsThreads, 2)
 GemmWsReal(const __grid_constant__ GemmParams p) {
   constexpr int STAGES = kRealStages;
@@ -287,11 +294,12 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
         if (warp == 0 && lane == 0) s_last = atomicAdd(&p.counters[2 + tile.ctr], 1u) == uint32_t(tile.nsplit) - 1u ? 1u : 0u;
         ConsumerBarrier();
         write_c = false;
-        if (s_last != 0) FixupTileR(p, tile, g, q, g4, t4);
+        if (s_last != 0) FixupTileR<ACC>(p, tile, g, q, g4, t4);
       }
       if (write_c) {
         for (uint32_t d = 0; d < p.n_out; ++d) {     // n_out > 1: fused exchange, the same tile goes to every NVLink peer
           double *Cg = static_cast<double *>(p.c_out[d]) + g.c_off;
+          const double *Ci = static_cast<const double *>(p.c_in) + g.c_in_off;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const uint32_t row = row0 + i * 8 + g4;
@@ -299,9 +307,15 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-              double *dst = Cg + (unsigned long long) row * g.n + col;
-              if (col < g.n) StoreOut(dst, acc[i][j][0], p.mcast);
-              if (col + 1 < g.n) StoreOut(dst + 1, acc[i][j][1], p.mcast);
+              const unsigned long long at = (unsigned long long) row * g.n + col;
+              double *dst = Cg + at;
+              if constexpr (ACC) {
+                if (col < g.n) StoreOut(dst, AxpbyOut(p, acc[i][j][0], Ci + at, g.beta_on != 0), p.mcast);
+                if (col + 1 < g.n) StoreOut(dst + 1, AxpbyOut(p, acc[i][j][1], Ci + at + 1, g.beta_on != 0), p.mcast);
+              } else {
+                if (col < g.n) StoreOut(dst, acc[i][j][0], p.mcast);
+                if (col + 1 < g.n) StoreOut(dst + 1, acc[i][j][1], p.mcast);
+              }
             }
           }
         }
@@ -313,14 +327,17 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
 }  // namespace
 
 cudaError_t ConfigureWsRealKernel() {
-  return cudaFuncSetAttribute(GemmWsReal, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRealWsSmem));
+  cudaError_t e = cudaFuncSetAttribute(GemmWsReal<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRealWsSmem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(GemmWsReal<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRealWsSmem));
 }
 
 cudaError_t LaunchGemmWsReal(const GemmParams &p, int num_sms, cudaStream_t stream) {
   if (p.ntiles == 0) return cudaSuccess;
   const uint32_t cap = 2u * uint32_t(num_sms);     // two resident CTAs per SM
   const uint32_t grid = p.seg != nullptr ? p.nseg : (p.ntiles < cap ? p.ntiles : cap);
-  GemmWsReal<<<grid, kWsThreads, kRealWsSmem, stream>>>(p);
+  if (p.accum) GemmWsReal<true><<<grid, kWsThreads, kRealWsSmem, stream>>>(p);
+  else GemmWsReal<false><<<grid, kWsThreads, kRealWsSmem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -75,5 +75,23 @@ int FermionReorderSign(const uint8_t *par, int rank, const int32_t *perm);
 
 void EstimateCost(const Match &m, int dtype, qlb200_cost *out);
 
+/// Output topology of the accumulate form C = beta * C + alpha * contract(A, B) (accum.cc).
+struct AccumLayout {
+  bool c_default = false;             // the output was a default tensor: the contraction's own topology
+  bool expanded = false;              // required blocks were missing: the output is rebuilt on the union topology
+  bool scalar = false;
+  int rank = 0;
+  std::vector<CBlock> blocks;         // resulting output blocks, ascending blk_idx, offsets in the NEW raw buffer
+  std::vector<uint64_t> old_off;      // per resulting block: offset in the OLD raw buffer, ~0 = block is new
+  std::vector<uint8_t> touched;       // per resulting block: the contraction writes it
+  std::vector<uint64_t> req_to_union; // contraction-result block ordinal -> resulting block ordinal
+  uint64_t elems = 0, old_elems = 0;  // raw sizes after / before
+  qlb200_accum_stats stats{};
+};
+/// c_old == nullptr: default output.  Returns "" on success; *layout_mismatch tells a ContractAccumulateLayoutMismatch
+/// (incompatible indexes / block shapes, or missing blocks with allow_expand == false) from a malformed argument.
+std::string BuildAccumLayout(const Match &m, const qlb200_shell *c_old, bool c_old_has_data, bool allow_expand, int dtype, bool beta_zero,
+                             bool beta_one, AccumLayout *out, bool *layout_mismatch);
+
 }  // namespace qlb200
 #endif

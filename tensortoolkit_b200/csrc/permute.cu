@@ -146,7 +146,40 @@ PermuteKernel(const PermBlk *__restrict__ blks, const uint32_t *__restrict__ til
   }
 }
 
+// dst[dst_off + j] = beta * src[src_off + j] over a short list of ranges (accumulate form: output blocks the contraction
+// does not touch).  Every CTA walks all ranges and takes a grid-strided share of each: coalesced, HBM-bound, no tables.
+template<typename T>
+__global__ void __launch_bounds__(256)
+ScaleCopyRanges(const unsigned long long *__restrict__ r3, uint32_t nranges, const T *__restrict__ src, T *__restrict__ dst,
+                double beta_re, double beta_im) {
+  const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+  for (uint32_t r = 0; r < nranges; ++r) {
+    const unsigned long long so = r3[3 * r], dof = r3[3 * r + 1], len = r3[3 * r + 2];
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+      if constexpr (sizeof(T) == 16) {
+        if (beta_re == 0.0 && beta_im == 0.0) { dst[dof + i] = make_double2(0.0, 0.0); continue; }     // exact zeros, nothing read
+        const double2 v = src[so + i];
+        dst[dof + i] = make_double2(beta_re * v.x - beta_im * v.y, beta_re * v.y + beta_im * v.x);
+      } else {
+        if (beta_re == 0.0) { dst[dof + i] = 0.0; continue; }
+        dst[dof + i] = beta_re * src[so + i];
+      }
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t LaunchScaleCopyRanges(int dtype, const unsigned long long *ranges3, uint32_t nranges, const void *src, void *dst,
+                                  double beta_re, double beta_im, int num_sms, cudaStream_t stream) {
+  if (nranges == 0) return cudaSuccess;
+  const uint32_t grid = uint32_t(num_sms) * 8u;
+  if (dtype == 0)
+    ScaleCopyRanges<double><<<grid, 256, 0, stream>>>(ranges3, nranges, static_cast<const double *>(src), static_cast<double *>(dst), beta_re, beta_im);
+  else
+    ScaleCopyRanges<double2><<<grid, 256, 0, stream>>>(ranges3, nranges, static_cast<const double2 *>(src), static_cast<double2 *>(dst), beta_re, beta_im);
+  return cudaGetLastError();
+}
 
 cudaError_t LaunchPermute(int dtype, const PermBlk *blks, const uint32_t *tile_base, uint32_t nblk,
                           uint32_t ntiles, const void *srcA, const void *srcB, void *dstA, void *dstB,

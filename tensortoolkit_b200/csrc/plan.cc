@@ -253,6 +253,9 @@ std::string BuildPlanHost(int dtype, uint32_t flags, int nctrct, int a_rank, con
     if (!err.empty()) return err;
   }
   if (h->perm_tile_base.empty()) h->perm_tile_base.push_back(0);
+  h->ws_off_a.assign(na, ~0ull); h->ws_off_b.assign(nb, ~0ull);
+  for (uint64_t b = 0; b < na; ++b) if (h->a_trans && a_used[b] && opa.mode[b] == kBlkPermute) h->ws_off_a[b] = a_new[b];
+  for (uint64_t b = 0; b < nb; ++b) if (h->b_trans && b_used[b] && opb.mode[b] == kBlkPermute) h->ws_off_b[b] = b_new[b];
 
   const uint64_t es = dtype == QLB200_C64 ? 16 : 8;
   const double fl = dtype == QLB200_C64 ? 8.0 : 2.0;

@@ -48,6 +48,7 @@ struct PlanHost {
   uint64_t a_elems = 0, b_elems = 0, c_elems = 0;      // raw sizes of the three tensors
   bool a_trans = false, b_trans = false;               // some block of A / B goes through the permute kernel
   uint64_t ws_a_elems = 0, ws_b_elems = 0;             // permuted operand sizes (workspace)
+  std::vector<uint64_t> ws_off_a, ws_off_b;            // per block: element offset of its permuted copy, ~0 = read in place
   std::vector<PermBlk> perm_blks;
   std::vector<uint32_t> perm_tile_base;                // [nblk+1]
   std::vector<GemmTask> tasks;
@@ -71,6 +72,13 @@ struct qlb200_plan {
   qlb200_ctx *ctx = nullptr;
   qlb200::PlanHost h;
   qlb200::DeviceTables d;
+  // accumulate form (qlb200_plan_create_accum): C_new = beta * C_old + alpha * sum of pairs
+  bool accum = false;
+  double alpha[2] = {1.0, 0.0}, beta[2] = {0.0, 0.0};
+  uint64_t c_old_elems = 0;
+  bool acc_expanded = false;                       // the output moves to a new (union) topology: C_old and C_new are distinct buffers
+  std::vector<unsigned long long> acc_ranges;      // {old offset, new offset, length} of every untouched block that must move / scale
+  unsigned long long *d_acc_ranges = nullptr;
 };
 
 struct qlb200_tplan {

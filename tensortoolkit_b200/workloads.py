@@ -11,6 +11,8 @@ tests/test_tensor_manipulation/test_ten_ctrct_1sct.cc:253-257:
 import math
 from typing import Dict, List
 
+import numpy as np
+
 from .tensor import IN, OUT, Index, QNSector, U1, fU1U1
 
 HEFF_STEPS = [  # (lhs, rhs, axes, out)
@@ -69,3 +71,53 @@ def heff_tensor_indexes(ix: Dict[str, Index]) -> Dict[str, List[Index]]:
         mpo2=[ix["wb_in"], ix["ph_in"], ix["ph_out"], ix["wb_out"]],
         renv=[ix["vb_in"], ix["wb_in"], ix["vb_out"]],
     )
+
+
+def ragged_tables(nC=2500, pairs=4, lo=8, hi=2048, seed=20260005):
+    """BASELINE configs[4] (SURVEY.md 8d, config 5): descriptor table built directly, no QLTensor.  SplitMix64 stream;
+    every C block has (m, n) log-uniform in [lo, hi] and `pairs` contributing pairs with k log-uniform in [lo, hi];
+    A blocks stored rank-3 (k, m1, m2) with m1 the largest divisor of m <= sqrt(m), permutation {1,2,0};
+    B blocks stored (n1, k, n2), permutation {1,0,2}."""
+    state = [seed & 0xFFFFFFFFFFFFFFFF]
+
+    def splitmix():
+        state[0] = (state[0] + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = state[0]
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
+
+    def loguniform():
+        u = (splitmix() >> 11) * (1.0 / (1 << 53))
+        return int(min(hi, max(lo, round(float(np.exp(np.log(lo) + u * (np.log(hi) - np.log(lo))))))))
+
+    def split(x):
+        d = int(x ** 0.5)
+        while x % d:
+            d -= 1
+        return d, x // d
+
+    a_shape, b_shape, a_off, b_off = [], [], [], []
+    tasks = np.zeros(nC * pairs, dtype=np.dtype([("a_blk_idx", "<u8"), ("b_blk_idx", "<u8"), ("c_blk_idx", "<u8"), ("a_off", "<u8"), ("b_off", "<u8"),
+                                                 ("c_off", "<u8"), ("a_ord", "<u4"), ("b_ord", "<u4"), ("c_ord", "<u4"), ("m", "<u4"), ("k", "<u4"),
+                                                 ("n", "<u4"), ("sign", "i1"), ("first", "u1"), ("pad_", "u1", (2,))], align=True))
+    ao = bo = co = 0
+    flops = 0.0
+    ti = 0
+    for c in range(nC):
+        m, n = loguniform(), loguniform()
+        m1, m2 = split(m)
+        n1, n2 = split(n)
+        for p in range(pairs):
+            k = loguniform()
+            t = tasks[ti]
+            t["a_blk_idx"] = t["a_ord"] = ti; t["b_blk_idx"] = t["b_ord"] = ti; t["c_blk_idx"] = t["c_ord"] = c
+            t["a_off"], t["b_off"], t["c_off"] = ao, bo, co
+            t["m"], t["k"], t["n"], t["sign"], t["first"] = m, k, n, 1, 1 if p == 0 else 0
+            a_shape.append((k, m1, m2)); b_shape.append((n1, k, n2)); a_off.append(ao); b_off.append(bo)
+            ao += m * k; bo += k * n
+            flops += 2.0 * m * k * n
+            ti += 1
+        co += m * n
+    return dict(a_shape=np.array(a_shape, np.uint32), b_shape=np.array(b_shape, np.uint32), a_off=np.array(a_off, np.uint64),
+                b_off=np.array(b_off, np.uint64), tasks=tasks, a_elems=ao, b_elems=bo, c_elems=co, flops=flops)
