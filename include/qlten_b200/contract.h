@@ -9,6 +9,9 @@
 //       (qltensor/qltensor_impl.h:449-464)
 //   qlten::b200::ContractContiguousAxes<T, QNT, ASide, BSide>(a, b, a_start, b_start, size, c)  as
 //       qlten::ContractContiguousAxes (tensor_manipulation/contract_contiguous_axes.h:849-873)
+//   qlten::b200::ContractTailHeadContiguousAccumulate(a, b, a_start, b_start, size, alpha, beta, c, stats)  and
+//   qlten::b200::TryContractTailHeadContiguousAccumulate(...)   as the reference's functions of the same names
+//       (contract_contiguous_axes.h:954-1041):  c <- beta * c + alpha * contraction, output topology union included
 //
 // Only PUBLIC reference API is used (GetBlkSparDataTen, GetBlkIdxDataBlkMap, GetActualRawDataPtr,
 // DataBlksInsert, TenCtrctGenSavedAxesSet, TenCtrctInitResTen), so the reference tree stays
@@ -216,7 +219,7 @@ void Contract1Sector(const QLTensor<TenElemT, QNT> *pa, const size_t idx_a, cons
 
 /// Same signature and result as qlten::ContractContiguousAxes.  ASide / BSide only tell the reference which operand
 /// to transpose physically; here every block is read in place by the grouped GEMM whatever the sides are, so they
-/// are accepted and ignored.  The accumulate variants (alpha / beta, output-topology union) are not provided.
+/// are accepted and ignored.
 template<typename TenElemT, typename QNT, CtrctSide ASide = CtrctSide::Tail, CtrctSide BSide = CtrctSide::Head>
 void ContractContiguousAxes(const QLTensor<TenElemT, QNT> &a, const QLTensor<TenElemT, QNT> &b,
                             const size_t a_ctrct_axes_start, const size_t b_ctrct_axes_start,
@@ -246,6 +249,154 @@ void ContractContiguousAxes(const QLTensor<TenElemT, QNT> &a, const QLTensor<Ten
                                                static_cast<int32_t>(ctrct_axes_size), &match.m),
                 "match_create_contiguous");
   detail::RunMatched(&a, &b, sa, sb, match.m, &c, ctx);
+}
+
+namespace detail {
+
+struct AccumGuard {
+  qlb200_accum *a = nullptr;
+  ~AccumGuard() { if (a) qlb200_accum_destroy(a); }
+};
+
+/// The reference's own exception type for layout mismatches, so that callers (and Try...) can tell it apart.
+using LayoutMismatch = qlten::detail::ContractAccumulateLayoutMismatch;
+
+template<typename ElemT> inline void SplitScalar(const ElemT &v, double out[2]);
+template<> inline void SplitScalar<QLTEN_Double>(const QLTEN_Double &v, double out[2]) { out[0] = v; out[1] = 0.0; }
+template<> inline void SplitScalar<QLTEN_Complex>(const QLTEN_Complex &v, double out[2]) { out[0] = v.real(); out[1] = v.imag(); }
+
+template<typename TenElemT, typename QNT>
+void ContractAccumulateImpl(const QLTensor<TenElemT, QNT> &a, const QLTensor<TenElemT, QNT> &b, const size_t a_start,
+                            const size_t b_start, const size_t size, const TenElemT alpha, const TenElemT beta,
+                            QLTensor<TenElemT, QNT> &c, ContiguousContractStats *stats, const bool allow_expand, qlb200_ctx *ctx) {
+  const size_t ra = a.Rank(), rb = b.Rank();
+  if (ra == 0 || rb == 0 || a_start >= ra || b_start >= rb || size > ra || size > rb) {
+    throw std::invalid_argument("b200::ContractTailHeadContiguousAccumulate: bad axis range");
+  }
+  std::vector<std::vector<size_t>> axes_set(2), saved_axes_set(2);
+  for (size_t i = 0; i < size; ++i) { axes_set[0].push_back((a_start + i) % ra); axes_set[1].push_back((b_start + i) % rb); }
+  for (size_t i = 0; i < ra - size; ++i) { saved_axes_set[0].push_back((a_start + size + i) % ra); }
+  for (size_t i = 0; i < rb - size; ++i) { saved_axes_set[1].push_back((b_start + size + i) % rb); }
+  for (size_t i = 0; i < size; ++i) {
+    if (!(a.GetIndex(axes_set[0][i]) == InverseIndex(b.GetIndex(axes_set[1][i])))) {
+      throw std::invalid_argument("b200::ContractTailHeadContiguousAccumulate: contracted indexes do not match");
+    }
+  }
+  const bool c_default = c.IsDefault();
+  if (c_default && beta != TenElemT(0)) {
+    throw std::invalid_argument("ContractTailHeadContiguousAccumulate requires beta == 0 when output is default.");
+  }
+  const auto expected_indexes = qlten::detail::MakeContractResultIndexes(a, b, saved_axes_set);
+  if (!c_default && c.GetIndexes() != expected_indexes) {
+    throw LayoutMismatch("ContractTailHeadContiguousAccumulate output indexes are not compatible with the contraction result.");
+  }
+  if (ctx == nullptr) { ctx = DefaultCtx(); }
+  ShellHolder sa, sb, sc;
+  FillShell(a, sa);
+  FillShell(b, sb);
+  MatchGuard match;
+  Check(qlb200_match_create_contiguous(&sa.shell, &sb.shell, static_cast<int32_t>(a_start), static_cast<int32_t>(b_start),
+                                       static_cast<int32_t>(size), &match.m), "match_create_contiguous");
+  const bool has_data = !c_default && c.GetBlkSparDataTen().GetActualRawDataSize() > 0;
+  if (!c_default) { FillShell(c, sc); }
+  double al[2], be[2];
+  SplitScalar(alpha, al);
+  SplitScalar(beta, be);
+  AccumGuard acc;
+  const int rc = qlb200_accum_create(match.m, c_default ? nullptr : &sc.shell, has_data ? 1 : 0, allow_expand ? 1 : 0,
+                                     DTypeOf<TenElemT>::value, al, be, &acc.a);
+  if (rc == QLB200_ERR_LAYOUT) { throw LayoutMismatch(std::string("ContractTailHeadContiguousAccumulate ") + qlb200_last_error()); }
+  if (rc == QLB200_ERR_ARG) { throw std::invalid_argument(std::string("ContractTailHeadContiguousAccumulate ") + qlb200_last_error()); }
+  Check(rc, "accum_create");
+  if (stats != nullptr) {
+    qlb200_accum_stats st;
+    Check(qlb200_accum_get_stats(acc.a, &st), "accum_get_stats");
+    stats->raw_data_contract_tasks = st.raw_data_contract_tasks;
+    stats->gemm_calls = st.gemm_calls;
+    stats->accumulate_calls = st.accumulate_calls;
+    stats->accumulate_gemm_calls = st.accumulate_gemm_calls;
+    stats->output_tensor_rebuilds = st.output_tensor_rebuilds;
+    stats->temporary_output_bytes_avoided = st.temporary_output_bytes_avoided;
+    stats->output_topology_expansions = st.output_topology_expansions;
+    stats->output_expand_copy_bytes = st.output_expand_copy_bytes;
+    stats->output_expand_new_blocks = st.output_expand_new_blocks;
+    stats->output_untouched_scale_bytes = st.output_untouched_scale_bytes;
+  }
+  const uint64_t ntask = qlb200_match_ntask(match.m);
+  const bool scalar = qlb200_match_is_scalar(match.m) != 0;
+  const bool expanded = qlb200_accum_expanded(acc.a) != 0;
+  // the output tensor on the resulting topology: a fresh one when c was default or must grow, c itself otherwise
+  QLTensor<TenElemT, QNT> grown;
+  QLTensor<TenElemT, QNT> *out = &c;
+  const TenElemT *old_raw = has_data ? c.GetBlkSparDataTen().GetActualRawDataPtr() : nullptr;
+  if (c_default || expanded) {
+    grown = QLTensor<TenElemT, QNT>(expected_indexes);
+    out = &grown;
+  }
+  if (scalar) {
+    if (!out->IsScalar() || out->GetBlkSparDataTen().GetActualRawDataSize() == 0) { out->SetElem({}, TenElemT(0)); }
+  } else if (c_default || expanded) {
+    const uint64_t nblk = qlb200_accum_nblk(acc.a);
+    const int32_t c_rank = qlb200_match_c_rank(match.m);
+    std::vector<uint64_t> blk_idx(nblk);
+    std::vector<uint32_t> coors(nblk * c_rank);
+    Check(qlb200_accum_blocks(acc.a, blk_idx.data(), coors.data(), nullptr, nullptr, nullptr, nullptr), "accum_blocks");
+    std::vector<size_t> idxs(blk_idx.begin(), blk_idx.end());
+    std::vector<CoorsT> coors_s(nblk, CoorsT(c_rank));
+    for (uint64_t blk = 0; blk < nblk; ++blk) {
+      for (int32_t i = 0; i < c_rank; ++i) { coors_s[blk][i] = coors[blk * c_rank + i]; }
+    }
+    if (nblk > 0) { out->GetBlkSparDataTen().DataBlksInsert(idxs, coors_s, true); }
+  } else if (!has_data) {
+    out->GetBlkSparDataTen().Allocate(true);     // existing shell without raw data (beta == 0 checked by the library)
+  }
+  TenElemT *new_raw = out->GetBlkSparDataTen().GetActualRawDataPtr();
+  if (new_raw != nullptr && (ntask > 0 || !c_default)) {
+    PlanGuard plan;
+    Check(qlb200_plan_create_accum(ctx, match.m, acc.a, DTypeOf<TenElemT>::value, QLB200_PLAN_DETERMINISTIC, &plan.p), "plan_create_accum");
+    Check(qlb200_execute_accum(ctx, plan.p, a.GetBlkSparDataTen().GetActualRawDataPtr(), b.GetBlkSparDataTen().GetActualRawDataPtr(),
+                               old_raw, new_raw, QLB200_MEM_HOST), "execute_accum");
+  }
+  if (out != &c) { c = std::move(grown); }
+}
+
+}  // namespace detail
+
+/// c <- beta * c + alpha * ContractTailHeadContiguous(a, b, ...): same signature and semantics as
+/// qlten::ContractTailHeadContiguousAccumulate (contract_contiguous_axes.h:954-1000), incl. the aliasing check, the
+/// beta == 0 rule for a default output, output blocks beyond the contraction's (scaled by beta only), output-topology
+/// expansion to the union of old and required blocks, and the ContiguousContractStats counters.
+template<typename TenElemT, typename QNT>
+void ContractTailHeadContiguousAccumulate(const QLTensor<TenElemT, QNT> &pa, const QLTensor<TenElemT, QNT> &pb,
+                                          const size_t a_ctrct_axes_start, const size_t b_ctrct_axes_start,
+                                          const size_t ctrct_axes_size, const TenElemT alpha, const TenElemT beta,
+                                          QLTensor<TenElemT, QNT> &pc, ContiguousContractStats *stats = nullptr,
+                                          qlb200_ctx *ctx = nullptr) {
+  if (stats != nullptr) { *stats = ContiguousContractStats{}; }
+  if (&pc == &pa || &pc == &pb) {
+    throw std::invalid_argument("ContractTailHeadContiguousAccumulate does not support aliasing between output and input tensors.");
+  }
+  detail::ContractAccumulateImpl(pa, pb, a_ctrct_axes_start, b_ctrct_axes_start, ctrct_axes_size, alpha, beta, pc, stats, true, ctx);
+}
+
+/// The no-expansion probe (contract_contiguous_axes.h:1002-1041): false -- pc untouched, stats reset -- on a layout mismatch.
+template<typename TenElemT, typename QNT>
+bool TryContractTailHeadContiguousAccumulate(const QLTensor<TenElemT, QNT> &pa, const QLTensor<TenElemT, QNT> &pb,
+                                             const size_t a_ctrct_axes_start, const size_t b_ctrct_axes_start,
+                                             const size_t ctrct_axes_size, const TenElemT alpha, const TenElemT beta,
+                                             QLTensor<TenElemT, QNT> &pc, ContiguousContractStats *stats = nullptr,
+                                             qlb200_ctx *ctx = nullptr) {
+  if (stats != nullptr) { *stats = ContiguousContractStats{}; }
+  if (&pc == &pa || &pc == &pb) {
+    throw std::invalid_argument("TryContractTailHeadContiguousAccumulate does not support aliasing between output and input tensors.");
+  }
+  try {
+    detail::ContractAccumulateImpl(pa, pb, a_ctrct_axes_start, b_ctrct_axes_start, ctrct_axes_size, alpha, beta, pc, stats, false, ctx);
+    return true;
+  } catch (const detail::LayoutMismatch &) {
+    if (stats != nullptr) { *stats = ContiguousContractStats{}; }
+    return false;
+  }
 }
 
 template<typename TenElemT, typename QNT>

@@ -89,6 +89,29 @@ void *qlref_b200_contract_contiguous(const void *a, const void *b, int64_t a_sta
   });
 }
 
+// returns 1 = done, 0 = the Try... probe reported a layout mismatch, -1 = exception (text on stderr)
+int qlref_b200_contract_accumulate(const void *a, const void *b, int64_t a_start, int64_t b_start, int64_t size, const double *alpha2,
+                                   const double *beta2, void *c, int try_only, uint64_t *stats10, void *ctx) {
+  try {
+    return Dispatch<int>(static_cast<const TenBase *>(a), [&](auto *A) -> int {
+      using Box = std::remove_const_t<std::remove_pointer_t<decltype(A)>>;
+      auto &tc = static_cast<Box *>(static_cast<TenBase *>(c))->t;
+      const auto &tb = Same(A, static_cast<const TenBase *>(b))->t;
+      ContiguousContractStats st;
+      int ok = 1;
+      if (try_only) {
+        ok = qlten::b200::TryContractTailHeadContiguousAccumulate(A->t, tb, (size_t) a_start, (size_t) b_start, (size_t) size,
+                                                                  Box::MakeScalar(alpha2), Box::MakeScalar(beta2), tc, &st, (qlb200_ctx *) ctx) ? 1 : 0;
+      } else {
+        qlten::b200::ContractTailHeadContiguousAccumulate(A->t, tb, (size_t) a_start, (size_t) b_start, (size_t) size,
+                                                          Box::MakeScalar(alpha2), Box::MakeScalar(beta2), tc, &st, (qlb200_ctx *) ctx);
+      }
+      if (stats10) Box::StoreStats(st, stats10);
+      return ok;
+    });
+  } catch (const std::exception &e) { std::fprintf(stderr, "qlref_b200_contract_accumulate: %s\n", e.what()); return -1; }
+}
+
 int qlref_b200_transpose(void *t, const int64_t *perm, void *ctx) {
   try {
     return Dispatch<int>(static_cast<const TenBase *>(t), [&](auto *A) -> int {

@@ -198,6 +198,55 @@ def contract_contiguous_np(a: BlockSparseTensor, b: BlockSparseTensor, a_start: 
     return c
 
 
+class AccumulateLayoutMismatchNp(ValueError):
+    pass
+
+
+def contract_accumulate_np(a: BlockSparseTensor, b: BlockSparseTensor, a_start: int, b_start: int, size: int, alpha, beta,
+                           c: BlockSparseTensor = None, allow_expand: bool = True) -> BlockSparseTensor:
+    """ContractTailHeadContiguousAccumulate -- tensor_manipulation/contract_contiguous_axes.h:954-1000 (executor
+    :333-475 GenerateDataBlk_, :567-640 ExpandOutputTopology_, :642-680 ScaleUntouchedOutputBlocks_, :682-782):
+        c <- beta * c + alpha * ContractContiguousAxes(a, b)
+    on the UNION of c's blocks and the blocks the contraction produces; c None = default tensor (beta must be 0);
+    blocks missing from c need allow_expand (the Try... probe forbids it)."""
+    prod = contract_contiguous_np(a, b, a_start, b_start, size)
+    if c is None:
+        if beta != 0:
+            raise ValueError("beta must be 0 for a default output")
+        out = BlockSparseTensor(prod.indexes, prod.dtype)
+        if prod.rank == 0:
+            out.data = alpha * prod.data if prod.data.size else np.zeros(1, prod.dtype)
+            return out
+        if prod.nblk:
+            out.set_blocks(prod.blk_coors, alpha * prod.data)
+        return out
+    if list(c.indexes) != list(prod.indexes):
+        raise AccumulateLayoutMismatchNp("indexes")
+    out = BlockSparseTensor(prod.indexes, prod.dtype)
+    if prod.rank == 0:
+        old = c.data[0] if c.data.size else 0.0
+        new = prod.data[0] if prod.data.size else 0.0
+        out.data = np.array([beta * old + alpha * new], dtype=prod.dtype)
+        return out
+    old_keys = {tuple(int(x) for x in c.blk_coors[i]): i for i in range(c.nblk)}
+    new_keys = {tuple(int(x) for x in prod.blk_coors[i]): i for i in range(prod.nblk)}
+    if not allow_expand and any(k not in old_keys for k in new_keys):
+        raise AccumulateLayoutMismatchNp("output block topology requires expansion")
+    keys = sorted(set(old_keys) | set(new_keys))
+    if not keys:
+        return out
+    out.set_blocks(np.array(keys, np.uint32).reshape(len(keys), prod.rank))
+    out.data[...] = 0
+    for nb in range(out.nblk):
+        k = tuple(int(x) for x in out.blk_coors[nb])
+        blk = out.block(nb)
+        if k in old_keys and beta != 0:
+            blk += beta * c.block(old_keys[k])
+        if k in new_keys:
+            blk += alpha * prod.block(new_keys[k])
+    return out
+
+
 def transpose_np(t: BlockSparseTensor, order) -> BlockSparseTensor:
     """QLTensor::Transpose -- qltensor/qltensor_impl.h:449-464 -> BlockSparseDataTensor::Transpose,
     global_operations.h:393-441: every block permuted, fermionic blocks scaled by the reorder sign

@@ -157,6 +157,23 @@ void qlref_contract_cost(const void *a, const void *b, int n, const int64_t *aa,
   static_cast<const TenBase *>(a)->cost(static_cast<const TenBase *>(b), n, aa, ba, out8);
 }
 
+// a default-constructed tensor of the same element / quantum-number type as `like` (output of the accumulate forms)
+void *qlref_tensor_new_default(const void *like) {
+  const TenBase *l = static_cast<const TenBase *>(like);
+  TenBase *c = l->clone();
+  int64_t none = 0;
+  (void) none;
+  c->reset_default();
+  return c;
+}
+// returns 1 = done, 0 = the Try... probe reported a layout mismatch, -1 = exception (text on stderr)
+int qlref_contract_accumulate(const void *a, const void *b, int64_t a_start, int64_t b_start, int64_t size, const double *alpha2,
+                              const double *beta2, void *c, int try_only, uint64_t *stats10) {
+  try {
+    return static_cast<const TenBase *>(a)->contract_accumulate(static_cast<const TenBase *>(b), a_start, b_start, size, alpha2, beta2,
+                                                                static_cast<TenBase *>(c), try_only, stats10);
+  } catch (const std::exception &e) { std::fprintf(stderr, "qlref_contract_accumulate: %s\n", e.what()); return -1; }
+}
 int qlref_tensor_write(const void *t, const char *path) { return static_cast<const TenBase *>(t)->write_file(path); }
 int qlref_tensor_read(void *t, const char *path) { return static_cast<TenBase *>(t)->read_file(path); }
 void *qlref_contract_contiguous(const void *a, const void *b, int64_t a_start, int64_t b_start, int64_t size, int side) {

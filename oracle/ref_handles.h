@@ -74,6 +74,7 @@ struct TenBase {
   virtual void blocks(uint64_t *idx, uint32_t *coors, uint32_t *shape, uint64_t *off) const = 0;
   virtual void random(const int64_t *div) = 0;
   virtual TenBase *clone() const = 0;
+  virtual void reset_default() = 0;
   virtual void transpose(const int64_t *perm) = 0;
   virtual double norm2() const = 0;
   virtual bool indexes_equal(const TenBase *o) const = 0;
@@ -83,6 +84,10 @@ struct TenBase {
   virtual int read_file(const char *path) = 0;
   // side: 0 = <Tail, Head> (default), 1 = <Head, Head>, 2 = <Tail, Tail>, 3 = <Head, Tail>
   virtual TenBase *contract_contiguous(const TenBase *b, int64_t a_start, int64_t b_start, int64_t size, int side) const = 0;
+  // c <- beta * c + alpha * contraction (ContractTailHeadContiguousAccumulate; try_only: the Try... probe).  Returns 1, or 0
+  // when the probe reports a layout mismatch; stats10 = the ContiguousContractStats counters this path defines.
+  virtual int contract_accumulate(const TenBase *b, int64_t a_start, int64_t b_start, int64_t size, const double *alpha2,
+                                  const double *beta2, TenBase *c, int try_only, uint64_t *stats10) const = 0;
   virtual std::vector<TaskRec> tasks(const TenBase *b, int n, const int64_t *aa, const int64_t *ba, bool sorted) const = 0;
   virtual void cost(const TenBase *b, int n, const int64_t *aa, const int64_t *ba, double *out8) const = 0;
 };
@@ -133,6 +138,7 @@ struct TenBox : TenBase {
   }
   void random(const int64_t *div) override { t.Random(QNMake<QNT>::make(div)); }
   TenBase *clone() const override { auto *p = new TenBox(*this); return p; }
+  void reset_default() override { t = Ten(); }
   void transpose(const int64_t *perm) override {
     std::vector<size_t> o(t.Rank()); for (size_t i = 0; i < t.Rank(); ++i) o[i] = (size_t) perm[i];
     t.Transpose(o);
@@ -169,6 +175,30 @@ struct TenBox : TenBase {
       default: ContractContiguousAxes<ElemT, QNT, CtrctSide::Tail, CtrctSide::Head>(t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c); break;
     }
     return wrap(std::move(c));
+  }
+  static ElemT MakeScalar(const double *v2) {
+    if constexpr (std::is_same<ElemT, QLTEN_Complex>::value) return ElemT(v2[0], v2[1]);
+    else return ElemT(v2[0]);
+  }
+  static void StoreStats(const ContiguousContractStats &st, uint64_t *o) {
+    o[0] = st.raw_data_contract_tasks; o[1] = st.gemm_calls; o[2] = st.accumulate_calls; o[3] = st.accumulate_gemm_calls;
+    o[4] = st.output_tensor_rebuilds; o[5] = st.temporary_output_bytes_avoided; o[6] = st.output_topology_expansions;
+    o[7] = st.output_expand_copy_bytes; o[8] = st.output_expand_new_blocks; o[9] = st.output_untouched_scale_bytes;
+  }
+  int contract_accumulate(const TenBase *b, int64_t a_start, int64_t b_start, int64_t size, const double *alpha2, const double *beta2,
+                          TenBase *c, int try_only, uint64_t *stats10) const override {
+    ContiguousContractStats st;
+    Ten &tc = static_cast<TenBox *>(c)->t;
+    int ok = 1;
+    if (try_only) {
+      ok = TryContractTailHeadContiguousAccumulate(t, cast(b)->t, (size_t) a_start, (size_t) b_start, (size_t) size, MakeScalar(alpha2),
+                                                   MakeScalar(beta2), tc, &st) ? 1 : 0;
+    } else {
+      ContractTailHeadContiguousAccumulate(t, cast(b)->t, (size_t) a_start, (size_t) b_start, (size_t) size, MakeScalar(alpha2),
+                                           MakeScalar(beta2), tc, &st);
+    }
+    if (stats10) StoreStats(st, stats10);
+    return ok;
   }
   std::vector<TaskRec> tasks(const TenBase *b, int n, const int64_t *aa, const int64_t *ba, bool sorted) const override {
     auto axes = MakeAxes(n, aa, ba);

@@ -61,6 +61,9 @@ def lib():
             "qlref_tensor_write": (C.c_int, [_P, C.c_char_p]),
             "qlref_tensor_read": (C.c_int, [_P, C.c_char_p]),
             "qlref_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+            "qlref_tensor_new_default": (_P, [_P]),
+            "qlref_contract_accumulate": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), _P,
+                                                    C.c_int, C.POINTER(C.c_uint64)]),
             "qlref_tensor_fill": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_uint32), _P, C.c_uint64]),
             "qlref_raw_contract": (C.c_double, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                                 C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
@@ -88,6 +91,8 @@ def adapter():
             "qlref_b200_contract_1sector": (_P, [_P, C.c_int64, C.c_int64, _P, C.c_int, _I64P, _I64P, _P]),
             "qlref_b200_transpose": (C.c_int, [_P, _I64P, _P]),
             "qlref_b200_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P]),
+            "qlref_b200_contract_accumulate": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), _P,
+                                                         C.c_int, C.POINTER(C.c_uint64), _P]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -117,9 +122,10 @@ class RefTensor:
         self.dtype = np.dtype(dtype)
 
     @staticmethod
-    def new(indexes, dtype=np.float64) -> "RefTensor":
+    def new(indexes, dtype=np.float64, kind=None) -> "RefTensor":
+        """`kind` names the quantum-number type of a rank-0 tensor (no index to read it from)."""
         L = lib()
-        kind = indexes[0].kind
+        kind = indexes[0].kind if len(indexes) else kind
         ko = KIND_ORDINAL[kind.name]
         hs = []
         for ix in indexes:
@@ -137,9 +143,9 @@ class RefTensor:
         return self
 
     @staticmethod
-    def from_bst(t: BlockSparseTensor) -> "RefTensor":
+    def from_bst(t: BlockSparseTensor, kind=None) -> "RefTensor":
         """A reference tensor with the same indexes, stored blocks and raw data as the product's host mirror."""
-        r = RefTensor.new(t.indexes, t.dtype)
+        r = RefTensor.new(t.indexes, t.dtype, kind)
         coors = np.ascontiguousarray(t.blk_coors, dtype=np.uint32)
         data = np.ascontiguousarray(t.data)
         if data.size:
@@ -300,6 +306,39 @@ def b200_contract_contiguous(a: RefTensor, b: RefTensor, a_start: int, b_start: 
     if not h:
         raise RuntimeError("qlref_b200_contract_contiguous failed (see stderr)")
     return RefTensor(h, _c_indexes_cyclic(a, b, a_start, b_start, size), a.dtype)
+
+
+ACCUM_STAT_NAMES = ("raw_data_contract_tasks", "gemm_calls", "accumulate_calls", "accumulate_gemm_calls", "output_tensor_rebuilds",
+                    "temporary_output_bytes_avoided", "output_topology_expansions", "output_expand_copy_bytes", "output_expand_new_blocks",
+                    "output_untouched_scale_bytes")
+
+
+def default_like(t: RefTensor) -> RefTensor:
+    """A default-constructed QLTensor of t's element / quantum-number type."""
+    return RefTensor(lib().qlref_tensor_new_default(t.h), None, t.dtype)
+
+
+def _accumulate(fn, a, b, a_start, b_start, size, alpha, beta, c, try_only, extra=()):
+    """Shared driver of the reference's / the adapter's ContractTailHeadContiguousAccumulate on handle `c` (updated in place).
+    Returns (ok, stats dict); raises RuntimeError when the callee threw."""
+    al = (C.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+    be = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
+    st = (C.c_uint64 * 10)()
+    rc = fn(a.h, b.h, int(a_start), int(b_start), int(size), al, be, c.h, int(try_only), st, *extra)
+    if rc < 0:
+        raise RuntimeError("ContractTailHeadContiguousAccumulate threw (see stderr)")
+    c.indexes = _c_indexes_cyclic(a, b, a_start, b_start, size)
+    return bool(rc), dict(zip(ACCUM_STAT_NAMES, (int(x) for x in st)))
+
+
+def contract_accumulate(a, b, a_start, b_start, size, alpha, beta, c: RefTensor, try_only=False):
+    """The reference's (Try)ContractTailHeadContiguousAccumulate (contract_contiguous_axes.h:954-1041) on handle c."""
+    return _accumulate(lib().qlref_contract_accumulate, a, b, a_start, b_start, size, alpha, beta, c, try_only)
+
+
+def b200_contract_accumulate(a, b, a_start, b_start, size, alpha, beta, c: RefTensor, try_only=False, ctx_handle=None):
+    """qlten::b200::(Try)ContractTailHeadContiguousAccumulate on reference tensors (the drop-in adapter)."""
+    return _accumulate(adapter().qlref_b200_contract_accumulate, a, b, a_start, b_start, size, alpha, beta, c, try_only, (ctx_handle,))
 
 
 def raw_contract(dtype, a_rank, a_perm, a_shape, a_off, b_rank, b_perm, b_shape, b_off, tasks, A, B, c_elems, keep_permuted=False):

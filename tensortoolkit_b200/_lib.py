@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libqlb200.so")
 
 QLB200_MAX_RANK = 8
 OK = 0
+ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_LAYOUT = -1, -2, -3, -4, -5
 F64, C64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 DIR_IN, DIR_OUT = -1, 1
@@ -53,6 +54,16 @@ class PlanStats(C.Structure):
         ("nrow_skinny", C.c_uint64), ("permute_elems_a", C.c_uint64), ("permute_elems_b", C.c_uint64),
         ("workspace_bytes", C.c_uint64), ("gemm_read_bytes", C.c_uint64), ("gemm_write_bytes", C.c_uint64),
     ]
+
+
+class AccumStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "raw_data_contract_tasks", "gemm_calls", "accumulate_calls", "accumulate_gemm_calls", "output_tensor_rebuilds",
+        "temporary_output_bytes_avoided", "output_topology_expansions", "output_expand_copy_bytes", "output_expand_new_blocks",
+        "output_untouched_scale_bytes")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 class Unit(C.Structure):
@@ -112,6 +123,15 @@ SYMBOLS = {
     "qlb200_execute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "qlb200_execute_permute": (C.c_int, [_P, _P, _P, _P]),
     "qlb200_execute_gemm": (C.c_int, [_P, _P, _P, _P, _P]),
+    "qlb200_accum_create": (C.c_int, [_P, _SH, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _PP]),
+    "qlb200_accum_destroy": (None, [_P]),
+    "qlb200_accum_nblk": (C.c_uint64, [_P]),
+    "qlb200_accum_elems": (C.c_uint64, [_P]),
+    "qlb200_accum_expanded": (C.c_int, [_P]),
+    "qlb200_accum_blocks": (C.c_int, [_P, _U64P, _U32P, _U32P, _U64P, _U64P, C.POINTER(C.c_uint8)]),
+    "qlb200_accum_get_stats": (C.c_int, [_P, C.POINTER(AccumStats)]),
+    "qlb200_plan_create_accum": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, _PP]),
+    "qlb200_execute_accum": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int]),
     "qlb200_execute_bcast": (C.c_int, [_P, _P, _P, _P, _PP, C.c_int32]),
     "qlb200_execute_mcast": (C.c_int, [_P, _P, _P, _P, _P]),
     "qlb200_graph_begin": (C.c_int, [_P]),

@@ -322,6 +322,85 @@ def contract_contiguous_axes(a: BlockSparseTensor, b: BlockSparseTensor, a_ctrct
         m.close()
 
 
+class AccumulateLayoutMismatch(ValueError):
+    """The existing output cannot take the contraction result (the reference's detail::ContractAccumulateLayoutMismatch,
+    contract_contiguous_axes.h:83-88): incompatible indexes or block shapes, or missing blocks when expansion is not allowed."""
+
+
+def contract_tail_head_contiguous_accumulate(a: BlockSparseTensor, b: BlockSparseTensor, a_ctrct_axes_start: int,
+                                             b_ctrct_axes_start: int, ctrct_axes_size: int, alpha, beta,
+                                             c: Optional[BlockSparseTensor] = None, ctx: Context = None, stats: dict = None,
+                                             allow_output_topology_expansion: bool = True) -> BlockSparseTensor:
+    """qlten::ContractTailHeadContiguousAccumulate (tensor_manipulation/contract_contiguous_axes.h:954-1000):
+        c  <-  beta * c + alpha * ContractContiguousAxes(a, b, ...)
+    without a temporary result tensor.  `c` None = a default tensor (beta must be 0).  An existing `c` may hold more blocks
+    than the contraction produces (scaled by beta only) or fewer (rebuilt on the union topology).  Returns the new c
+    (the argument is not modified); `stats`, if given, receives the reference's ContiguousContractStats counters."""
+    if c is a or c is b:
+        raise ValueError("ContractTailHeadContiguousAccumulate does not support aliasing between output and input tensors")
+    m = Match(a, b, None, contiguous=(a_ctrct_axes_start, b_ctrct_axes_start, ctrct_axes_size))
+    acc = C.c_void_p()
+    plan = C.c_void_p()
+    try:
+        dtype = a.dtype
+        if c is not None and list(c.indexes) != list(m.c_indexes):
+            raise AccumulateLayoutMismatch("output indexes are not compatible with the contraction result")
+        cplx = np.dtype(dtype) == np.complex128
+        if not cplx and (np.iscomplexobj(alpha) and complex(alpha).imag != 0 or np.iscomplexobj(beta) and complex(beta).imag != 0):
+            raise TypeError("complex alpha / beta on real tensors")
+        al = (C.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+        be = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
+        sh = c.shell() if c is not None else None
+        has_data = int(c is not None and c.data.size > 0)
+        rc = lib.qlb200_accum_create(m.h, sh.ptr() if sh is not None else None, has_data, int(allow_output_topology_expansion),
+                                     _dtype_code(dtype), al, be, C.byref(acc))
+        if rc == _lib.ERR_LAYOUT:
+            raise AccumulateLayoutMismatch(lib.qlb200_last_error().decode())
+        if rc == _lib.ERR_ARG:
+            raise ValueError(lib.qlb200_last_error().decode())
+        check(rc, "qlb200_accum_create")
+        if stats is not None:
+            st = _lib.AccumStats()
+            check(lib.qlb200_accum_get_stats(acc, C.byref(st)), "qlb200_accum_get_stats")
+            stats.update(st.as_dict())
+        out = BlockSparseTensor(m.c_indexes, dtype)
+        n = int(lib.qlb200_accum_nblk(acc))
+        if m.is_scalar:
+            out.data = np.zeros(1, dtype=out.dtype)
+        elif n:
+            coors = np.zeros((n, m.c_rank), np.uint32)
+            check(lib.qlb200_accum_blocks(acc, None, coors.ctypes.data_as(C.POINTER(C.c_uint32)), None, None, None, None), "qlb200_accum_blocks")
+            out.set_blocks(coors)
+            assert out.data.size == int(lib.qlb200_accum_elems(acc))
+        if out.data.size == 0:
+            return out
+        ctx = ctx or default_context()
+        check(lib.qlb200_plan_create_accum(ctx.h, m.h, acc, _dtype_code(dtype), _lib.PLAN_DETERMINISTIC, C.byref(plan)), "qlb200_plan_create_accum")
+        old = c.data.ctypes.data if (c is not None and c.data.size) else None
+        check(lib.qlb200_execute_accum(ctx.h, plan, a.data.ctypes.data, b.data.ctypes.data, old, out.data.ctypes.data, _lib.MEM_HOST),
+              "qlb200_execute_accum")
+        return out
+    finally:
+        if plan:
+            lib.qlb200_plan_destroy(plan)
+        if acc:
+            lib.qlb200_accum_destroy(acc)
+        m.close()
+
+
+def try_contract_tail_head_contiguous_accumulate(a, b, a_ctrct_axes_start, b_ctrct_axes_start, ctrct_axes_size, alpha, beta,
+                                                 c=None, ctx: Context = None, stats: dict = None):
+    """qlten::TryContractTailHeadContiguousAccumulate (contract_contiguous_axes.h:1002-1041): the no-expansion probe.
+    Returns (True, new c) or (False, c unchanged) on a layout mismatch; other errors still raise."""
+    try:
+        return True, contract_tail_head_contiguous_accumulate(a, b, a_ctrct_axes_start, b_ctrct_axes_start, ctrct_axes_size, alpha, beta,
+                                                              c, ctx, stats, allow_output_topology_expansion=False)
+    except AccumulateLayoutMismatch:
+        if stats is not None:
+            stats.clear()
+        return False, c
+
+
 def contract_1sector(a, idx_a: int, qn_sector_idx_a: int, b, axes, ctx: Context = None) -> BlockSparseTensor:
     if idx_a in list(axes[0]):
         raise ValueError("the split index must be a free index of A")

@@ -729,7 +729,8 @@ int qlb200_accum_create(const qlb200_match *m, const qlb200_shell *c_old, int c_
   const bool beta_zero = beta2[0] == 0.0 && bi == 0.0, beta_one = beta2[0] == 1.0 && bi == 0.0;
   // the reference's argument checks (contract_contiguous_axes.h:376-380, :683-688): no existing values to scale
   if (c_old == nullptr && !beta_zero) return Fail(QLB200_ERR_ARG, "accumulate into a default output requires beta == 0");
-  if (c_old != nullptr && !c_old_has_data && !beta_zero) return Fail(QLB200_ERR_ARG, "accumulate requires allocated output raw data unless beta == 0");
+  if (c_old != nullptr && !c_old_has_data && !beta_zero && (c_old->nblk > 0 || c_old->rank == 0))
+    return Fail(QLB200_ERR_ARG, "accumulate requires allocated output raw data unless beta == 0");
   qlb200_accum *a = new (std::nothrow) qlb200_accum();
   if (!a) return Fail(QLB200_ERR_NOMEM, "out of memory");
   a->dtype = dtype;
