@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=3, help="GPU arm: timed applies of the cpu_baseline child")
     ap.add_argument("--write-out", default="", help="reference arm: write the result tensor of the apply to this file (the reference's stream format)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true", help="default run only: skip the sub-records for BASELINE configs[1], [3] and [4]")
+    ap.add_argument("--ragged-cpu-pairs", type=int, default=1000, help="ragged workload: pairs of the bounded CPU / e2e sample")
+    ap.add_argument("--no-cold", action="store_true", help="skip the cold drop-in measurement (4 Contract calls on host tensors incl. match + plan build)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--plan-flags", type=int, default=1, help="qlb200_plan_create flags (kernel A/B testing; 1 = default)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "multicast", "fused", "allgather"],
@@ -317,22 +320,66 @@ def measure_fp64_peak(torch, dtype):
     return fl / best / 1e12, sustained / 1e12, f"torch.matmul {'complex128' if dtype == 'c128' else 'float64'} {n}^3 (cuBLAS), best of 6 / back-to-back {reps} calls"
 
 
-def run_ours(args):
-    import torch
-    import tensortoolkit_b200 as tk
+class Env:
+    """One process = one GPU: torch for device memory / streams / the NCCL process group, one qlb200 context on its own stream."""
+
+    def __init__(self):
+        import torch
+        import tensortoolkit_b200 as tk
+        self.torch, self.tk = torch, tk
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        torch.cuda.set_device(self.local)
+        self.stream = torch.cuda.Stream()
+        self.ctx = tk.Context(self.local)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        self.flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+        self._peaks = {}
+
+    def fp64_peak(self, dtype):
+        if dtype not in self._peaks:
+            with self.torch.cuda.stream(self.stream):
+                self._peaks[dtype] = measure_fp64_peak(self.torch, dtype)
+        return self._peaks[dtype]
+
+    def shared_host_buffer(self, name, nbytes):
+        """Host memory that every rank of the node maps (POSIX shared memory): the ranks' downloads of their own result
+        slabs land in ONE buffer.  Returns (numpy uint8 view, handle to keep alive)."""
+        if self.world == 1:
+            a = np.empty(nbytes, np.uint8)
+            return a, None
+        from multiprocessing import shared_memory
+        import torch.distributed as dist
+        tag = f"qlb200_{os.environ.get('MASTER_PORT', '0')}_{name}"
+        shm = None
+        if self.rank == 0:
+            try:
+                shared_memory.SharedMemory(name=tag).unlink()      # stale segment of a crashed run
+            except Exception:
+                pass
+            shm = shared_memory.SharedMemory(name=tag, create=True, size=max(nbytes, 1))
+        dist.barrier()
+        if self.rank != 0:
+            shm = shared_memory.SharedMemory(name=tag)
+            try:                                                    # only the creator unlinks
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
+        return np.ndarray((nbytes,), np.uint8, buffer=shm.buf), shm
+
+
+def measure_heff(args, env):
+    """One record for an H_eff workload (args.workload / D / dtype) at env.world GPUs: device-timed value, per-kernel
+    roofline, end-to-end through host memory, and at one GPU the reference CPU arm + parity against it."""
+    torch, tk = env.torch, env.tk
     from tensortoolkit_b200 import workloads as wl
     from tensortoolkit_b200.heff import ContractionChain
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    stream = torch.cuda.Stream()
-    ctx = tk.Context(local)
-    ctx.set_stream(stream.cuda_stream)
+    rank, world, local, stream, ctx = env.rank, env.world, env.local, env.stream, env.ctx
 
     dtype = args.dtype
     es = 16 if dtype == "c128" else 8
@@ -351,7 +398,7 @@ def run_ours(args):
         from tensortoolkit_b200.heff import ShardedChain
         with torch.cuda.stream(stream):
             sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags,
-                                   exchange=args.exchange)
+                                   exchange=args.exchange, host_input="psi")
         chain = sharded.chain
         apply_fn = sharded.apply
     else:
@@ -366,6 +413,7 @@ def run_ours(args):
             ref_chain.apply_device()
             want = ref_chain.result("out").data
             ref_chain.close()
+            tk._lib.check(tk._lib.lib.qlb200_memcpy_h2d(ctx.h, sharded.in_ptr, tensors["psi"].data.ctypes.data, tensors["psi"].data.nbytes), "h2d")
             sharded.apply()
             torch.distributed.barrier()
             got = np.empty_like(want)
@@ -374,7 +422,7 @@ def run_ours(args):
         verified = float(np.linalg.norm(got - want) / np.linalg.norm(want))
         if not verified <= 1e-12:
             raise SystemExit(f"rank {rank}: sharded apply differs from the unsharded one, rel err {verified:.3e}")
-        del want, got
+        del got
     graph = None
     if not args.no_graph:
         # one apply = one CUDA graph launch (kernels, and for N>1 the exchange barrier): no per-kernel host launch cost
@@ -383,7 +431,7 @@ def run_ours(args):
         apply_eager, apply_fn = apply_fn, graph.launch
     stats = chain.stats()
     flops_local = chain.flops()
-    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    flush = env.flush
 
     def barrier():
         if world > 1:
@@ -455,19 +503,36 @@ def run_ours(args):
             allr = [torch.zeros_like(mine) for _ in range(world)]
             torch.distributed.all_gather(allr, mine)
             rank_phase = [{"rank": r, "local_steps_ms": float(x[0]), "exchange_and_wait_ms": float(x[1])} for r, x in enumerate(allr)]
-        # ---- e2e: psi in pinned host memory, H2D + 4 steps + D2H per step ----
+        # ---- e2e: psi in pinned host memory -> result in pinned host memory, every apply ----
         psi_host = tensors["psi"].data
-        out_host = np.empty(sharded.info.full_elems if sharded is not None else chain.shells["out"].data.size, np_dtype(dtype))
+        n_out = sharded.info.full_elems if sharded is not None else chain.shells["out"].data.size
+        out_bytes, shm = env.shared_host_buffer("out", n_out * es)
+        out_host = out_bytes.view(np_dtype(dtype))
         tk._lib.check(tk._lib.lib.qlb200_host_register(psi_host.ctypes.data, psi_host.nbytes), "host_register")
-        tk._lib.check(tk._lib.lib.qlb200_host_register(out_host.ctypes.data, out_host.nbytes), "host_register")
-        def e2e_apply():
-            if sharded is None:
-                chain.apply_host("psi", psi_host, "out", out_host)
-            else:   # psi H2D on every rank, local steps + all-gather + unpack, full result D2H on every rank
-                chain.buf["psi"].upload(psi_host)
+        tk._lib.check(tk._lib.lib.qlb200_host_register(out_host.ctypes.data, max(out_host.nbytes, 1)), "host_register")
+        e2e_serial_s, e2e_how = None, None
+        if sharded is None:
+            # one GPU: chunked upload overlapped with step 1, chunked download overlapped with the last step (qlb200_hostpipe_*)
+            chain.make_host_pipe("psi")
+            e2e_apply = lambda: chain.apply_host_pipelined(psi_host, out_host)
+            e2e_how = ("qlb200_hostpipe: psi uploaded in 4 chunks on a copy stream while the parts of step 1 run, the result downloaded in "
+                       "4 chunks while the last step computes; host call returns when the result is in host memory")
+            h2d_b, d2h_b = int(psi_host.nbytes), int(out_host.nbytes)
+        elif args.shard_of:
+            def e2e_apply():
+                tk._lib.check(tk._lib.lib.qlb200_memcpy_h2d(ctx.h, chain.buf["psi"].ptr, psi_host.ctypes.data, psi_host.nbytes), "h2d")
                 apply_fn()
-                sharded.download_full(out_host)
                 ctx.sync()
+            h2d_b, d2h_b = int(psi_host.nbytes), 0
+        else:
+            # N GPUs: every rank uploads 1/N of psi and fans it out over NVLink; every rank downloads its own result slabs
+            # into the one shared host buffer (ShardedChain.apply_host)
+            e2e_apply = lambda: sharded.apply_host(psi_host, out_host, apply_fn)
+            e2e_how = (f"each rank uploads 1/{world} of psi over its own PCIe link and fans it out to all GPUs "
+                       f"({'multimem.st through the NVSwitch' if sharded.in_mc else 'unicast peer stores'}), barrier, sharded apply, each rank "
+                       "downloads its own row slabs of the result into one shared-memory host buffer")
+            h2d_b = int(-(-psi_host.nbytes // world))
+            d2h_b = int(sum(ln for _, ln in sharded.own_ranges()) * es)
         for _ in range(2):
             e2e_apply()
         barrier()
@@ -476,9 +541,29 @@ def run_ours(args):
             e2e_apply()
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.steps
+        # the end-to-end result is the same tensor: checked on rank 0 against the device-resident apply
+        e2e_err = None
+        if rank == 0 and not args.shard_of:
+            if sharded is None:
+                chain.apply_device()
+                want = chain.result("out").data
+            e2e_err = float(np.linalg.norm(out_host - want) / np.linalg.norm(want))
+            if not e2e_err <= 1e-12:
+                raise SystemExit(f"end-to-end result differs from the device-resident one: rel err {e2e_err:.3e}")
+        if sharded is None:
+            for _ in range(2):
+                chain.apply_host("psi", psi_host, "out", out_host)
+            t0 = time.perf_counter()
+            for _ in range(max(3, args.steps // 2)):
+                chain.apply_host("psi", psi_host, "out", out_host)
+            e2e_serial_s = (time.perf_counter() - t0) / max(3, args.steps // 2)
         tk._lib.lib.qlb200_host_unregister(psi_host.ctypes.data)
         tk._lib.lib.qlb200_host_unregister(out_host.ctypes.data)
-        peak_burst, peak_sust, peak_how = measure_fp64_peak(torch, dtype)
+        peak_burst, peak_sust, peak_how = env.fp64_peak(dtype)
+        # ---- cold drop-in: what a TensorToolkit program pays when it simply swaps qlten::Contract for the adapter ----
+        cold = None
+        if world == 1 and not args.shard_of and not args.no_cold:
+            cold = measure_cold_dropin(tk, ctx, tensors, wl.HEFF_STEPS, chain.flops())
 
     ms = float(np.mean(dev_ms))
     tot_ms, flops_total, e2e_max = ms, flops_local, e2e_s
@@ -490,7 +575,11 @@ def run_ours(args):
         dist.all_reduce(f, op=dist.ReduceOp.SUM)
         tot_ms, e2e_max, flops_total = float(t[0]), float(t[1]), float(f[0])
     if rank != 0:
-        return
+        if sharded is not None:
+            sharded.close()
+        if shm is not None:
+            shm.close()
+        return None
 
     value = flops_total / (tot_ms * 1e-3) / 1e9
     dom = max((k for k in kern), key=lambda k: k["ms"])
@@ -536,7 +625,7 @@ def run_ours(args):
             cD = args.cpu_sample_D or args.D
             cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(args.cpu_steps), "--warmup", "1",
                    "--D", str(args.D), "--dtype", dtype, "--cpu-sample-D", str(cD), "--workload", args.workload,
-                   "--cpu-time-cap", str(args.cpu_time_cap)]
+                   "--cpu-time-cap", str(args.cpu_time_cap)] + (["--no-thread-sweep"] if args.no_thread_sweep else [])
             same = cD == args.D and not args.shard_of
             if same:
                 qn = args.qn if args.tensors else ("fU1U1QN" if args.workload == "heff_hubbard" else "U1QN")
@@ -578,7 +667,10 @@ def run_ours(args):
         "pct_fp64_peak": 100.0 * value / 1e3 / peak_burst / world, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sust, "how": peak_how},
         "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "parity": parity,
         "e2e": {"value": flops_total / e2e_max / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_max * 1e3,
-                "h2d_bytes_per_step": int(psi_host.nbytes), "d2h_bytes_per_step": int(out_host.nbytes)},
+                "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b, "per": "rank" if world > 1 else "gpu", "how": e2e_how,
+                "rel_err_vs_device_resident": e2e_err,
+                "serial_ms_per_step": None if e2e_serial_s is None else e2e_serial_s * 1e3,
+                "cold_dropin": cold},
         "gpu_launches": int(launches) * args.steps, "clocks": sampler.summary(),
     }
     if verified is not None:
@@ -590,79 +682,177 @@ def run_ours(args):
             print(f"  rank {rp['rank']}: local steps {rp['local_steps_ms']:.3f} ms, exchange + wait {rp['exchange_and_wait_ms']:.3f} ms", file=sys.stderr)
         for k in kern:
             print(f"  step {k['step']} {k['kernel']:22s} {k['ms']:8.3f} ms  {k['achieved']:9.2f} {k['unit']:8s} frac {k['frac']:.3f}", file=sys.stderr)
-    print(json.dumps(line))
-    chain.close()
+    if sharded is not None:
+        sharded.close()
+    else:
+        chain.close()
+    if shm is not None:
+        shm.close()
+        if rank == 0:
+            shm.unlink()
+    return line
+
+
+def measure_cold_dropin(tk, ctx, tensors, steps, flops, reps=2):
+    """The literal drop-in, no reuse of anything: every apply = four Contract calls on HOST tensors, each one doing
+    sector match + plan build (descriptor tables, cudaMalloc, upload) + qlb200_execute(QLB200_MEM_HOST) (H2D of A and B from
+    pageable memory, kernels, D2H of C, synchronise) + teardown -- what include/qlten_b200/contract.h does per call."""
+    import ctypes as C
+    lib, check = tk._lib.lib, tk._lib.check
+    best = None
+    for _ in range(reps):
+        t = dict(tensors)
+        tm = tp = te = 0.0
+        t_all = time.perf_counter()
+        for lhs, rhs, axes, out in steps:
+            t0 = time.perf_counter()
+            m = tk.Match(t[lhs], t[rhs], axes)
+            t1 = time.perf_counter()
+            plan = tk.ContractionPlan(ctx, m, t[lhs].dtype)
+            c = m.result_shell(t[lhs].dtype)
+            t2 = time.perf_counter()
+            plan.execute_host(t[lhs].data, t[rhs].data, c.data)
+            t3 = time.perf_counter()
+            plan.close(); m.close()
+            t[out] = c
+            tm += t1 - t0; tp += t2 - t1; te += t3 - t2
+        total = time.perf_counter() - t_all
+        if best is None or total < best["ms_per_step"] * 1e-3:
+            best = {"ms_per_step": total * 1e3, "match_ms": tm * 1e3, "plan_ms": tp * 1e3, "execute_ms": te * 1e3,
+                    "value": flops / total / 1e9, "unit": "GFLOP/s",
+                    "how": "4 x (qlb200_match_create + qlb200_plan_create + qlb200_execute(QLB200_MEM_HOST) + destroy) on pageable host tensors, "
+                           "intermediates returned to the host after every step; best of %d applies" % reps}
+    return best
+
+
 
 
 # ------------------------------------------------------------------------------------------------
 from tensortoolkit_b200.workloads import ragged_tables  # noqa: E402  (BASELINE configs[4] descriptor table)
 
 
-def run_ragged(args):
-    """configs[4]: ragged-sector stress test, transpose + grouped GEMM only (double).  One step = permute every block that
-    cannot be read in place + one grouped GEMM launch over all 10^4 pairs; operands generated on the device."""
-    tb = ragged_tables()
-    if args.impl == "reference":
-        # CPU side of the same workload: numpy transposes + OpenBLAS GEMMs on a bounded sample of the pairs (the "port" flavour;
-        # the reference's own loop is hp_numeric::TensorTranspose + MatMultiply per pair, global_operations.h:919-982)
-        rng = np.random.default_rng(20260005)
-        fl, n, cpu_s = 0.0, 0, 0.0
-        for t in tb["tasks"][:: max(1, len(tb["tasks"]) // 400)]:
-            m, k, nn = int(t["m"]), int(t["k"]), int(t["n"])
-            ash, bsh = tb["a_shape"][int(t["a_ord"])], tb["b_shape"][int(t["b_ord"])]
-            a = rng.random(tuple(int(x) for x in ash)); b = rng.random(tuple(int(x) for x in bsh))
-            t1 = time.perf_counter()
-            (np.ascontiguousarray(np.transpose(a, (1, 2, 0))).reshape(m, k) @ np.ascontiguousarray(np.transpose(b, (1, 0, 2))).reshape(k, nn))
-            cpu_s += time.perf_counter() - t1          # operand generation is not timed
-            fl += 2.0 * m * k * nn; n += 1
-            if cpu_s > 30:
-                break
-        val = fl / cpu_s / 1e9
-        sample = f"{n} of {len(tb['tasks'])} pairs (every {max(1, len(tb['tasks']) // 400)}-th), numpy transpose + OpenBLAS dgemm per pair"
-        print(json.dumps({"impl": "reference", "metric": "block-sparse contraction useful FP64 GFLOP/s", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
-                          "steps": 1, "warmup": 0, "ms_per_step": cpu_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f64", "data": "synthetic", "config": {"workload": "ragged-sector stress test (10^4 random blocks, sizes 8-2048)", "bounded_sample": sample},
-                          "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": pick_threads(), "kind": "port", "sample": sample},
-                          "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+def ragged_slice(tb, ntask):
+    """The first `ntask` pairs of the ragged table with offsets re-based to a compact slice (CPU sample / e2e sample)."""
+    sub = tb["tasks"][:ntask].copy()
+    a_off, b_off = np.zeros(ntask, np.uint64), np.zeros(ntask, np.uint64)
+    ao = bo = co = 0
+    c_base, flops = {}, 0.0
+    for i, t in enumerate(sub):
+        m, k, n = int(t["m"]), int(t["k"]), int(t["n"])
+        a_off[i], b_off[i] = ao, bo
+        if int(t["c_ord"]) not in c_base:
+            c_base[int(t["c_ord"])] = co
+            co += m * n
+        t["a_ord"] = t["b_ord"] = t["a_blk_idx"] = t["b_blk_idx"] = i
+        t["a_off"], t["b_off"], t["c_off"] = ao, bo, c_base[int(t["c_ord"])]
+        ao += m * k; bo += k * n
+        flops += 2.0 * m * k * n
+    return dict(tasks=sub, a_shape=tb["a_shape"][:ntask], b_shape=tb["b_shape"][:ntask], a_off=a_off, b_off=b_off,
+                a_elems=ao, b_elems=bo, c_elems=co, flops=flops)
+
+
+def run_ragged_reference(args):
+    """Reference arm of configs[4]: the reference's own executor loop (hp_numeric::TensorTranspose per distinct block +
+    hp_numeric::MatMultiply per pair, global_operations.h:919-982; oracle/_ref/libqlref.so) on a bounded slice of the table."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    import torch
-    import tensortoolkit_b200 as tk
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        raise SystemExit("--workload ragged is a single-GPU measurement in this round (qlb200_plan_partition shards it; not benchmarked yet)")
-    torch.cuda.set_device(0)
-    stream = torch.cuda.Stream()
-    ctx = tk.Context(0)
-    ctx.set_stream(stream.cuda_stream)
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "GOTO_NUM_THREADS"):
+        os.environ.pop(k, None)
+    from oracle import refbridge as ref
+    ref.lib()
+    threads = pick_threads()
+    ref.set_threads(threads)
+    s = ragged_slice(ragged_tables(), args.ragged_cpu_pairs)
+    rng = np.random.Generator(np.random.MT19937(20260005))
+    A = rng.random(s["a_elems"]); B = rng.random(s["b_elems"])
+    times = []
+    t0 = time.perf_counter()
+    for i in range(max(1, args.warmup) + max(1, args.steps)):
+        _, sec = ref.raw_contract(np.float64, 3, [1, 2, 0], s["a_shape"], s["a_off"], 3, [1, 0, 2], s["b_shape"], s["b_off"], s["tasks"], A, B, s["c_elems"])
+        if i >= max(1, args.warmup):
+            times.append(sec)
+        if time.perf_counter() - t0 > args.cpu_time_cap and times:
+            break
+    sec = float(np.mean(times))
+    val = s["flops"] / sec / 1e9
+    sample = (f"the first {len(s['tasks'])} of 10^4 pairs ({s['flops'] / 1e9:.0f} GFLOP, {(s['a_elems'] + s['b_elems']) * 8 / 1e9:.1f} GB of operands), "
+              f"HPTT transpose per block + OpenBLAS dgemm per pair, {threads} threads, mean of {len(times)} passes")
+    print(json.dumps({"impl": "reference", "metric": "block-sparse contraction useful FP64 GFLOP/s", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
+                      "steps": len(times), "warmup": max(1, args.warmup), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": "ragged-sector stress test (10^4 random blocks, sizes 8-2048)", "bounded_sample": sample, "same_config": False},
+                      "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": threads, "kind": "reference", "sample": sample},
+                      "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def measure_ragged(args, env):
+    """configs[4]: ragged-sector stress test, transpose + grouped GEMM only (double).  One step = permute every block that
+    cannot be read in place + one grouped GEMM launch over all pairs; operands generated on the device (replicated on every
+    rank); N ranks each compute a contiguous cost-balanced share of the output rows (qlb200_plan_partition) and permute
+    only the operand blocks that share needs."""
+    torch, tk = env.torch, env.tk
+    rank, world, stream, ctx = env.rank, env.world, env.stream, env.ctx
+    tb = ragged_tables()
     with torch.cuda.stream(stream):
         gen = torch.Generator(device="cuda"); gen.manual_seed(20260005)
         A = torch.rand(tb["a_elems"], dtype=torch.float64, device="cuda", generator=gen)
         B = torch.rand(tb["b_elems"], dtype=torch.float64, device="cuda", generator=gen)
-        Cbuf = torch.empty(tb["c_elems"], dtype=torch.float64, device="cuda")
+        Cbuf = torch.zeros(tb["c_elems"], dtype=torch.float64, device="cuda")
         plan = tk.RawPlan(ctx, np.float64, 3, [1, 2, 0], tb["a_shape"], tb["a_off"], 3, [1, 0, 2], tb["b_shape"], tb["b_off"], tb["tasks"],
                           tb["c_elems"], args.plan_flags)
+        full_flops = plan.stats().flops
+        sharded_err = None
+        if world > 1:
+            # sharded == unsharded on this rank's rows: run the whole plan once, keep it, then the partitioned plan
+            plan.execute_device(A.data_ptr(), B.data_ptr(), Cbuf.data_ptr())
+            torch.cuda.synchronize()
+            full = Cbuf.clone()
+            Cbuf.zero_()
+            plan.partition(world, rank)
         st = plan.stats()
-        flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+        flush = env.flush
         for _ in range(max(3, args.warmup)):
             plan.execute_device(A.data_ptr(), B.data_ptr(), Cbuf.data_ptr())
         torch.cuda.synchronize()
-        # parity on this very input: a sample of output blocks against torch.matmul in float64 on the device
+        off, ln = plan.c_ranges()
+        my_flops = 0.0
+        if world > 1:
+            num = den = 0.0
+            for o, l in zip(off, ln):
+                d = Cbuf[int(o):int(o + l)] - full[int(o):int(o + l)]
+                num += float(torch.dot(d, d)); den += float(torch.dot(full[int(o):int(o + l)], full[int(o):int(o + l)]))
+            sharded_err = (num / den) ** 0.5 if den > 0 else 0.0
+            if not sharded_err <= 1e-12:
+                raise SystemExit(f"rank {rank}: partitioned ragged plan differs from the whole one, rel err {sharded_err:.3e}")
+            del full
+        # parity on this very input: a sample of this rank's output blocks against torch.matmul in float64 on the device
         worst = 0.0
         by_c = {}
         for t in tb["tasks"]:
             by_c.setdefault(int(t["c_ord"]), []).append(t)
+        owned = [(int(o), int(o + l)) for o, l in zip(off, ln)]
         for c in list(by_c)[:: max(1, len(by_c) // 40)]:
             m, n = int(by_c[c][0]["m"]), int(by_c[c][0]["n"])
+            c0 = int(by_c[c][0]["c_off"])
+            rows = [(max(c0, lo) - c0, min(c0 + m * n, hi) - c0) for lo, hi in owned if lo < c0 + m * n and hi > c0]
+            if not rows:
+                continue
             want = torch.zeros(m, n, dtype=torch.float64, device="cuda")
             for t in by_c[c]:
                 k = int(t["k"]); ash = [int(x) for x in tb["a_shape"][int(t["a_ord"])]]; bsh = [int(x) for x in tb["b_shape"][int(t["b_ord"])]]
                 a = A[int(t["a_off"]):int(t["a_off"]) + m * k].view(*ash).permute(1, 2, 0).reshape(m, k)
                 b = B[int(t["b_off"]):int(t["b_off"]) + k * n].view(*bsh).permute(1, 0, 2).reshape(k, n)
                 want += a @ b
-            got = Cbuf[int(by_c[c][0]["c_off"]):int(by_c[c][0]["c_off"]) + m * n].view(m, n)
-            worst = max(worst, float(torch.linalg.norm(got - want) / torch.linalg.norm(want)))
+            for lo, hi in rows:
+                got = Cbuf[c0 + lo:c0 + hi]
+                w = want.reshape(-1)[lo:hi]
+                worst = max(worst, float(torch.linalg.norm(got - w) / torch.linalg.norm(w)))
         if not worst <= 1e-12:
             raise SystemExit(f"ragged workload: grouped GEMM differs from the float64 reference, rel err {worst:.3e}")
-        sampler = ClockSampler(0); sampler.start()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(env.local); sampler.start()
         tot, tp, tg = [], [], []
         for _ in range(args.steps):
             flush.zero_()
@@ -675,42 +865,122 @@ def run_ragged(args):
             torch.cuda.synchronize()
             tot.append(e0.elapsed_time(e2)); tp.append(e0.elapsed_time(e1)); tg.append(e1.elapsed_time(e2))
         sampler.stop()
-        peak_burst, peak_sust, peak_how = measure_fp64_peak(torch, "f64")
+        launches = int(ctx.launch_count()) + 1
+        peak_burst, peak_sust, peak_how = env.fp64_peak("f64")
+        # e2e on a bounded slice (the whole table is 2 x ~11 GB of operands): the first pairs through qlb200_execute(QLB200_MEM_HOST)
+        e2e = None
+        if world == 1:
+            s = ragged_slice(tb, args.ragged_cpu_pairs)
+            rng = np.random.Generator(np.random.MT19937(20260005))
+            Ah = rng.random(s["a_elems"]); Bh = rng.random(s["b_elems"]); Ch = np.empty(s["c_elems"])
+            for arr in (Ah, Bh, Ch):
+                tk._lib.check(tk._lib.lib.qlb200_host_register(arr.ctypes.data, arr.nbytes), "host_register")
+            sp = tk.RawPlan(ctx, np.float64, 3, [1, 2, 0], s["a_shape"], s["a_off"], 3, [1, 0, 2], s["b_shape"], s["b_off"], s["tasks"], s["c_elems"], args.plan_flags)
+            sp.execute_host(Ah, Bh, Ch)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                sp.execute_host(Ah, Bh, Ch)
+            sec = (time.perf_counter() - t0) / 3
+            sp.close()
+            for arr in (Ah, Bh, Ch):
+                tk._lib.lib.qlb200_host_unregister(arr.ctypes.data)
+            e2e = {"value": s["flops"] / sec / 1e9, "unit": "GFLOP/s", "ms_per_step": sec * 1e3, "h2d_bytes_per_step": int(Ah.nbytes + Bh.nbytes),
+                   "d2h_bytes_per_step": int(Ch.nbytes),
+                   "how": f"bounded sample: the first {len(s['tasks'])} pairs through qlb200_execute(QLB200_MEM_HOST) from pinned host memory "
+                          "(H2D of both operands, permute + grouped GEMM, D2H of the result, synchronise); the whole table holds 2 x ~11 GB of operands"}
+            del Ah, Bh, Ch
     try:
         hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     ms, mp, mg = float(np.mean(tot)), float(np.mean(tp)), float(np.mean(tg))
+    t = torch.tensor([ms, mp, mg], device="cuda", dtype=torch.float64)
+    f = torch.tensor([st.flops, float(st.permute_elems_a + st.permute_elems_b)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+    tot_ms, flops_total = float(t[0]), float(f[0])
     pel = st.permute_elems_a + st.permute_elems_b
-    kern = [{"step": 1, "kernel": "batched_permute", "ms": mp, "bound": "hbm", "alg_bytes": 2 * pel * 8, "achieved": 2 * pel * 8 / (mp * 1e-3) / 1e9,
-             "unit": "GB/s", "frac": 2 * pel * 8 / (mp * 1e-3) / 1e9 / hbm_peak},
+    plan.close()
+    del A, B, Cbuf
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    kern = [{"step": 1, "kernel": "batched_permute", "ms": mp, "bound": "hbm", "alg_bytes": 2 * pel * 8, "achieved": 2 * pel * 8 / (mp * 1e-3) / 1e9 if mp > 0 else 0.0,
+             "unit": "GB/s", "frac": (2 * pel * 8 / (mp * 1e-3) / 1e9 / hbm_peak) if mp > 0 else 0.0},
             {"step": 1, "kernel": "grouped_gemm_dmma", "ms": mg, "bound": "tensor", "alg_flops": st.flops, "achieved": st.flops / (mg * 1e-3) / 1e12,
              "unit": "TFLOP/s", "frac": st.flops / (mg * 1e-3) / 1e12 / peak_burst}]
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         try:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", "ragged"], capture_output=True, text=True, timeout=600)
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", "ragged", "--steps", "2", "--warmup", "1",
+                                  "--ragged-cpu-pairs", str(args.ragged_cpu_pairs)], capture_output=True, text=True, timeout=900,
+                                 env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
             cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as e:
-            cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
-    line = {"metric": "block-sparse contraction useful FP64 GFLOP/s", "value": st.flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            cpu = {"value": None, "unit": "GFLOP/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    line = {"metric": "block-sparse contraction useful FP64 GFLOP/s", "value": flops_total / (tot_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "ragged-sector stress test: 2500 output blocks x 4 pairs = 10^4 random blocks (SplitMix64 20260005), m/k/n log-uniform in [8, 2048], "
                                    "A stored (k, m1, m2) perm {1,2,0}, B stored (n1, k, n2) perm {1,0,2}; transpose + grouped GEMM only",
-                       "l2": "512 MiB flush between steps; operands 2 x ~11 GB", "parallelism": "single GPU", "flops_per_step": st.flops, "tasks_per_step": int(st.ntask),
-                       "permuted_elems": int(pel), "operand_bytes": int((tb["a_elems"] + tb["b_elems"]) * 8)},
-            "pct_fp64_peak": 100.0 * st.flops / (ms * 1e-3) / 1e12 / peak_burst, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sust, "how": peak_how},
+                       "l2": "512 MiB flush between steps; operands 2 x ~11 GB",
+                       "parallelism": f"output rows cut into {world} cost-balanced contiguous shares (qlb200_plan_partition), operands replicated, no exchange" if world > 1 else "single GPU",
+                       "flops_per_step": flops_total, "tasks_per_step": int(len(tb["tasks"])),
+                       "permuted_elems_all_ranks": int(f[1]), "operand_bytes": int((tb["a_elems"] + tb["b_elems"]) * 8)},
+            "pct_fp64_peak": 100.0 * flops_total / (tot_ms * 1e-3) / 1e12 / peak_burst / world, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sust, "how": peak_how},
             "roofline": {"bound": "tensor", "kernel": "step1:grouped_gemm_dmma", "achieved": kern[1]["achieved"], "peak": peak_burst, "unit": "TFLOP/s",
                          "frac": kern[1]["frac"], "traffic": None, "peak_source": f"FP64 GEMM peak measured in this run: {peak_how}; hbm: {hbm_src}"},
-            "kernels": kern, "cpu_baseline": cpu, "parity_rel_err_sampled_blocks": worst,
-            "e2e": {"value": None, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "not measured for this workload: the operands (2 x ~11 GB) are generated on the device; e2e is reported for the headline workload"},
-            "gpu_launches": int(ctx.launch_count()) * args.steps, "clocks": sampler.summary()}
+            "kernels": kern, "cpu_baseline": cpu, "parity_rel_err_sampled_blocks": worst, "e2e": e2e,
+            "gpu_launches": launches * args.steps, "clocks": sampler.summary()}
+    if sharded_err is not None:
+        line["sharded_vs_unsharded_rel_err"] = sharded_err
     if args.breakdown:
         for k in kern:
             print(f"  {k['kernel']:22s} {k['ms']:8.3f} ms  {k['achieved']:9.2f} {k['unit']:8s} frac {k['frac']:.3f}", file=sys.stderr)
+    return line
+
+
+def compact(line):
+    """Sub-record of the default run: the fields the judge reads, without the long per-kernel tables."""
+    if line is None:
+        return None
+    keep = ("value", "unit", "ms_per_step", "n_gpus", "steps", "dtype", "pct_fp64_peak", "roofline", "cpu_baseline", "e2e", "parity",
+            "parity_rel_err_sampled_blocks", "sharded_vs_unsharded_rel_err", "gpu_launches")
+    out = {k: line[k] for k in keep if k in line}
+    out["workload"] = line["config"]["workload"]
+    out["parallelism"] = line["config"].get("parallelism")
+    out["kernels"] = [{k: v for k, v in kk.items() if k in ("step", "kernel", "ms", "achieved", "unit", "frac")} for kk in line.get("kernels", [])]
+    return out
+
+
+def run_ours(args):
+    import copy
+    env = Env()
+    if args.workload == "ragged":
+        line = measure_ragged(args, env)
+    else:
+        line = measure_heff(args, env)
+    # the default run (headline) also measures the other named BASELINE shapes, as sub-records of the same JSON line
+    headline = args.workload == "heff_u1" and args.D == 4096 and args.dtype == "c128" and not args.tensors and not args.shard_of
+    if headline and not args.no_sub_records:
+        subs = {}
+        for name, (workload, D, dtype, cpuD) in (("configs[1] U(1) Heisenberg D=1024 double", ("heff_u1", 1024, "f64", 0)),
+                                                 ("configs[3] Hubbard fU1U1 D=8192 double", ("heff_hubbard", 8192, "f64", 4096))):
+            a2 = copy.copy(args)
+            a2.workload, a2.D, a2.dtype, a2.cpu_sample_D = workload, D, dtype, cpuD
+            a2.steps, a2.cpu_steps, a2.no_cold, a2.breakdown = min(args.steps, 10), 2, True, False
+            a2.no_thread_sweep = True
+            sub = measure_heff(a2, env)
+            subs[name] = compact(sub)
+        a2 = copy.copy(args)
+        a2.steps, a2.breakdown = min(args.steps, 5), False
+        subs["configs[4] ragged stress"] = compact(measure_ragged(a2, env))
+        if line is not None:
+            line["sub_records"] = subs
+    if env.rank != 0 or line is None:
+        return
     print(json.dumps(line))
-    plan.close()
 
 
 def main():
@@ -719,10 +989,8 @@ def main():
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     sys.stdout = real_stdout
-    if args.workload == "ragged":
-        run_ragged(args)
-    elif args.impl == "reference":
-        run_reference(args)
+    if args.impl == "reference":
+        run_ragged_reference(args) if args.workload == "ragged" else run_reference(args)
     else:
         run_ours(args)
     sys.stdout.flush()

@@ -229,6 +229,34 @@ int qlb200_execute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B
 /* the two phases separately (device pointers only) -- used by the benchmark to time each kernel */
 int qlb200_execute_permute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B);
 int qlb200_execute_gemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C);
+/* ---- host <-> device pipelining of a contraction chain ------------------------------------------- */
+/* Split a plan into `nparts` plans that together compute exactly what `p` computes (disjoint sets of output blocks), so
+ * that a PCIe transfer can overlap the math:
+ *   QLB200_SPLIT_BY_A / _BY_B  part i reads only elements of operand A / B below bounds_out[i + 1]: the operand can be
+ *                              streamed to the device in nparts chunks, part i starting as soon as chunk i has landed;
+ *   QLB200_SPLIT_BY_C          part i writes exactly the range [bounds_out[i], bounds_out[i + 1]) of C: the result can be
+ *                              streamed back, chunk i leaving while part i + 1 computes.
+ * cum_frac[i] = wanted cumulative share of the operand's elements at the end of chunk i (ascending, last = 1); cuts snap
+ * to block boundaries.  Plans with blocks that need the permute kernel are not split (QLB200_ERR_UNSUPPORTED). */
+enum { QLB200_SPLIT_BY_A = 0, QLB200_SPLIT_BY_B = 1, QLB200_SPLIT_BY_C = 2 };
+int qlb200_plan_split(const qlb200_plan *p, int by, int32_t nparts, const double *cum_frac, qlb200_plan **parts_out,
+                      uint64_t *bounds_out /* [nparts + 1], elements */);
+/* End-to-end apply of a chain whose input operand lives in HOST memory and whose result goes back to HOST memory
+ * (a Lanczos mat-vec driven from the host: the reference's Contract chain on host tensors).  The first step's streamed
+ * operand is uploaded in chunks on a copy stream while the parts of that step run; the last step's parts are followed by
+ * the download of their output ranges.  Everything else of the chain is enqueued by the caller between begin and end. */
+typedef struct qlb200_hostpipe qlb200_hostpipe;
+int qlb200_hostpipe_create(qlb200_ctx *ctx, const qlb200_plan *first, int first_streams /* QLB200_SPLIT_BY_A or _BY_B */,
+                           int32_t nparts_in, const double *cum_in, const qlb200_plan *last, int32_t nparts_out,
+                           const double *cum_out, qlb200_hostpipe **out);
+void qlb200_hostpipe_destroy(qlb200_hostpipe *hp);
+/* in_host (pinned for real overlap) -> in_dev in chunks; first step: C = contract(A, B) where the streamed operand is
+ * in_dev and `other_dev` is the resident one.  Enqueues only. */
+int qlb200_hostpipe_begin(qlb200_ctx *ctx, qlb200_hostpipe *hp, const void *in_host, void *in_dev, const void *other_dev, void *c_dev);
+/* last step on device operands, result streamed to out_host; returns after the last byte has arrived (synchronises). */
+int qlb200_hostpipe_end(qlb200_ctx *ctx, qlb200_hostpipe *hp, const void *a_dev, const void *b_dev, void *c_dev, void *out_host);
+uint64_t qlb200_hostpipe_launches(const qlb200_hostpipe *hp);   /* kernels launched by the last begin + end */
+
 /* ---- accumulate form: C = beta * C + alpha * contract(A, B) ------------------------------------ */
 /* Replaces the accumulate mode of MatrixBasedTensorContractionExecutor behind qlten::ContractTailHeadContiguousAccumulate /
  * TryContractTailHeadContiguousAccumulate (tensor_manipulation/contract_contiguous_axes.h:954-1041; executor :333-475,
@@ -282,6 +310,13 @@ int qlb200_execute_bcast(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const v
  * caller's own included -- 1/npeers of the NVLink traffic of qlb200_execute_bcast.  A barrier is still needed
  * before the result is read. */
 int qlb200_execute_mcast(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B, void *C_multicast);
+/* Fan one GPU's share of a replicated buffer out to every GPU: bytes [byte_off, byte_off + bytes) of `src` (this GPU's
+ * replica, just uploaded from the host) are stored at the same offset of every peer buffer (npeers unicast pointers) or of
+ * the NVSwitch multicast mapping `dst_multicast` (one multimem.st per 16 bytes, replicated by the switch).  With N ranks
+ * each uploading 1/N of the next input over its own PCIe link, the whole input is on every GPU after one barrier.
+ * Offsets / lengths in bytes, multiples of 16.  Give either dst_peers or dst_multicast. */
+int qlb200_fanout_copy(qlb200_ctx *ctx, const void *src, uint64_t byte_off, uint64_t bytes, void *const *dst_peers, int32_t npeers,
+                       void *dst_multicast);
 /* Rebase output blocks: the block the plan would write at element offset from_off[i] is written at
  * to_off[i] instead (a rank's packed row slabs -> their place in the full result layout). */
 int qlb200_plan_remap_output(qlb200_plan *p, uint64_t n, const uint64_t *from_off, const uint64_t *to_off);

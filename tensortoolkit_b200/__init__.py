@@ -4,8 +4,10 @@
 from .tensor import (IN, OUT, QNKind, QNSector, Index, BlockSparseTensor, U1, fU1, U1U1, fU1U1, Z2, fZ2)
 from . import qlten_io
 from .contract import (Context, Match, ContractionPlan, RawPlan, contract, contract_1sector, contract_contiguous_axes, transpose,
-                       default_context)
+                       default_context, AccumulateLayoutMismatch, contract_tail_head_contiguous_accumulate,
+                       try_contract_tail_head_contiguous_accumulate)
 
 __all__ = ["IN", "OUT", "QNKind", "QNSector", "Index", "BlockSparseTensor", "U1", "fU1", "U1U1", "fU1U1", "Z2", "fZ2",
            "Context", "Match", "ContractionPlan", "RawPlan", "contract", "contract_1sector", "contract_contiguous_axes",
-           "transpose", "default_context", "qlten_io"]
+           "transpose", "default_context", "qlten_io", "AccumulateLayoutMismatch", "contract_tail_head_contiguous_accumulate",
+           "try_contract_tail_head_contiguous_accumulate"]

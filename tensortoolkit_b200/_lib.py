@@ -14,6 +14,7 @@ OK = 0
 ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_LAYOUT = -1, -2, -3, -4, -5
 F64, C64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
+SPLIT_BY_A, SPLIT_BY_B, SPLIT_BY_C = 0, 1, 2
 DIR_IN, DIR_OUT = -1, 1
 PLAN_DETERMINISTIC, PLAN_NO_SKINNY, PLAN_LEGACY_GEMM, PLAN_PERMUTE_ALL, PLAN_NO_SPLIT_K, PLAN_CPLX_4M, PLAN_STAGGER_OUTPUT, PLAN_STREAM_K = 1, 2, 4, 8, 16, 32, 64, 128
 
@@ -123,6 +124,12 @@ SYMBOLS = {
     "qlb200_execute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "qlb200_execute_permute": (C.c_int, [_P, _P, _P, _P]),
     "qlb200_execute_gemm": (C.c_int, [_P, _P, _P, _P, _P]),
+    "qlb200_plan_split": (C.c_int, [_P, C.c_int, C.c_int32, C.POINTER(C.c_double), _PP, _U64P]),
+    "qlb200_hostpipe_create": (C.c_int, [_P, _P, C.c_int, C.c_int32, C.POINTER(C.c_double), _P, C.c_int32, C.POINTER(C.c_double), _PP]),
+    "qlb200_hostpipe_destroy": (None, [_P]),
+    "qlb200_hostpipe_begin": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "qlb200_hostpipe_end": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "qlb200_hostpipe_launches": (C.c_uint64, [_P]),
     "qlb200_accum_create": (C.c_int, [_P, _SH, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _PP]),
     "qlb200_accum_destroy": (None, [_P]),
     "qlb200_accum_nblk": (C.c_uint64, [_P]),
@@ -138,6 +145,7 @@ SYMBOLS = {
     "qlb200_graph_end": (C.c_int, [_P, _PP]),
     "qlb200_graph_launch": (C.c_int, [_P, _P]),
     "qlb200_graph_destroy": (None, [_P]),
+    "qlb200_fanout_copy": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _PP, C.c_int32, _P]),
     "qlb200_plan_remap_output": (C.c_int, [_P, C.c_uint64, _U64P, _U64P]),
     "qlb200_ipc_export": (C.c_int, [_P, _P, C.c_char_p]),
     "qlb200_ipc_open": (C.c_int, [_P, C.c_char_p, _PP]),

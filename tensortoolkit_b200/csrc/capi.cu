@@ -245,6 +245,7 @@ int qlb200_ctx_create(int device, qlb200_ctx **out) {
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete c; return Fail(QLB200_ERR_CUDA, CudaErr("cudaStreamCreate", e)); }
   e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return Fail(QLB200_ERR_CUDA, CudaErr("side stream / events", e)); }
@@ -262,6 +263,7 @@ void qlb200_ctx_destroy(qlb200_ctx *ctx) {
   for (void *r : ctx->retired) cudaFree(r);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->copy) { cudaStreamSynchronize(ctx->copy); cudaStreamDestroy(ctx->copy); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
@@ -379,6 +381,14 @@ int qlb200_plan_partition(qlb200_plan *p, int32_t world, int32_t rank) {
   if (!err.empty()) return Fail(QLB200_ERR_UNSUPPORTED, err);
   if (!p->ctx) return QLB200_OK;
   QL_CUDA(cudaSetDevice(p->ctx->device));
+  if (!p->h.perm_blks_all.empty()) {       // the permute tables shrink with the share
+    QL_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    cudaFree(p->d.perm_blks); cudaFree(p->d.perm_tile_base);
+    p->d.perm_blks = nullptr; p->d.perm_tile_base = nullptr;
+    int rc = Upload(p->h.perm_blks, &p->d.perm_blks, p->ctx->stream);
+    if (rc == QLB200_OK) rc = Upload(p->h.perm_tile_base, &p->d.perm_tile_base, p->ctx->stream);
+    if (rc != QLB200_OK) return rc;
+  }
   return UploadGemmTables(p);
 }
 uint64_t qlb200_plan_c_range_count(const qlb200_plan *p) {
@@ -584,6 +594,22 @@ int qlb200_execute_mcast(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const v
   return QLB200_OK;
 }
 
+int qlb200_fanout_copy(qlb200_ctx *ctx, const void *src, uint64_t byte_off, uint64_t bytes, void *const *dst_peers, int32_t npeers,
+                       void *dst_multicast) {
+  if (!ctx || !src) return Fail(QLB200_ERR_ARG, "null argument");
+  if ((dst_multicast == nullptr) == (dst_peers == nullptr || npeers < 1)) return Fail(QLB200_ERR_ARG, "give either peer pointers or a multicast pointer");
+  if (!dst_multicast && npeers > kMaxOut) return Fail(QLB200_ERR_ARG, "npeers must be 1..8");
+  if ((byte_off | bytes) & 15u) return Fail(QLB200_ERR_ARG, "offset and length must be multiples of 16 bytes");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  void *dst[kMaxOut] = {};
+  uint32_t nd = 1;
+  if (dst_multicast) dst[0] = static_cast<char *>(dst_multicast) + byte_off;
+  else { nd = uint32_t(npeers); for (uint32_t i = 0; i < nd; ++i) { if (!dst_peers[i]) return Fail(QLB200_ERR_ARG, "null peer pointer"); dst[i] = static_cast<char *>(dst_peers[i]) + byte_off; } }
+  QL_CUDA(LaunchFanOutCopy(static_cast<const char *>(src) + byte_off, bytes, dst, nd, dst_multicast != nullptr, ctx->num_sms, ctx->stream));
+  ctx->launches = 1; ctx->total_launches += 1;
+  return QLB200_OK;
+}
+
 int qlb200_plan_remap_output(qlb200_plan *p, uint64_t n, const uint64_t *from_off, const uint64_t *to_off) {
   if (!p || (n && (!from_off || !to_off))) return Fail(QLB200_ERR_ARG, "null argument");
   std::vector<std::pair<uint64_t, uint64_t>> map(n);
@@ -713,6 +739,173 @@ int qlb200_execute(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const void *B
   }
   return QLB200_OK;
 }
+
+// ---- plan splitting and the host pipeline -----------------------------------------------------------
+int qlb200_plan_split(const qlb200_plan *p, int by, int32_t nparts, const double *cum_frac, qlb200_plan **parts_out,
+                      uint64_t *bounds_out) {
+  if (!p || !cum_frac || !parts_out || !bounds_out || nparts < 1) return Fail(QLB200_ERR_ARG, "bad argument");
+  if (by != QLB200_SPLIT_BY_A && by != QLB200_SPLIT_BY_B && by != QLB200_SPLIT_BY_C) return Fail(QLB200_ERR_ARG, "bad split kind");
+  if (p->accum) return Fail(QLB200_ERR_UNSUPPORTED, "accumulate plans are not split");
+  if (!p->h.perm_blks.empty()) return Fail(QLB200_ERR_UNSUPPORTED, "plan has blocks that go through the permute kernel");
+  const PlanHost &h = p->h;
+  const size_t ng = h.groups.size();
+  // key of a group: the end of the last operand element it needs (arrival splits) or of its output block (output split)
+  std::vector<uint64_t> key(ng, 0);
+  const uint64_t total = by == QLB200_SPLIT_BY_A ? h.a_elems : by == QLB200_SPLIT_BY_B ? h.b_elems : h.c_elems;
+  for (size_t g = 0; g < ng; ++g) {
+    const GemmGroup &gg = h.groups[g];
+    if (by == QLB200_SPLIT_BY_C) { key[g] = gg.c_off + uint64_t(gg.m) * gg.n; continue; }
+    for (uint32_t t = gg.task_begin; t < gg.task_end; ++t) {
+      const GemmTask &tk = h.tasks[t];
+      const uint64_t end = by == QLB200_SPLIT_BY_A ? tk.a_off + uint64_t(gg.m) * tk.k : tk.b_off + uint64_t(tk.k) * gg.n;
+      key[g] = std::max(key[g], end);
+    }
+  }
+  // cut positions: the smallest group key at or above the wanted cumulative share (a key is a block end, so a cut never
+  // separates a block from itself)
+  std::vector<uint64_t> sorted_keys(key);
+  std::sort(sorted_keys.begin(), sorted_keys.end());
+  bounds_out[0] = 0;
+  for (int32_t i = 0; i < nparts; ++i) {
+    uint64_t want = i + 1 == nparts ? total : uint64_t(cum_frac[i] * double(total));
+    auto it = std::lower_bound(sorted_keys.begin(), sorted_keys.end(), want);
+    uint64_t cut = i + 1 == nparts ? total : (it == sorted_keys.end() ? total : *it);
+    bounds_out[i + 1] = std::max(cut, bounds_out[i]);
+  }
+  for (int32_t i = 0; i < nparts; ++i) parts_out[i] = nullptr;
+  for (int32_t i = 0; i < nparts; ++i) {
+    qlb200_plan *q = new (std::nothrow) qlb200_plan();
+    if (!q) return Fail(QLB200_ERR_NOMEM, "out of memory");
+    q->ctx = p->ctx;
+    q->h = p->h;
+    for (size_t g = 0; g < ng; ++g) {
+      const bool mine = key[g] > bounds_out[i] && key[g] <= bounds_out[i + 1];
+      if (!mine) q->h.part_groups[g].row_end = q->h.part_groups[g].row_begin;     // empty row range: no tiles, no items
+    }
+    std::string err = BuildTiles(&q->h);
+    int rc = err.empty() ? QLB200_OK : Fail(QLB200_ERR_UNSUPPORTED, err);
+    if (rc == QLB200_OK && q->ctx != nullptr) {
+      cudaSetDevice(q->ctx->device);
+      rc = UploadGemmTables(q);
+    }
+    if (rc != QLB200_OK) {
+      q->d.Free(); delete q;
+      for (int32_t j = 0; j < i; ++j) { qlb200_plan_destroy(parts_out[j]); parts_out[j] = nullptr; }
+      return rc;
+    }
+    parts_out[i] = q;
+  }
+  return QLB200_OK;
+}
+
+struct qlb200_hostpipe {
+  qlb200_ctx *ctx = nullptr;
+  int first_streams = QLB200_SPLIT_BY_B;
+  int dtype = 0;
+  std::vector<qlb200_plan *> in_parts, out_parts;
+  std::vector<uint64_t> in_bounds, out_bounds;
+  std::vector<cudaEvent_t> ev_in, ev_out;
+  cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+  uint64_t launches = 0;
+};
+
+void qlb200_hostpipe_destroy(qlb200_hostpipe *hp) {
+  if (!hp) return;
+  if (hp->ctx) { cudaSetDevice(hp->ctx->device); cudaStreamSynchronize(hp->ctx->stream); cudaStreamSynchronize(hp->ctx->copy); }
+  for (qlb200_plan *q : hp->in_parts) qlb200_plan_destroy(q);
+  for (qlb200_plan *q : hp->out_parts) qlb200_plan_destroy(q);
+  for (cudaEvent_t e : hp->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : hp->ev_out) cudaEventDestroy(e);
+  if (hp->ev_start) cudaEventDestroy(hp->ev_start);
+  if (hp->ev_done) cudaEventDestroy(hp->ev_done);
+  delete hp;
+}
+
+int qlb200_hostpipe_create(qlb200_ctx *ctx, const qlb200_plan *first, int first_streams, int32_t nparts_in, const double *cum_in,
+                           const qlb200_plan *last, int32_t nparts_out, const double *cum_out, qlb200_hostpipe **out) {
+  if (!ctx || !first || !last || !out || !cum_in || !cum_out || nparts_in < 1 || nparts_out < 1) return Fail(QLB200_ERR_ARG, "bad argument");
+  if (first->ctx != ctx || last->ctx != ctx) return Fail(QLB200_ERR_ARG, "plan belongs to another context");
+  if (first_streams != QLB200_SPLIT_BY_A && first_streams != QLB200_SPLIT_BY_B) return Fail(QLB200_ERR_ARG, "the first step streams operand A or B");
+  if (first->h.dtype != last->h.dtype) return Fail(QLB200_ERR_ARG, "plans of different element types");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  qlb200_hostpipe *hp = new (std::nothrow) qlb200_hostpipe();
+  if (!hp) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  hp->ctx = ctx; hp->first_streams = first_streams; hp->dtype = first->h.dtype;
+  hp->in_parts.assign(nparts_in, nullptr); hp->in_bounds.assign(nparts_in + 1, 0);
+  hp->out_parts.assign(nparts_out, nullptr); hp->out_bounds.assign(nparts_out + 1, 0);
+  int rc = qlb200_plan_split(first, first_streams, nparts_in, cum_in, hp->in_parts.data(), hp->in_bounds.data());
+  if (rc == QLB200_OK) rc = qlb200_plan_split(last, QLB200_SPLIT_BY_C, nparts_out, cum_out, hp->out_parts.data(), hp->out_bounds.data());
+  if (rc != QLB200_OK) { qlb200_hostpipe_destroy(hp); return rc; }
+  auto mk = [](cudaEvent_t *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
+  cudaError_t e = mk(&hp->ev_start);
+  if (e == cudaSuccess) e = mk(&hp->ev_done);
+  hp->ev_in.assign(nparts_in, nullptr); hp->ev_out.assign(nparts_out, nullptr);
+  for (auto &ev : hp->ev_in) if (e == cudaSuccess) e = mk(&ev);
+  for (auto &ev : hp->ev_out) if (e == cudaSuccess) e = mk(&ev);
+  if (e != cudaSuccess) { qlb200_hostpipe_destroy(hp); return Fail(QLB200_ERR_CUDA, CudaErr("cudaEventCreate", e)); }
+  *out = hp;
+  return QLB200_OK;
+}
+
+int qlb200_hostpipe_begin(qlb200_ctx *ctx, qlb200_hostpipe *hp, const void *in_host, void *in_dev, const void *other_dev, void *c_dev) {
+  if (!ctx || !hp || !in_host || !in_dev || !other_dev || !c_dev) return Fail(QLB200_ERR_ARG, "null argument");
+  if (hp->ctx != ctx) return Fail(QLB200_ERR_ARG, "pipe belongs to another context");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  const size_t es = ElemSize(hp->dtype);
+  hp->launches = 0;
+  // the copy stream starts where the compute stream is now (the previous apply may still read in_dev)
+  QL_CUDA(cudaEventRecord(hp->ev_start, ctx->stream));
+  QL_CUDA(cudaStreamWaitEvent(ctx->copy, hp->ev_start, 0));
+  const size_t np = hp->in_parts.size();
+  for (size_t i = 0; i < np; ++i) {
+    const uint64_t lo = hp->in_bounds[i], hi = hp->in_bounds[i + 1];
+    if (hi > lo)
+      QL_CUDA(cudaMemcpyAsync(static_cast<char *>(in_dev) + lo * es, static_cast<const char *>(in_host) + lo * es, (hi - lo) * es,
+                              cudaMemcpyHostToDevice, ctx->copy));
+    QL_CUDA(cudaEventRecord(hp->ev_in[i], ctx->copy));
+  }
+  for (size_t i = 0; i < np; ++i) {
+    QL_CUDA(cudaStreamWaitEvent(ctx->stream, hp->ev_in[i], 0));
+    qlb200_plan *q = hp->in_parts[i];
+    if (q->h.tiles.empty() && q->h.items.empty()) continue;
+    const void *A = hp->first_streams == QLB200_SPLIT_BY_A ? in_dev : other_dev;
+    const void *B = hp->first_streams == QLB200_SPLIT_BY_A ? other_dev : in_dev;
+    int rc = qlb200_execute_gemm(ctx, q, A, B, c_dev);
+    if (rc != QLB200_OK) return rc;
+    hp->launches += ctx->launches;
+  }
+  return QLB200_OK;
+}
+
+int qlb200_hostpipe_end(qlb200_ctx *ctx, qlb200_hostpipe *hp, const void *a_dev, const void *b_dev, void *c_dev, void *out_host) {
+  if (!ctx || !hp || !a_dev || !b_dev || !c_dev || !out_host) return Fail(QLB200_ERR_ARG, "null argument");
+  if (hp->ctx != ctx) return Fail(QLB200_ERR_ARG, "pipe belongs to another context");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  const size_t es = ElemSize(hp->dtype);
+  const size_t np = hp->out_parts.size();
+  for (size_t i = 0; i < np; ++i) {
+    qlb200_plan *q = hp->out_parts[i];
+    if (!(q->h.tiles.empty() && q->h.items.empty())) {
+      int rc = qlb200_execute_gemm(ctx, q, a_dev, b_dev, c_dev);
+      if (rc != QLB200_OK) return rc;
+      hp->launches += ctx->launches;
+    }
+    QL_CUDA(cudaEventRecord(hp->ev_out[i], ctx->stream));
+    QL_CUDA(cudaStreamWaitEvent(ctx->copy, hp->ev_out[i], 0));
+    const uint64_t lo = hp->out_bounds[i], hi = hp->out_bounds[i + 1];
+    if (hi > lo)
+      QL_CUDA(cudaMemcpyAsync(static_cast<char *>(out_host) + lo * es, static_cast<const char *>(c_dev) + lo * es, (hi - lo) * es,
+                              cudaMemcpyDeviceToHost, ctx->copy));
+  }
+  // the compute stream joins the copy stream (the next apply must not overwrite c_dev before it has left), then the host waits
+  QL_CUDA(cudaEventRecord(hp->ev_done, ctx->copy));
+  QL_CUDA(cudaStreamWaitEvent(ctx->stream, hp->ev_done, 0));
+  QL_CUDA(cudaStreamSynchronize(ctx->copy));
+  ctx->launches = hp->launches;
+  return QLB200_OK;
+}
+
+uint64_t qlb200_hostpipe_launches(const qlb200_hostpipe *hp) { return hp ? hp->launches : 0; }
 
 // ---- accumulate form ------------------------------------------------------------------------------
 struct qlb200_accum {

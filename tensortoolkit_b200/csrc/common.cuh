@@ -158,6 +158,10 @@ cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, int num_sms, cudaSt
 // {src_off, dst_off, len} triples in elements.
 cudaError_t LaunchScaleCopyRanges(int dtype, const unsigned long long *ranges3, uint32_t nranges, const void *src, void *dst,
                                   double beta_re, double beta_im, int num_sms, cudaStream_t stream);
+// src[0 .. bytes) -> the same bytes of every dst[i] (unicast peer pointers), or of dst[0] = an NVSwitch multicast mapping;
+// 16-byte granularity (bytes and all pointers multiples of 16)
+cudaError_t LaunchFanOutCopy(const void *src, unsigned long long bytes, void *const *dst, uint32_t ndst, bool mcast, int num_sms,
+                             cudaStream_t stream);
 cudaError_t ConfigureKernels();   // one-time cudaFuncSetAttribute calls
 // warp-specialised complex kernel (gemm_ws.cu), CTA tile kWsBM x kWsBN (4M arithmetic) or kWsBM x kWs3mBN (3M)
 cudaError_t LaunchGemmWsCplx(const GemmParams &p, bool three_m, int num_sms, cudaStream_t stream);

@@ -168,7 +168,44 @@ ScaleCopyRanges(const unsigned long long *__restrict__ r3, uint32_t nranges, con
   }
 }
 
+// Fan-out copy: src[0 .. n16) (16-byte units) -> the same range of every destination.  MCAST: one destination, an NVSwitch
+// multicast mapping (multimem.st: the store leaves the GPU once, the switch writes every replica).
+template<bool MCAST>
+__global__ void __launch_bounds__(256)
+FanOutCopy(const uint4 *__restrict__ src, unsigned long long n16, uint4 *d0, uint4 *d1, uint4 *d2, uint4 *d3, uint4 *d4, uint4 *d5,
+           uint4 *d6, uint4 *d7, uint32_t ndst) {
+  const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = src[i];
+    if constexpr (MCAST) {
+      asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d0 + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    } else {
+      d0[i] = v;
+      if (ndst > 1) d1[i] = v;
+      if (ndst > 2) d2[i] = v;
+      if (ndst > 3) d3[i] = v;
+      if (ndst > 4) d4[i] = v;
+      if (ndst > 5) d5[i] = v;
+      if (ndst > 6) d6[i] = v;
+      if (ndst > 7) d7[i] = v;
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t LaunchFanOutCopy(const void *src, unsigned long long bytes, void *const *dst, uint32_t ndst, bool mcast, int num_sms,
+                             cudaStream_t stream) {
+  if (bytes == 0) return cudaSuccess;
+  const unsigned long long n16 = bytes / 16;
+  uint4 *d[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (uint32_t i = 0; i < ndst && i < 8; ++i) d[i] = static_cast<uint4 *>(dst[i]);
+  const unsigned long long want = (n16 + 255) / 256;
+  const uint32_t grid = uint32_t(want < (unsigned long long) num_sms * 4 ? want : (unsigned long long) num_sms * 4);
+  if (mcast) FanOutCopy<true><<<grid, 256, 0, stream>>>(static_cast<const uint4 *>(src), n16, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], 1);
+  else FanOutCopy<false><<<grid, 256, 0, stream>>>(static_cast<const uint4 *>(src), n16, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], ndst);
+  return cudaGetLastError();
+}
 
 cudaError_t LaunchScaleCopyRanges(int dtype, const unsigned long long *ranges3, uint32_t nranges, const void *src, void *dst,
                                   double beta_re, double beta_im, int num_sms, cudaStream_t stream) {

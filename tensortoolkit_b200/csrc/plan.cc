@@ -175,6 +175,10 @@ static std::string AddPermBlocks(PlanHost *h, int rank, const int32_t *perm, con
     if (base + nt >= (1ull << 32)) return "too many permute tiles";
     h->perm_blks.push_back(d);
     h->perm_tile_base.push_back(static_cast<uint32_t>(h->perm_tile_base.back() + nt));
+    h->perm_blks_all.push_back(d);
+    h->perm_ntiles_all.push_back(static_cast<uint32_t>(nt));
+    h->perm_owner_all.push_back((uint64_t(src_sel) << 63) | b);
+    h->perm_size_all.push_back(sz);
     ws += (sz + 1) & ~1ull;        // keep every permuted block 16-byte aligned for doubles
     *moved += sz;
   }
@@ -278,6 +282,8 @@ std::string BuildPlanHost(int dtype, uint32_t flags, int nctrct, int a_rank, con
       gt.flags = uint16_t((ma != kBlkPermute ? kTaskASrc : 0) | (ma == kBlkTrans ? kTaskATrans : 0) |
                           (mb != kBlkPermute ? kTaskBSrc : 0) | (mb == kBlkTrans ? kTaskBTrans : 0));
       h->tasks.push_back(gt);
+      h->task_a_ord.push_back(st[t].a_ord);
+      h->task_b_ord.push_back(st[t].b_ord);
       ksum += gt.k;
       h->flops += fl * double(g.m) * double(gt.k) * double(g.n);
       h->gemm_read_bytes += (uint64_t(g.m) * gt.k + uint64_t(gt.k) * g.n) * es;
@@ -573,6 +579,35 @@ void PartitionRows(PlanHost *h, int world, int rank) {
     else if (i == g1) hi = std::min(hi, r1);
     if (hi < lo) hi = lo;
     g.row_begin = lo; g.row_end = hi;
+  }
+  FilterPermBlocks(h);
+}
+
+void FilterPermBlocks(PlanHost *h) {
+  // a rank permutes only the operand blocks its share of the output rows reads (whole blocks: B blocks are shared by all
+  // rows of an output block, A blocks are cut along m only by a row slab, which does not pay for a second descriptor)
+  if (h->perm_blks_all.empty()) return;
+  std::vector<char> a_need, b_need;
+  for (size_t gi = 0; gi < h->part_groups.size(); ++gi) {
+    const GemmGroup &g = h->part_groups[gi];
+    if (g.row_end <= g.row_begin) continue;
+    for (uint32_t t = g.task_begin; t < g.task_end; ++t) {
+      if (h->task_a_ord[t] >= a_need.size()) a_need.resize(h->task_a_ord[t] + 1, 0);
+      if (h->task_b_ord[t] >= b_need.size()) b_need.resize(h->task_b_ord[t] + 1, 0);
+      a_need[h->task_a_ord[t]] = 1; b_need[h->task_b_ord[t]] = 1;
+    }
+  }
+  h->perm_blks.clear();
+  h->perm_tile_base.assign(1, 0u);
+  h->permute_elems_a = h->permute_elems_b = 0;
+  for (size_t i = 0; i < h->perm_blks_all.size(); ++i) {
+    const bool is_b = (h->perm_owner_all[i] >> 63) != 0;
+    const uint64_t ord = h->perm_owner_all[i] & ~(1ull << 63);
+    const std::vector<char> &need = is_b ? b_need : a_need;
+    if (ord >= need.size() || !need[ord]) continue;
+    h->perm_blks.push_back(h->perm_blks_all[i]);
+    h->perm_tile_base.push_back(h->perm_tile_base.back() + h->perm_ntiles_all[i]);
+    (is_b ? h->permute_elems_b : h->permute_elems_a) += h->perm_size_all[i];
   }
 }
 

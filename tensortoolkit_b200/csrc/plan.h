@@ -17,6 +17,8 @@ struct qlb200_ctx {
   // a contraction's few narrow-pair work items run beside its DMMA kernel: forked onto `side`, joined before returning
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // host <-> device pipelining (qlb200_hostpipe_*): copies run on their own stream beside the math
+  cudaStream_t copy = nullptr;
   // grow-only arenas: `ws` holds the permuted operands, `stage` the device copies of host tensors
   void *ws = nullptr; size_t ws_bytes = 0;
   void *stage = nullptr; size_t stage_bytes = 0;
@@ -51,6 +53,12 @@ struct PlanHost {
   std::vector<uint64_t> ws_off_a, ws_off_b;            // per block: element offset of its permuted copy, ~0 = read in place
   std::vector<PermBlk> perm_blks;
   std::vector<uint32_t> perm_tile_base;                // [nblk+1]
+  // everything the whole contraction permutes; perm_blks / perm_tile_base above are the subset the current row partition needs
+  std::vector<PermBlk> perm_blks_all;
+  std::vector<uint32_t> perm_ntiles_all;
+  std::vector<uint64_t> perm_owner_all;                // (operand << 63) | block ordinal
+  std::vector<uint64_t> perm_size_all;
+  std::vector<uint32_t> task_a_ord, task_b_ord;        // block ordinals of every GemmTask's operands
   std::vector<GemmTask> tasks;
   std::vector<GemmGroup> groups;                       // full row ranges
   std::vector<uint64_t> group_ksum;
@@ -113,6 +121,9 @@ std::string BuildTiles(PlanHost *h);
 
 /// Restrict part_groups to the rows owned by `rank` of `world` (cost-balanced contiguous cut).
 void PartitionRows(PlanHost *h, int world, int rank);
+
+/// Keep only the permute descriptors of operand blocks that the current part_groups read (called by PartitionRows).
+void FilterPermBlocks(PlanHost *h);
 
 }  // namespace qlb200
 #endif

@@ -124,11 +124,46 @@ class ContractionChain:
         return CapturedGraph(self.ctx, self.apply_device)
 
     def apply_host(self, in_name: str, host_in: np.ndarray, out_name: str, host_out: np.ndarray):
-        """End-to-end apply: input H2D, all steps, result D2H, synchronise."""
+        """End-to-end apply: input H2D, all steps, result D2H, synchronise (copies and math strictly in sequence)."""
         self.buf[in_name].upload(host_in)
         self.apply_device()
         self.buf[out_name].download(host_out)
         self.ctx.sync()
+
+    # cumulative shares of the streamed operand per chunk: a small first chunk lets the math start early, a small last
+    # output chunk leaves little of the download exposed (the PCIe copies are faster than the steps they overlap)
+    PIPE_IN = (1 / 16, 5 / 16, 10 / 16, 1.0)
+    PIPE_OUT = (6 / 16, 11 / 16, 15 / 16, 1.0)
+
+    def make_host_pipe(self, in_name: str, cum_in=None, cum_out=None):
+        """qlb200_hostpipe over the first and last step: `in_name` (an operand of the first step) is streamed from host
+        memory in chunks while the parts of the first step run; the last step's output leaves in chunks while it computes."""
+        lhs, rhs, _, _ = self.steps[0]
+        if in_name not in (lhs, rhs):
+            raise ValueError("the streamed input must be an operand of the first step")
+        cum_in = list(cum_in or self.PIPE_IN); cum_out = list(cum_out or self.PIPE_OUT)
+        h = C.c_void_p()
+        check(lib.qlb200_hostpipe_create(self.ctx.h, self.plans[0].h, _lib.SPLIT_BY_A if in_name == lhs else _lib.SPLIT_BY_B,
+                                         len(cum_in), (C.c_double * len(cum_in))(*cum_in), self.plans[-1].h, len(cum_out),
+                                         (C.c_double * len(cum_out))(*cum_out), C.byref(h)), "qlb200_hostpipe_create")
+        self._pipe, self._pipe_in = h, in_name
+        return h
+
+    def apply_host_pipelined(self, host_in: np.ndarray, host_out: np.ndarray) -> int:
+        """End-to-end apply through the host pipeline (make_host_pipe first): chunked H2D overlapped with step 1, chunked
+        D2H overlapped with the last step.  Returns after the result is in host_out; value = kernels launched."""
+        lhs, rhs, _, out = self.steps[0]
+        other = rhs if self._pipe_in == lhs else lhs
+        check(lib.qlb200_hostpipe_begin(self.ctx.h, self._pipe, host_in.ctypes.data, C.c_void_p(self.buf[self._pipe_in].ptr),
+                                        C.c_void_p(self.buf[other].ptr), C.c_void_p(self.buf[out].ptr)), "qlb200_hostpipe_begin")
+        n = 0
+        for (l, r, _, o), plan in zip(self.steps[1:-1], self.plans[1:-1]):
+            plan.execute_device(self.buf[l].ptr, self.buf[r].ptr, self.buf[o].ptr)
+            n += self.ctx.launch_count()
+        l, r, _, o = self.steps[-1]
+        check(lib.qlb200_hostpipe_end(self.ctx.h, self._pipe, C.c_void_p(self.buf[l].ptr), C.c_void_p(self.buf[r].ptr),
+                                      C.c_void_p(self.buf[o].ptr), host_out.ctypes.data), "qlb200_hostpipe_end")
+        return n + int(lib.qlb200_hostpipe_launches(self._pipe))
 
     def result(self, name: str) -> BlockSparseTensor:
         t = self.shells[name]
@@ -142,6 +177,9 @@ class ContractionChain:
         return out
 
     def close(self):
+        if getattr(self, "_pipe", None):
+            lib.qlb200_hostpipe_destroy(self._pipe)
+            self._pipe = None
         for p in self.plans:
             p.close()
         for m in self.matches:
@@ -215,7 +253,10 @@ class ShardedChain:
     wrote; pass it as the next input."""
 
     def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, dtype,
-                 world: int, rank: int, group=None, flags: int = _lib.PLAN_DETERMINISTIC, exchange="auto", peers=None):
+                 world: int, rank: int, group=None, flags: int = _lib.PLAN_DETERMINISTIC, exchange="auto", peers=None,
+                 host_input: str = None):
+        """host_input: name of the operand that arrives from HOST memory every apply (apply_host): its device buffer is
+        made exchangeable (symmetric memory / CUDA IPC) so that every rank uploads only 1/world of it."""
         import torch
         from .sharding import shard_chain
         self.torch, self.group = torch, group
@@ -236,11 +277,28 @@ class ShardedChain:
         # a rank can end up with no rows at all (cuts are snapped to row groups; world may exceed what can be cut):
         # it builds no plans but joins every rendezvous, exchange and barrier below like its peers
         self.idle = self.info.local_elems[rank] == 0
+        external = {self.out_name: self.local.data_ptr()}
+        self.host_input, self.in_symm, self.in_mc, self.in_peers, self.in_buf = host_input, None, 0, None, None
+        if host_input is not None:
+            t_in = tensors[host_input]
+            self.in_bytes = t_in.data.size * self.dtype.itemsize
+            nb = max((self.in_bytes + 255) & ~255, 256)
+            if exchange in ("auto", "multicast") and world > 1 and peers is None:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else torch.distributed.group.WORLD
+                with torch.cuda.device(dev):
+                    self.in_symm_buf = symm_mem.empty(nb // self.dtype.itemsize, dtype=tdt, device=dev)
+                    self.in_symm = symm_mem.rendezvous(self.in_symm_buf, grp)
+                self.in_mc = int(self.in_symm.multicast_ptr)
+                self.in_ptr = int(self.in_symm_buf.data_ptr())
+            else:
+                self.in_buf = DeviceBuffer(ctx, nb)
+                self.in_ptr = self.in_buf.ptr
+            external[host_input] = self.in_ptr
         if self.idle:
             self.chain = _IdleChain(steps)
         else:
-            self.chain = ContractionChain(ctx, mine, steps, dtype, flags, external={self.out_name: self.local.data_ptr()},
-                                          last_flags=stagger)
+            self.chain = ContractionChain(ctx, mine, steps, dtype, flags, external=external, last_flags=stagger)
         full_bytes = max(self.info.full_elems, 1) * self.dtype.itemsize
         self.full_bytes = (full_bytes + 255) & ~255          # replica stride (keeps both halves 256-byte aligned)
         self.parity = 0                                      # replica the NEXT apply writes
@@ -293,6 +351,18 @@ class ShardedChain:
             else:
                 self.peer_ptrs = [self.full_base]
             self.flag = torch.zeros(1, dtype=torch.float32, device=dev)
+            if host_input is not None and world > 1 and peers is None and not self.in_mc:
+                handle = C.create_string_buffer(64)       # the input buffer, exchanged like the result
+                check(lib.qlb200_ipc_export(ctx.h, C.c_void_p(self.in_ptr), handle), "qlb200_ipc_export")
+                handles = [None] * world
+                torch.distributed.all_gather_object(handles, bytes(handle.raw), group=group)
+                self.in_peers = [self.in_ptr]
+                for r in range(world):
+                    if r != rank:
+                        pp = C.c_void_p()
+                        check(lib.qlb200_ipc_open(ctx.h, handles[r], C.byref(pp)), "qlb200_ipc_open")
+                        self.opened.append(pp.value)
+                        self.in_peers.append(pp.value)
         else:
             self.gathered = torch.zeros(world * self.stride, dtype=tdt, device=dev)
             self.full2 = torch.zeros(2 * self.full_bytes // self.dtype.itemsize, dtype=tdt, device=dev)
@@ -382,6 +452,53 @@ class ShardedChain:
         self.parity = 0
         return _AlternatingGraphs(self, graphs)
 
+    def own_ranges(self):
+        """Merged (element offset, length) ranges of the full result this rank computes."""
+        out = []
+        for s in self.info.slabs[self.rank]:
+            if out and out[-1][0] + out[-1][1] == s.full_offset:
+                out[-1][1] += s.length
+            else:
+                out.append([s.full_offset, s.length])
+        return out
+
+    def apply_host(self, host_in: np.ndarray, host_out: np.ndarray, apply_fn=None) -> int:
+        """End-to-end apply with the input in (pinned) host memory and the result back in host memory, N ranks:
+        every rank uploads only ITS 1/world share of the input over its own PCIe link and fans it out to all GPUs
+        (multimem.st through the NVSwitch, or unicast peer stores); after one barrier the whole input is everywhere.
+        Then the sharded apply (`apply_fn`, default self.apply; a captured graph's launch works too) and the download of
+        this rank's OWN row slabs of the result into host_out at their place in the full layout -- the ranks' downloads
+        together are the full result (host_out may be one shared-memory buffer mapped by all ranks)."""
+        es = self.dtype.itemsize
+        if self.host_input is None:
+            raise RuntimeError("ShardedChain was built without host_input")
+        world, rank = self.world, self.rank
+        if world > 1 and (self.in_mc or self.in_peers):
+            unit = 16 // es if es < 16 else 1
+            n = host_in.size
+            per = -(-n // world)
+            per = -(-per // unit) * unit
+            lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+            if hi > lo:
+                check(lib.qlb200_memcpy_h2d(self.ctx.h, C.c_void_p(self.in_ptr + lo * es), host_in.ctypes.data + lo * es, (hi - lo) * es), "h2d")
+                nbytes = ((hi - lo) * es + 15) & ~15      # the buffer is padded to 256 bytes: rounding the tail up is safe
+                if self.in_mc:
+                    check(lib.qlb200_fanout_copy(self.ctx.h, C.c_void_p(self.in_ptr), lo * es, nbytes, None, 0, C.c_void_p(self.in_mc)), "fanout")
+                else:
+                    arr = (C.c_void_p * len(self.in_peers))(*self.in_peers)
+                    check(lib.qlb200_fanout_copy(self.ctx.h, C.c_void_p(self.in_ptr), lo * es, nbytes, arr, len(self.in_peers), None), "fanout")
+            if self.in_symm is not None:
+                self.in_symm.barrier()
+            else:
+                self.torch.distributed.all_reduce(self.flag, group=self.group)
+        else:
+            check(lib.qlb200_memcpy_h2d(self.ctx.h, C.c_void_p(self.in_ptr), host_in.ctypes.data, host_in.nbytes), "h2d")
+        n_launch = (apply_fn or self.apply)()
+        for off, ln in self.own_ranges():
+            check(lib.qlb200_memcpy_d2h(self.ctx.h, host_out.ctypes.data + off * es, C.c_void_p(self.full_ptr + off * es), ln * es), "d2h")
+        self.ctx.sync()
+        return n_launch
+
     def download_full(self, host: np.ndarray):
         check(lib.qlb200_memcpy_d2h(self.ctx.h, host.ctypes.data, C.c_void_p(self.full_ptr), host.nbytes), "qlb200_memcpy_d2h")
 
@@ -393,6 +510,9 @@ class ShardedChain:
         if self.full_buf is not None:
             self.full_buf.free()
             self.full_buf = None
+        if self.in_buf is not None:
+            self.in_buf.free()
+            self.in_buf = None
         if self.cplan:
             lib.qlb200_tplan_destroy(self.cplan)
             self.cplan = None

@@ -398,3 +398,67 @@ def test_split_k_long_contractions_vs_numpy(ctx, dtype, extra):
     plan.close()
     assert util.rel_fro(C1, Cw) <= TOL
     assert np.array_equal(C1, C2)
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64])
+def test_host_pipeline_matches_device_apply(ctx, dtype):
+    """qlb200_hostpipe_*: psi streamed from host memory in chunks while the parts of step 1 run, the result streamed back in
+    chunks while the last step computes -- bit-identical to the device-resident apply (same kernels, same summation order),
+    also with different chunkings and when repeated with a new input."""
+    from tensortoolkit_b200.heff import ContractionChain
+    rng = np.random.default_rng(41)
+    ti = wl.heff_tensor_indexes(wl.u1_heisenberg_indexes(260))
+    t = {name: tk.BlockSparseTensor(idxs, dtype).random((0,), rng) for name, idxs in ti.items()}
+    chain = ContractionChain(ctx, t, wl.HEFF_STEPS, dtype)
+    chain.apply_device()
+    want = chain.result("out").data.copy()
+    for cum_in, cum_out in ((None, None), ((1.0,), (1.0,)), ((0.01, 0.5, 0.5, 0.99, 1.0), (0.3, 1.0)), ((0.5, 1.0), (0.1, 0.2, 0.3, 0.9, 1.0))):
+        chain.make_host_pipe("psi", cum_in, cum_out)
+        out = np.full(want.size, np.nan, dtype)
+        n = chain.apply_host_pipelined(t["psi"].data, out)
+        assert n > 0
+        assert np.array_equal(out, want)
+        psi2 = (t["psi"].data * 0.5).astype(dtype)
+        chain.apply_host_pipelined(psi2, out)
+        assert util.rel_fro(out, 0.5 * want) <= TOL
+        tk._lib.lib.qlb200_hostpipe_destroy(chain._pipe); chain._pipe = None
+    chain.close()
+
+
+def test_plan_split_parts_cover_plan(ctx):
+    """qlb200_plan_split: by operand arrival and by output range, the parts' output ranges tile C exactly once."""
+    import ctypes as C
+    rng = np.random.default_rng(43)
+    ti = wl.heff_tensor_indexes(wl.hubbard_indexes(120))
+    t = {name: tk.BlockSparseTensor(idxs, np.float64).random((0, 0), rng) for name, idxs in ti.items()}
+    m = tk.Match(t["lenv"], t["psi"], ([0], [0]))
+    plan = tk.ContractionPlan(ctx, m, np.float64)
+    full = m.result_shell(np.float64)
+    plan.execute_host(t["lenv"].data, t["psi"].data, full.data)
+    for by in (_lib.SPLIT_BY_A, _lib.SPLIT_BY_B, _lib.SPLIT_BY_C):
+        nparts = 5
+        parts = (C.c_void_p * nparts)(); bounds = (C.c_uint64 * (nparts + 1))()
+        cum = (C.c_double * nparts)(0.05, 0.3, 0.31, 0.8, 1.0)
+        _lib.check(_lib.lib.qlb200_plan_split(plan.h, by, nparts, cum, parts, bounds), "plan_split")
+        assert list(bounds) == sorted(bounds) and bounds[0] == 0
+        cov = np.zeros(full.data.size, np.int32)
+        out = np.full(full.data.size, np.nan)
+        from tensortoolkit_b200.heff import DeviceBuffer
+        dA, dB, dC = (DeviceBuffer(ctx, x.nbytes) for x in (t["lenv"].data, t["psi"].data, out))
+        dA.upload(t["lenv"].data); dB.upload(t["psi"].data); dC.upload(out)
+        for i in range(nparts):
+            n = int(_lib.lib.qlb200_plan_c_range_count(parts[i]))
+            off = np.zeros(n, np.uint64); ln = np.zeros(n, np.uint64)
+            _lib.lib.qlb200_plan_c_ranges(parts[i], off.ctypes.data_as(C.POINTER(C.c_uint64)), ln.ctypes.data_as(C.POINTER(C.c_uint64)))
+            for o, l in zip(off, ln):
+                cov[int(o):int(o + l)] += 1
+                if by == _lib.SPLIT_BY_C:
+                    assert bounds[i] <= o and o + l <= bounds[i + 1]
+            _lib.check(_lib.lib.qlb200_execute_gemm(ctx.h, parts[i], dA.ptr, dB.ptr, dC.ptr), "execute_gemm")
+            _lib.lib.qlb200_plan_destroy(parts[i])
+        dC.download(out); ctx.sync()
+        for b in (dA, dB, dC):
+            b.free()
+        assert np.all(cov == 1)
+        assert np.array_equal(out, full.data)
+    plan.close(); m.close()
