@@ -168,6 +168,8 @@ int qlb200_host_unregister(void *p);
                                          workload (0.60 / 0.63 ms vs 0.54 / 0.57 ms per GEMM step): ~2 partial tiles per CTA cost
                                          more than the imbalance they remove. */
 #define QLB200_PLAN_NO_SPLIT_K 16u     /* never cut a tile's k loop into several units (testing / tuning) */
+#define QLB200_PLAN_NO_VIEW 256u       /* do not read (n1, k, n2)-stored B blocks as strided k x (n1 n2) views in the GEMM producer: send them
+                                          through the permute kernel instead (testing / measuring the permute kernel) */
 #define QLB200_PLAN_PERMUTE_ALL 8u     /* send every block of a transposed operand through the permute kernel
                                           (default: blocks whose permutation is trivial or one 2-D transposition
                                           are read in place by the GEMM) */

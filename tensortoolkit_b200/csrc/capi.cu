@@ -119,7 +119,8 @@ void SetPlanKnobs(const qlb200_ctx *ctx, uint32_t *flags, PlanHost *h) {
 
 size_t WsBytes(const qlb200_plan *p) {
   const size_t es = ElemSize(p->h.dtype);
-  return Align256(p->h.ws_a_elems * es) + Align256(p->h.ws_b_elems * es) + Align256(p->h.n_part_slots * p->h.part_slot_elems * es);
+  return Align256(p->h.ws_a_elems * es) + Align256(p->h.ws_b_elems * es) + p->partials_shift +
+         Align256(p->h.n_part_slots * p->h.part_slot_elems * es);
 }
 
 }  // namespace
@@ -246,6 +247,7 @@ int qlb200_ctx_create(int device, qlb200_ctx **out) {
   if (e != cudaSuccess) { delete c; return Fail(QLB200_ERR_CUDA, CudaErr("cudaStreamCreate", e)); }
   e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->alt, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return Fail(QLB200_ERR_CUDA, CudaErr("side stream / events", e)); }
@@ -264,6 +266,7 @@ void qlb200_ctx_destroy(qlb200_ctx *ctx) {
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->copy) { cudaStreamSynchronize(ctx->copy); cudaStreamDestroy(ctx->copy); }
+  if (ctx->alt) { cudaStreamSynchronize(ctx->alt); cudaStreamDestroy(ctx->alt); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
@@ -489,7 +492,7 @@ static int ResolveWorkspace(qlb200_ctx *ctx, qlb200_plan *p, void **wsA, void **
   if (rc != QLB200_OK) return rc;
   *wsA = ctx->ws;
   *wsB = static_cast<char *>(ctx->ws) + Align256(p->h.ws_a_elems * es);
-  if (partials) *partials = static_cast<char *>(*wsB) + Align256(p->h.ws_b_elems * es);
+  if (partials) *partials = static_cast<char *>(*wsB) + Align256(p->h.ws_b_elems * es) + p->partials_shift;
   return QLB200_OK;
 }
 
@@ -805,9 +808,18 @@ struct qlb200_hostpipe {
   std::vector<qlb200_plan *> in_parts, out_parts;
   std::vector<uint64_t> in_bounds, out_bounds;
   std::vector<cudaEvent_t> ev_in, ev_out;
-  cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_alt_in = nullptr, ev_alt_out = nullptr, ev_mid = nullptr;
   uint64_t launches = 0;
 };
+
+// Runs one part on `on` (the context's main stream or its alternate stream): the kernels only see ctx->stream.
+static int ExecutePartOn(qlb200_ctx *ctx, cudaStream_t on, qlb200_plan *q, const void *A, const void *B, void *C) {
+  cudaStream_t saved = ctx->stream;
+  ctx->stream = on;
+  const int rc = qlb200_execute_gemm(ctx, q, A, B, C);
+  ctx->stream = saved;
+  return rc;
+}
 
 void qlb200_hostpipe_destroy(qlb200_hostpipe *hp) {
   if (!hp) return;
@@ -816,8 +828,7 @@ void qlb200_hostpipe_destroy(qlb200_hostpipe *hp) {
   for (qlb200_plan *q : hp->out_parts) qlb200_plan_destroy(q);
   for (cudaEvent_t e : hp->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : hp->ev_out) cudaEventDestroy(e);
-  if (hp->ev_start) cudaEventDestroy(hp->ev_start);
-  if (hp->ev_done) cudaEventDestroy(hp->ev_done);
+  for (cudaEvent_t e : {hp->ev_start, hp->ev_done, hp->ev_alt_in, hp->ev_alt_out, hp->ev_mid}) if (e) cudaEventDestroy(e);
   delete hp;
 }
 
@@ -836,9 +847,28 @@ int qlb200_hostpipe_create(qlb200_ctx *ctx, const qlb200_plan *first, int first_
   int rc = qlb200_plan_split(first, first_streams, nparts_in, cum_in, hp->in_parts.data(), hp->in_bounds.data());
   if (rc == QLB200_OK) rc = qlb200_plan_split(last, QLB200_SPLIT_BY_C, nparts_out, cum_out, hp->out_parts.data(), hp->out_bounds.data());
   if (rc != QLB200_OK) { qlb200_hostpipe_destroy(hp); return rc; }
+  // concurrent parts need disjoint split-K partial-tile regions, and the arena must have its final size before any part
+  // runs on the alternate stream (growth synchronises only the main stream)
+  {
+    uint64_t shift = 0, need = 0;
+    const size_t es = ElemSize(hp->dtype);
+    for (auto *vec : {&hp->in_parts, &hp->out_parts}) {
+      shift = 0;
+      for (qlb200_plan *q : *vec) {
+        q->partials_shift = shift;
+        shift += Align256(q->h.n_part_slots * q->h.part_slot_elems * es);
+        need = std::max<uint64_t>(need, WsBytes(q));
+      }
+    }
+    rc = EnsureArena(ctx, &ctx->ws, &ctx->ws_bytes, need);
+    if (rc != QLB200_OK) { qlb200_hostpipe_destroy(hp); return rc; }
+  }
   auto mk = [](cudaEvent_t *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
   cudaError_t e = mk(&hp->ev_start);
   if (e == cudaSuccess) e = mk(&hp->ev_done);
+  if (e == cudaSuccess) e = mk(&hp->ev_alt_in);
+  if (e == cudaSuccess) e = mk(&hp->ev_alt_out);
+  if (e == cudaSuccess) e = mk(&hp->ev_mid);
   hp->ev_in.assign(nparts_in, nullptr); hp->ev_out.assign(nparts_out, nullptr);
   for (auto &ev : hp->ev_in) if (e == cudaSuccess) e = mk(&ev);
   for (auto &ev : hp->ev_out) if (e == cudaSuccess) e = mk(&ev);
@@ -864,15 +894,24 @@ int qlb200_hostpipe_begin(qlb200_ctx *ctx, qlb200_hostpipe *hp, const void *in_h
                               cudaMemcpyHostToDevice, ctx->copy));
     QL_CUDA(cudaEventRecord(hp->ev_in[i], ctx->copy));
   }
+  // parts alternate between the main and the alternate stream: part i + 1 fills the SMs part i's last units leave idle
+  QL_CUDA(cudaStreamWaitEvent(ctx->alt, hp->ev_start, 0));
+  bool used_alt = false;
   for (size_t i = 0; i < np; ++i) {
-    QL_CUDA(cudaStreamWaitEvent(ctx->stream, hp->ev_in[i], 0));
+    cudaStream_t on = (i & 1) ? ctx->alt : ctx->stream;
+    QL_CUDA(cudaStreamWaitEvent(on, hp->ev_in[i], 0));
     qlb200_plan *q = hp->in_parts[i];
     if (q->h.tiles.empty() && q->h.items.empty()) continue;
     const void *A = hp->first_streams == QLB200_SPLIT_BY_A ? in_dev : other_dev;
     const void *B = hp->first_streams == QLB200_SPLIT_BY_A ? other_dev : in_dev;
-    int rc = qlb200_execute_gemm(ctx, q, A, B, c_dev);
+    int rc = ExecutePartOn(ctx, on, q, A, B, c_dev);
     if (rc != QLB200_OK) return rc;
     hp->launches += ctx->launches;
+    used_alt = used_alt || (i & 1);
+  }
+  if (used_alt) {      // whatever follows on the main stream needs every part
+    QL_CUDA(cudaEventRecord(hp->ev_alt_in, ctx->alt));
+    QL_CUDA(cudaStreamWaitEvent(ctx->stream, hp->ev_alt_in, 0));
   }
   return QLB200_OK;
 }
@@ -883,20 +922,25 @@ int qlb200_hostpipe_end(qlb200_ctx *ctx, qlb200_hostpipe *hp, const void *a_dev,
   QL_CUDA(cudaSetDevice(ctx->device));
   const size_t es = ElemSize(hp->dtype);
   const size_t np = hp->out_parts.size();
+  QL_CUDA(cudaEventRecord(hp->ev_mid, ctx->stream));          // the last step's operands are ready here
+  QL_CUDA(cudaStreamWaitEvent(ctx->alt, hp->ev_mid, 0));
   for (size_t i = 0; i < np; ++i) {
+    cudaStream_t on = (i & 1) ? ctx->alt : ctx->stream;
     qlb200_plan *q = hp->out_parts[i];
     if (!(q->h.tiles.empty() && q->h.items.empty())) {
-      int rc = qlb200_execute_gemm(ctx, q, a_dev, b_dev, c_dev);
+      int rc = ExecutePartOn(ctx, on, q, a_dev, b_dev, c_dev);
       if (rc != QLB200_OK) return rc;
       hp->launches += ctx->launches;
     }
-    QL_CUDA(cudaEventRecord(hp->ev_out[i], ctx->stream));
+    QL_CUDA(cudaEventRecord(hp->ev_out[i], on));
     QL_CUDA(cudaStreamWaitEvent(ctx->copy, hp->ev_out[i], 0));
     const uint64_t lo = hp->out_bounds[i], hi = hp->out_bounds[i + 1];
     if (hi > lo)
       QL_CUDA(cudaMemcpyAsync(static_cast<char *>(out_host) + lo * es, static_cast<const char *>(c_dev) + lo * es, (hi - lo) * es,
                               cudaMemcpyDeviceToHost, ctx->copy));
   }
+  QL_CUDA(cudaEventRecord(hp->ev_alt_out, ctx->alt));
+  QL_CUDA(cudaStreamWaitEvent(ctx->stream, hp->ev_alt_out, 0));
   // the compute stream joins the copy stream (the next apply must not overwrite c_dev before it has left), then the host waits
   QL_CUDA(cudaEventRecord(hp->ev_done, ctx->copy));
   QL_CUDA(cudaStreamWaitEvent(ctx->stream, hp->ev_done, 0));

@@ -48,6 +48,13 @@ struct GemmTask {
   uint32_t k;
   int16_t sign;                     // +1 / -1
   uint16_t flags;                   // kTask* bits
+  // B as a k x n matrix VIEW of the stored block (not for kTaskBTrans): element (kk, col) lies at
+  //     b_off + kk * b_rs + (col / b_run) * b_cs + col % b_run
+  // Row-major k x n (also every permuted copy): b_rs = b_run = n, b_cs = 0.  A block stored (n1, k, n2) and contracted
+  // over k -- permutation {1, 0, 2}, the ragged stress test's B -- is read in place with b_rs = b_run = n2, b_cs = k * n2:
+  // rows of the view are n1 runs of n2 contiguous elements, so the producer's copies stay contiguous per run.
+  uint32_t b_rs, b_cs, b_run;
+  uint32_t pad_;
 };
 constexpr uint16_t kTaskASrc = 1;    // A block is read from the caller's buffer, not the workspace
 constexpr uint16_t kTaskATrans = 2;  // ... where it is stored as a row-major k x m matrix

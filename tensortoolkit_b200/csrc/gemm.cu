@@ -393,7 +393,10 @@ GemmSkinny(GemmParams p) {
           if (tk.flags & kTaskATrans) { s_ap[tid] = a + (unsigned long long) k1 * g.m; s_as[tid] = 1; }
           else { s_ap[tid] = a + k1; s_as[tid] = tk.k; }
           for (uint32_t j = 0; j < n; ++j) {
-            const T v = (tk.flags & kTaskBTrans) ? b[(unsigned long long) j * tk.k + k1] : b[(unsigned long long) k1 * n + j];
+            // B(k1, j): stored n x k (transposed), row-major k x n (b_run >= n: no division), or a strided view of the block
+            const T v = (tk.flags & kTaskBTrans) ? b[(unsigned long long) j * tk.k + k1]
+                        : tk.b_run >= n         ? b[(unsigned long long) k1 * tk.b_rs + j]
+                                                 : b[(unsigned long long) k1 * tk.b_rs + (j / tk.b_run) * tk.b_cs + j % tk.b_run];
             s_coef[tid][j] = E::Signed(v, tk.sign);
           }
         }

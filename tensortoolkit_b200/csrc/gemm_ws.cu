@@ -215,6 +215,24 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
   if (q == 0 && g4 == 0 && t4 == 0) p.counters[2 + tile.ctr] = 0;
 }
 
+// Accumulate epilogue of one tile row, out of line (like FixupTile: it must not disturb the register allocation of the main
+// loop, which has no register to spare next to the 3M accumulators): out = beta * C_in + alpha * v for the lane's up to
+// eight elements of the row; column of element (j, e) = col + 32 * j + e.
+__device__ __noinline__ void StoreAccRow(const GemmParams &p, double2 *crow, const double2 *cin_row, uint32_t col, uint32_t n, uint32_t beta_on,
+                                         int nt, double2 v00, double2 v01, double2 v10, double2 v11, double2 v20, double2 v21, double2 v30,
+                                         double2 v31) {
+  const double2 v[4][2] = {{v00, v01}, {v10, v11}, {v20, v21}, {v30, v31}};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j >= nt) break;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const uint32_t c = col + 32u * j + e;
+      if (c < n) crow[c] = AxpbyOut(p, v[j][e], cin_row + c, beta_on != 0);
+    }
+  }
+}
+
 // MCAST: the output address is an NVSwitch multicast mapping (multimem.st); a compile-time switch, because a
 // run-time branch around every store of the unrolled epilogue costs registers the main loop cannot spare.
 // ACC: accumulate form, the epilogue computes beta * C_in + alpha * (sum of pairs) (qlb200_execute_accum); also compile-time.
@@ -278,6 +296,13 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
         const double2 *bBase = static_cast<const double2 *>((task.flags & kTaskBSrc) ? p.b_src : p.b_ws) + task.b_off;
         const bool ta = (task.flags & kTaskATrans) != 0, tb = (task.flags & kTaskBTrans) != 0;
         const uint32_t tflags = extents | (task.sign < 0 ? kFlagNeg : 0u) | (ta ? kFlagATrans : 0u) | (tb ? kFlagBTrans : 0u);
+        // B as a k x n view of the stored block (GemmTask::b_rs / b_cs / b_run): offset of this lane's columns inside a row
+        uint32_t bcol[WBN / 32];
+#pragma unroll
+        for (uint32_t c = 0; c < uint32_t(WBN / 32); ++c) {
+          const uint32_t colg = col0 + lane + 32u * c;
+          bcol[c] = task.b_run >= g.n ? colg : (colg / task.b_run) * task.b_cs + colg % task.b_run;
+        }
         for (uint32_t st = st_lo, k0 = (st_lo - st_base) * WBK; st < st_hi; ++st, ++it, k0 += WBK) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
           MbarWait(&empty[s], ph ^ 1u);
@@ -308,12 +333,12 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
             for (uint32_t rr = 0; rr < WBK / 4; ++rr) {
               const uint32_t kr = (WBK / 4) * pw + rr;
               const bool rok = k0 + kr < task.k;
-              const double2 *src = bBase + (unsigned long long) (k0 + kr) * g.n + col0 + lane;
+              const double2 *src = bBase + (unsigned long long) (k0 + kr) * task.b_rs;
 #pragma unroll
               for (uint32_t c = 0; c < uint32_t(WBN / 32); ++c) {
                 const uint32_t col = lane + 32u * c;
                 const bool ok = rok && col < cols;
-                CpAsync16Z(sB + (kr * WLDB + col) * 16u, ok ? src + 32u * c : bBase, ok);
+                CpAsync16Z(sB + (kr * WLDB + col) * 16u, ok ? src + bcol[c] : bBase, ok);
               }
             }
           } else {     // B stored n x k: a lane copies element (a_r + RP*r, a_kc) of the WBN x WBK tile
@@ -414,20 +439,31 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
       if (write_c) {
         for (uint32_t d = 0; d < p.n_out; ++d) {     // n_out > 1: fused exchange, the same tile goes to every NVLink peer
           double2 *Cg = static_cast<double2 *>(p.c_out[d]) + g.c_off;
-          const double2 *Ci = static_cast<const double2 *>(p.c_in) + g.c_in_off;
+          if constexpr (ACC) {
+            const double2 *Ci = static_cast<const double2 *>(p.c_in) + g.c_in_off;
+            const double2 z = make_double2(0.0, 0.0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t row = row0 + i * 8 + g4;
-            if (row >= g.row_end) continue;
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t row = row0 + i * 8 + g4;
+              if (row >= g.row_end) continue;
+              const unsigned long long at = (unsigned long long) row * g.n;
+              if constexpr (NTMAX == 4)
+                StoreAccRow(p, Cg + at, Ci + at, col0 + q * 8 + 2 * t4, g.n, g.beta_on, 4, AccValue<CFG>(acc, i, 0, 0), AccValue<CFG>(acc, i, 0, 1),
+                            AccValue<CFG>(acc, i, 1, 0), AccValue<CFG>(acc, i, 1, 1), AccValue<CFG>(acc, i, 2, 0), AccValue<CFG>(acc, i, 2, 1),
+                            AccValue<CFG>(acc, i, NTMAX - 1, 0), AccValue<CFG>(acc, i, NTMAX - 1, 1));
+              else
+                StoreAccRow(p, Cg + at, Ci + at, col0 + q * 8 + 2 * t4, g.n, g.beta_on, 3, AccValue<CFG>(acc, i, 0, 0), AccValue<CFG>(acc, i, 0, 1),
+                            AccValue<CFG>(acc, i, 1, 0), AccValue<CFG>(acc, i, 1, 1), AccValue<CFG>(acc, i, 2, 0), AccValue<CFG>(acc, i, 2, 1), z, z);
+            }
+          } else {
 #pragma unroll
-            for (int j = 0; j < NTMAX; ++j) {
-              const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
-              const unsigned long long at = (unsigned long long) row * g.n + col;
-              double2 *dst = Cg + at;
-              if constexpr (ACC) {
-                if (col < g.n) StoreOut(dst, AxpbyOut(p, AccValue<CFG>(acc, i, j, 0), Ci + at, g.beta_on != 0), MCAST);
-                if (col + 1 < g.n) StoreOut(dst + 1, AxpbyOut(p, AccValue<CFG>(acc, i, j, 1), Ci + at + 1, g.beta_on != 0), MCAST);
-              } else {
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t row = row0 + i * 8 + g4;
+              if (row >= g.row_end) continue;
+#pragma unroll
+              for (int j = 0; j < NTMAX; ++j) {
+                const uint32_t col = col0 + (q + 4 * j) * 8 + 2 * t4;
+                double2 *dst = Cg + (unsigned long long) row * g.n + col;
                 if (col < g.n) StoreOut(dst, AccValue<CFG>(acc, i, j, 0), MCAST);
                 if (col + 1 < g.n) StoreOut(dst + 1, AccValue<CFG>(acc, i, j, 1), MCAST);
               }

@@ -159,6 +159,13 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
         const double *bBase = static_cast<const double *>((task.flags & kTaskBSrc) ? p.b_src : p.b_ws) + task.b_off;
         const bool ta = (task.flags & kTaskATrans) != 0, tb = (task.flags & kTaskBTrans) != 0;
         const uint32_t tflags = extents | (task.sign < 0 ? kFlagNeg : 0u) | (ta ? kFlagATrans : 0u) | (tb ? kFlagBTrans : 0u);
+        // B as a k x n view of the stored block (GemmTask::b_rs / b_cs / b_run): offset of this lane's four columns inside a row
+        uint32_t bcol[4];
+#pragma unroll
+        for (uint32_t c = 0; c < 4; ++c) {
+          const uint32_t colg = col0 + lane + 32u * c;
+          bcol[c] = task.b_run >= g.n ? colg : (colg / task.b_run) * task.b_cs + colg % task.b_run;
+        }
         for (uint32_t st = st_lo, k0 = (st_lo - st_base) * RBK; st < st_hi; ++st, ++it, k0 += RBK) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
           MbarWait(&empty[s], ph ^ 1u);
@@ -193,12 +200,12 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
             for (uint32_t rr = 0; rr < 4; ++rr) {
               const uint32_t kr = 4u * pw + rr;
               const bool rok = k0 + kr < task.k;
-              const double *src = bBase + (unsigned long long) (k0 + kr) * g.n + col0 + lane;
+              const double *src = bBase + (unsigned long long) (k0 + kr) * task.b_rs;
 #pragma unroll
               for (uint32_t c = 0; c < 4; ++c) {
                 const uint32_t col = lane + 32u * c;
                 const bool ok = rok && col < cols;
-                CpAsync8Z(sB + (kr * RLDB + col) * 8u, ok ? src + 32u * c : bBase, ok);
+                CpAsync8Z(sB + (kr * RLDB + col) * 8u, ok ? src + bcol[c] : bBase, ok);
               }
             }
           } else {     // B stored n x k: a lane copies element (a_r + 2r, a_kc) of the 128 x 16 tile

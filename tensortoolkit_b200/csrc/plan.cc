@@ -114,9 +114,15 @@ PermBlk MakePermBlk(int rank, const uint32_t *shape, const int32_t *perm, uint64
 //               is a row-major Cc x R matrix in the caller's buffer and the GEMM loads it transposed;
 //   kBlkPermute everything else goes through the batched permute kernel into the workspace.
 // ------------------------------------------------------------------------------------------------
-enum : uint8_t { kBlkDirect = 0, kBlkTrans = 1, kBlkPermute = 2 };
+//   kBlkView    (B only) three merged axes (k | n1, n2) whose last one is contiguous in the source, e.g. a block stored
+//               (n1, k, n2): the k x (n1 n2) matrix is a strided VIEW of the stored block, rows made of n1 runs of n2
+//               contiguous elements (GemmTask::b_rs / b_cs / b_run) -> read in place as well
+enum : uint8_t { kBlkDirect = 0, kBlkTrans = 1, kBlkPermute = 2, kBlkView = 3 };
 
-static uint8_t ClassifyBlock(int rank, const uint32_t *shape, const int32_t *perm, uint64_t rows, bool allow_trans) {
+struct BlockView { uint32_t rs = 0, cs = 0, run = 0; };
+
+static uint8_t ClassifyBlock(int rank, const uint32_t *shape, const int32_t *perm, uint64_t rows, bool allow_trans,
+                             bool allow_view = false, BlockView *view = nullptr) {
   uint64_t istr[QLB200_MAX_RANK];
   uint64_t s = 1;
   for (int i = rank - 1; i >= 0; --i) { istr[i] = s; s *= shape[i]; }
@@ -130,23 +136,32 @@ static uint8_t ClassifyBlock(int rank, const uint32_t *shape, const int32_t *per
   }
   if (nd <= 1) return kBlkDirect;
   if (nd == 2 && allow_trans && ext[0] == rows) return kBlkTrans;
+  // runs shorter than 4 elements would make every copy its own 32-byte sector: leave those to the permute kernel
+  if (nd == 3 && allow_view && view != nullptr && ext[0] == rows && sst[2] == 1 && ext[2] >= 4 && sst[0] < (1ull << 32) &&
+      sst[1] < (1ull << 32)) {
+    view->rs = uint32_t(sst[0]); view->cs = uint32_t(sst[1]); view->run = uint32_t(ext[2]);
+    return kBlkView;
+  }
   return kBlkPermute;
 }
 
 struct OperandPlan {
   std::vector<uint8_t> mode;      // per block (unused blocks: kBlkDirect)
+  std::vector<BlockView> view;    // per block, for kBlkView
   uint64_t permute_elems = 0;
 };
 
 static OperandPlan ClassifyOperand(int rank, const int32_t *perm, uint64_t n, const uint32_t *shape,
                                    const std::vector<char> &used, const std::vector<uint64_t> &rows,
-                                   bool tensor_trans, bool per_block, bool allow_trans) {
+                                   bool tensor_trans, bool per_block, bool allow_trans, bool allow_view = false) {
   OperandPlan op;
   op.mode.assign(n, kBlkDirect);
+  op.view.assign(allow_view ? n : 0, BlockView());
   if (!tensor_trans) return op;
   for (uint64_t b = 0; b < n; ++b) {
     if (!used[b]) continue;
-    op.mode[b] = per_block ? ClassifyBlock(rank, shape + b * rank, perm, rows[b], allow_trans) : uint8_t(kBlkPermute);
+    op.mode[b] = per_block ? ClassifyBlock(rank, shape + b * rank, perm, rows[b], allow_trans, allow_view, allow_view ? &op.view[b] : nullptr)
+                           : uint8_t(kBlkPermute);
     if (op.mode[b] == kBlkPermute) {
       uint64_t sz = 1;
       for (int i = 0; i < rank; ++i) sz *= shape[b * rank + i];
@@ -238,7 +253,8 @@ std::string BuildPlanHost(int dtype, uint32_t flags, int nctrct, int a_rank, con
       std::vector<int32_t> pa = a_perm, pb = b_perm;
       for (int i = 0; i < nctrct; ++i) { pa[a_rank - nctrct + i] = a_perm[a_rank - nctrct + sig[i]]; pb[i] = b_perm[sig[i]]; }
       OperandPlan ca = ClassifyOperand(a_rank, pa.data(), na, a_shape, a_used, a_rows, !is_ident(a_rank, pa.data()), per_block, allow_trans);
-      OperandPlan cb = ClassifyOperand(b_rank, pb.data(), nb, b_shape, b_used, b_rows, !is_ident(b_rank, pb.data()), per_block, allow_trans);
+      OperandPlan cb = ClassifyOperand(b_rank, pb.data(), nb, b_shape, b_used, b_rows, !is_ident(b_rank, pb.data()), per_block, allow_trans,
+                                       allow_trans && !(flags & QLB200_PLAN_NO_VIEW));
       const uint64_t cost = ca.permute_elems + cb.permute_elems;
       if (cost < best_cost) { best_cost = cost; best_a = pa; best_b = pb; opa = std::move(ca); opb = std::move(cb); }
     }
@@ -281,6 +297,8 @@ std::string BuildPlanHost(int dtype, uint32_t flags, int nctrct, int a_rank, con
       gt.k = st[t].k; gt.sign = st[t].sign < 0 ? -1 : 1;
       gt.flags = uint16_t((ma != kBlkPermute ? kTaskASrc : 0) | (ma == kBlkTrans ? kTaskATrans : 0) |
                           (mb != kBlkPermute ? kTaskBSrc : 0) | (mb == kBlkTrans ? kTaskBTrans : 0));
+      gt.b_rs = gt.b_run = g.n; gt.b_cs = 0; gt.pad_ = 0;          // row-major k x n (in place or permuted copy)
+      if (mb == kBlkView) { gt.b_rs = opb.view[st[t].b_ord].rs; gt.b_cs = opb.view[st[t].b_ord].cs; gt.b_run = opb.view[st[t].b_ord].run; }
       h->tasks.push_back(gt);
       h->task_a_ord.push_back(st[t].a_ord);
       h->task_b_ord.push_back(st[t].b_ord);

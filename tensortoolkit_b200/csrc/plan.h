@@ -19,6 +19,7 @@ struct qlb200_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // host <-> device pipelining (qlb200_hostpipe_*): copies run on their own stream beside the math
   cudaStream_t copy = nullptr;
+  cudaStream_t alt = nullptr;     // odd-numbered parts of a split step run here, so that a part's tail overlaps the next part's head
   // grow-only arenas: `ws` holds the permuted operands, `stage` the device copies of host tensors
   void *ws = nullptr; size_t ws_bytes = 0;
   void *stage = nullptr; size_t stage_bytes = 0;
@@ -80,6 +81,8 @@ struct qlb200_plan {
   qlb200_ctx *ctx = nullptr;
   qlb200::PlanHost h;
   qlb200::DeviceTables d;
+  // parts of a split plan may run concurrently on two streams: each gets its own split-K partial-tile region of the arena
+  uint64_t partials_shift = 0;    // bytes
   // accumulate form (qlb200_plan_create_accum): C_new = beta * C_old + alpha * sum of pairs
   bool accum = false;
   double alpha[2] = {1.0, 0.0}, beta[2] = {0.0, 0.0};

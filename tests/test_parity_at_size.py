@@ -86,7 +86,7 @@ def _ragged_slice(ntask):
                 a_elems=ao, b_elems=bo, c_elems=co)
 
 
-@pytest.mark.parametrize("flags", [0, _lib.PLAN_PERMUTE_ALL], ids=["in_place_where_possible", "permute_all"])
+@pytest.mark.parametrize("flags", [0, _lib.PLAN_NO_VIEW, _lib.PLAN_PERMUTE_ALL], ids=["in_place_and_views", "in_place_no_views", "permute_all"])
 def test_ragged_slice_vs_reference_executor_loop(ref, ctx, flags):
     """1000 pairs of the ragged table: A stored (k, m1, m2) perm {1,2,0}, B stored (n1, k, n2) perm {1,0,2}.
     Values against HPTT + OpenBLAS; every block that goes through the permute kernel bit-exact against HPTT."""
@@ -116,8 +116,12 @@ def test_ragged_slice_vs_reference_executor_loop(ref, ctx, flags):
             checked += 1
     if flags & _lib.PLAN_PERMUTE_ALL:
         assert checked == 2 * len(s["tasks"])
+    elif flags & _lib.PLAN_NO_VIEW:
+        assert checked > len(s["tasks"]) // 2      # most (n1, k, n2) blocks of B go through the permute kernel
     else:
-        assert checked > 0
+        # default: A blocks are 2-D transpositions and B blocks strided views, both read in place by the GEMM producers;
+        # only B blocks whose inner run is 2 or 3 elements long are permuted
+        assert st.permute_elems_a == 0 and st.permute_elems_b < 0.01 * s["b_elems"]
     plan.close()
     # values: whole slice and worst output block
     assert util.rel_fro(got, want) <= TOL

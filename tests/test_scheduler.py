@@ -151,3 +151,25 @@ def test_stream_k_segments_are_balanced(world, rank):
             assert sum(1 for u in units if u.nsplit > 1) <= 3 * len(costs)
             sk.close()
         m.close()
+
+
+def test_ragged_b_blocks_are_read_as_views():
+    """BASELINE configs[4]: B stored (n1, k, n2), contracted over k.  The k x (n1 n2) matrix is a strided view of the stored
+    block (rows = n1 runs of n2 contiguous elements), which the GEMM producers read in place: the plan sends (almost) nothing
+    through the permute kernel; QLB200_PLAN_NO_VIEW restores the permute pass (86 % of B)."""
+    import numpy as np
+    import tensortoolkit_b200 as tk
+    from tensortoolkit_b200 import _lib, workloads as wl
+    tb = wl.ragged_tables()
+    mk = lambda fl: tk.RawPlan(None, np.float64, 3, [1, 2, 0], tb["a_shape"], tb["a_off"], 3, [1, 0, 2], tb["b_shape"], tb["b_off"],
+                               tb["tasks"], tb["c_elems"], fl)
+    view, noview = mk(_lib.PLAN_DETERMINISTIC), mk(_lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_VIEW)
+    sv, sn = view.stats(), noview.stats()
+    assert sv.permute_elems_a == 0 and sn.permute_elems_a == 0
+    assert sv.permute_elems_b < 1e-3 * tb["b_elems"]
+    assert sn.permute_elems_b > 0.8 * tb["b_elems"]
+    assert sv.ntile_dmma == sn.ntile_dmma and sv.flops == sn.flops
+    # every block is either read in place or has a workspace slot
+    for b in (0, 17, 4321):
+        assert (view.operand_block(1, b) is None) or sv.permute_elems_b > 0
+    view.close(); noview.close()
