@@ -831,6 +831,19 @@ def measure_ragged(args, env):
         for t in tb["tasks"]:
             by_c.setdefault(int(t["c_ord"]), []).append(t)
         owned = [(int(o), int(o + l)) for o, l in zip(off, ln)]
+        # flops of this rank's share: every output block's pairs, weighted by the fraction of its rows the rank owns
+        c_start = {int(ts[0]["c_off"]): (int(ts[0]["m"]) * int(ts[0]["n"]), sum(2.0 * int(t["m"]) * int(t["k"]) * int(t["n"]) for t in ts))
+                   for ts in by_c.values()}
+        starts = sorted(c_start)
+        import bisect
+        for lo, hi in owned:
+            i = bisect.bisect_right(starts, lo) - 1
+            while i < len(starts) and starts[i] < hi:
+                size, fl = c_start[starts[i]]
+                ov = min(hi, starts[i] + size) - max(lo, starts[i])
+                if ov > 0:
+                    my_flops += fl * ov / size
+                i += 1
         for c in list(by_c)[:: max(1, len(by_c) // 40)]:
             m, n = int(by_c[c][0]["m"]), int(by_c[c][0]["n"])
             c0 = int(by_c[c][0]["c_off"])
@@ -895,7 +908,7 @@ def measure_ragged(args, env):
         hbm_peak, hbm_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     ms, mp, mg = float(np.mean(tot)), float(np.mean(tp)), float(np.mean(tg))
     t = torch.tensor([ms, mp, mg], device="cuda", dtype=torch.float64)
-    f = torch.tensor([st.flops, float(st.permute_elems_a + st.permute_elems_b)], device="cuda", dtype=torch.float64)
+    f = torch.tensor([my_flops, float(st.permute_elems_a + st.permute_elems_b)], device="cuda", dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -909,8 +922,8 @@ def measure_ragged(args, env):
         return None
     kern = [{"step": 1, "kernel": "batched_permute", "ms": mp, "bound": "hbm", "alg_bytes": 2 * pel * 8, "achieved": 2 * pel * 8 / (mp * 1e-3) / 1e9 if mp > 0 else 0.0,
              "unit": "GB/s", "frac": (2 * pel * 8 / (mp * 1e-3) / 1e9 / hbm_peak) if mp > 0 else 0.0},
-            {"step": 1, "kernel": "grouped_gemm_dmma", "ms": mg, "bound": "tensor", "alg_flops": st.flops, "achieved": st.flops / (mg * 1e-3) / 1e12,
-             "unit": "TFLOP/s", "frac": st.flops / (mg * 1e-3) / 1e12 / peak_burst}]
+            {"step": 1, "kernel": "grouped_gemm_dmma", "ms": mg, "bound": "tensor", "alg_flops": my_flops, "achieved": my_flops / (mg * 1e-3) / 1e12,
+             "unit": "TFLOP/s", "frac": my_flops / (mg * 1e-3) / 1e12 / peak_burst}]
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:

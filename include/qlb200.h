@@ -356,6 +356,32 @@ int qlb200_tplan_blocks(const qlb200_tplan *p, uint64_t *blk_idx, uint32_t *blk_
 int qlb200_transpose_execute(qlb200_ctx *ctx, qlb200_tplan *p, const void *src, void *dst,
                              int mem_kind);
 
+/* ---- matrix-free axis operations (dmrg/axis_ops.h) -------------------------------------------- */
+/* out = in with one / two axes multiplied by rank-2 operators, AXIS ORDER PRESERVED:
+ *     out[.., j1, .., j2, ..] = sum_{i1, i2} in[.., i1, .., i2, ..] * op1[i1, j1] * op2[i2, j2]
+ * Replaces qlten::dmrg::ApplyRank2ToAxisPreserveOrder (tensor_manipulation/dmrg/axis_ops.h:2889-2992; per-block kernel
+ * AddRank2AxisBlock :1695-1775) and ApplyTwoRank2ToAxesPreserveOrder (:2994-3125) -- bosonic quantum numbers only, as in
+ * the reference.  op shells are rank 2 in the reference's {input_index, output_index} layout, op.index(0) ==
+ * InverseIndex(in.index(axis)).  One kernel launch applies the operator(s) to every block in a single pass over the input
+ * (no single-axis intermediate, no transposes).  The launch handles operator blocks up to 8 x 8 (site operators of a DMRG
+ * Hamiltonian); larger ones return QLB200_ERR_UNSUPPORTED from qlb200_axis_plan_create and go through
+ * qlb200_match_create + qlb200_tplan_create (contract, then move the new index into place) in the host adapters. */
+typedef struct qlb200_axis qlb200_axis;           /* block pairing + output topology (host only) */
+typedef struct qlb200_axis_plan qlb200_axis_plan; /* device tables */
+int qlb200_axis_create(const qlb200_shell *in, int32_t nops, const qlb200_shell *op1, int32_t axis1, const qlb200_shell *op2,
+                       int32_t axis2, qlb200_axis **out);
+void qlb200_axis_destroy(qlb200_axis *a);
+uint64_t qlb200_axis_out_nblk(const qlb200_axis *a);
+uint64_t qlb200_axis_out_elems(const qlb200_axis *a);
+uint64_t qlb200_axis_nterm(const qlb200_axis *a);            /* (input block, op block[s]) triples */
+int qlb200_axis_out_blocks(const qlb200_axis *a, uint64_t *blk_idx, uint32_t *blk_coors, uint32_t *shape, uint64_t *offset);
+int qlb200_axis_plan_create(qlb200_ctx *ctx, const qlb200_axis *a, int dtype, qlb200_axis_plan **out);
+void qlb200_axis_plan_destroy(qlb200_axis_plan *p);
+/* algorithmic traffic of one execute: every contributing input block once per output block it feeds, the output once */
+int qlb200_axis_plan_bytes(const qlb200_axis_plan *p, uint64_t *read_bytes, uint64_t *write_bytes);
+int qlb200_axis_execute(qlb200_ctx *ctx, qlb200_axis_plan *p, const void *in, const void *op1, const void *op2, void *out,
+                        int mem_kind);
+
 /* ---- batched range copy (multi-GPU: unpack all-gathered output slabs into the full layout) --- */
 /* dst[dst_off[i] .. +len[i]) = src[src_off[i] .. +len[i]) for every i, one launch of the permute
  * kernel in its contiguous-run mode.  Offsets / lengths in elements; device pointers only. */

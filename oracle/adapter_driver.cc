@@ -7,6 +7,7 @@
 #include "ref_handles.h"
 
 #include "qlten_b200/contract.h"
+#include "qlten_b200/axis_ops.h"
 
 using namespace qlref;
 
@@ -110,6 +111,24 @@ int qlref_b200_contract_accumulate(const void *a, const void *b, int64_t a_start
       return ok;
     });
   } catch (const std::exception &e) { std::fprintf(stderr, "qlref_b200_contract_accumulate: %s\n", e.what()); return -1; }
+}
+
+void *qlref_b200_apply_rank2(const void *x, const void *op1, int64_t axis1, const void *op2, int64_t axis2, void *ctx) {
+  return Guard("qlref_b200_apply_rank2", [&]() -> void * {
+    return Dispatch<TenBase *>(static_cast<const TenBase *>(x), [&](auto *X) -> TenBase * {
+      using Box = std::remove_const_t<std::remove_pointer_t<decltype(X)>>;
+      if constexpr (Fermionicable<typename Box::QN>::IsFermionic()) {
+        return nullptr;
+      } else {
+        typename Box::Ten out;
+        const auto &o1 = Same(X, static_cast<const TenBase *>(op1))->t;
+        if (op2 == nullptr) qlten::b200::dmrg::ApplyRank2ToAxisPreserveOrder(X->t, o1, (size_t) axis1, out, (qlb200_ctx *) ctx);
+        else qlten::b200::dmrg::ApplyTwoRank2ToAxesPreserveOrder(X->t, o1, (size_t) axis1, Same(X, static_cast<const TenBase *>(op2))->t,
+                                                                 (size_t) axis2, out, (qlb200_ctx *) ctx);
+        return X->wrap(std::move(out));
+      }
+    });
+  });
 }
 
 int qlref_b200_transpose(void *t, const int64_t *perm, void *ctx) {

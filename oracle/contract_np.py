@@ -247,6 +247,45 @@ def contract_accumulate_np(a: BlockSparseTensor, b: BlockSparseTensor, a_start: 
     return out
 
 
+def apply_rank2_axes_np(x: BlockSparseTensor, ops) -> BlockSparseTensor:
+    """dmrg::ApplyRank2ToAxisPreserveOrder / ApplyTwoRank2ToAxesPreserveOrder -- tensor_manipulation/dmrg/axis_ops.h:2889-3125.
+    `ops` = [(rank-2 op, axis), ...] (one or two, distinct axes); op in {input_index, output_index} layout.  For every input
+    block and every op block whose input sector matches the block's sector on that axis (Rank2OpBlockIndicesByInputSector
+    :960-982), the output block with the axis coordinates replaced (:2950-2953, :3078-3081) accumulates
+    in[.., i1, .., i2, ..] * op1[i1, j1] * op2[i2, j2] (AddRank2AxisBlock :1695-1775, AddTwoRank2AxesBlockGemm :1932-1986)."""
+    idxs = list(x.indexes)
+    for op, ax in ops:
+        idxs[ax] = op.indexes[1]
+    out = BlockSparseTensor(idxs, x.dtype)
+    by_sector = []
+    for op, ax in ops:
+        d = {}
+        for b in range(op.nblk):
+            d.setdefault(int(op.blk_coors[b, 0]), []).append(b)
+        by_sector.append(d)
+    contrib = {}
+    for ib in range(x.nblk):
+        lists = [by_sector[o].get(int(x.blk_coors[ib, ax]), []) for o, (op, ax) in enumerate(ops)]
+        combos = [(b1,) for b1 in lists[0]] if len(ops) == 1 else [(b1, b2) for b1 in lists[0] for b2 in lists[1]]
+        for combo in combos:
+            c = [int(v) for v in x.blk_coors[ib]]
+            for (op, ax), b in zip(ops, combo):
+                c[ax] = int(op.blk_coors[b, 1])
+            contrib.setdefault(tuple(c), []).append((ib, combo))
+    if not contrib:
+        return out
+    out.set_blocks(np.array(sorted(contrib), np.uint32).reshape(len(contrib), x.rank))
+    out.data[...] = 0
+    for nb in range(out.nblk):
+        acc = out.block(nb)
+        for ib, combo in contrib[tuple(int(v) for v in out.blk_coors[nb])]:
+            v = x.block(ib)
+            for (op, ax), b in zip(ops, combo):
+                v = np.moveaxis(np.tensordot(v, op.block(b), axes=([ax], [0])), -1, ax)
+            acc += v
+    return out
+
+
 def transpose_np(t: BlockSparseTensor, order) -> BlockSparseTensor:
     """QLTensor::Transpose -- qltensor/qltensor_impl.h:449-464 -> BlockSparseDataTensor::Transpose,
     global_operations.h:393-441: every block permuted, fermionic blocks scaled by the reorder sign

@@ -174,6 +174,11 @@ int qlref_contract_accumulate(const void *a, const void *b, int64_t a_start, int
                                                                 static_cast<TenBase *>(c), try_only, stats10);
   } catch (const std::exception &e) { std::fprintf(stderr, "qlref_contract_accumulate: %s\n", e.what()); return -1; }
 }
+void *qlref_apply_rank2(const void *x, const void *op1, int64_t axis1, const void *op2, int64_t axis2) {
+  try {
+    return static_cast<const TenBase *>(x)->apply_rank2(static_cast<const TenBase *>(op1), axis1, static_cast<const TenBase *>(op2), axis2);
+  } catch (const std::exception &e) { std::fprintf(stderr, "qlref_apply_rank2: %s\n", e.what()); return nullptr; }
+}
 int qlref_tensor_write(const void *t, const char *path) { return static_cast<const TenBase *>(t)->write_file(path); }
 int qlref_tensor_read(void *t, const char *path) { return static_cast<TenBase *>(t)->read_file(path); }
 void *qlref_contract_contiguous(const void *a, const void *b, int64_t a_start, int64_t b_start, int64_t size, int side) {

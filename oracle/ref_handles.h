@@ -23,6 +23,7 @@
 #include "qlten/tensor_manipulation/tensor_op_cost.h"
 #include "qlten/tensor_manipulation/dmrg/contract_1sector.h"
 #include "qlten/tensor_manipulation/contract_contiguous_axes.h"
+#include "qlten/tensor_manipulation/dmrg/axis_ops.h"
 
 using namespace qlten;
 using special_qn::U1QN;
@@ -88,6 +89,8 @@ struct TenBase {
   // when the probe reports a layout mismatch; stats10 = the ContiguousContractStats counters this path defines.
   virtual int contract_accumulate(const TenBase *b, int64_t a_start, int64_t b_start, int64_t size, const double *alpha2,
                                   const double *beta2, TenBase *c, int try_only, uint64_t *stats10) const = 0;
+  // dmrg::ApplyRank2ToAxisPreserveOrder (op2 == nullptr) / ApplyTwoRank2ToAxesPreserveOrder; bosonic kinds only (nullptr otherwise)
+  virtual TenBase *apply_rank2(const TenBase *op1, int64_t axis1, const TenBase *op2, int64_t axis2) const = 0;
   virtual std::vector<TaskRec> tasks(const TenBase *b, int n, const int64_t *aa, const int64_t *ba, bool sorted) const = 0;
   virtual void cost(const TenBase *b, int n, const int64_t *aa, const int64_t *ba, double *out8) const = 0;
 };
@@ -175,6 +178,16 @@ struct TenBox : TenBase {
       default: ContractContiguousAxes<ElemT, QNT, CtrctSide::Tail, CtrctSide::Head>(t, tb, (size_t) a_start, (size_t) b_start, (size_t) size, c); break;
     }
     return wrap(std::move(c));
+  }
+  TenBase *apply_rank2(const TenBase *op1, int64_t axis1, const TenBase *op2, int64_t axis2) const override {
+    if constexpr (Fermionicable<QNT>::IsFermionic()) {
+      return nullptr;
+    } else {
+      Ten out;
+      if (op2 == nullptr) dmrg::ApplyRank2ToAxisPreserveOrder(t, cast(op1)->t, (size_t) axis1, out);
+      else dmrg::ApplyTwoRank2ToAxesPreserveOrder(t, cast(op1)->t, (size_t) axis1, cast(op2)->t, (size_t) axis2, out);
+      return wrap(std::move(out));
+    }
   }
   static ElemT MakeScalar(const double *v2) {
     if constexpr (std::is_same<ElemT, QLTEN_Complex>::value) return ElemT(v2[0], v2[1]);

@@ -64,6 +64,7 @@ def lib():
             "qlref_tensor_new_default": (_P, [_P]),
             "qlref_contract_accumulate": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), _P,
                                                     C.c_int, C.POINTER(C.c_uint64)]),
+            "qlref_apply_rank2": (_P, [_P, _P, C.c_int64, _P, C.c_int64]),
             "qlref_tensor_fill": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_uint32), _P, C.c_uint64]),
             "qlref_raw_contract": (C.c_double, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                                 C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
@@ -91,6 +92,7 @@ def adapter():
             "qlref_b200_contract_1sector": (_P, [_P, C.c_int64, C.c_int64, _P, C.c_int, _I64P, _I64P, _P]),
             "qlref_b200_transpose": (C.c_int, [_P, _I64P, _P]),
             "qlref_b200_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P]),
+            "qlref_b200_apply_rank2": (_P, [_P, _P, C.c_int64, _P, C.c_int64, _P]),
             "qlref_b200_contract_accumulate": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), _P,
                                                          C.c_int, C.POINTER(C.c_uint64), _P]),
         }
@@ -339,6 +341,31 @@ def contract_accumulate(a, b, a_start, b_start, size, alpha, beta, c: RefTensor,
 def b200_contract_accumulate(a, b, a_start, b_start, size, alpha, beta, c: RefTensor, try_only=False, ctx_handle=None):
     """qlten::b200::(Try)ContractTailHeadContiguousAccumulate on reference tensors (the drop-in adapter)."""
     return _accumulate(adapter().qlref_b200_contract_accumulate, a, b, a_start, b_start, size, alpha, beta, c, try_only, (ctx_handle,))
+
+
+def _axis_indexes(x, ops):
+    idxs = list(x.indexes)
+    for op, ax in ops:
+        idxs[ax] = op.indexes[1]
+    return idxs
+
+
+def apply_rank2(x: RefTensor, ops) -> RefTensor:
+    """The reference's dmrg::ApplyRank2ToAxisPreserveOrder (one (op, axis)) / ApplyTwoRank2ToAxesPreserveOrder (two)."""
+    (o1, a1), (o2, a2) = ops[0], (ops[1] if len(ops) > 1 else (None, 0))
+    h = lib().qlref_apply_rank2(x.h, o1.h, int(a1), o2.h if o2 is not None else None, int(a2))
+    if not h:
+        raise RuntimeError("reference axis operation failed (see stderr)")
+    return RefTensor(h, _axis_indexes(x, ops), x.dtype)
+
+
+def b200_apply_rank2(x: RefTensor, ops, ctx_handle=None) -> RefTensor:
+    """qlten::b200::dmrg::Apply(Two)Rank2To...PreserveOrder on reference tensors (the drop-in adapter)."""
+    (o1, a1), (o2, a2) = ops[0], (ops[1] if len(ops) > 1 else (None, 0))
+    h = adapter().qlref_b200_apply_rank2(x.h, o1.h, int(a1), o2.h if o2 is not None else None, int(a2), ctx_handle)
+    if not h:
+        raise RuntimeError("qlten::b200::dmrg axis operation failed (see stderr)")
+    return RefTensor(h, _axis_indexes(x, ops), x.dtype)
 
 
 def raw_contract(dtype, a_rank, a_perm, a_shape, a_off, b_rank, b_perm, b_shape, b_off, tasks, A, B, c_elems, keep_permuted=False):

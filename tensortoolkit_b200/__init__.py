@@ -7,7 +7,9 @@ from .contract import (Context, Match, ContractionPlan, RawPlan, contract, contr
                        default_context, AccumulateLayoutMismatch, contract_tail_head_contiguous_accumulate,
                        try_contract_tail_head_contiguous_accumulate)
 
-__all__ = ["IN", "OUT", "QNKind", "QNSector", "Index", "BlockSparseTensor", "U1", "fU1", "U1U1", "fU1U1", "Z2", "fZ2",
+from .axis_ops import AxisPlan, apply_rank2_to_axis_preserve_order, apply_two_rank2_to_axes_preserve_order  # noqa: E402
+
+__all__ = ["AxisPlan", "apply_rank2_to_axis_preserve_order", "apply_two_rank2_to_axes_preserve_order", "IN", "OUT", "QNKind", "QNSector", "Index", "BlockSparseTensor", "U1", "fU1", "U1U1", "fU1U1", "Z2", "fZ2",
            "Context", "Match", "ContractionPlan", "RawPlan", "contract", "contract_1sector", "contract_contiguous_axes",
            "transpose", "default_context", "qlten_io", "AccumulateLayoutMismatch", "contract_tail_head_contiguous_accumulate",
            "try_contract_tail_head_contiguous_accumulate"]

@@ -131,6 +131,16 @@ SYMBOLS = {
     "qlb200_hostpipe_begin": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "qlb200_hostpipe_end": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "qlb200_hostpipe_launches": (C.c_uint64, [_P]),
+    "qlb200_axis_create": (C.c_int, [_SH, C.c_int32, _SH, C.c_int32, _SH, C.c_int32, _PP]),
+    "qlb200_axis_destroy": (None, [_P]),
+    "qlb200_axis_out_nblk": (C.c_uint64, [_P]),
+    "qlb200_axis_out_elems": (C.c_uint64, [_P]),
+    "qlb200_axis_nterm": (C.c_uint64, [_P]),
+    "qlb200_axis_out_blocks": (C.c_int, [_P, _U64P, _U32P, _U32P, _U64P]),
+    "qlb200_axis_plan_create": (C.c_int, [_P, _P, C.c_int, _PP]),
+    "qlb200_axis_plan_destroy": (None, [_P]),
+    "qlb200_axis_plan_bytes": (C.c_int, [_P, _U64P, _U64P]),
+    "qlb200_axis_execute": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int]),
     "qlb200_accum_create": (C.c_int, [_P, _SH, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _PP]),
     "qlb200_accum_destroy": (None, [_P]),
     "qlb200_accum_nblk": (C.c_uint64, [_P]),

@@ -1120,6 +1120,162 @@ int qlb200_execute_accum(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const v
   return QLB200_OK;
 }
 
+// ---- matrix-free axis operations -----------------------------------------------------------------
+struct qlb200_axis { AxisMatch m; };
+
+int qlb200_axis_create(const qlb200_shell *in, int32_t nops, const qlb200_shell *op1, int32_t axis1, const qlb200_shell *op2,
+                       int32_t axis2, qlb200_axis **out) {
+  if (!in || !op1 || !out || (nops == 2 && !op2)) return Fail(QLB200_ERR_ARG, "null argument");
+  qlb200_axis *a = new (std::nothrow) qlb200_axis();
+  if (!a) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  std::string err = BuildAxisMatch(in, nops, op1, axis1, op2, axis2, &a->m);
+  if (!err.empty()) { delete a; return Fail(QLB200_ERR_ARG, err); }
+  *out = a;
+  return QLB200_OK;
+}
+void qlb200_axis_destroy(qlb200_axis *a) { delete a; }
+uint64_t qlb200_axis_out_nblk(const qlb200_axis *a) { return a ? a->m.out_blocks.size() : 0; }
+uint64_t qlb200_axis_out_elems(const qlb200_axis *a) { return a ? a->m.out_elems : 0; }
+uint64_t qlb200_axis_nterm(const qlb200_axis *a) { return a ? a->m.terms.size() : 0; }
+int qlb200_axis_out_blocks(const qlb200_axis *a, uint64_t *blk_idx, uint32_t *blk_coors, uint32_t *shape, uint64_t *offset) {
+  if (!a) return Fail(QLB200_ERR_ARG, "null argument");
+  const int r = a->m.in.rank;
+  for (size_t b = 0; b < a->m.out_blocks.size(); ++b) {
+    const CBlock &cb = a->m.out_blocks[b];
+    if (blk_idx) blk_idx[b] = cb.blk_idx;
+    if (offset) offset[b] = cb.offset;
+    for (int i = 0; i < r; ++i) {
+      if (blk_coors) blk_coors[b * r + i] = cb.coors[i];
+      if (shape) shape[b * r + i] = cb.shape[i];
+    }
+  }
+  return QLB200_OK;
+}
+
+struct qlb200_axis_plan {
+  qlb200_ctx *ctx = nullptr;
+  int dtype = 0, nops = 1;
+  bool swapped = false;                 // the kernel's first operator acts on the EARLIER axis: op1 / op2 swapped if axis1 > axis2
+  uint64_t in_elems = 0, op_elems[2] = {0, 0}, out_elems = 0;
+  uint64_t read_bytes = 0, write_bytes = 0;
+  std::vector<AxisOut> outs;
+  std::vector<AxisFlatTerm> terms;
+  std::vector<AxisItem> items;
+  AxisOut *d_outs = nullptr;
+  AxisFlatTerm *d_terms = nullptr;
+  AxisItem *d_items = nullptr;
+};
+
+void qlb200_axis_plan_destroy(qlb200_axis_plan *p) {
+  if (!p) return;
+  if (p->ctx) { cudaSetDevice(p->ctx->device); cudaStreamSynchronize(p->ctx->stream); }
+  cudaFree(p->d_outs); cudaFree(p->d_terms); cudaFree(p->d_items);
+  delete p;
+}
+
+int qlb200_axis_plan_create(qlb200_ctx *ctx, const qlb200_axis *a, int dtype, qlb200_axis_plan **out) {
+  if (!ctx || !a || !out) return Fail(QLB200_ERR_ARG, "null argument");
+  if (dtype != QLB200_F64 && dtype != QLB200_C64) return Fail(QLB200_ERR_ARG, "bad dtype");
+  const AxisMatch &m = a->m;
+  const int r = m.in.rank;
+  qlb200_axis_plan *p = new (std::nothrow) qlb200_axis_plan();
+  if (!p) return Fail(QLB200_ERR_NOMEM, "out of memory");
+  p->ctx = ctx; p->dtype = dtype; p->nops = m.nops;
+  p->in_elems = m.in.elems; p->op_elems[0] = m.op[0].elems; p->op_elems[1] = m.nops == 2 ? m.op[1].elems : 0; p->out_elems = m.out_elems;
+  // kernel operator A acts on the earlier axis
+  int oa = 0, ob = 1;
+  if (m.nops == 2 && m.axis[0] > m.axis[1]) { oa = 1; ob = 0; p->swapped = true; }
+  const int a1 = m.axis[oa], a2 = m.nops == 2 ? m.axis[ob] : -1;
+  const size_t es = ElemSize(dtype);
+  for (size_t b = 0; b < m.out_blocks.size(); ++b) {
+    const CBlock &cb = m.out_blocks[b];
+    AxisOut o;
+    std::memset(&o, 0, sizeof(o));
+    o.out_off = cb.offset; o.size = uint32_t(cb.size);
+    uint64_t P1 = 1, P2 = 1;
+    if (a2 >= 0) {
+      for (int i = a1 + 1; i < a2; ++i) P1 *= cb.shape[i];
+      for (int i = a2 + 1; i < r; ++i) P2 *= cb.shape[i];
+    } else {
+      for (int i = a1 + 1; i < r; ++i) P2 *= cb.shape[i];
+    }
+    o.J1 = cb.shape[a1]; o.P1 = uint32_t(P1); o.J2 = a2 >= 0 ? cb.shape[a2] : 1u; o.P2 = uint32_t(P2);
+    o.term_begin = uint32_t(p->terms.size());
+    if (o.J1 > uint32_t(kAxisMaxDim) || o.J2 > uint32_t(kAxisMaxDim)) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, "operator block wider than 8: use the contraction path"); }
+    for (uint32_t t = m.term_begin[b]; t < m.term_begin[b + 1]; ++t) {
+      const AxisTerm &tm = m.terms[t];
+      const uint32_t opa_blk = oa == 0 ? tm.op1_ord : tm.op2_ord, opb_blk = oa == 0 ? tm.op2_ord : tm.op1_ord;
+      const uint32_t I1 = m.in.shape[uint64_t(tm.in_ord) * r + a1], I2 = a2 >= 0 ? m.in.shape[uint64_t(tm.in_ord) * r + a2] : 1u;
+      if (I1 > uint32_t(kAxisMaxDim) || I2 > uint32_t(kAxisMaxDim)) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, "operator block taller than 8: use the contraction path"); }
+      const uint64_t s_i1 = P1 * I2 * P2, s_i2 = P2;
+      if (uint64_t(I1) * s_i1 >= (1ull << 32)) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, "input block too large"); }
+      for (uint32_t i1 = 0; i1 < I1; ++i1)
+        for (uint32_t i2 = 0; i2 < I2; ++i2) {
+          AxisFlatTerm ft;
+          ft.in_base = m.in.offset[tm.in_ord] + i1 * s_i1 + i2 * s_i2;
+          ft.c1_off = m.op[oa].offset[opa_blk] + uint64_t(i1) * o.J1;
+          ft.c2_off = a2 >= 0 ? m.op[ob].offset[opb_blk] + uint64_t(i2) * o.J2 : 0;
+          ft.sp0 = uint32_t(I1 * s_i1); ft.sp1 = uint32_t(I2 * P2);
+          p->terms.push_back(ft);
+        }
+      p->read_bytes += m.in.size[tm.in_ord] * es;
+    }
+    o.term_end = uint32_t(p->terms.size());
+    p->outs.push_back(o);
+    for (uint64_t e = 0; e < cb.size; e += 1024) p->items.push_back({uint32_t(b), uint32_t(e)});
+    p->write_bytes += cb.size * es;
+  }
+  if (p->items.size() >= (1ull << 32)) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, "too many work items"); }
+  QL_CUDA(cudaSetDevice(ctx->device));
+  int rc = Upload(p->outs, &p->d_outs, ctx->stream);
+  if (rc == QLB200_OK) rc = Upload(p->terms, &p->d_terms, ctx->stream);
+  if (rc == QLB200_OK) rc = Upload(p->items, &p->d_items, ctx->stream);
+  if (rc != QLB200_OK) { qlb200_axis_plan_destroy(p); return rc; }
+  QL_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = p;
+  return QLB200_OK;
+}
+
+int qlb200_axis_plan_bytes(const qlb200_axis_plan *p, uint64_t *read_bytes, uint64_t *write_bytes) {
+  if (!p) return Fail(QLB200_ERR_ARG, "null argument");
+  if (read_bytes) *read_bytes = p->read_bytes;
+  if (write_bytes) *write_bytes = p->write_bytes;
+  return QLB200_OK;
+}
+
+int qlb200_axis_execute(qlb200_ctx *ctx, qlb200_axis_plan *p, const void *in, const void *op1, const void *op2, void *out, int mem_kind) {
+  if (!ctx || !p || !in || !op1 || !out || (p->nops == 2 && !op2)) return Fail(QLB200_ERR_ARG, "null argument");
+  if (p->ctx != ctx) return Fail(QLB200_ERR_ARG, "plan belongs to another context");
+  QL_CUDA(cudaSetDevice(ctx->device));
+  const size_t es = ElemSize(p->dtype);
+  const void *d_in = in, *d_o1 = op1, *d_o2 = p->nops == 2 ? op2 : nullptr;
+  void *d_out = out;
+  if (mem_kind == QLB200_MEM_HOST) {
+    const size_t ib = Align256(p->in_elems * es), o1b = Align256(p->op_elems[0] * es), o2b = Align256(p->op_elems[1] * es), ob = Align256(p->out_elems * es);
+    int rc = EnsureArena(ctx, &ctx->stage, &ctx->stage_bytes, ib + o1b + o2b + ob);
+    if (rc != QLB200_OK) return rc;
+    char *base = static_cast<char *>(ctx->stage);
+    QL_CUDA(cudaMemcpyAsync(base, in, p->in_elems * es, cudaMemcpyHostToDevice, ctx->stream));
+    QL_CUDA(cudaMemcpyAsync(base + ib, op1, p->op_elems[0] * es, cudaMemcpyHostToDevice, ctx->stream));
+    if (p->nops == 2) QL_CUDA(cudaMemcpyAsync(base + ib + o1b, op2, p->op_elems[1] * es, cudaMemcpyHostToDevice, ctx->stream));
+    d_in = base; d_o1 = base + ib; d_o2 = p->nops == 2 ? base + ib + o1b : nullptr; d_out = base + ib + o1b + o2b;
+  } else if (mem_kind != QLB200_MEM_DEVICE) {
+    return Fail(QLB200_ERR_ARG, "bad mem_kind");
+  }
+  if (p->swapped) std::swap(d_o1, d_o2);
+  ctx->launches = 0;
+  if (!p->items.empty()) {
+    QL_CUDA(LaunchAxisApply(p->dtype, p->d_outs, p->d_terms, p->d_items, static_cast<uint32_t>(p->items.size()), d_in, d_o1, d_o2, d_out,
+                            ctx->num_sms, ctx->stream));
+    ctx->launches = 1; ++ctx->total_launches;
+  }
+  if (mem_kind == QLB200_MEM_HOST) {
+    QL_CUDA(cudaMemcpyAsync(out, d_out, p->out_elems * es, cudaMemcpyDeviceToHost, ctx->stream));
+    QL_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return QLB200_OK;
+}
+
 // ---- whole-tensor transpose ---------------------------------------------------------------------
 int qlb200_tplan_create(qlb200_ctx *ctx, const qlb200_shell *t, const int32_t *perm, int dtype, qlb200_tplan **out) {
   if (!ctx || !t || !perm || !out) return Fail(QLB200_ERR_ARG, "null argument");

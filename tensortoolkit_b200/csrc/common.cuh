@@ -92,6 +92,25 @@ struct SkinnyItem {     // rows [row0, row0 + kSkinnyElems / n) of a narrow grou
   uint32_t row0;
 };
 
+// ------------------------------------------------------------------------------------------------
+// Matrix-free axis operations (axis_kernel.cu).  A block is viewed as (P0, X1, P1, X2, P2): X1 / X2 the two target axes.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAxisMaxDim = 8;    // largest operator block edge the kernel keeps in its shared-memory coefficient rows
+struct AxisOut {                  // one output block
+  unsigned long long out_off;
+  uint32_t size, J1, P1, J2, P2;  // P0 = size / (J1 P1 J2 P2)
+  uint32_t term_begin, term_end;  // flat terms
+  uint32_t pad_;
+};
+struct AxisFlatTerm {             // one (input block, i1, i2) slice feeding an output block
+  unsigned long long in_base;     // input offset of element (p0 = 0, i1, p1 = 0, i2, p2 = 0)
+  unsigned long long c1_off, c2_off;   // row i1 of the op1 block / row i2 of the op2 block (J1 / J2 consecutive values)
+  uint32_t sp0, sp1;              // input strides of p0 and p1 (they depend on the INPUT block's own I1, I2)
+};
+struct AxisItem { uint32_t out, elem0; };   // a 1024-element chunk of an output block
+cudaError_t LaunchAxisApply(int dtype, const AxisOut *outs, const AxisFlatTerm *terms, const AxisItem *items, uint32_t nitems, const void *in,
+                            const void *op1, const void *op2, void *out, int num_sms, cudaStream_t stream);
+
 constexpr int kMaxOut = 8;        // output replicas (this GPU + NVLink peers)
 
 struct GemmParams {

@@ -93,5 +93,21 @@ struct AccumLayout {
 std::string BuildAccumLayout(const Match &m, const qlb200_shell *c_old, bool c_old_has_data, bool allow_expand, int dtype, bool beta_zero,
                              bool beta_one, AccumLayout *out, bool *layout_mismatch);
 
+
+/// Block pairing of the matrix-free axis operations (axis.cc): out = in with one / two axes multiplied by rank-2 operators.
+struct AxisTerm { uint32_t in_ord, op1_ord, op2_ord; };
+struct AxisMatch {
+  Shell in, op[2];
+  int nops = 0;
+  int axis[2] = {-1, -1};
+  std::vector<uint32_t> out_nsct;
+  std::vector<CBlock> out_blocks;        // ascending blk_idx, offsets in the output raw buffer
+  std::vector<uint32_t> term_begin;      // [nblk + 1] into terms
+  std::vector<AxisTerm> terms;           // contributing (input block, op1 block, op2 block) per output block
+  uint64_t out_elems = 0;
+};
+std::string BuildAxisMatch(const qlb200_shell *in, int nops, const qlb200_shell *op1, int axis1, const qlb200_shell *op2, int axis2,
+                           AxisMatch *out);
+
 }  // namespace qlb200
 #endif
