@@ -44,8 +44,11 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=3, help="GPU arm: timed applies of the cpu_baseline child")
     ap.add_argument("--write-out", default="", help="reference arm: write the result tensor of the apply to this file (the reference's stream format)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rebalance", type=int, default=2, help="N>1: feedback iterations of the row partitioner (measure every rank's share, re-weigh, cut again)")
+    ap.add_argument("--snap", type=int, default=8, help="N>1: row cuts inside a sector are multiples of this")
     ap.add_argument("--no-sub-records", action="store_true", help="default run only: skip the sub-records for BASELINE configs[1], [3] and [4]")
     ap.add_argument("--ragged-cpu-pairs", type=int, default=1000, help="ragged workload: pairs of the bounded CPU / e2e sample")
+    ap.add_argument("--no-fused-mpo", action="store_true", help="skip the measurement of the chain with the two MPO tensors pre-contracted")
     ap.add_argument("--no-cold", action="store_true", help="skip the cold drop-in measurement (4 Contract calls on host tensors incl. match + plan build)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--plan-flags", type=int, default=1, help="qlb200_plan_create flags (kernel A/B testing; 1 = default)")
@@ -399,6 +402,34 @@ def measure_heff(args, env):
         with torch.cuda.stream(stream):
             sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags,
                                    exchange=args.exchange, host_input="psi")
+        # partitioner feedback: time every rank's share, re-weigh the row line by (measured time / modelled flops) per rank,
+        # cut again (sharding.reweigh_pieces) -- an autotuning step at set-up, like the planner's split-K simulation
+        rebalance_log = []
+        for it in range(args.rebalance):
+            from tensortoolkit_b200 import sharding as shd
+            with torch.cuda.stream(stream):
+                ts = []
+                for i in range(6):
+                    env.flush.zero_()
+                    torch.distributed.barrier()
+                    marks = {}
+                    e0 = torch.cuda.Event(enable_timing=True); e0.record(stream)
+                    def mark(label, marks=marks):
+                        ev = torch.cuda.Event(enable_timing=True); ev.record(stream); marks[label] = ev
+                    sharded.apply(mark)
+                    torch.cuda.synchronize()
+                    if i >= 2:
+                        ts.append(e0.elapsed_time(marks["compute"]))
+                mine_t = torch.tensor([float(np.mean(ts))], device="cuda", dtype=torch.float64)
+                allt = [torch.zeros_like(mine_t) for _ in range(world)]
+                torch.distributed.all_gather(allt, mine_t)
+                times = [float(x[0]) for x in allt]
+            rebalance_log.append([round(t, 4) for t in times])
+            pieces = shd.reweigh_pieces(sharded.info.pieces, sharded.info.sector_ranges, times)
+            sharded.close()
+            with torch.cuda.stream(stream):
+                sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags,
+                                       exchange=args.exchange, host_input="psi", pieces=pieces, snap=args.snap)
         chain = sharded.chain
         apply_fn = sharded.apply
     else:
@@ -564,6 +595,46 @@ def measure_heff(args, env):
         cold = None
         if world == 1 and not args.shard_of and not args.no_cold:
             cold = measure_cold_dropin(tk, ctx, tensors, wl.HEFF_STEPS, chain.flops())
+        # ---- the same apply with the two MPO tensors pre-contracted (static across a Lanczos run): one pass over the rank-5
+        # intermediate instead of two (workloads.HEFF_STEPS_FUSED); flops numerator stays the reference recipe's
+        fused = None
+        if world == 1 and not args.shard_of and not args.no_fused_mpo:
+            l, r, ax, o = wl.HEFF_FUSE_PREP
+            t2 = dict(tensors)
+            t2[o] = tk.contract(tensors[l], tensors[r], ax, ctx)
+            fchain = ContractionChain(ctx, t2, wl.HEFF_STEPS_FUSED, np_dtype(dtype), args.plan_flags)
+            fchain.apply_device()
+            got = fchain.result("out").data
+            chain.apply_device()
+            base = chain.result("out").data
+            ferr = float(np.linalg.norm(got - base) / np.linalg.norm(base))
+            fgraph = fchain.capture()
+            for _ in range(3):
+                fgraph.launch()
+            fev = []
+            for _ in range(args.steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); fgraph.launch(); e1.record(stream)
+                fev.append((e0, e1))
+            torch.cuda.synchronize()
+            fms = float(np.mean([a.elapsed_time(b) for a, b in fev]))
+            fst = fchain.stats()[1]
+            tf = []
+            for _ in range(5):
+                flush.zero_()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(stream)
+                fchain.plans[1].execute_device(fchain.buf["t1"].ptr, fchain.buf["w12"].ptr, fchain.buf["t3"].ptr)
+                a1.record(stream); torch.cuda.synchronize()
+                tf.append(a0.elapsed_time(a1))
+            fby = fst.gemm_read_bytes + fst.gemm_write_bytes
+            fused = {"ms_per_step": fms, "value": chain.flops() / (fms * 1e-3) / 1e9, "unit": "GFLOP/s (flops of the reference's 4-Contract recipe)",
+                     "rel_err_vs_unfused": ferr, "mpo_step_ms": float(np.mean(tf)), "mpo_step_gbs": fby / (np.mean(tf) * 1e-3) / 1e9,
+                     "how": "w12 = Contract(mpo1, mpo2) once; every apply = lenv x psi, x w12 (one narrow-pair launch over the rank-5 intermediate), x renv"}
+            if not ferr <= 1e-12:
+                raise SystemExit(f"fused-MPO chain differs from the 4-step chain: rel err {ferr:.3e}")
+            fgraph.close(); fchain.close()
 
     ms = float(np.mean(dev_ms))
     tot_ms, flops_total, e2e_max = ms, flops_local, e2e_s
@@ -671,12 +742,15 @@ def measure_heff(args, env):
                 "rel_err_vs_device_resident": e2e_err,
                 "serial_ms_per_step": None if e2e_serial_s is None else e2e_serial_s * 1e3,
                 "cold_dropin": cold},
+        "fused_mpo": fused,
         "gpu_launches": int(launches) * args.steps, "clocks": sampler.summary(),
     }
     if verified is not None:
         line["sharded_vs_unsharded_rel_err"] = verified
     if rank_phase is not None:
         line["rank_phases"] = rank_phase
+        line["partition_feedback"] = {"iterations": args.rebalance, "local_ms_by_rank_before_each": rebalance_log,
+                                      "how": "rows of the split bond re-weighted by measured time / modelled flops per rank, cut again (set-up time)"}
     if args.breakdown:
         for rp in rank_phase or []:
             print(f"  rank {rp['rank']}: local steps {rp['local_steps_ms']:.3f} ms, exchange + wait {rp['exchange_and_wait_ms']:.3f} ms", file=sys.stderr)
@@ -983,6 +1057,7 @@ def run_ours(args):
             a2 = copy.copy(args)
             a2.workload, a2.D, a2.dtype, a2.cpu_sample_D = workload, D, dtype, cpuD
             a2.steps, a2.cpu_steps, a2.no_cold, a2.breakdown = min(args.steps, 10), 2, True, False
+            a2.no_fused_mpo = False
             a2.no_thread_sweep = True
             sub = measure_heff(a2, env)
             subs[name] = compact(sub)

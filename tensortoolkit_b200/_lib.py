@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqlb200.so")
+# QLB200_LIB: load another build of the same library (kernel A/B experiments, exp/); default = the in-tree build
+LIB_PATH = os.environ.get("QLB200_LIB") or os.path.join(_HERE, "libqlb200.so")
 
 QLB200_MAX_RANK = 8
 OK = 0

@@ -101,6 +101,7 @@ GemmParams MakeParams(const qlb200_plan *p, const void *A, const void *B, const 
   gp.tasks = p->d.tasks; gp.groups = p->d.groups; gp.tiles = p->d.tiles; gp.items = p->d.items;
   gp.ntiles = static_cast<uint32_t>(p->h.tiles.size());
   gp.nitems = static_cast<uint32_t>(p->h.items.size());
+  gp.skinny_sub = p->h.skinny_sub;
   gp.seg = p->h.seg.empty() ? nullptr : p->d.seg;
   gp.nseg = p->h.seg.empty() ? 0u : static_cast<uint32_t>(p->h.seg.size() - 1);
   gp.counters = p->d.counters;

@@ -87,7 +87,7 @@ struct GemmTile {
   uint32_t pad_;
 };
 
-struct SkinnyItem {     // rows [row0, row0 + kSkinnyElems / n) of a narrow group
+struct SkinnyItem {     // rows [row0, row0 + skinny_sub * (kSkinnyElems / n)) of a narrow group
   uint32_t group;
   uint32_t row0;
 };
@@ -123,6 +123,7 @@ struct GemmParams {
   const GemmTile *tiles;
   const SkinnyItem *items;
   uint32_t ntiles, nitems;
+  uint32_t skinny_sub;              // sub-chunks of kSkinnyElems outputs per narrow-pair work item
   const uint32_t *seg;              // stream-K: CTA b runs units [seg[b], seg[b+1]) (nullptr: units are pulled from counters[0])
   uint32_t nseg;
   unsigned int *counters;           // [0] next tile, [1] finished CTAs, [2 + ctr] split-K arrivals (all self-resetting)
@@ -206,9 +207,15 @@ constexpr int kWs3mBK = 16;                                // 3M kernel: two hal
 constexpr int kWs3mStages = kWs3mBK == 16 ? 3 : 5;
 // narrow-pair kernel: 4 outputs per thread keep it at 64 registers -> 4 CTAs (32 warps) per SM; the kernel is
 // latency-bound, so resident warps (loads in flight) matter more than per-thread reuse (measured: 8 per thread /
-// 2 CTAs 0.83 ms, 4 / 4 CTAs 0.69 ms, 2 / 6 CTAs 0.99 ms for the two MPO steps of the D=4096 apply)
+// 2 CTAs 0.83 ms, 4 / 4 CTAs 0.69 ms, 2 / 6 CTAs 0.99 ms for the two MPO steps of the D=4096 apply; a one-thread-per-row
+// variant -- every A value loaded once instead of n times, n strided stores per thread, 2 CTAs -- measured 0.90 ms)
 constexpr int kSkinnyMaxN = 8, kSkinnyMaxK = 32, kSkinnyThreads = 256, kSkinnyPerThread = 4, kSkinnyMinCtas = 4;
-constexpr int kSkinnyElems = kSkinnyThreads * kSkinnyPerThread;   // output elements per work item
+constexpr int kSkinnyElems = kSkinnyThreads * kSkinnyPerThread;   // output elements per sub-chunk of a work item
+// sub-chunks per work item: the descriptor fetch (a chain of dependent global loads) and the term table are amortised over
+// them.  Chosen per plan (PlanHost::skinny_sub): as many as possible, up to 8, while every resident CTA still gets about
+// eight items (measured on the MPO steps, HBM fraction with 1 / 4 / 8 sub-chunks: D=4096 complex 0.70 / 0.81 / 0.79,
+// Hubbard D=8192 0.62 / 0.72 / 0.78, D=1024 0.30 / 0.32 / 0.26)
+constexpr int kSkinnyMaxSub = 8;
 
 }  // namespace qlb200
 #endif

@@ -361,74 +361,94 @@ GemmSkinny(GemmParams p) {
   __shared__ const T *s_ap[kSkinnyTermChunk];
   __shared__ uint32_t s_as[kSkinnyTermChunk];
   __shared__ T s_coef[kSkinnyTermChunk][kSkinnyMaxN];
+  __shared__ uint32_t s_nterm;
   const uint32_t tid = threadIdx.x;
   for (uint32_t it = blockIdx.x; it < p.nitems; it += gridDim.x) {
     const SkinnyItem item = p.items[it];
     const GemmGroup g = p.groups[item.group];
     const uint32_t n = g.n;
-    const uint32_t rows = min(uint32_t(kSkinnyElems) / n, g.row_end - item.row0);
-    const uint32_t total = rows * n;
-    uint32_t row[kSkinnyPerThread], col[kSkinnyPerThread];
-    T acc[kSkinnyPerThread];
-#pragma unroll
-    for (int u = 0; u < kSkinnyPerThread; ++u) {
-      const uint32_t e = tid + u * kSkinnyThreads;
-      const uint32_t r = e / n;
-      row[u] = item.row0 + r; col[u] = e - r * n;
-      acc[u] = E::Zero();
-    }
-    // walk the group's (pair, kk) terms in chunks of kSkinnyTermChunk
-    uint32_t t = g.task_begin, kk0 = 0;
-    while (t < g.task_end) {
-      __syncthreads();   // previous chunk (or previous item) fully consumed
-      // every thread walks the same short task list; thread x fills term x
-      uint32_t nterm = 0, tt = t, kk = kk0;
-      while (tt < g.task_end && nterm < uint32_t(kSkinnyTermChunk)) {
-        const GemmTask tk = p.tasks[tt];
-        const uint32_t take = min(tk.k - kk, uint32_t(kSkinnyTermChunk) - nterm);
-        if (tid >= nterm && tid < nterm + take) {
-          const uint32_t k1 = kk + (tid - nterm);
-          const T *a = static_cast<const T *>((tk.flags & kTaskASrc) ? p.a_src : p.a_ws) + tk.a_off;
-          const T *b = static_cast<const T *>((tk.flags & kTaskBSrc) ? p.b_src : p.b_ws) + tk.b_off;
-          if (tk.flags & kTaskATrans) { s_ap[tid] = a + (unsigned long long) k1 * g.m; s_as[tid] = 1; }
-          else { s_ap[tid] = a + k1; s_as[tid] = tk.k; }
-          for (uint32_t j = 0; j < n; ++j) {
-            // B(k1, j): stored n x k (transposed), row-major k x n (b_run >= n: no division), or a strided view of the block
-            const T v = (tk.flags & kTaskBTrans) ? b[(unsigned long long) j * tk.k + k1]
-                        : tk.b_run >= n         ? b[(unsigned long long) k1 * tk.b_rs + j]
-                                                 : b[(unsigned long long) k1 * tk.b_rs + (j / tk.b_run) * tk.b_cs + j % tk.b_run];
-            s_coef[tid][j] = E::Signed(v, tk.sign);
-          }
-        }
-        nterm += take; kk += take;
-        if (kk >= tk.k) { ++tt; kk = 0; }
-      }
-      t = tt; kk0 = kk;
-      __syncthreads();
-#pragma unroll 1
-      for (uint32_t x = 0; x < nterm; ++x) {
-        const T *ap = s_ap[x];
-        const unsigned long long as = s_as[x];
-        T av[kSkinnyPerThread];
-#pragma unroll
-        for (int u = 0; u < kSkinnyPerThread; ++u)
-          if (tid + u * kSkinnyThreads < total) av[u] = ap[row[u] * as];
-#pragma unroll
-        for (int u = 0; u < kSkinnyPerThread; ++u)
-          if (tid + u * kSkinnyThreads < total) E::Fma(acc[u], av[u], s_coef[x][col[u]]);
-      }
-    }
-    const unsigned long long cbase = g.c_off + (unsigned long long) item.row0 * n;
-    for (uint32_t d = 0; d < p.n_out; ++d) {
-      T *cb = static_cast<T *>(p.c_out[d]) + cbase;
-      const T *ci = static_cast<const T *>(p.c_in) + g.c_in_off + (unsigned long long) item.row0 * n;
+    // An item holds p.skinny_sub sub-chunks of about kSkinnyElems outputs: fetching the item / group / task descriptors is a
+    // chain of dependent global loads (microseconds), so it is paid once per item, and when all (pair, kk) terms of the block
+    // fit one table chunk -- every MPO-step block does -- the table is built once and reused by all sub-chunks.
+    const uint32_t sub_rows = uint32_t(kSkinnyElems) / n;
+    const uint32_t item_rows = min(sub_rows * p.skinny_sub, g.row_end - item.row0);
+    bool table_valid = false;      // the shared table holds ALL terms of this block
+    for (uint32_t sr = 0; sr < item_rows; sr += sub_rows) {
+      const uint32_t row_base = item.row0 + sr;
+      const uint32_t rows = min(sub_rows, item_rows - sr);
+      const uint32_t total = rows * n;
+      uint32_t row[kSkinnyPerThread], col[kSkinnyPerThread];
+      T acc[kSkinnyPerThread];
 #pragma unroll
       for (int u = 0; u < kSkinnyPerThread; ++u) {
         const uint32_t e = tid + u * kSkinnyThreads;
-        if constexpr (ACC) {
-          if (e < total) StoreOut(cb + e, AxpbyOut(p, acc[u], ci + e, g.beta_on != 0), p.mcast);
+        const uint32_t r = e / n;
+        row[u] = row_base + r; col[u] = e - r * n;
+        acc[u] = E::Zero();
+      }
+      // walk the group's (pair, kk) terms in chunks of kSkinnyTermChunk
+      uint32_t t = g.task_begin, kk0 = 0;
+      uint32_t nterm_kept = 0;
+      while (t < g.task_end) {
+        uint32_t nterm = 0;
+        if (!table_valid) {
+          __syncthreads();   // previous chunk (or previous item) fully consumed
+          // every thread walks the same short task list; thread x fills term x
+          uint32_t tt = t, kk = kk0;
+          while (tt < g.task_end && nterm < uint32_t(kSkinnyTermChunk)) {
+            const GemmTask tk = p.tasks[tt];
+            const uint32_t take = min(tk.k - kk, uint32_t(kSkinnyTermChunk) - nterm);
+            if (tid >= nterm && tid < nterm + take) {
+              const uint32_t k1 = kk + (tid - nterm);
+              const T *a = static_cast<const T *>((tk.flags & kTaskASrc) ? p.a_src : p.a_ws) + tk.a_off;
+              const T *b = static_cast<const T *>((tk.flags & kTaskBSrc) ? p.b_src : p.b_ws) + tk.b_off;
+              if (tk.flags & kTaskATrans) { s_ap[tid] = a + (unsigned long long) k1 * g.m; s_as[tid] = 1; }
+              else { s_ap[tid] = a + k1; s_as[tid] = tk.k; }
+              for (uint32_t j = 0; j < n; ++j) {
+                // B(k1, j): stored n x k (transposed), row-major k x n (b_run >= n: no division), or a strided view of the block
+                const T v = (tk.flags & kTaskBTrans) ? b[(unsigned long long) j * tk.k + k1]
+                            : tk.b_run >= n         ? b[(unsigned long long) k1 * tk.b_rs + j]
+                                                     : b[(unsigned long long) k1 * tk.b_rs + (j / tk.b_run) * tk.b_cs + j % tk.b_run];
+                s_coef[tid][j] = E::Signed(v, tk.sign);
+              }
+            }
+            nterm += take; kk += take;
+            if (kk >= tk.k) { ++tt; kk = 0; }
+          }
+          // first chunk reached the end of the task list: the table is complete and serves every sub-chunk of the item
+          if (t == g.task_begin && kk0 == 0 && tt >= g.task_end) { table_valid = true; s_nterm = nterm; }
+          t = tt; kk0 = kk;
+          __syncthreads();
         } else {
-          if (e < total) StoreOut(cb + e, acc[u], p.mcast);
+          nterm = nterm_kept = s_nterm;
+          t = g.task_end;
+        }
+#pragma unroll 1
+        for (uint32_t x = 0; x < nterm; ++x) {
+          const T *ap = s_ap[x];
+          const unsigned long long as = s_as[x];
+          T av[kSkinnyPerThread];
+#pragma unroll
+          for (int u = 0; u < kSkinnyPerThread; ++u)
+            if (tid + u * kSkinnyThreads < total) av[u] = ap[row[u] * as];
+#pragma unroll
+          for (int u = 0; u < kSkinnyPerThread; ++u)
+            if (tid + u * kSkinnyThreads < total) E::Fma(acc[u], av[u], s_coef[x][col[u]]);
+        }
+      }
+      (void) nterm_kept;
+      const unsigned long long cbase = g.c_off + (unsigned long long) row_base * n;
+      for (uint32_t d = 0; d < p.n_out; ++d) {
+        T *cb = static_cast<T *>(p.c_out[d]) + cbase;
+        const T *ci = static_cast<const T *>(p.c_in) + g.c_in_off + (unsigned long long) row_base * n;
+#pragma unroll
+        for (int u = 0; u < kSkinnyPerThread; ++u) {
+          const uint32_t e = tid + u * kSkinnyThreads;
+          if constexpr (ACC) {
+            if (e < total) StoreOut(cb + e, AxpbyOut(p, acc[u], ci + e, g.beta_on != 0), p.mcast);
+          } else {
+            if (e < total) StoreOut(cb + e, acc[u], p.mcast);
+          }
         }
       }
     }

@@ -347,12 +347,22 @@ std::string BuildTiles(PlanHost *h) {
   struct GInfo { uint32_t gi, tm, tn, stages; };
   std::vector<GInfo> dm;
   uint64_t total_stage_tiles = 0;
+  {   // narrow-pair items: how many sub-chunks each may hold while every resident CTA (4 per SM) still gets ~8 items
+    uint64_t chunks = 0;
+    for (const GemmGroup &g : h->part_groups) {
+      if (g.row_end <= g.row_begin || !Classify(h, g, 8).skinny) continue;
+      const uint32_t per = uint32_t(kSkinnyElems) / g.n;
+      chunks += (g.row_end - g.row_begin + per - 1) / per;
+    }
+    const uint64_t want_items = uint64_t(std::max(1, h->num_sms)) * 4 * 8;
+    h->skinny_sub = uint32_t(std::min<uint64_t>(kSkinnyMaxSub, std::max<uint64_t>(1, chunks / want_items)));
+  }
   for (uint32_t gi = 0; gi < h->part_groups.size(); ++gi) {
     const GemmGroup &g = h->part_groups[gi];
     if (g.row_end <= g.row_begin) continue;
     const uint32_t rows = g.row_end - g.row_begin;
     if (Classify(h, g, 8).skinny) {
-      const uint32_t per = uint32_t(kSkinnyElems) / g.n;   // rows per work item (n <= kSkinnyMaxN)
+      const uint32_t per = uint32_t(kSkinnyElems) / g.n * h->skinny_sub;   // rows per work item (n <= kSkinnyMaxN)
       for (uint32_t r = 0; r < rows; r += per) h->items.push_back({gi, g.row_begin + r});
       continue;
     }

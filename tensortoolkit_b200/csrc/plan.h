@@ -70,6 +70,7 @@ struct PlanHost {
   uint64_t n_part_slots = 0;                           // split-K partial-tile slots
   uint64_t part_slot_elems = 0;                        // elements per slot (BM x BN)
   std::vector<SkinnyItem> items;
+  uint32_t skinny_sub = 1;                             // sub-chunks per narrow-pair item (see kSkinnyMaxSub)
   double flops = 0;
   uint64_t permute_elems_a = 0, permute_elems_b = 0;
   uint64_t gemm_read_bytes = 0, gemm_write_bytes = 0;

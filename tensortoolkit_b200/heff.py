@@ -254,14 +254,14 @@ class ShardedChain:
 
     def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, dtype,
                  world: int, rank: int, group=None, flags: int = _lib.PLAN_DETERMINISTIC, exchange="auto", peers=None,
-                 host_input: str = None):
+                 host_input: str = None, pieces=None, snap: int = 8):
         """host_input: name of the operand that arrives from HOST memory every apply (apply_host): its device buffer is
         made exchangeable (symmetric memory / CUDA IPC) so that every rank uploads only 1/world of it."""
         import torch
         from .sharding import shard_chain
         self.torch, self.group = torch, group
         self.ctx, self.world, self.rank = ctx, world, rank
-        mine, self.info = shard_chain(tensors, steps, name, axis, world, rank, dtype)
+        mine, self.info = shard_chain(tensors, steps, name, axis, world, rank, dtype, pieces=pieces, snap=snap)
         self.dtype = np.dtype(dtype)
         tdt = torch.complex128 if self.dtype == np.complex128 else torch.float64
         dev = torch.device("cuda", ctx.device)

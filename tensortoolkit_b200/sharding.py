@@ -77,22 +77,32 @@ def sector_costs(tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: 
     return cost, shells, out_axis
 
 
-def row_line_cuts(cost: np.ndarray, degs: Sequence[int], world: int, snap: int = 8) -> List[List[Tuple[int, int]]]:
-    """Cut the line of rows (sector-major) into `world` segments of equal cost."""
+def line_pieces(cost: np.ndarray, degs: Sequence[int]) -> List[Tuple[int, int, int, float]]:
+    """The line of rows of the split index as pieces (sector, lo, hi, weight per row); initially one piece per sector,
+    weighted by the flops a row of that sector causes in the whole chain."""
+    return [(s, 0, int(d), (float(c) / int(d)) if d else 0.0) for s, (c, d) in enumerate(zip(cost, degs))]
+
+
+def cut_line(pieces, nsct: int, degs: Sequence[int], world: int, snap: int = 8) -> List[List[Tuple[int, int]]]:
+    """Cut the line of rows (sector-major) into `world` contiguous segments of equal weight.  Cuts are snapped to
+    multiples of `snap` rows inside a sector.  Returns [rank][sector] -> (lo, hi)."""
     degs = [int(d) for d in degs]
-    per_row = [c / d if d else 0.0 for c, d in zip(cost, degs)]
-    total = float(sum(cost))
-    # cumulative position -> (sector, row)
+    total = sum((hi - lo) * w for _, lo, hi, w in pieces)
+
     def locate(target):
         acc = 0.0
-        for s, d in enumerate(degs):
-            c = per_row[s] * d
+        for s, lo, hi, w in pieces:
+            c = (hi - lo) * w
             if acc + c > target and c > 0:
-                r = int(round((target - acc) / per_row[s] / snap)) * snap
-                return s, max(0, min(d, r))
+                r = lo + (target - acc) / w
+                r = int(round(r / snap)) * snap
+                return s, max(0, min(degs[s], r))
             acc += c
-        return len(degs), 0
-    cuts = [(0, 0)] + [locate(total * r / world) for r in range(1, world)] + [(len(degs), 0)]
+        return nsct, 0
+    cuts = [(0, 0)] + [locate(total * r / world) for r in range(1, world)] + [(nsct, 0)]
+    for i in range(1, len(cuts)):                      # snapping must not make the cuts run backwards
+        if cuts[i] < cuts[i - 1]:
+            cuts[i] = cuts[i - 1]
     out = []
     for r in range(world):
         (s0, r0), (s1, r1) = cuts[r], cuts[r + 1]
@@ -108,6 +118,38 @@ def row_line_cuts(cost: np.ndarray, degs: Sequence[int], world: int, snap: int =
                     hi = r1
             ranges.append((lo, max(lo, hi)))
         out.append(ranges)
+    return out
+
+
+def row_line_cuts(cost: np.ndarray, degs: Sequence[int], world: int, snap: int = 8) -> List[List[Tuple[int, int]]]:
+    """Cut the line of rows (sector-major) into `world` segments of equal cost."""
+    return cut_line(line_pieces(cost, degs), len(degs), degs, world, snap)
+
+
+def reweigh_pieces(pieces, ranges_per_rank, times_ms: Sequence[float]):
+    """Feedback step of the partitioner.  `times_ms[r]` = measured time of rank r's share under the cuts `ranges_per_rank`
+    (made from `pieces`).  Time is not proportional to flops -- tile quantisation, small sectors, the memory-bound steps --
+    so every rank's rows are re-weighted by (measured time / modelled weight) of that rank; cutting the re-weighted line
+    into equal parts moves rows from slow ranks to fast ones.  Returns the new pieces (split at the old cuts)."""
+    world = len(ranges_per_rank)
+    model = []
+    for r in range(world):
+        w = 0.0
+        for s, lo, hi, wt in pieces:
+            a, b = max(lo, ranges_per_rank[r][s][0]), min(hi, ranges_per_rank[r][s][1])
+            if b > a:
+                w += (b - a) * wt
+        model.append(w)
+    mean_t = float(np.mean([t for t, m in zip(times_ms, model) if m > 0])) or 1.0
+    mean_m = float(np.mean([m for m in model if m > 0])) or 1.0
+    out = []
+    for s, lo, hi, wt in pieces:
+        for r in range(world):
+            a, b = max(lo, ranges_per_rank[r][s][0]), min(hi, ranges_per_rank[r][s][1])
+            if b > a:
+                f = (times_ms[r] / mean_t) / (model[r] / mean_m) if model[r] > 0 else 1.0
+                out.append((s, a, b, wt * f))
+    out.sort(key=lambda p: (p[0], p[1]))
     return out
 
 
@@ -135,14 +177,17 @@ def restrict_tensor(t: BlockSparseTensor, axis: int, ranges: Sequence[Tuple[int,
 
 
 def shard_chain(tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, world: int, rank: int,
-                dtype=None) -> Tuple[Dict[str, BlockSparseTensor], ShardInfo]:
-    """Returns this rank's operand set (only `name` differs) and the slab map of every rank."""
+                dtype=None, pieces=None, snap: int = 8) -> Tuple[Dict[str, BlockSparseTensor], ShardInfo]:
+    """Returns this rank's operand set (only `name` differs) and the slab map of every rank.  `pieces`: a re-weighted row
+    line from reweigh_pieces (measured feedback); default = rows weighted by their flops."""
     dtype = dtype or tensors[name].dtype
     cost, shells, out_axis = sector_costs(tensors, steps, name, axis, dtype)
     if out_axis != 0:
         raise ValueError("the split index must end up as the first index of the result (row slabs must be contiguous)")
     degs = tensors[name].indexes[axis].degs()
-    ranges = row_line_cuts(cost, degs, world)
+    if pieces is None:
+        pieces = line_pieces(cost, degs)
+    ranges = cut_line(pieces, len(degs), degs, world, snap)
     full_out = shells[steps[-1][3]]
     per_row = [c / d if d else 0.0 for c, d in zip(cost, degs)]
     total = float(cost.sum()) or 1.0
@@ -162,7 +207,9 @@ def shard_chain(tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: i
         share.append(sum(per_row[s] * (hi - lo) for s, (lo, hi) in enumerate(ranges[r])) / total)
     mine = dict(tensors)
     mine[name] = restrict_tensor(tensors[name], axis, ranges[rank])
-    return mine, ShardInfo(world, rank, ranges, slabs, local_elems, int(full_out.data.size), share)
+    info = ShardInfo(world, rank, ranges, slabs, local_elems, int(full_out.data.size), share)
+    info.pieces = pieces
+    return mine, info
 
 
 def shard_heff_tensors(tensors, world, rank):

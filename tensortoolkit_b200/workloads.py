@@ -23,6 +23,20 @@ HEFF_STEPS = [  # (lhs, rhs, axes, out)
 ]
 
 
+# The same apply with the two MPO tensors pre-contracted into one two-site operator (they are static across the applies of a
+# Lanczos run):  w12 = Contract(mpo1, mpo2, {{3},{0}}) = [wb IN, ph IN, ph OUT, ph IN, ph OUT, wb OUT], and the two
+# memory-bound MPO steps become ONE pass over the rank-5 intermediate:
+#     t3 = Contract(t1, w12, {{0,2,3},{0,1,3}})      # (a2, b) ++ (p1', p2', w'') -- exactly t3's index order above
+# It is the matrix-free MPO application of SURVEY.md section 8f rank 4 expressed with the contraction machinery: t1 blocks
+# are read in place (stored k x m), w12 blocks are <= 3 x 3 coefficient matrices, the narrow-pair kernel does the rest.
+HEFF_FUSE_PREP = ("mpo1", "mpo2", ([3], [0]), "w12")
+HEFF_STEPS_FUSED = [
+    ("lenv", "psi", ([0], [0]), "t1"),
+    ("t1", "w12", ([0, 2, 3], [0, 1, 3]), "t3"),
+    ("t3", "renv", ([4, 1], [1, 0]), "out"),
+]
+
+
 def gaussian_degeneracies(weights: List[float], D: int, centre: int) -> List[int]:
     """degeneracy_j = max(1, floor(D * g_j / sum g)), remainder added to the centre sector."""
     tot = sum(weights)
