@@ -328,6 +328,28 @@ int qlb200_ipc_export(qlb200_ctx *ctx, const void *dev_ptr, unsigned char *handl
 int qlb200_ipc_open(qlb200_ctx *ctx, const unsigned char *handle64, void **peer_ptr);
 int qlb200_ipc_close(qlb200_ctx *ctx, void *peer_ptr);
 
+/* ---- multi-GPU plumbing without torch / NCCL: symmetric buffers, multicast mapping, device barrier -------------- */
+/* One communicator per rank (a process, or a thread driving its own context) of ONE NVLink domain, world <= 8.  The only
+ * thing the caller supplies is an all-gather of a few bytes for the bootstrap -- MPI_Allgather in a TensorToolkit program
+ * (the reference distributes its DMRG mat-vec over MPI ranks, dmrg/contract_1sector.h:181-228), torch.distributed in the
+ * Python harness, a std::barrier in a threaded test: gather `bytes` from every rank into recv[world * bytes], return 0. */
+typedef int (*qlb200_allgather_fn)(void *user, const void *send, void *recv, size_t bytes);
+typedef struct qlb200_comm qlb200_comm;
+int qlb200_comm_create(qlb200_ctx *ctx, int32_t world, int32_t rank, qlb200_allgather_fn allgather, void *user, qlb200_comm **out);
+void qlb200_comm_destroy(qlb200_comm *c);      /* collective */
+int qlb200_comm_has_multicast(const qlb200_comm *c);
+/* Collective: a buffer of `bytes` on every rank (CUDA virtual-memory management; handles travel as file descriptors over
+ * abstract unix sockets).  local = this rank's buffer; peers[world] = every rank's buffer mapped into this process
+ * (unicast loads / stores over NVLink; peers[rank] == local), for qlb200_execute_bcast / qlb200_fanout_copy; multicast, if
+ * not NULL on entry, receives the NVSwitch multicast mapping of all of them (NULL when the fabric has none), for
+ * qlb200_execute_mcast.  Zero-filled. */
+int qlb200_comm_alloc(qlb200_comm *c, size_t bytes, void **local, void **peers, void **multicast);
+int qlb200_comm_free(qlb200_comm *c, void *local);     /* collective */
+/* Device-side barrier on the context's stream (a one-block kernel exchanging epochs through peer memory with system-scope
+ * release / acquire): everything every rank enqueued before it -- e.g. the peer stores of a GEMM epilogue -- is visible to
+ * everything any rank enqueues after it.  No host synchronisation; legal under stream capture. */
+int qlb200_comm_barrier(qlb200_comm *c);
+
 /* ---- CUDA graphs: replay a fixed sequence of executes (one Lanczos mat-vec) with one launch ---- */
 /* Everything enqueued on the context's stream between begin and end -- this library's kernels and foreign work
  * such as an NCCL collective or a symmetric-memory barrier -- is captured (relaxed mode) instead of executed;

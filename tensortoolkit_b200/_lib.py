@@ -69,6 +69,9 @@ class AccumStats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
 class Unit(C.Structure):
     _fields_ = [("group", C.c_uint32), ("tm", C.c_uint32), ("tn", C.c_uint32), ("s_begin", C.c_uint32), ("s_end", C.c_uint32),
                 ("split", C.c_uint32), ("nsplit", C.c_uint32), ("rows", C.c_uint32), ("cols", C.c_uint32)]
@@ -157,6 +160,12 @@ SYMBOLS = {
     "qlb200_graph_end": (C.c_int, [_P, _PP]),
     "qlb200_graph_launch": (C.c_int, [_P, _P]),
     "qlb200_graph_destroy": (None, [_P]),
+    "qlb200_comm_create": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _PP]),
+    "qlb200_comm_destroy": (None, [_P]),
+    "qlb200_comm_has_multicast": (C.c_int, [_P]),
+    "qlb200_comm_alloc": (C.c_int, [_P, C.c_size_t, _PP, _PP, _PP]),
+    "qlb200_comm_free": (C.c_int, [_P, _P]),
+    "qlb200_comm_barrier": (C.c_int, [_P]),
     "qlb200_fanout_copy": (C.c_int, [_P, _P, C.c_uint64, C.c_uint64, _PP, C.c_int32, _P]),
     "qlb200_plan_remap_output": (C.c_int, [_P, C.c_uint64, _U64P, _U64P]),
     "qlb200_ipc_export": (C.c_int, [_P, _P, C.c_char_p]),

@@ -126,6 +126,10 @@ size_t WsBytes(const qlb200_plan *p) {
 
 }  // namespace
 
+namespace qlb200 {
+int FailWith(int code, const std::string &msg) { return Fail(code, msg); }   // for the other translation units (comm.cu)
+}
+
 void qlb200::DeviceTables::Free() {
   cudaFree(perm_blks); cudaFree(perm_tile_base); cudaFree(tasks); cudaFree(groups); cudaFree(tiles);
   cudaFree(items); cudaFree(counters); cudaFree(seg);

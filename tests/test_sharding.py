@@ -268,3 +268,19 @@ def test_plan_reads_heff_blocks_in_place():
             p.close()
     assert moved_default == 0
     assert moved_all > 0
+
+
+@pytest.mark.gpu
+def test_comm_ranks_through_the_c_abi_only():
+    """tests/cpp/comm_ranks: N threads, one GPU each, NO torch / NCCL / Python in the data path -- qlb200_comm_* (symmetric
+    buffers over CUDA VMM, fd passing over unix sockets, multicast mapping, device barrier), qlb200_fanout_copy,
+    qlb200_plan_partition + qlb200_execute_bcast / _mcast.  One rank where the box has one GPU, all of them otherwise."""
+    import subprocess
+    import torch
+    exe = os.path.join(os.path.dirname(__file__), "cpp", "comm_ranks")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cpp/comm_ranks not built (make -C tensortoolkit_b200/csrc comm_test)")
+    n = min(torch.cuda.device_count(), 8)
+    for world in sorted({1, min(n, 2), n}):
+        out = subprocess.run([exe, str(world)], capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "PASS" in out.stdout, out.stdout + out.stderr
