@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-steps", type=int, default=3, help="GPU arm: timed applies of the cpu_baseline child")
     ap.add_argument("--write-out", default="", help="reference arm: write the result tensor of the apply to this file (the reference's stream format)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--plumbing", default="capi", choices=["capi", "torch"],
+                    help="N>1: symmetric buffers / multicast mapping / barrier from qlb200_comm_* (C ABI, default) or from torch symmetric memory + CUDA IPC")
     ap.add_argument("--rebalance", type=int, default=2, help="N>1: feedback iterations of the row partitioner (measure every rank's share, re-weigh, cut again)")
     ap.add_argument("--snap", type=int, default=8, help="N>1: row cuts inside a sector are multiples of this")
     ap.add_argument("--no-sub-records", action="store_true", help="default run only: skip the sub-records for BASELINE configs[1], [3] and [4]")
@@ -401,7 +403,7 @@ def measure_heff(args, env):
         from tensortoolkit_b200.heff import ShardedChain
         with torch.cuda.stream(stream):
             sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags,
-                                   exchange=args.exchange, host_input="psi")
+                                   exchange=args.exchange, host_input="psi", snap=args.snap, plumbing=args.plumbing)
         # partitioner feedback: time every rank's share, re-weigh the row line by (measured time / modelled flops) per rank,
         # cut again (sharding.reweigh_pieces) -- an autotuning step at set-up, like the planner's split-K simulation
         rebalance_log = []
@@ -429,7 +431,7 @@ def measure_heff(args, env):
             sharded.close()
             with torch.cuda.stream(stream):
                 sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags,
-                                       exchange=args.exchange, host_input="psi", pieces=pieces, snap=args.snap)
+                                       exchange=args.exchange, host_input="psi", pieces=pieces, snap=args.snap, plumbing=args.plumbing)
         chain = sharded.chain
         apply_fn = sharded.apply
     else:
@@ -732,7 +734,7 @@ def measure_heff(args, env):
         "warmup": max(3, args.warmup), "ms_per_step": tot_ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "c64(f64 pairs)" if dtype == "c128" else "f64", "data": "files" if args.tensors else "synthetic",
         "config": {"workload": (f"H_eff apply on tensors read from {args.tensors} ({args.qn})" if args.tensors else workload_name(args.D, dtype, args.workload)), "l2": "512 MiB flush written between timed applies; operands+intermediates (>1 GB) exceed the 126 MB L2",
-                   "parallelism": (f"output-sector/row-slab x{world}, exchange={sharded.exchange}" + {"fused": " (unicast peer stores over NVLink from the GEMM epilogue)", "multicast": " (multimem.st from the GEMM epilogue, replicated by the NVSwitch)"}.get(sharded.exchange, " (NCCL)")) if world > 1 else "single GPU", "flops_per_step": flops_total,
+                   "parallelism": (f"output-sector/row-slab x{world}, exchange={sharded.exchange}" + {"fused": " (unicast peer stores over NVLink from the GEMM epilogue)", "multicast": " (multimem.st from the GEMM epilogue, replicated by the NVSwitch)"}.get(sharded.exchange, " (NCCL)") + f"; buffers + barrier: {'qlb200_comm (C ABI)' if sharded.comm is not None else 'torch symmetric memory / IPC'}") if world > 1 else "single GPU", "flops_per_step": flops_total,
                    "tasks_per_step": int(sum(s.ntask for s in stats)),
                    "launch": "one CUDA graph replay per apply" if graph is not None else "one host launch per kernel"},
         "pct_fp64_peak": 100.0 * value / 1e3 / peak_burst / world, "fp64_peak_tflops": {"burst": peak_burst, "sustained": peak_sust, "how": peak_how},
@@ -1082,6 +1084,12 @@ def main():
     else:
         run_ours(args)
     sys.stdout.flush()
+    try:                                  # leave the NCCL process group cleanly (N > 1)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

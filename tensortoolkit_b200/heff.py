@@ -189,6 +189,52 @@ class ContractionChain:
         self.plans, self.matches, self.buf = [], [], {}
 
 
+class Comm:
+    """qlb200_comm: symmetric buffers (unicast peer pointers + NVSwitch multicast mapping) and the device-side barrier, all
+    behind the C ABI.  The only thing taken from torch is the bootstrap all-gather of a few bytes (the callback a
+    TensorToolkit program would implement with MPI_Allgather)."""
+
+    def __init__(self, ctx: Context, world: int, rank: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.world, self.rank = ctx, world, rank
+        dev = torch.device("cuda", ctx.device)
+
+        def allgather(user, send, recv, nbytes):
+            try:
+                mine = torch.frombuffer(bytearray(C.string_at(send, nbytes)), dtype=torch.uint8).to(dev)
+                outs = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(outs, mine, group=group)
+                data = b"".join(bytes(o.cpu().numpy().tobytes()) for o in outs)
+                C.memmove(recv, data, len(data))
+                return 0
+            except Exception as e:      # never let an exception cross the C boundary
+                import sys
+                print(f"qlb200 all-gather callback failed: {e}", file=sys.stderr)
+                return 1
+        self._cb = _lib.ALLGATHER_FN(allgather)           # keep alive as long as the communicator
+        h = C.c_void_p()
+        check(lib.qlb200_comm_create(ctx.h, world, rank, C.cast(self._cb, C.c_void_p) if world > 1 else None, None, C.byref(h)), "qlb200_comm_create")
+        self.h = h
+        self.has_multicast = bool(lib.qlb200_comm_has_multicast(h))
+
+    def alloc(self, nbytes: int):
+        """Collective.  Returns (local pointer, [pointer of every rank's buffer, own first], multicast pointer or 0)."""
+        local, mc = C.c_void_p(), C.c_void_p()
+        peers = (C.c_void_p * self.world)()
+        check(lib.qlb200_comm_alloc(self.h, nbytes, C.byref(local), peers, C.byref(mc)), "qlb200_comm_alloc")
+        order = [int(peers[self.rank])] + [int(peers[p]) for p in range(self.world) if p != self.rank]
+        return int(local.value), order, int(mc.value or 0)
+
+    def barrier(self):
+        check(lib.qlb200_comm_barrier(self.h), "qlb200_comm_barrier")
+
+    def close(self):
+        if self.h:
+            lib.qlb200_comm_destroy(self.h)
+            self.h = None
+
+
 class _IdleChain:
     """Stand-in for a rank whose share of the split index is empty (world larger than the number of cuttable row
     groups): no plans, no launches -- the rank still takes part in the exchange barrier."""
@@ -254,7 +300,7 @@ class ShardedChain:
 
     def __init__(self, ctx: Context, tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: int, dtype,
                  world: int, rank: int, group=None, flags: int = _lib.PLAN_DETERMINISTIC, exchange="auto", peers=None,
-                 host_input: str = None, pieces=None, snap: int = 8):
+                 host_input: str = None, pieces=None, snap: int = 8, plumbing: str = "capi"):
         """host_input: name of the operand that arrives from HOST memory every apply (apply_host): its device buffer is
         made exchangeable (symmetric memory / CUDA IPC) so that every rank uploads only 1/world of it."""
         import torch
@@ -279,11 +325,22 @@ class ShardedChain:
         self.idle = self.info.local_elems[rank] == 0
         external = {self.out_name: self.local.data_ptr()}
         self.host_input, self.in_symm, self.in_mc, self.in_peers, self.in_buf = host_input, None, 0, None, None
+        # plumbing="capi" (default): symmetric buffers, multicast mapping and barrier come from qlb200_comm_* (no torch
+        # symmetric memory, no CUDA IPC, no NCCL call per apply); "torch": the round-1 path kept for comparison
+        self.comm = None
+        use_capi = plumbing == "capi" and world > 1 and peers is None and exchange in ("auto", "multicast", "fused")
+        if use_capi:
+            self.comm = Comm(ctx, world, rank, group)
+            if exchange == "multicast" and not self.comm.has_multicast:
+                raise RuntimeError("exchange='multicast': this NVLink domain offers no multicast (NVLS) mapping")
         if host_input is not None:
             t_in = tensors[host_input]
             self.in_bytes = t_in.data.size * self.dtype.itemsize
             nb = max((self.in_bytes + 255) & ~255, 256)
-            if exchange in ("auto", "multicast") and world > 1 and peers is None:
+            if use_capi:
+                self.in_ptr, self.in_peers, mc = self.comm.alloc(nb)
+                self.in_mc = mc if exchange != "fused" else 0
+            elif exchange in ("auto", "multicast") and world > 1 and peers is None:
                 import torch.distributed._symmetric_memory as symm_mem
                 grp = group if group is not None else torch.distributed.group.WORLD
                 with torch.cuda.device(dev):
@@ -304,7 +361,17 @@ class ShardedChain:
         self.parity = 0                                      # replica the NEXT apply writes
         self.full_base = None
         self.symm = None
-        if exchange in ("auto", "multicast") and world > 1 and peers is None:
+        if use_capi:
+            self.full_base, order, mc = self.comm.alloc(2 * self.full_bytes)
+            my = self.info.slabs[rank]
+            if not self.idle:
+                self.chain.plans[-1].remap_output([s.local_offset for s in my], [s.full_offset for s in my])
+            if mc and exchange != "fused":
+                exchange, self.mc_base = "multicast", mc
+            else:
+                exchange, self.peer_ptrs = "fused", order
+                self.flag = None
+        elif exchange in ("auto", "multicast") and world > 1 and peers is None:
             import torch.distributed._symmetric_memory as symm_mem
             grp = group if group is not None else torch.distributed.group.WORLD
             with torch.cuda.device(dev):
@@ -324,7 +391,7 @@ class ShardedChain:
         elif exchange == "auto":
             exchange = "fused"
         self.exchange = exchange
-        if exchange == "multicast":
+        if exchange == "multicast" or use_capi:
             pass
         elif exchange == "fused":
             # the full result lives in a cudaMalloc'ed buffer of its own so that it can be exported over CUDA IPC
@@ -398,7 +465,7 @@ class ShardedChain:
                 ch.plans[-1].execute_mcast(ch.buf[lhs].ptr, ch.buf[rhs].ptr, self.mc_base + off)
                 n += self.ctx.launch_count()
             mark("compute")
-            self.symm.barrier()      # every rank's tiles have landed in every replica
+            self._barrier()          # every rank's tiles have landed in every replica
             mark("exchange")
             return n
         if self.exchange == "fused":
@@ -411,8 +478,8 @@ class ShardedChain:
                 ch.plans[-1].execute_bcast(ch.buf[lhs].ptr, ch.buf[rhs].ptr, [p + off for p in self.peer_ptrs])
                 n += self.ctx.launch_count()
             mark("compute")
-            if self.world > 1 and self.opened:
-                self.torch.distributed.all_reduce(self.flag, group=self.group)    # barrier: every peer's tiles have landed
+            if self.world > 1 and (self.opened or self.comm is not None):
+                self._barrier()      # every peer's tiles have landed
             mark("exchange")
             return n
         n = ch.apply_device()
@@ -427,6 +494,18 @@ class ShardedChain:
               "qlb200_copy_execute")
         mark("exchange")
         return n + 1
+
+    def _barrier(self):
+        """Barrier across the ranks on the context's stream: qlb200_comm_barrier (device-side epochs through peer memory),
+        or with plumbing='torch' the symmetric-memory signal-pad barrier / a one-element NCCL all-reduce."""
+        if self.comm is not None:
+            self.comm.barrier()
+        elif self.symm is not None:
+            self.symm.barrier()
+        elif self.in_symm is not None:
+            self.in_symm.barrier()
+        else:
+            self.torch.distributed.all_reduce(self.flag, group=self.group)
 
     @property
     def full_ptr(self) -> int:
@@ -487,10 +566,7 @@ class ShardedChain:
                 else:
                     arr = (C.c_void_p * len(self.in_peers))(*self.in_peers)
                     check(lib.qlb200_fanout_copy(self.ctx.h, C.c_void_p(self.in_ptr), lo * es, nbytes, arr, len(self.in_peers), None), "fanout")
-            if self.in_symm is not None:
-                self.in_symm.barrier()
-            else:
-                self.torch.distributed.all_reduce(self.flag, group=self.group)
+            self._barrier()
         else:
             check(lib.qlb200_memcpy_h2d(self.ctx.h, C.c_void_p(self.in_ptr), host_in.ctypes.data, host_in.nbytes), "h2d")
         n_launch = (apply_fn or self.apply)()
@@ -513,6 +589,9 @@ class ShardedChain:
         if self.in_buf is not None:
             self.in_buf.free()
             self.in_buf = None
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
         if self.cplan:
             lib.qlb200_tplan_destroy(self.cplan)
             self.cplan = None
