@@ -3,7 +3,7 @@
 N=$1; shift
 mkdir -p gpurun_out
 tag=${TAG:-n$N}
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --breakdown "$@" > gpurun_out/r2_bench_$tag.json 2> gpurun_out/r2_bench_$tag.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 --breakdown "$@" > gpurun_out/r2_bench_$tag.json 2> gpurun_out/r2_bench_$tag.err
 echo "rc=$?"
 tail -c 3000 gpurun_out/r2_bench_$tag.err
 python - <<PY

@@ -1325,7 +1325,7 @@ int qlb200_tplan_create(qlb200_ctx *ctx, const qlb200_shell *t, const int32_t *p
     p->scale[i] = static_cast<int8_t>(sign);
     if (s.size[b] >= (1ull << 32)) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, "block with 2^32 or more elements"); }
     uint64_t nt = 0;
-    PermBlk d = MakePermBlk(r, &s.shape[b * r], perm, s.offset[b], off, 0, float(sign), &nt);
+    PermBlk d = MakePermBlk(r, &s.shape[b * r], perm, s.offset[b], off, 0, float(sign), &nt, int(ElemSize(dtype)));
     if (p->perm_tile_base.back() + nt >= (1ull << 32)) { delete p; return Fail(QLB200_ERR_UNSUPPORTED, "too many permute tiles"); }
     p->perm_blks.push_back(d);
     p->perm_tile_base.push_back(static_cast<uint32_t>(p->perm_tile_base.back() + nt));

@@ -33,6 +33,9 @@ struct PermBlk {
   uint32_t txi_log2, txo_log2;          // log2 of the thread-row width used in the load / store phase
   uint32_t src_sel;                     // 0 = operand A buffer, 1 = operand B buffer
   float scale;                          // +1 / -1 (fermionic whole-tensor transpose), applied on the fly
+  uint32_t bulk;                        // run mode only: every run is 16-byte aligned on both sides and needs no scaling, so the
+                                        // tile moves as bulk asynchronous copies (cp.async.bulk, SASS UBLKCP): TO pieces
+                                        // global -> shared completing on an mbarrier, then one shared -> global copy per run
   uint32_t vec;                         // 0, or V = ext[nd-1]: "run" mode -- the fastest axis is the same on both sides but
                                         // short (V elements); the tile is then a 2-D transposition of V-element runs:
                                         // jin = source-next-fastest axis (source stride V, tiled by TI), jout = nd-2

@@ -33,6 +33,9 @@
 //     order (the parity bar is a relative Frobenius error <= 1e-12, tests/test_parity_gpu.py).
 #include "common.cuh"
 #include "ws_common.cuh"
+#ifndef QLB200_WS_FULLSTAGE
+#define QLB200_WS_FULLSTAGE 1
+#endif
 
 
 namespace qlb200 {
@@ -73,93 +76,127 @@ struct FragAddr {
   uint32_t b_sw, b_x;       //    + ((ks ^ b_x) * b_sw)                   (transposed B: swizzled k4 groups; b_ks = 0)
 };
 
-// Two k4 steps (k4 groups KS0, KS0+1 of the stage) of a warp's sub-tile: MT valid m8 row groups x NT valid
-// n8 column groups.  Specialised at compile time so that skipped MMAs are not even issued.
+// One k4 step of a warp's sub-tile: MT valid m8 row groups x NT valid n8 column groups, fragments at pa + i * a_i and
+// pb + j * b_j.  Specialised at compile time so that skipped MMAs are not even issued; with compile-time strides (the
+// full-tile path below) every fragment load is a base register + immediate.
 // acc[0] / acc[1] = real / imaginary sums (4M);  acc[0..2] = P1, P2, P3 (3M).
-template<class CFG, int MT, int NT, int KS0>
-__device__ __forceinline__ void ComputeStage(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f, uint32_t smask) {
+// The pair's sign is NOT applied here: the consumer keeps the accumulators in the sign frame of the current pair
+// (NegateAcc on a change of sign, bit-identical to negating the A fragments: fma(-a, b, c) = -fma(a, b, -c)).
+template<class CFG, int MT, int NT>
+__device__ __forceinline__ void KStep(double (&acc)[CFG::NACC][4][CFG::NT][2], const double2 *pa, uint32_t a_i, const double2 *pb, uint32_t b_j) {
+  if constexpr (CFG::k3M) {
+    double as[MT], ai[MT], ar[MT];
+    double br[NT], bs[NT], bi[NT];
 #pragma unroll
-  for (int ks = KS0; ks < KS0 + 2; ++ks) {
-    const double2 *pa = f.a + ks * f.a_ks;
-    const double2 *pb = f.b + ks * f.b_ks + ((uint32_t(ks) ^ f.b_x) * f.b_sw);
-    if constexpr (CFG::k3M) {
-      double as[MT], ai[MT], ar[MT];
-      double br[NT], bs[NT], bi[NT];
+    for (int i = 0; i < MT; ++i) {
+      const double2 a = pa[i * a_i];
+      ar[i] = a.x; ai[i] = a.y; as[i] = a.x + a.y;
+    }
 #pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        const double2 a = pa[i * f.a_i];
-        as[i] = FlipSign(a.x + a.y, smask);
-        ai[i] = FlipSign(a.y, smask);
-        ar[i] = FlipSign(a.x, smask);
-      }
+    for (int j = 0; j < NT; ++j) {
+      const double2 b = pb[j * b_j];
+      br[j] = b.x; bi[j] = b.y; bs[j] = b.x + b.y;
+    }
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) DmmaNv(acc[0][i][j][0], acc[0][i][j][1], ar[i], br[j]);
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) DmmaNv(acc[1][i][j][0], acc[1][i][j][1], ai[i], bi[j]);
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) DmmaNv(acc[2][i][j][0], acc[2][i][j][1], as[i], bs[j]);
+  } else {
+    double ax[MT], ay[MT], nay[MT];
+    double2 b[NT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      const double2 a = pa[i * a_i];
+      ax[i] = a.x; ay[i] = a.y; nay[i] = FlipSign(a.y, 0x80000000u);
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) b[j] = pb[j * b_j];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        const double2 b = pb[j * f.b_j];
-        br[j] = b.x; bi[j] = b.y; bs[j] = b.x + b.y;
+        DmmaNv(acc[0][i][j][0], acc[0][i][j][1], ax[i], b[j].x);
+        DmmaNv(acc[1][i][j][0], acc[1][i][j][1], ax[i], b[j].y);
       }
 #pragma unroll
-      for (int i = 0; i < MT; ++i)
+    for (int i = 0; i < MT; ++i)
 #pragma unroll
-        for (int j = 0; j < NT; ++j) DmmaNv(acc[0][i][j][0], acc[0][i][j][1], ar[i], br[j]);
-#pragma unroll
-      for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j) DmmaNv(acc[1][i][j][0], acc[1][i][j][1], ai[i], bi[j]);
-#pragma unroll
-      for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j) DmmaNv(acc[2][i][j][0], acc[2][i][j][1], as[i], bs[j]);
-    } else {
-      double ax[MT], ay[MT], nay[MT];
-      double2 b[NT];
-#pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        const double2 a = pa[i * f.a_i];
-        ax[i] = FlipSign(a.x, smask);
-        ay[i] = FlipSign(a.y, smask);
-        nay[i] = FlipSign(a.y, smask ^ 0x80000000u);
+      for (int j = 0; j < NT; ++j) {
+        DmmaNv(acc[0][i][j][0], acc[0][i][j][1], nay[i], b[j].y);
+        DmmaNv(acc[1][i][j][0], acc[1][i][j][1], ay[i], b[j].x);
       }
-#pragma unroll
-      for (int j = 0; j < NT; ++j) b[j] = pb[j * f.b_j];
-#pragma unroll
-      for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          DmmaNv(acc[0][i][j][0], acc[0][i][j][1], ax[i], b[j].x);
-          DmmaNv(acc[1][i][j][0], acc[1][i][j][1], ax[i], b[j].y);
-        }
-#pragma unroll
-      for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          DmmaNv(acc[0][i][j][0], acc[0][i][j][1], nay[i], b[j].y);
-          DmmaNv(acc[1][i][j][0], acc[1][i][j][1], ay[i], b[j].x);
-        }
-    }
   }
 }
 
+// Two k4 steps (k4 groups KS0, KS0+1 of the stage) of a ragged sub-tile, run-time strides.
+template<class CFG, int MT, int NT, int KS0>
+__device__ __forceinline__ void ComputeStage(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f) {
+#pragma unroll
+  for (int ks = KS0; ks < KS0 + 2; ++ks)
+    KStep<CFG, MT, NT>(acc, f.a + ks * f.a_ks, f.a_i, f.b + ks * f.b_ks + ((uint32_t(ks) ^ f.b_x) * f.b_sw), f.b_j);
+}
+
+// A whole stage (CFG::BK / 4 k4 steps) of a full sub-tile with the operand layouts known at compile time: the common case
+// (interior tiles of large blocks), one straight-line run of MMAs per stage, no address arithmetic between them.
+template<class CFG, bool AT, bool BT>
+__device__ __forceinline__ void ComputeFullStage(double (&acc)[CFG::NACC][4][CFG::NT][2], const double2 *tileA, const double2 *tileB,
+                                                 int q, int g4, int t4) {
+  constexpr int WBK = CFG::BK, WLDA = Lay<CFG>::WLDA, WLDB = Lay<CFG>::WLDB;
+  constexpr uint32_t a_i = AT ? 8 : 8 * WLDA, a_ks = AT ? 4 * WLDAT : 4;
+  constexpr uint32_t b_j = BT ? 32 * WBK : 32, b_ks = BT ? 4 : 4 * WLDB;
+  const double2 *pa = tileA + (AT ? t4 * WLDAT + g4 : g4 * WLDA + t4);
+  const double2 *pb = tileB + (BT ? (q * 8 + g4) * WBK + t4 : t4 * WLDB + q * 8 + g4);
+  // transposed B: the k4 groups of odd rows are swapped in pairs (k ^ 4 * (n & 1)); even steps then sit 4 * (g4 & 1) elements
+  // further, odd steps as many elements earlier -- two lane-constant bases, immediates for everything else
+  const int sw = BT ? 4 * (g4 & 1) : 0;
+  const double2 *pb_even = pb + sw, *pb_odd = pb - sw;
+#pragma unroll
+  for (int ks = 0; ks < WBK / 4; ++ks)
+    KStep<CFG, 4, CFG::NT>(acc, pa + ks * a_ks, a_i, ((ks & 1) ? pb_odd : pb_even) + ks * b_ks, b_j);
+}
+
+template<class CFG>
+__device__ __forceinline__ void NegateAcc(double (&acc)[CFG::NACC][4][CFG::NT][2]) {
+#pragma unroll
+  for (int a = 0; a < CFG::NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < CFG::NT; ++j) {
+        acc[a][i][j][0] = -acc[a][i][j][0];
+        acc[a][i][j][1] = -acc[a][i][j][1];
+      }
+}
+
 template<class CFG, int MT, int KS0>
-__device__ __forceinline__ void ComputeStageN(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f, uint32_t smask, int nt) {
-  if constexpr (CFG::NT >= 4) { if (nt == 4) { ComputeStage<CFG, MT, 4, KS0>(acc, f, smask); return; } }
+__device__ __forceinline__ void ComputeStageN(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f, int nt) {
+  if constexpr (CFG::NT >= 4) { if (nt == 4) { ComputeStage<CFG, MT, 4, KS0>(acc, f); return; } }
   switch (nt) {
-    case 3: ComputeStage<CFG, MT, 3, KS0>(acc, f, smask); break;
-    case 2: ComputeStage<CFG, MT, 2, KS0>(acc, f, smask); break;
-    case 1: ComputeStage<CFG, MT, 1, KS0>(acc, f, smask); break;
+    case 3: ComputeStage<CFG, MT, 3, KS0>(acc, f); break;
+    case 2: ComputeStage<CFG, MT, 2, KS0>(acc, f); break;
+    case 1: ComputeStage<CFG, MT, 1, KS0>(acc, f); break;
     default: break;
   }
 }
 
 template<class CFG, int KS0>
-__device__ __forceinline__ void ComputeHalf(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f, uint32_t smask, int mt, int nt) {
+__device__ __forceinline__ void ComputeHalf(double (&acc)[CFG::NACC][4][CFG::NT][2], const FragAddr &f, int mt, int nt) {
   if (mt == 4 && nt == CFG::NT) {
-    ComputeStage<CFG, 4, CFG::NT, KS0>(acc, f, smask);
+    ComputeStage<CFG, 4, CFG::NT, KS0>(acc, f);
   } else {
     switch (mt) {
-      case 4: ComputeStageN<CFG, 4, KS0>(acc, f, smask, nt); break;
-      case 3: ComputeStageN<CFG, 3, KS0>(acc, f, smask, nt); break;
-      case 2: ComputeStageN<CFG, 2, KS0>(acc, f, smask, nt); break;
-      default: ComputeStageN<CFG, 1, KS0>(acc, f, smask, nt); break;
+      case 4: ComputeStageN<CFG, 4, KS0>(acc, f, nt); break;
+      case 3: ComputeStageN<CFG, 3, KS0>(acc, f, nt); break;
+      case 2: ComputeStageN<CFG, 2, KS0>(acc, f, nt); break;
+      default: ComputeStageN<CFG, 1, KS0>(acc, f, nt); break;
     }
   }
 }
@@ -287,6 +324,7 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
       uint32_t sidx = 0;     // stage index of the current pair's first stage in the group's concatenated k loop
       for (uint32_t t = g.task_begin; t < g.task_end && sidx < tile.s_end; ++t) {
         const GemmTask task = p.tasks[t];
+        const int next_sign = t + 1 < g.task_end ? p.tasks[t + 1].sign : 0;
         const uint32_t nst = (task.k + WBK - 1) / WBK;
         const uint32_t st_lo = max(sidx, tile.s_begin), st_hi = min(sidx + nst, tile.s_end);
         const uint32_t st_base = sidx;
@@ -295,7 +333,10 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
         const double2 *aBase = static_cast<const double2 *>((task.flags & kTaskASrc) ? p.a_src : p.a_ws) + task.a_off;
         const double2 *bBase = static_cast<const double2 *>((task.flags & kTaskBSrc) ? p.b_src : p.b_ws) + task.b_off;
         const bool ta = (task.flags & kTaskATrans) != 0, tb = (task.flags & kTaskBTrans) != 0;
-        const uint32_t tflags = extents | (task.sign < 0 ? kFlagNeg : 0u) | (ta ? kFlagATrans : 0u) | (tb ? kFlagBTrans : 0u);
+        const uint32_t tflags = extents | (ta ? kFlagATrans : 0u) | (tb ? kFlagBTrans : 0u);
+        // accumulator sign frame (see the consumer): flip after this pair's last stage if the unit goes on with a pair of the
+        // other sign, or ends here in a negative frame
+        const bool flip_after = st_hi == tile.s_end ? task.sign < 0 : (task.sign < 0) != (next_sign < 0);
         // B as a k x n view of the stored block (GemmTask::b_rs / b_cs / b_run): offset of this lane's columns inside a row
         uint32_t bcol[WBN / 32];
 #pragma unroll
@@ -357,6 +398,7 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
             uint32_t fl = tflags | (min(uint32_t(WBK / 4), (task.k - k0 + 3u) >> 2) << 24);
             if (st == tile.s_begin) fl |= kFlagFirst;
             if (st + 1 == tile.s_end) fl |= kFlagLast;
+            if (st + 1 == st_hi && flip_after) fl |= kFlagFlip;
             meta[s].tile = tile_id; meta[s].flags = fl;
             MbarArrive(&full[s]);
           }
@@ -401,18 +443,31 @@ GemmWsCplx(const __grid_constant__ GemmParams p) {
     const int nt = n8 > q ? (n8 - q + 3) >> 2 : 0;
     const double2 *tileA = stages + size_t(s) * STAGE_ELEMS;
     const double2 *tileB = tileA + A_ELEMS;
-    FragAddr f;
-    if (sm.flags & kFlagATrans) { f.a = tileA + t4 * WLDAT + g4; f.a_i = 8; f.a_ks = 4 * WLDAT; }
-    else { f.a = tileA + g4 * WLDA + t4; f.a_i = 8 * WLDA; f.a_ks = 4; }
-    if (sm.flags & kFlagBTrans) { f.b = tileB + (q * 8 + g4) * WBK + t4; f.b_j = 32 * WBK; f.b_ks = 0; f.b_sw = 4; f.b_x = g4 & 1; }
-    else { f.b = tileB + t4 * WLDB + q * 8 + g4; f.b_j = 32; f.b_ks = 4 * WLDB; f.b_sw = 0; f.b_x = 0; }
-    const uint32_t smask = (sm.flags & kFlagNeg) ? 0x80000000u : 0u;
-    ComputeHalf<CFG, 0>(acc, f, smask, mt, nt);
-    if constexpr (WBK == 16) {
-      if (((sm.flags >> 24) & 7u) > 2u) ComputeHalf<CFG, 2>(acc, f, smask, mt, nt);   // K tail: skip an all-zero half stage
+    const uint32_t nk4 = (sm.flags >> 24) & 7u;      // valid k4 steps of the stage (fewer than WBK / 4 only in a K tail)
+    if (QLB200_WS_FULLSTAGE && mt == 4 && nt == NTMAX && nk4 == uint32_t(WBK / 4)) {
+      switch (sm.flags & (kFlagATrans | kFlagBTrans)) {
+        case 0: ComputeFullStage<CFG, false, false>(acc, tileA, tileB, q, g4, t4); break;
+        case kFlagATrans: ComputeFullStage<CFG, true, false>(acc, tileA, tileB, q, g4, t4); break;
+        case kFlagBTrans: ComputeFullStage<CFG, false, true>(acc, tileA, tileB, q, g4, t4); break;
+        default: ComputeFullStage<CFG, true, true>(acc, tileA, tileB, q, g4, t4); break;
+      }
+    } else {
+      FragAddr f;
+      if (sm.flags & kFlagATrans) { f.a = tileA + t4 * WLDAT + g4; f.a_i = 8; f.a_ks = 4 * WLDAT; }
+      else { f.a = tileA + g4 * WLDA + t4; f.a_i = 8 * WLDA; f.a_ks = 4; }
+      if (sm.flags & kFlagBTrans) { f.b = tileB + (q * 8 + g4) * WBK + t4; f.b_j = 32 * WBK; f.b_ks = 0; f.b_sw = 4; f.b_x = g4 & 1; }
+      else { f.b = tileB + t4 * WLDB + q * 8 + g4; f.b_j = 32; f.b_ks = 4 * WLDB; f.b_sw = 0; f.b_x = 0; }
+      ComputeHalf<CFG, 0>(acc, f, mt, nt);
+      if constexpr (WBK == 16) {
+        if (nk4 > 2u) ComputeHalf<CFG, 2>(acc, f, mt, nt);   // K tail: skip an all-zero half stage
+      }
     }
     __syncwarp();
     if (lane == 0) MbarArrive(&empty[s]);
+    // Sign frame: the accumulators hold (sign of the current pair) x (sum so far).  The producer marks the stage after which
+    // the frame changes (the next pair has the other sign, or the unit ends in a negative frame): one flip of the
+    // accumulators there instead of a flip of every A fragment of every k step.
+    if (sm.flags & kFlagFlip) NegateAcc<CFG>(acc);
     if (sm.flags & kFlagLast) {
       const GemmTile tile = p.tiles[sm.tile];
       const GemmGroup g = p.groups[tile.group];

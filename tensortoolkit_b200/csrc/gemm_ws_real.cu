@@ -33,31 +33,56 @@ struct FragAddrR {
   uint32_t b_j, b_k, b_x;   // B: + j * b_j (owned n8 group) + (ks ^ b_x) * b_k
 };
 
+// One k4 step of a warp's sub-tile (MT valid m8 row groups x NT valid n8 column groups), fragments at pa + i * a_i and
+// pb + j * b_j.  The pair's sign is not applied here: the accumulators live in the sign frame of the current pair and
+// are flipped once where the frame changes (kFlagFlip, see gemm_ws.cu).
 template<int MT, int NT>
-__device__ __forceinline__ void ComputeStageR(double (&acc)[8][4][2], const FragAddrR &f, uint32_t smask) {
+__device__ __forceinline__ void KStepR(double (&acc)[8][4][2], const double *pa, uint32_t a_i, const double *pb, uint32_t b_j) {
+  double a[MT], b[NT];
 #pragma unroll
-  for (int ks = 0; ks < RBK / 4; ++ks) {
-    double a[MT], b[NT];
-    const double *pa = f.a + ks * f.a_k;
-    const double *pb = f.b + (uint32_t(ks) ^ f.b_x) * f.b_k;
+  for (int i = 0; i < MT; ++i) a[i] = pa[i * a_i];
 #pragma unroll
-    for (int i = 0; i < MT; ++i) a[i] = FlipSign(pa[i * f.a_i], smask);
+  for (int j = 0; j < NT; ++j) b[j] = pb[j * b_j];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) b[j] = pb[j * f.b_j];
+  for (int i = 0; i < MT; ++i)
 #pragma unroll
-    for (int i = 0; i < MT; ++i)
+    for (int j = 0; j < NT; ++j) DmmaNv(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+}
+
+// ragged sub-tile: run-time strides
+template<int MT, int NT>
+__device__ __forceinline__ void ComputeStageR(double (&acc)[8][4][2], const FragAddrR &f) {
 #pragma unroll
-      for (int j = 0; j < NT; ++j) DmmaNv(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-  }
+  for (int ks = 0; ks < RBK / 4; ++ks) KStepR<MT, NT>(acc, f.a + ks * f.a_k, f.a_i, f.b + (uint32_t(ks) ^ f.b_x) * f.b_k, f.b_j);
+}
+
+// full sub-tile, operand layouts known at compile time: every fragment load is a base register + immediate
+template<bool AT, bool BT>
+__device__ __forceinline__ void ComputeFullStageR(double (&acc)[8][4][2], const double *tileA, const double *tileB, int q, int g4, int t4) {
+  constexpr uint32_t a_i = AT ? 8 : 8 * RLDA, a_k = AT ? 4 * RLDAT : 4;
+  constexpr uint32_t b_j = BT ? 32 * RBK : 32, b_k = BT ? 4 : 4 * RLDB;
+  const double *pa = tileA + (AT ? t4 * RLDAT + g4 : g4 * RLDA + t4);
+  const double *pb = tileB + (BT ? (q * 8 + g4) * RBK + t4 : t4 * RLDB + q * 8 + g4);
+  // transposed B: k4 group ks of row n sits at (ks ^ (n & 3)) -- one lane-constant base per step
+  const int x = BT ? (g4 & 3) : 0;
+#pragma unroll
+  for (int ks = 0; ks < RBK / 4; ++ks) KStepR<8, 4>(acc, pa + ks * a_k, a_i, pb + (BT ? ((ks ^ x) * 4) : ks * int(b_k)), b_j);
+}
+
+__device__ __forceinline__ void NegateAccR(double (&acc)[8][4][2]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = -acc[i][j][0]; acc[i][j][1] = -acc[i][j][1]; }
 }
 
 template<int MT>
-__device__ __forceinline__ void ComputeStageRN(double (&acc)[8][4][2], const FragAddrR &f, uint32_t smask, int nt) {
+__device__ __forceinline__ void ComputeStageRN(double (&acc)[8][4][2], const FragAddrR &f, int nt) {
   switch (nt) {
-    case 4: ComputeStageR<MT, 4>(acc, f, smask); break;
-    case 3: ComputeStageR<MT, 3>(acc, f, smask); break;
-    case 2: ComputeStageR<MT, 2>(acc, f, smask); break;
-    case 1: ComputeStageR<MT, 1>(acc, f, smask); break;
+    case 4: ComputeStageR<MT, 4>(acc, f); break;
+    case 3: ComputeStageR<MT, 3>(acc, f); break;
+    case 2: ComputeStageR<MT, 2>(acc, f); break;
+    case 1: ComputeStageR<MT, 1>(acc, f); break;
     default: break;
   }
 }
@@ -150,6 +175,7 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
       uint32_t sidx = 0;     // stage index of the current pair's first stage in the group's concatenated k loop
       for (uint32_t t = g.task_begin; t < g.task_end && sidx < tile.s_end; ++t) {
         const GemmTask task = p.tasks[t];
+        const int next_sign = t + 1 < g.task_end ? p.tasks[t + 1].sign : 0;
         const uint32_t nst = (task.k + RBK - 1) / RBK;
         const uint32_t st_lo = max(sidx, tile.s_begin), st_hi = min(sidx + nst, tile.s_end);
         const uint32_t st_base = sidx;
@@ -158,7 +184,10 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
         const double *aBase = static_cast<const double *>((task.flags & kTaskASrc) ? p.a_src : p.a_ws) + task.a_off;
         const double *bBase = static_cast<const double *>((task.flags & kTaskBSrc) ? p.b_src : p.b_ws) + task.b_off;
         const bool ta = (task.flags & kTaskATrans) != 0, tb = (task.flags & kTaskBTrans) != 0;
-        const uint32_t tflags = extents | (task.sign < 0 ? kFlagNeg : 0u) | (ta ? kFlagATrans : 0u) | (tb ? kFlagBTrans : 0u);
+        const uint32_t tflags = extents | (ta ? kFlagATrans : 0u) | (tb ? kFlagBTrans : 0u);
+        // accumulator sign frame: flip after this pair's last stage if the unit goes on with a pair of the other sign, or
+        // ends here in a negative frame
+        const bool flip_after = st_hi == tile.s_end ? task.sign < 0 : (task.sign < 0) != (next_sign < 0);
         // B as a k x n view of the stored block (GemmTask::b_rs / b_cs / b_run): offset of this lane's four columns inside a row
         uint32_t bcol[4];
 #pragma unroll
@@ -224,6 +253,7 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
             uint32_t fl = tflags;
             if (st == tile.s_begin) fl |= kFlagFirst;
             if (st + 1 == tile.s_end) fl |= kFlagLast;
+            if (st + 1 == st_hi && flip_after) fl |= kFlagFlip;
             meta[s].tile = tile_id; meta[s].flags = fl;
             MbarArrive(&full[s]);
           }
@@ -264,24 +294,29 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
     const int nt = n8 > q ? (n8 - q + 3) >> 2 : 0;
     const double *tileA = stages + size_t(s) * RSTAGE_ELEMS;
     const double *tileB = tileA + RA_ELEMS;
-    FragAddrR f;
-    if (sm.flags & kFlagATrans) { f.a = tileA + t4 * RLDAT + g4; f.a_i = 8; f.a_k = 4 * RLDAT; }
-    else { f.a = tileA + g4 * RLDA + t4; f.a_i = 8 * RLDA; f.a_k = 4; }
-    if (sm.flags & kFlagBTrans) { f.b = tileB + (q * 8 + g4) * RBK + t4; f.b_j = 32 * RBK; f.b_k = 4; f.b_x = g4 & 3; }
-    else { f.b = tileB + t4 * RLDB + q * 8 + g4; f.b_j = 32; f.b_k = 4 * RLDB; f.b_x = 0; }
-    const uint32_t smask = (sm.flags & kFlagNeg) ? 0x80000000u : 0u;
     if (mt == 8 && nt == 4) {
-      ComputeStageR<8, 4>(acc, f, smask);
+      switch (sm.flags & (kFlagATrans | kFlagBTrans)) {
+        case 0: ComputeFullStageR<false, false>(acc, tileA, tileB, q, g4, t4); break;
+        case kFlagATrans: ComputeFullStageR<true, false>(acc, tileA, tileB, q, g4, t4); break;
+        case kFlagBTrans: ComputeFullStageR<false, true>(acc, tileA, tileB, q, g4, t4); break;
+        default: ComputeFullStageR<true, true>(acc, tileA, tileB, q, g4, t4); break;
+      }
     } else {
+      FragAddrR f;
+      if (sm.flags & kFlagATrans) { f.a = tileA + t4 * RLDAT + g4; f.a_i = 8; f.a_k = 4 * RLDAT; }
+      else { f.a = tileA + g4 * RLDA + t4; f.a_i = 8 * RLDA; f.a_k = 4; }
+      if (sm.flags & kFlagBTrans) { f.b = tileB + (q * 8 + g4) * RBK + t4; f.b_j = 32 * RBK; f.b_k = 4; f.b_x = g4 & 3; }
+      else { f.b = tileB + t4 * RLDB + q * 8 + g4; f.b_j = 32; f.b_k = 4 * RLDB; f.b_x = 0; }
       switch ((mt + 1) >> 1) {      // m8 groups are specialised in pairs
-        case 4: ComputeStageRN<8>(acc, f, smask, nt); break;
-        case 3: ComputeStageRN<6>(acc, f, smask, nt); break;
-        case 2: ComputeStageRN<4>(acc, f, smask, nt); break;
-        default: ComputeStageRN<2>(acc, f, smask, nt); break;
+        case 4: ComputeStageRN<8>(acc, f, nt); break;
+        case 3: ComputeStageRN<6>(acc, f, nt); break;
+        case 2: ComputeStageRN<4>(acc, f, nt); break;
+        default: ComputeStageRN<2>(acc, f, nt); break;
       }
     }
     __syncwarp();
     if (lane == 0) MbarArrive(&empty[s]);
+    if (sm.flags & kFlagFlip) NegateAccR(acc);      // sign frame change (producer-marked)
     if (sm.flags & kFlagLast) {
       const GemmTile tile = p.tiles[sm.tile];
       const GemmGroup g = p.groups[tile.group];

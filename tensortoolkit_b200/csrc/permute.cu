@@ -35,8 +35,15 @@ PermuteKernel(const PermBlk *__restrict__ blks, const uint32_t *__restrict__ til
   __shared__ PermBlk sd;
   __shared__ uint32_t s_blk;
   __shared__ uint16_t s_off[kPermSmemElems];   // run mode: shared-memory offset of every element of a destination piece
+  __shared__ __align__(8) uint64_t s_bar;      // bulk path: completion barrier of the global -> shared copies
   const int tid = threadIdx.x;
   uint32_t cur_blk = 0xffffffffu;
+  uint32_t bulk_phase = 0;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar))) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // --- locate the block owning this tile (largest b with tile_base[b] <= tile) ---
@@ -83,7 +90,36 @@ PermuteKernel(const PermBlk *__restrict__ blks, const uint32_t *__restrict__ til
     const float scale = sd.scale;
     const uint32_t s_out = sd.sstr[jout], d_in = sd.dstr[jin], d_out = sd.dstr[jout];
 
-    if (V != 0u) {
+    if (V != 0u && sd.bulk != 0u) {
+      // run mode, bulk asynchronous copies (no per-element instructions at all): thread 0 queues TOa copies of TIa*V contiguous
+      // source elements into shared memory, completing on the mbarrier; then every thread queues one shared -> global copy
+      // per V-element run of the tile (TIa*TOa runs), commits them and waits until shared memory has been read
+      const uint32_t L = TIa * V, P = sd.TI * V;
+      const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar));
+      const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(s));
+      if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(uint32_t(TOa * L * sizeof(T))) : "memory");
+        for (uint32_t to = 0; to < TOa; ++to)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + uint32_t(to * P * sizeof(T))),
+                       "l"(src + (unsigned long long) to * s_out), "r"(uint32_t(L * sizeof(T))), "r"(bar)
+                       : "memory");
+      }
+      {
+        uint32_t done = 0;
+        while (!done)
+          asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(bulk_phase) : "memory");
+        bulk_phase ^= 1u;
+      }
+      const uint32_t nruns = TIa * TOa;
+      for (uint32_t idx = tid; idx < nruns; idx += kPermThreads) {
+        const uint32_t ti = idx / TOa, to = idx - ti * TOa;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (unsigned long long) ti * d_in + (unsigned long long) to * V),
+                     "r"(sbase + uint32_t((to * P + ti * V) * sizeof(T))), "r"(uint32_t(V * sizeof(T)))
+                     : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else if (V != 0u) {
       // run mode: TOa pieces of TIa*V contiguous source elements in, TIa pieces of TOa*V contiguous destination elements out
       const uint32_t L = TIa * V, P = sd.TI * V + 1u, M = TOa * V;
       // index arithmetic without a division per element: each thread advances its (piece, offset) pair by the block

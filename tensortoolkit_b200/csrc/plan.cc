@@ -20,7 +20,7 @@ constexpr uint32_t kSmemCap = 2304;
 }  // namespace
 
 PermBlk MakePermBlk(int rank, const uint32_t *shape, const int32_t *perm, uint64_t src_off, uint64_t dst_off,
-                    uint32_t src_sel, float scale, uint64_t *ntiles_out) {
+                    uint32_t src_sel, float scale, uint64_t *ntiles_out, int elem_bytes) {
   PermBlk d;
   std::memset(&d, 0, sizeof(d));
   d.src_off = src_off; d.dst_off = dst_off; d.src_sel = src_sel; d.scale = scale;
@@ -60,14 +60,19 @@ PermBlk MakePermBlk(int rank, const uint32_t *shape, const int32_t *perm, uint64
     // js != jd: otherwise the two axes would have been merged above (dense block: the stride that follows V is V itself)
     if (js != jd && sst[js] == V) {
       d.vec = V; d.jin = js; d.jout = jd;
+      // bulk-copy path: every run starts 16-byte aligned in the source and in the destination and is a multiple of 16
+      // bytes long (all other strides of a dense block are multiples of V), and nothing is scaled on the way
+      const uint64_t eb = uint64_t(elem_bytes);
+      d.bulk = (eb != 0 && scale == 1.0f && (V * eb) % 16 == 0 && (src_off * eb) % 16 == 0 && (dst_off * eb) % 16 == 0) ? 1u : 0u;
+      const uint32_t pad = d.bulk ? 0u : 1u;            // the element-wise path pads rows against bank conflicts
       const uint32_t ei = d.ext[js], eo = d.ext[jd];
       uint32_t side = 1;
       while ((side + 1) * (side + 1) * V + (side + 1) <= kSmemCap) ++side;      // square-ish tile of runs
       uint32_t TI = std::min(ei, side), TO = std::min(eo, side);
       // a short axis leaves room for more of the other one
-      if (TI < side) TO = std::min<uint32_t>(eo, kSmemCap / (TI * V + 1));
-      else if (TO < side) TI = std::min<uint32_t>(ei, (kSmemCap / TO - 1) / V);
-      while ((TI * V + 1) * TO > kSmemCap) { if (TO > 1) --TO; else --TI; }
+      if (TI < side) TO = std::min<uint32_t>(eo, kSmemCap / (TI * V + pad));
+      else if (TO < side) TI = std::min<uint32_t>(ei, (kSmemCap / TO - pad) / V);
+      while ((TI * V + pad) * TO > kSmemCap) { if (TO > 1) --TO; else --TI; }
       d.TI = TI; d.TO = TO;
       d.nti = (ei + TI - 1) / TI; d.nto = (eo + TO - 1) / TO;
       d.txi_log2 = d.txo_log2 = 0;
@@ -184,7 +189,7 @@ static std::string AddPermBlocks(PlanHost *h, int rank, const int32_t *perm, con
     if (sz >= (1ull << 32)) return "block with 2^32 or more elements";
     (*new_off)[b] = ws;
     uint64_t nt = 0;
-    PermBlk d = MakePermBlk(rank, shape + b * rank, perm, off[b], ws, src_sel, 1.0f, &nt);
+    PermBlk d = MakePermBlk(rank, shape + b * rank, perm, off[b], ws, src_sel, 1.0f, &nt, h->dtype == QLB200_C64 ? 16 : 8);
     const uint64_t base = h->perm_tile_base.empty() ? 0 : h->perm_tile_base.back();
     if (h->perm_tile_base.empty()) h->perm_tile_base.push_back(0);
     if (base + nt >= (1ull << 32)) return "too many permute tiles";

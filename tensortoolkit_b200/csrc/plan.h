@@ -109,8 +109,9 @@ struct qlb200_tplan {
 namespace qlb200 {
 
 /// Canonicalise one block permutation and choose its tiling. `perm[j]` = input axis of output axis j.
+/// elem_bytes (8 / 16; 0 = unknown) lets run-mode blocks whose runs are 16-byte aligned take the bulk-copy path.
 PermBlk MakePermBlk(int rank, const uint32_t *shape, const int32_t *perm, uint64_t src_off, uint64_t dst_off,
-                    uint32_t src_sel, float scale, uint64_t *ntiles_out);
+                    uint32_t src_sel, float scale, uint64_t *ntiles_out, int elem_bytes = 0);
 
 /// Build the host-side tables of a contraction from sorted tasks.  `nctrct` = number of contracted
 /// axes (the last nctrct entries of a_perm and the first nctrct of b_perm; 0 = unknown, keep order).

@@ -13,7 +13,7 @@ constexpr int kConsumerWarps = 4;
 // registers per thread at launch; the budget is re-split at run time with setmaxnreg (consumers 208,
 // producer warpgroup 48: per SM sub-partition 2 x (208 + 48) = 512 registers per lane).
 constexpr int kWsThreads = (kConsumerWarps + 4) * 32;
-constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u, kFlagNeg = 4u, kFlagATrans = 8u, kFlagBTrans = 16u;
+constexpr uint32_t kFlagFirst = 1u, kFlagLast = 2u, kFlagNeg = 4u, kFlagATrans = 8u, kFlagBTrans = 16u, kFlagFlip = 32u;
 constexpr uint32_t kSentinel = 0xffffffffu;
 constexpr int kProducerWarps = 4;
 constexpr uint32_t kFullArrivals = kProducerWarps * 32 + 1;   // async copy arrivals of every producer lane + the meta release
@@ -65,7 +65,8 @@ __device__ __forceinline__ void CpAsync8Z(uint32_t smem, const void *gmem, bool 
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem), "l"(gmem), "r"(sz) : "memory");
 }
 
-// flags word of a stage: bits 0..2 first/last/neg, 8..11 valid m8 groups, 16..20 valid n8 groups
+// flags word of a stage: bits 0..5 first / last / neg / A, B transposed / flip the accumulators after the stage,
+// 8..11 valid m8 groups, 16..20 valid n8 groups, 24..26 valid k4 steps
 struct StageMeta { uint32_t tile, flags; };
 
 }  // namespace
