@@ -26,6 +26,16 @@ sys.path.insert(0, ROOT)
 SEEDS = {"f64": 20260002, "c128": 20260003}
 
 
+
+def _fatal(msg):
+    """Verification failure: fatal, except in kernel attribution experiments (exp/, QLB200_BENCH_NO_VERIFY=1) that run
+    deliberately wrong kernel variants for their timing only."""
+    if os.environ.get("QLB200_BENCH_NO_VERIFY") == "1":
+        print("[not verified] " + msg, file=sys.stderr)
+        return
+    raise SystemExit(msg)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -46,7 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plumbing", default="capi", choices=["capi", "torch"],
                     help="N>1: symmetric buffers / multicast mapping / barrier from qlb200_comm_* (C ABI, default) or from torch symmetric memory + CUDA IPC")
-    ap.add_argument("--rebalance", type=int, default=2, help="N>1: feedback iterations of the row partitioner (measure every rank's share, re-weigh, cut again)")
+    ap.add_argument("--rebalance", type=int, default=3, help="N>1: feedback iterations of the row partitioner (measure every rank's share, re-weigh, cut again)")
     ap.add_argument("--snap", type=int, default=8, help="N>1: row cuts inside a sector are multiples of this")
     ap.add_argument("--no-sub-records", action="store_true", help="default run only: skip the sub-records for BASELINE configs[1], [3] and [4]")
     ap.add_argument("--ragged-cpu-pairs", type=int, default=1000, help="ragged workload: pairs of the bounded CPU / e2e sample")
@@ -407,11 +417,19 @@ def measure_heff(args, env):
         # partitioner feedback: time every rank's share, re-weigh the row line by (measured time / modelled flops) per rank,
         # cut again (sharding.reweigh_pieces) -- an autotuning step at set-up, like the planner's split-K simulation
         rebalance_log = []
-        for it in range(args.rebalance):
-            from tensortoolkit_b200 import sharding as shd
+        from tensortoolkit_b200 import sharding as shd
+
+        def build(pieces):
+            with torch.cuda.stream(stream):
+                return ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags,
+                                    exchange=args.exchange, host_input="psi", pieces=pieces, snap=args.snap, plumbing=args.plumbing)
+
+        def local_times():
+            """Median local-step time of every rank under the current cuts (host-launched applies; the launch overhead is the
+            same on every rank and only damps the correction)."""
             with torch.cuda.stream(stream):
                 ts = []
-                for i in range(6):
+                for i in range(12):
                     env.flush.zero_()
                     torch.distributed.barrier()
                     marks = {}
@@ -422,16 +440,28 @@ def measure_heff(args, env):
                     torch.cuda.synchronize()
                     if i >= 2:
                         ts.append(e0.elapsed_time(marks["compute"]))
-                mine_t = torch.tensor([float(np.mean(ts))], device="cuda", dtype=torch.float64)
+                mine_t = torch.tensor([float(np.median(ts))], device="cuda", dtype=torch.float64)
                 allt = [torch.zeros_like(mine_t) for _ in range(world)]
                 torch.distributed.all_gather(allt, mine_t)
-                times = [float(x[0]) for x in allt]
+                return [float(x[0]) for x in allt]
+
+        # every candidate partition is measured, the one whose slowest rank is fastest is kept (the feedback is a heuristic:
+        # moving rows changes tile counts, so a step can overshoot); all ranks see the same gathered times and decide alike
+        best = None
+        for it in range(args.rebalance + 1):
+            times = local_times()
             rebalance_log.append([round(t, 4) for t in times])
+            if best is None or max(times) < best[0]:
+                best = (max(times), sharded.info.pieces, it)
+            if it == args.rebalance:
+                break
             pieces = shd.reweigh_pieces(sharded.info.pieces, sharded.info.sector_ranges, times)
             sharded.close()
-            with torch.cuda.stream(stream):
-                sharded = ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags,
-                                       exchange=args.exchange, host_input="psi", pieces=pieces, snap=args.snap, plumbing=args.plumbing)
+            sharded = build(pieces)
+        if args.rebalance and best[2] != args.rebalance:
+            sharded.close()
+            sharded = build(best[1])
+        rebalance_kept = best[2] if args.rebalance else 0
         chain = sharded.chain
         apply_fn = sharded.apply
     else:
@@ -454,7 +484,7 @@ def measure_heff(args, env):
             ctx.sync()
         verified = float(np.linalg.norm(got - want) / np.linalg.norm(want))
         if not verified <= 1e-12:
-            raise SystemExit(f"rank {rank}: sharded apply differs from the unsharded one, rel err {verified:.3e}")
+            _fatal(f"rank {rank}: sharded apply differs from the unsharded one, rel err {verified:.3e}")
         del got
     graph = None
     if not args.no_graph:
@@ -582,7 +612,7 @@ def measure_heff(args, env):
                 want = chain.result("out").data
             e2e_err = float(np.linalg.norm(out_host - want) / np.linalg.norm(want))
             if not e2e_err <= 1e-12:
-                raise SystemExit(f"end-to-end result differs from the device-resident one: rel err {e2e_err:.3e}")
+                _fatal(f"end-to-end result differs from the device-resident one: rel err {e2e_err:.3e}")
         if sharded is None:
             for _ in range(2):
                 chain.apply_host("psi", psi_host, "out", out_host)
@@ -635,7 +665,7 @@ def measure_heff(args, env):
                      "rel_err_vs_unfused": ferr, "mpo_step_ms": float(np.mean(tf)), "mpo_step_gbs": fby / (np.mean(tf) * 1e-3) / 1e9,
                      "how": "w12 = Contract(mpo1, mpo2) once; every apply = lenv x psi, x w12 (one narrow-pair launch over the rank-5 intermediate), x renv"}
             if not ferr <= 1e-12:
-                raise SystemExit(f"fused-MPO chain differs from the 4-step chain: rel err {ferr:.3e}")
+                _fatal(f"fused-MPO chain differs from the 4-step chain: rel err {ferr:.3e}")
             fgraph.close(); fchain.close()
 
     ms = float(np.mean(dev_ms))
@@ -669,7 +699,7 @@ def measure_heff(args, env):
     # the default complex kernel multiplies with three real DMMAs per complex step (Karatsuba / "3M") instead of four:
     # `achieved` stays ALGORITHMIC flops (the reference's cost model, 8*m*k*n) / time, so it may exceed the 4-product
     # cuBLAS ZGEMM rate used as `peak`; `executed_ratio` says how many of those flops the tensor pipe really issues
-    three_m = dtype == "c128" and not (args.plan_flags & (4 | 32))
+    three_m = dtype == "c128" and not (args.plan_flags & 32)
     if dom["bound"] == "tensor":
         roof = {"bound": "tensor", "kernel": f"step{dom['step']}:{dom['kernel']}", "achieved": dom["achieved"], "peak": peak_burst,
                 "unit": "TFLOP/s", "frac": dom["achieved"] / peak_burst, "traffic": traffic.get(f"step{dom['step']}:{dom['kernel']}"),
@@ -721,7 +751,7 @@ def measure_heff(args, env):
                           "same_block_structure": bool(got.same_structure(want)), "tolerance": 1e-12,
                           "how": "result of this apply vs the reference's qlten::Contract chain on the same operands (exchanged as .qlten files)"}
                 if not (parity["same_block_structure"] and parity["rel_fro_vs_reference"] <= 1e-12):
-                    raise SystemExit(f"parity against the reference FAILED: {parity}")
+                    _fatal(f"parity against the reference FAILED: {parity}")
         except SystemExit:
             raise
         except Exception as e:   # the oracle library is test infrastructure; never fatal for the product bench
@@ -751,7 +781,7 @@ def measure_heff(args, env):
         line["sharded_vs_unsharded_rel_err"] = verified
     if rank_phase is not None:
         line["rank_phases"] = rank_phase
-        line["partition_feedback"] = {"iterations": args.rebalance, "local_ms_by_rank_before_each": rebalance_log,
+        line["partition_feedback"] = {"iterations": args.rebalance, "kept_partition": rebalance_kept, "local_ms_by_rank_of_each_partition": rebalance_log,
                                       "how": "rows of the split bond re-weighted by measured time / modelled flops per rank, cut again (set-up time)"}
     if args.breakdown:
         for rp in rank_phase or []:
@@ -899,7 +929,7 @@ def measure_ragged(args, env):
                 num += float(torch.dot(d, d)); den += float(torch.dot(full[int(o):int(o + l)], full[int(o):int(o + l)]))
             sharded_err = (num / den) ** 0.5 if den > 0 else 0.0
             if not sharded_err <= 1e-12:
-                raise SystemExit(f"rank {rank}: partitioned ragged plan differs from the whole one, rel err {sharded_err:.3e}")
+                _fatal(f"rank {rank}: partitioned ragged plan differs from the whole one, rel err {sharded_err:.3e}")
             del full
         # parity on this very input: a sample of this rank's output blocks against torch.matmul in float64 on the device
         worst = 0.0
@@ -937,7 +967,7 @@ def measure_ragged(args, env):
                 w = want.reshape(-1)[lo:hi]
                 worst = max(worst, float(torch.linalg.norm(got - w) / torch.linalg.norm(w)))
         if not worst <= 1e-12:
-            raise SystemExit(f"ragged workload: grouped GEMM differs from the float64 reference, rel err {worst:.3e}")
+            _fatal(f"ragged workload: grouped GEMM differs from the float64 reference, rel err {worst:.3e}")
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()

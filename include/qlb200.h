@@ -155,7 +155,7 @@ int qlb200_host_unregister(void *p);
  * ctx == NULL builds a host-only plan: stats, partition and c_ranges work, execute does not. */
 #define QLB200_PLAN_DETERMINISTIC 1u   /* default and only mode: no atomics, fixed summation order */
 #define QLB200_PLAN_NO_SKINNY 2u       /* force every task through the DMMA kernel (testing) */
-#define QLB200_PLAN_LEGACY_GEMM 4u     /* use the cp.async kernels instead of the warp-specialised ones */
+/* 4u: reserved (the first-generation cp.async kernels it selected were removed in round 2) */
 #define QLB200_PLAN_CPLX_4M 32u       /* complex GEMM: four real DMMAs per complex step instead of the default three
                                          (Gauss / 3M product: 25 % fewer tensor-pipe instructions, same error order) */
 #define QLB200_PLAN_STAGGER_OUTPUT 64u /* cut every long k loop into ~4 units queued back to back, so that output tiles complete

@@ -17,7 +17,7 @@ F64, C64 = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 SPLIT_BY_A, SPLIT_BY_B, SPLIT_BY_C = 0, 1, 2
 DIR_IN, DIR_OUT = -1, 1
-PLAN_DETERMINISTIC, PLAN_NO_SKINNY, PLAN_LEGACY_GEMM, PLAN_PERMUTE_ALL, PLAN_NO_SPLIT_K, PLAN_CPLX_4M, PLAN_STAGGER_OUTPUT, PLAN_STREAM_K = 1, 2, 4, 8, 16, 32, 64, 128
+PLAN_DETERMINISTIC, PLAN_NO_SKINNY, PLAN_PERMUTE_ALL, PLAN_NO_SPLIT_K, PLAN_CPLX_4M, PLAN_STAGGER_OUTPUT, PLAN_STREAM_K = 1, 2, 8, 16, 32, 64, 128
 PLAN_NO_VIEW = 256
 
 

@@ -456,10 +456,10 @@ int qlb200_plan_read_workspace(qlb200_ctx *ctx, qlb200_plan *p, int which, uint6
 uint64_t qlb200_plan_units(const qlb200_plan *p, uint64_t cap, qlb200_unit *out, uint32_t *tile_rows, uint32_t *tile_cols,
                            uint32_t *stage_k) {
   if (!p) return 0;
-  const bool legacy = (p->h.flags & QLB200_PLAN_LEGACY_GEMM) != 0, four_m = (p->h.flags & QLB200_PLAN_CPLX_4M) != 0;
+  const bool four_m = (p->h.flags & QLB200_PLAN_CPLX_4M) != 0;
   uint32_t BM, BN, BK;
-  if (p->h.dtype == QLB200_C64) { BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : (four_m ? kWsBN : kWs3mBN); BK = legacy ? kCplxBK : (four_m ? kWsBK : kWs3mBK); }
-  else { BM = legacy ? kRealBM : kWsRealBM; BN = legacy ? kRealBN : kWsRealBN; BK = legacy ? kRealBK : kWsRealBK; }
+  if (p->h.dtype == QLB200_C64) { BM = kWsBM; BN = four_m ? kWsBN : kWs3mBN; BK = four_m ? kWsBK : kWs3mBK; }
+  else { BM = kWsRealBM; BN = kWsRealBN; BK = kWsRealBK; }
   if (tile_rows) *tile_rows = BM;
   if (tile_cols) *tile_cols = BN;
   if (stage_k) *stage_k = BK;
@@ -532,7 +532,6 @@ static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const voi
   GemmParams gp = MakeParams(p, A, B, wa, wb, parts, c_out, n_out, mcast);
   if (p->accum) {
     if (n_out != 1 || mcast) return Fail(QLB200_ERR_UNSUPPORTED, "an accumulate plan writes one local output (use qlb200_execute_accum)");
-    if (p->h.flags & QLB200_PLAN_LEGACY_GEMM) return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels have no accumulate epilogue");
     gp.accum = 1; gp.c_in = c_in;
     gp.alpha_re = p->alpha[0]; gp.alpha_im = p->alpha[1]; gp.beta_re = p->beta[0]; gp.beta_im = p->beta[1];
   }
@@ -541,8 +540,6 @@ static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const voi
   // persistent DMMA CTAs fill the remaining SMs at once and the narrow kernel costs no time of its own (two in-order
   // launches on one stream would serialise).  The two kernels write disjoint output blocks.  Fork / join by events is
   // legal under stream capture (qlb200_graph_*).
-  if (gp.ntiles > 0 && (p->h.flags & QLB200_PLAN_LEGACY_GEMM) && (n_out != 1 || mcast))
-    return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels cannot broadcast their output");
   const bool beside = gp.ntiles > 0 && gp.nitems > 0 && gp.nitems <= uint32_t(ctx->num_sms) && ctx->side != nullptr;
   if (beside) {
     QL_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -552,9 +549,7 @@ static int ExecuteGemm(qlb200_ctx *ctx, qlb200_plan *p, const void *A, const voi
     ctx->launches += 1; ctx->total_launches += 1;
   }
   if (gp.ntiles > 0) {
-    if (p->h.flags & QLB200_PLAN_LEGACY_GEMM) {
-      QL_CUDA(LaunchGemmDmma(p->h.dtype, gp, ctx->num_sms, ctx->stream));
-    } else if (p->h.dtype == QLB200_C64) {
+    if (p->h.dtype == QLB200_C64) {
       QL_CUDA(LaunchGemmWsCplx(gp, !(p->h.flags & QLB200_PLAN_CPLX_4M), ctx->num_sms, ctx->stream));
     } else {
       QL_CUDA(LaunchGemmWsReal(gp, ctx->num_sms, ctx->stream));
@@ -1014,7 +1009,6 @@ int qlb200_plan_create_accum(qlb200_ctx *ctx, const qlb200_match *m, const qlb20
                              qlb200_plan **out) {
   if (!m || !a || !out) return Fail(QLB200_ERR_ARG, "null argument");
   if (dtype != a->dtype) return Fail(QLB200_ERR_ARG, "dtype differs from the accumulate layout's");
-  if (flags & QLB200_PLAN_LEGACY_GEMM) return Fail(QLB200_ERR_UNSUPPORTED, "the legacy GEMM kernels have no accumulate epilogue");
   const Match &mm = m->m;
   const AccumLayout &L = a->L;
   const bool beta_zero = a->beta[0] == 0.0 && a->beta[1] == 0.0, beta_one = a->beta[0] == 1.0 && a->beta[1] == 0.0;

@@ -181,7 +181,6 @@ inline std::string CudaErr(const char *what, cudaError_t e) {
 cudaError_t LaunchPermute(int dtype, const PermBlk *blks, const uint32_t *tile_base, uint32_t nblk,
                           uint32_t ntiles, const void *srcA, const void *srcB, void *dstA, void *dstB,
                           int num_sms, cudaStream_t stream);
-cudaError_t LaunchGemmDmma(int dtype, const GemmParams &p, int num_sms, cudaStream_t stream);     // writes c_out[0] only
 cudaError_t LaunchGemmSkinny(int dtype, const GemmParams &p, int num_sms, cudaStream_t stream);
 // dst[dst_off[i] + j] = beta * src[src_off[i] + j], j < len[i]: the output blocks of an accumulate call that the contraction
 // does not touch (ScaleUntouchedOutputBlocks_ / ExpandOutputTopology_, contract_contiguous_axes.h:567-671).  Ranges are
@@ -201,8 +200,6 @@ cudaError_t LaunchGemmWsReal(const GemmParams &p, int num_sms, cudaStream_t stre
 cudaError_t ConfigureWsRealKernel();
 
 // tile shapes of the DMMA kernel, needed by the host-side tiler
-constexpr int kRealBM = 128, kRealBN = 128, kRealBK = 16;
-constexpr int kCplxBM = 64, kCplxBN = 128, kCplxBK = 8;   // legacy cp.async kernel
 constexpr int kWsBM = 32, kWsBN = 128, kWs3mBN = 96;       // warp-specialised complex kernel (4M / 3M tile width)
 constexpr int kWsRealBM = 64, kWsRealBN = 128;             // warp-specialised real kernel
 constexpr int kWsBK = 8, kWsRealBK = 16;                   // k extent of one pipeline stage

@@ -229,11 +229,9 @@ std::string BuildPlanHost(int dtype, uint32_t flags, int nctrct, int a_rank, con
   for (int i = 0; i < a_rank; ++i) a_perm[i] = a_perm_in ? a_perm_in[i] : i;
   for (int i = 0; i < b_rank; ++i) b_perm[i] = b_perm_in ? b_perm_in[i] : i;
 
-  // The warp-specialised kernels and the narrow-pair kernel read blocks in place (direct or 2-D
-  // transposed); the legacy cp.async kernels only understand row-major operands.
-  const bool legacy = (flags & QLB200_PLAN_LEGACY_GEMM) != 0;
+  // The GEMM kernels read blocks in place (direct or 2-D transposed) unless the caller forces the permute pass.
   const bool per_block = !(flags & QLB200_PLAN_PERMUTE_ALL);
-  const bool allow_trans = per_block && !legacy;
+  const bool allow_trans = per_block;
 
   // The order of the contracted axes inside the k index is free as long as A and B agree (it only
   // permutes the terms of each dot product).  Candidates: the caller's order, A's storage order,
@@ -319,6 +317,15 @@ std::string BuildPlanHost(int dtype, uint32_t flags, int nctrct, int a_rank, con
     i = e;
   }
   h->part_groups = h->groups;
+  if (std::getenv("QLB200_DEBUG_TILES")) {
+    unsigned cnt[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // tasks by operand mode: in place, 2-D transposed, strided view (B), permuted copy
+    for (const GemmTask &t : h->tasks) {
+      cnt[0][!(t.flags & kTaskASrc) ? 3 : (t.flags & kTaskATrans) ? 1 : 0]++;
+      cnt[1][!(t.flags & kTaskBSrc) ? 3 : (t.flags & kTaskBTrans) ? 1 : (t.b_run < t.b_rs && t.b_cs != 0) ? 2 : 0]++;
+    }
+    std::fprintf(stderr, "[qlb200 plan] tasks %zu: A in place %u / transposed %u / permuted %u;  B in place %u / transposed %u / view %u / permuted %u\n",
+                 h->tasks.size(), cnt[0][0], cnt[0][1], cnt[0][3], cnt[1][0], cnt[1][1], cnt[1][2], cnt[1][3]);
+  }
   return BuildTiles(h);
 }
 
@@ -342,11 +349,10 @@ GroupClass Classify(const PlanHost *h, const GemmGroup &g, int bk) {
 std::string BuildTiles(PlanHost *h) {
   h->tiles.clear(); h->items.clear(); h->seg.clear();
   h->n_split_ctrs = 0; h->n_part_slots = 0;
-  const bool legacy = (h->flags & QLB200_PLAN_LEGACY_GEMM) != 0;
   int BM, BN, BK;
   const bool four_m = (h->flags & QLB200_PLAN_CPLX_4M) != 0;
-  if (h->dtype == QLB200_C64) { BM = legacy ? kCplxBM : kWsBM; BN = legacy ? kCplxBN : (four_m ? kWsBN : kWs3mBN); BK = legacy ? kCplxBK : (four_m ? kWsBK : kWs3mBK); }
-  else { BM = legacy ? kRealBM : kWsRealBM; BN = legacy ? kRealBN : kWsRealBN; BK = legacy ? kRealBK : kWsRealBK; }
+  if (h->dtype == QLB200_C64) { BM = kWsBM; BN = four_m ? kWsBN : kWs3mBN; BK = four_m ? kWsBK : kWs3mBK; }
+  else { BM = kWsRealBM; BN = kWsRealBN; BK = kWsRealBK; }
   h->part_slot_elems = uint64_t(BM) * BN;
 
   struct GInfo { uint32_t gi, tm, tn, stages; };
@@ -424,7 +430,7 @@ std::string BuildTiles(PlanHost *h) {
     return *std::max_element(bins.begin(), bins.end());
   };
   uint64_t chunk = ~0ull;
-  if (!legacy && !dm.empty() && !(h->flags & QLB200_PLAN_NO_SPLIT_K)) {
+  if (!dm.empty() && !(h->flags & QLB200_PLAN_NO_SPLIT_K)) {
     constexpr uint64_t kMinChunk = 16;
     const uint64_t budget = std::max<uint64_t>(1, total_stage_tiles / slots);
     double best = makespan(~0ull);
@@ -435,12 +441,12 @@ std::string BuildTiles(PlanHost *h) {
       if (cand == kMinChunk) break;
     }
   }
-  if (!legacy && !dm.empty() && (h->flags & QLB200_PLAN_STAGGER_OUTPUT) && !(h->flags & QLB200_PLAN_NO_SPLIT_K)) {
+  if (!dm.empty() && (h->flags & QLB200_PLAN_STAGGER_OUTPUT) && !(h->flags & QLB200_PLAN_NO_SPLIT_K)) {
     uint32_t longest = 0;
     for (const GInfo &d : dm) longest = std::max(longest, d.stages);
     chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(8, (longest + 3) / 4));
   }
-  if (!legacy && !dm.empty() && (h->flags & QLB200_PLAN_STREAM_K) && !(h->flags & QLB200_PLAN_NO_SPLIT_K)) {
+  if (!dm.empty() && (h->flags & QLB200_PLAN_STREAM_K) && !(h->flags & QLB200_PLAN_NO_SPLIT_K)) {
     // Stream-K.  Tiles in block order (neighbours share operand panels in L2), their k loops laid end to end and weighted
     // by the share of MMA groups a tile issues; the line is cut into one equal-cost segment per resident CTA and CTA b runs
     // segment b (GemmParams::seg).  A tile that straddles a cut becomes 2+ units finished by the split-K fix-up; cuts that
@@ -522,7 +528,7 @@ std::string BuildTiles(PlanHost *h) {
   }
   if (const char *ov = std::getenv("QLB200_SPLIT_CHUNK")) {      // tuning aid: force the split-K cut length (stages)
     const long long v = std::atoll(ov);
-    if (v > 0 && !legacy) chunk = uint64_t(v);
+    if (v > 0) chunk = uint64_t(v);
   }
   if (std::getenv("QLB200_DEBUG_TILES") && !dm.empty()) {
     double wsum = 0;

@@ -280,17 +280,16 @@ def test_full_size_properties_heff_d4096_complex(ctx):
 
 
 @pytest.mark.parametrize("dtype", [np.complex128, np.float64])
-@pytest.mark.parametrize("variant", ["ws", "ws_4m", "ws_stagger", "ws_4m_stagger", "ws_stream_k", "ws_4m_stream_k", "legacy", "ws_permute_all",
-                                     "ws_4m_permute_all", "legacy_permute_all"])
+@pytest.mark.parametrize("variant", ["ws", "ws_4m", "ws_stagger", "ws_4m_stagger", "ws_stream_k", "ws_4m_stream_k", "ws_permute_all",
+                                     "ws_4m_permute_all"])
 def test_gemm_kernel_variants(ref, ctx, variant, dtype):
-    """The warp-specialised kernels (blocks read in place or through the permute kernel) and the
-    cp.async kernels against the reference on a fermionic chain with ragged K tails, ragged tile
-    edges, -1 exchange signs and several pairs per block."""
-    flags = {"legacy": _lib.PLAN_LEGACY_GEMM, "ws": 0, "ws_permute_all": _lib.PLAN_PERMUTE_ALL,
+    """The warp-specialised kernels (blocks read in place or through the permute kernel) against the
+    reference on a fermionic chain with ragged K tails, ragged tile edges, -1 exchange signs (accumulator
+    sign frames flipping inside a tile) and several pairs per block."""
+    flags = {"ws": 0, "ws_permute_all": _lib.PLAN_PERMUTE_ALL,
              "ws_4m": _lib.PLAN_CPLX_4M, "ws_4m_permute_all": _lib.PLAN_CPLX_4M | _lib.PLAN_PERMUTE_ALL,
              "ws_stream_k": _lib.PLAN_STREAM_K, "ws_4m_stream_k": _lib.PLAN_CPLX_4M | _lib.PLAN_STREAM_K,
-             "ws_stagger": _lib.PLAN_STAGGER_OUTPUT, "ws_4m_stagger": _lib.PLAN_CPLX_4M | _lib.PLAN_STAGGER_OUTPUT,
-             "legacy_permute_all": _lib.PLAN_LEGACY_GEMM | _lib.PLAN_PERMUTE_ALL}[variant]
+             "ws_stagger": _lib.PLAN_STAGGER_OUTPUT, "ws_4m_stagger": _lib.PLAN_CPLX_4M | _lib.PLAN_STAGGER_OUTPUT}[variant]
     flags |= _lib.PLAN_DETERMINISTIC | _lib.PLAN_NO_SKINNY
     ti = wl.heff_tensor_indexes(wl.hubbard_indexes(150))
     ref.set_seed(77)
