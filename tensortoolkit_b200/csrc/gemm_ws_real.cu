@@ -14,6 +14,16 @@
 //       B transposed  [128 n][16] with k ^ 4*(n&3): 4*((g4&3) ^ ks) + t4 distinct
 #include "common.cuh"
 #include "ws_common.cuh"
+// L2 prefetch distance of the producer for ROW-MAJOR A operands, in stages (0 = off).  The rows of such a tile lie a whole block
+// row (k elements) apart: every stage touches 64 different DRAM pages for 128 bytes each, and it is complete only when its
+// SLOWEST line has landed.  One lane per row asks L2 (prefetch.global.L2, SASS CCTL.E.PF2) for the line the row needs kPf
+// stages from now; the copy that comes for it later finds a short, uniform latency.  Measured (exp/r2_call23.sh): step 4 of the
+// U(1) chain 0.76 -> 0.82 of DGEMM at D=4096, 0.79 -> 0.85 on the Hubbard chain; the distance (4 / 8 / 16) does not matter.
+// Prefetching the other three operand layouts as well (k x m stored A, both B layouts: 16 rows of 512 .. 1024 contiguous
+// bytes per stage, or an L2-resident operand) was measured too and LOSES 1 - 4 % (exp/r2_call24.sh): not done.
+#ifndef QLB200_REAL_PF_STAGES
+#define QLB200_REAL_PF_STAGES 8
+#endif
 #ifdef QLB200_EXP_NOCOPY
 #define CpAsync8Z(a, b, c) ((void) 0)
 #endif
@@ -219,6 +229,15 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
               const bool ok = kok && row < rows;
               CpAsync8Z(sA + (row * RLDA + a_kc) * 8u, ok ? src + (unsigned long long) (2u * r) * task.k : aBase, ok);
             }
+#if QLB200_REAL_PF_STAGES > 0
+            if (a_kc == 0 && k0 + uint32_t(QLB200_REAL_PF_STAGES) * RBK < task.k) {      // one lane per row, see the top of the file
+#pragma unroll
+              for (uint32_t rr = 0; rr < 8; ++rr) {
+                const uint32_t r = 8u * pw + rr, row = a_r + 2u * r;
+                if (row < rows) PrefetchL2(src + (unsigned long long) (2u * r) * task.k + uint32_t(QLB200_REAL_PF_STAGES) * RBK);
+              }
+            }
+#endif
           } else {     // A stored k x m: 16 k-rows of 64 contiguous elements
             const double *src = aBase + (unsigned long long) k0 * g.m + row0 + lane;
 #pragma unroll

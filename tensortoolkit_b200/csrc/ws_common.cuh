@@ -60,10 +60,24 @@ __device__ __forceinline__ double FlipSign(double v, uint32_t mask) {
   return __hiloint2double(__double2hiint(v) ^ int(mask), __double2loint(v));
 }
 
+// L2 prefetch hint of the 8-byte copies: .L2::256B (SASS LDGSTS.E.LTC256B) measured +1 % on row-major A operands, neutral
+// elsewhere (exp/r2_call22.sh); 0 = none, 128 = .L2::128B
+#ifndef QLB200_CP8_L2PF
+#define QLB200_CP8_L2PF 256
+#endif
+#if QLB200_CP8_L2PF == 256
+#define QLB200_CP8_QUAL ".L2::256B"
+#elif QLB200_CP8_L2PF == 128
+#define QLB200_CP8_QUAL ".L2::128B"
+#else
+#define QLB200_CP8_QUAL ""
+#endif
 __device__ __forceinline__ void CpAsync8Z(uint32_t smem, const void *gmem, bool pred) {
   const int sz = pred ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem), "l"(gmem), "r"(sz) : "memory");
+  asm volatile("cp.async.ca.shared.global" QLB200_CP8_QUAL " [%0], [%1], 8, %2;" ::"r"(smem), "l"(gmem), "r"(sz) : "memory");
 }
+
+__device__ __forceinline__ void PrefetchL2(const void *gmem) { asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem) : "memory"); }
 
 // flags word of a stage: bits 0..5 first / last / neg / A, B transposed / flip the accumulators after the stage,
 // 8..11 valid m8 groups, 16..20 valid n8 groups, 24..26 valid k4 steps
