@@ -20,7 +20,8 @@
 // stages from now; the copy that comes for it later finds a short, uniform latency.  Measured (exp/r2_call23.sh): step 4 of the
 // U(1) chain 0.76 -> 0.82 of DGEMM at D=4096, 0.79 -> 0.85 on the Hubbard chain; the distance (4 / 8 / 16) does not matter.
 // Prefetching the other three operand layouts as well (k x m stored A, both B layouts: 16 rows of 512 .. 1024 contiguous
-// bytes per stage, or an L2-resident operand) was measured too and LOSES 1 - 4 % (exp/r2_call24.sh): not done.
+// bytes per stage, or an L2-resident operand) was measured too and LOSES 1 - 4 % (exp/r2_call24.sh): not done.  The complex
+// kernel (16-byte elements: 256 bytes per row and stage) gains nothing from it either (exp/r2_call25.sh).
 #ifndef QLB200_REAL_PF_STAGES
 #define QLB200_REAL_PF_STAGES 8
 #endif
@@ -138,8 +139,12 @@ __device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &til
             if (col < g.n) sum[j].x = AxpbyOut(p, sum[j].x, Ci + col, g.beta_on != 0);
             if (col + 1 < g.n) sum[j].y = AxpbyOut(p, sum[j].y, Ci + col + 1, g.beta_on != 0);
           }
-          if (col < g.n) StoreOut(Cg + col, sum[j].x, p.mcast);
-          if (col + 1 < g.n) StoreOut(Cg + col + 1, sum[j].y, p.mcast);
+          if (col + 1 < g.n && (reinterpret_cast<unsigned long long>(Cg + col) & 15ull) == 0) {
+            StoreOut(reinterpret_cast<double2 *>(Cg + col), sum[j], p.mcast);
+          } else {
+            if (col < g.n) StoreOut(Cg + col, sum[j].x, p.mcast);
+            if (col + 1 < g.n) StoreOut(Cg + col + 1, sum[j].y, p.mcast);
+          }
         }
       }
     }
@@ -385,6 +390,10 @@ GemmWsReal(const __grid_constant__ GemmParams p) {
               if constexpr (ACC) {
                 if (col < g.n) StoreOut(dst, AxpbyOut(p, acc[i][j][0], Ci + at, g.beta_on != 0), p.mcast);
                 if (col + 1 < g.n) StoreOut(dst + 1, AxpbyOut(p, acc[i][j][1], Ci + at + 1, g.beta_on != 0), p.mcast);
+              } else if (col + 1 < g.n && (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
+                // the lane's two adjacent columns as one 16-byte store where the row happens to be aligned (half as many store
+                // instructions per tile; rows of odd length alternate)
+                StoreOut(reinterpret_cast<double2 *>(dst), make_double2(acc[i][j][0], acc[i][j][1]), p.mcast);
               } else {
                 if (col < g.n) StoreOut(dst, acc[i][j][0], p.mcast);
                 if (col + 1 < g.n) StoreOut(dst + 1, acc[i][j][1], p.mcast);
