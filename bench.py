@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--ragged-cpu-pairs", type=int, default=1000, help="ragged workload: pairs of the bounded CPU / e2e sample")
     ap.add_argument("--no-fused-mpo", action="store_true", help="skip the measurement of the chain with the two MPO tensors pre-contracted")
     ap.add_argument("--no-cold", action="store_true", help="skip the cold drop-in measurement (4 Contract calls on host tensors incl. match + plan build)")
+    ap.add_argument("--pipe-in", default="", help="N=1 e2e: cumulative fractions of the streamed input at which the parts of step 1 are cut (tuning; default ContractionChain.pipe_fractions)")
+    ap.add_argument("--pipe-out", default="", help="N=1 e2e: cumulative fractions of the output at which the parts of the last step are cut (tuning)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--plan-flags", type=int, default=1, help="qlb200_plan_create flags (kernel A/B testing; 1 = default)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "multicast", "fused", "allgather"],
@@ -576,10 +578,13 @@ def measure_heff(args, env):
         e2e_serial_s, e2e_how = None, None
         if sharded is None:
             # one GPU: chunked upload overlapped with step 1, chunked download overlapped with the last step (qlb200_hostpipe_*)
-            chain.make_host_pipe("psi")
+            pipe_in = [float(x) for x in args.pipe_in.split(",")] if args.pipe_in else None
+            pipe_out = [float(x) for x in args.pipe_out.split(",")] if args.pipe_out else None
+            chain.make_host_pipe("psi", pipe_in, pipe_out)
             e2e_apply = lambda: chain.apply_host_pipelined(psi_host, out_host)
-            e2e_how = ("qlb200_hostpipe: psi uploaded in 4 chunks on a copy stream while the parts of step 1 run, the result downloaded in "
-                       "4 chunks while the last step computes; host call returns when the result is in host memory")
+            n_parts = len(pipe_in) if pipe_in else len(chain.pipe_fractions(chain.buf["psi"].nbytes)[0])
+            e2e_how = (f"qlb200_hostpipe: psi uploaded in {n_parts} chunks on a copy stream while the parts of step 1 run, the result downloaded in "
+                       f"{len(pipe_out) if pipe_out else n_parts} chunks while the last step computes; host call returns when the result is in host memory")
             h2d_b, d2h_b = int(psi_host.nbytes), int(out_host.nbytes)
         elif args.shard_of:
             def e2e_apply():

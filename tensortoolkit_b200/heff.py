@@ -132,8 +132,16 @@ class ContractionChain:
 
     # cumulative shares of the streamed operand per chunk: a small first chunk lets the math start early, a small last
     # output chunk leaves little of the download exposed (the PCIe copies are faster than the steps they overlap)
-    PIPE_IN = (1 / 16, 5 / 16, 10 / 16, 1.0)
-    PIPE_OUT = (6 / 16, 11 / 16, 15 / 16, 1.0)
+    # Host pipeline chunking: n parts with cumulative fractions (i/n)^p of the streamed input (small first chunks: step 1 starts
+    # early) and 1 - (1 - i/n)^p of the output (small last chunks: little is left to download when the last part ends).
+    # Measured at D=4096 complex (exp/r2_call30.sh, r2_call31.sh): 4 parts 9.48 ms, 8 parts 8.84, 12 parts p=2.2 8.78, 24 parts 9.00
+    # (device-resident apply 8.26).  Every part costs a launch tail, so small tensors get fewer parts (one per PIPE_BYTES).
+    PIPE_PARTS, PIPE_POWER, PIPE_BYTES = 12, 2.2, 8 << 20
+
+    @classmethod
+    def pipe_fractions(cls, nbytes: int):
+        n = max(1, min(cls.PIPE_PARTS, int(nbytes) // cls.PIPE_BYTES))
+        return ([(i / n) ** cls.PIPE_POWER for i in range(1, n + 1)], [1.0 - (1.0 - i / n) ** cls.PIPE_POWER for i in range(1, n + 1)])
 
     def make_host_pipe(self, in_name: str, cum_in=None, cum_out=None):
         """qlb200_hostpipe over the first and last step: `in_name` (an operand of the first step) is streamed from host
@@ -141,7 +149,8 @@ class ContractionChain:
         lhs, rhs, _, _ = self.steps[0]
         if in_name not in (lhs, rhs):
             raise ValueError("the streamed input must be an operand of the first step")
-        cum_in = list(cum_in or self.PIPE_IN); cum_out = list(cum_out or self.PIPE_OUT)
+        d_in, d_out = self.pipe_fractions(self.buf[in_name].nbytes)
+        cum_in = list(cum_in or d_in); cum_out = list(cum_out or d_out)
         h = C.c_void_p()
         check(lib.qlb200_hostpipe_create(self.ctx.h, self.plans[0].h, _lib.SPLIT_BY_A if in_name == lhs else _lib.SPLIT_BY_B,
                                          len(cum_in), (C.c_double * len(cum_in))(*cum_in), self.plans[-1].h, len(cum_out),
