@@ -56,7 +56,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plumbing", default="capi", choices=["capi", "torch"],
                     help="N>1: symmetric buffers / multicast mapping / barrier from qlb200_comm_* (C ABI, default) or from torch symmetric memory + CUDA IPC")
-    ap.add_argument("--rebalance", type=int, default=3, help="N>1: feedback iterations of the row partitioner (measure every rank's share, re-weigh, cut again)")
+    ap.add_argument("--rebalance", type=int, default=4, help="N>1: feedback iterations of the row partitioner (measure every rank's share, re-weigh, cut again)")
+    ap.add_argument("--rebalance-damp", type=float, default=0.5, help="N>1: fraction (exponent) of the feedback correction applied per iteration")
     ap.add_argument("--snap", type=int, default=8, help="N>1: row cuts inside a sector are multiples of this")
     ap.add_argument("--no-sub-records", action="store_true", help="default run only: skip the sub-records for BASELINE configs[1], [3] and [4]")
     ap.add_argument("--ragged-cpu-pairs", type=int, default=1000, help="ragged workload: pairs of the bounded CPU / e2e sample")
@@ -457,7 +458,7 @@ def measure_heff(args, env):
                 best = (max(times), sharded.info.pieces, it)
             if it == args.rebalance:
                 break
-            pieces = shd.reweigh_pieces(sharded.info.pieces, sharded.info.sector_ranges, times)
+            pieces = shd.reweigh_pieces(sharded.info.pieces, sharded.info.sector_ranges, times, damp=args.rebalance_damp)
             sharded.close()
             sharded = build(pieces)
         if args.rebalance and best[2] != args.rebalance:
@@ -513,6 +514,9 @@ def measure_heff(args, env):
         evs = []
         for _ in range(args.steps):
             flush.zero_()
+            if sharded is not None and world > 1:
+                sharded.barrier()     # the ranks leave their L2 flushes at different times: start every timed apply together
+                                      # (stream-ordered, before the first event: not part of the timed region)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             launches = apply_fn()

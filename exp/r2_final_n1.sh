@@ -14,6 +14,7 @@ grep -c "Gemm\|Permute" gpurun_out/r2_launches.csv
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:GemmWsCplx -s 2 -c 2 -o gpurun_out/r2_gemm_ws_cplx3m -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-sub-records --no-cold --no-fused-mpo --no-graph > gpurun_out/r2_ncu_full_gemm.log 2>&1; tail -2 gpurun_out/r2_ncu_full_gemm.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:GemmSkinny -s 2 -c 2 -o gpurun_out/r2_skinny -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-sub-records --no-cold --no-fused-mpo --no-graph > gpurun_out/r2_ncu_full_skinny.log 2>&1; tail -2 gpurun_out/r2_ncu_full_skinny.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"PermuteKernel|GemmWsReal" -c 2 -o gpurun_out/r2_ragged_permute_gemm -f python bench.py --workload ragged --plan-flags 257 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/r2_ncu_full_ragged.log 2>&1; tail -2 gpurun_out/r2_ncu_full_ragged.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:GemmWsReal -c 2 -o gpurun_out/r2_gemm_ws_real_d4096 -f python bench.py --D 4096 --dtype f64 --steps 1 --warmup 1 --no-cpu-baseline --no-cold --no-fused-mpo --no-sub-records --no-graph > gpurun_out/r2_ncu_full_real.log 2>&1; tail -2 gpurun_out/r2_ncu_full_real.log
 for tool in memcheck racecheck synccheck; do
   ( time timeout 900 compute-sanitizer --tool $tool python exp/sanitizer_cases.py ) > gpurun_out/r2_sanitizer_$tool.log 2>&1
   echo "== $tool"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitizer cases ok|Error|hazard" gpurun_out/r2_sanitizer_$tool.log | head -5

@@ -56,8 +56,8 @@ GemmSkinny(GemmParams p) {
   __shared__ uint32_t s_nterm;
   const uint32_t tid = threadIdx.x;
   for (uint32_t it = blockIdx.x; it < p.nitems; it += gridDim.x) {
-    // (prefetching the next item's descriptors under this item's main loop was measured: the registers it costs slow the
-    // main loop by more than the hidden latency gains -- exp/r2_call21.sh)
+    // (prefetching the next item's descriptors under this item's main loop was measured and changes nothing: with 3-4
+    // resident CTAs per SM the chain of one CTA hides behind the streaming of the others -- exp/r2_call21.sh)
     const SkinnyItem item = p.items[it];
     const GemmGroup g = p.groups[item.group];
     const uint32_t n = g.n;

@@ -516,6 +516,11 @@ class ShardedChain:
         else:
             self.torch.distributed.all_reduce(self.flag, group=self.group)
 
+    def barrier(self):
+        """Public form of the stream-ordered barrier across the ranks (e.g. to let all ranks start a timed apply together)."""
+        if self.world > 1:
+            self._barrier()
+
     @property
     def full_ptr(self) -> int:
         """Device address of the full result the LAST apply produced (before the first apply: replica 0)."""

@@ -126,11 +126,13 @@ def row_line_cuts(cost: np.ndarray, degs: Sequence[int], world: int, snap: int =
     return cut_line(line_pieces(cost, degs), len(degs), degs, world, snap)
 
 
-def reweigh_pieces(pieces, ranges_per_rank, times_ms: Sequence[float]):
+def reweigh_pieces(pieces, ranges_per_rank, times_ms: Sequence[float], damp: float = 1.0):
     """Feedback step of the partitioner.  `times_ms[r]` = measured time of rank r's share under the cuts `ranges_per_rank`
     (made from `pieces`).  Time is not proportional to flops -- tile quantisation, small sectors, the memory-bound steps --
     so every rank's rows are re-weighted by (measured time / modelled weight) of that rank; cutting the re-weighted line
-    into equal parts moves rows from slow ranks to fast ones.  Returns the new pieces (split at the old cuts)."""
+    into equal parts moves rows from slow ranks to fast ones.  `damp` < 1 takes only part of the step (factor ** damp): moving
+    rows changes tile counts, so the full step tends to overshoot and swap the roles of the ranks.  Returns the new pieces
+    (split at the old cuts)."""
     world = len(ranges_per_rank)
     model = []
     for r in range(world):
@@ -148,7 +150,7 @@ def reweigh_pieces(pieces, ranges_per_rank, times_ms: Sequence[float]):
             a, b = max(lo, ranges_per_rank[r][s][0]), min(hi, ranges_per_rank[r][s][1])
             if b > a:
                 f = (times_ms[r] / mean_t) / (model[r] / mean_m) if model[r] > 0 else 1.0
-                out.append((s, a, b, wt * f))
+                out.append((s, a, b, wt * f ** damp))
     out.sort(key=lambda p: (p[0], p[1]))
     return out
 

@@ -63,6 +63,43 @@ def test_small_bonds_leave_idle_ranks_not_crashes(D, world):
     assert n_idle < world
 
 
+def test_partition_feedback_moves_rows_from_slow_ranks():
+    """sharding.reweigh_pieces: after the step the modelled share of every rank equals its measured share (damp = 1) or lies
+    between the old and the measured one (damp < 1); the re-cut line still tiles every sector exactly once."""
+    degs = [40, 200, 680, 200, 40]
+    cost = np.array([1.0, 2.0, 3.0, 2.0, 1.0])          # per-row cost of each sector
+    world = 4
+    pieces = sh.line_pieces(cost, degs)
+    cuts = sh.cut_line(pieces, len(degs), degs, world, snap=8)
+    times = [1.0, 1.3, 0.9, 1.1]                        # rank 1 is slow, rank 2 fast
+
+    def model(pcs, ranges):
+        out = []
+        for r in range(world):
+            w = 0.0
+            for s, lo, hi, wt in pcs:
+                a, b = max(lo, ranges[r][s][0]), min(hi, ranges[r][s][1])
+                w += max(0, b - a) * wt
+            out.append(w)
+        return np.array(out) / sum(out)
+
+    before = model(pieces, cuts)
+    want = np.array(times) / sum(times)                  # measured shares
+    full = model(sh.reweigh_pieces(pieces, cuts, times, damp=1.0), cuts)
+    assert np.allclose(full, want, rtol=1e-12)
+    half = model(sh.reweigh_pieces(pieces, cuts, times, damp=0.5), cuts)
+    for r in range(world):
+        lo, hi = sorted((before[r], want[r]))
+        assert lo - 1e-12 <= half[r] <= hi + 1e-12
+    # the slow rank's rows got heavier: an equal cut of the new line gives it fewer rows
+    new_cuts = sh.cut_line(sh.reweigh_pieces(pieces, cuts, times, damp=0.5), len(degs), degs, world, snap=8)
+    rows = lambda c, r: sum(hi - lo for lo, hi in c[r])
+    assert rows(new_cuts, 1) < rows(cuts, 1) and rows(new_cuts, 2) > rows(cuts, 2)
+    for s, d in enumerate(degs):                         # every sector still tiled exactly once
+        segs = sorted((c[s] for c in new_cuts if c[s][1] > c[s][0]))
+        assert segs[0][0] == 0 and segs[-1][1] == d and all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
+
+
 def test_restricted_operand_is_a_row_slice():
     ts = make_tensors(64, np.complex128, 2)
     mine, info = sh.shard_heff_tensors(ts, 4, 1)
