@@ -358,14 +358,18 @@ std::string BuildTiles(PlanHost *h) {
   struct GInfo { uint32_t gi, tm, tn, stages; };
   std::vector<GInfo> dm;
   uint64_t total_stage_tiles = 0;
-  {   // narrow-pair items: how many sub-chunks each may hold while every resident CTA (4 per SM) still gets ~8 items
+  {   // narrow-pair items: how many sub-chunks each may hold while every resident CTA (4 per SM) still gets ~2 items
     uint64_t chunks = 0;
     for (const GemmGroup &g : h->part_groups) {
       if (g.row_end <= g.row_begin || !Classify(h, g, 8).skinny) continue;
       const uint32_t per = uint32_t(kSkinnyElems) / g.n;
       chunks += (g.row_end - g.row_begin + per - 1) / per;
     }
-    const uint64_t want_items = uint64_t(std::max(1, h->num_sms)) * 4 * 8;
+    // items per resident CTA slot: 2 keeps the tail short and pays the descriptor chain + table build of an item (3-4 us, as
+    // much as 1024 outputs take to stream) seldom; 8 was measured 25 % slower on 8-way shards, equal elsewhere (exp/r2_call34.sh)
+    uint64_t per_slot = 2;
+    if (const char *ov = std::getenv("QLB200_SKINNY_ITEMS_PER_SLOT")) per_slot = uint64_t(std::max(1, std::atoi(ov)));      // tuning aid
+    const uint64_t want_items = uint64_t(std::max(1, h->num_sms)) * 4 * per_slot;
     h->skinny_sub = uint32_t(std::min<uint64_t>(kSkinnyMaxSub, std::max<uint64_t>(1, chunks / want_items)));
   }
   for (uint32_t gi = 0; gi < h->part_groups.size(); ++gi) {
@@ -530,6 +534,8 @@ std::string BuildTiles(PlanHost *h) {
     const long long v = std::atoll(ov);
     if (v > 0) chunk = uint64_t(v);
   }
+  if (std::getenv("QLB200_DEBUG_TILES") && !h->items.empty())
+    std::fprintf(stderr, "[qlb200 tiles] narrow-pair items %zu, sub-chunks per item %u\n", h->items.size(), h->skinny_sub);
   if (std::getenv("QLB200_DEBUG_TILES") && !dm.empty()) {
     double wsum = 0;
     for (const GInfo &d : dm)
