@@ -427,7 +427,7 @@ def measure_heff(args, env):
                 return ShardedChain(ctx, tensors, wl.HEFF_STEPS, "lenv", 2, np_dtype(dtype), world, rank, flags=args.plan_flags,
                                     exchange=args.exchange, host_input="psi", pieces=pieces, snap=args.snap, plumbing=args.plumbing)
 
-        def local_times():
+        def local_times(sharded):
             """Median local-step time of every rank under the current cuts (host-launched applies; the launch overhead is the
             same on every rank and only damps the correction)."""
             with torch.cuda.stream(stream):
@@ -448,23 +448,11 @@ def measure_heff(args, env):
                 torch.distributed.all_gather(allt, mine_t)
                 return [float(x[0]) for x in allt]
 
-        # every candidate partition is measured, the one whose slowest rank is fastest is kept (the feedback is a heuristic:
-        # moving rows changes tile counts, so a step can overshoot); all ranks see the same gathered times and decide alike
-        best = None
-        for it in range(args.rebalance + 1):
-            times = local_times()
-            rebalance_log.append([round(t, 4) for t in times])
-            if best is None or max(times) < best[0]:
-                best = (max(times), sharded.info.pieces, it)
-            if it == args.rebalance:
-                break
-            pieces = shd.reweigh_pieces(sharded.info.pieces, sharded.info.sector_ranges, times, damp=args.rebalance_damp)
-            sharded.close()
-            sharded = build(pieces)
-        if args.rebalance and best[2] != args.rebalance:
-            sharded.close()
-            sharded = build(best[1])
-        rebalance_kept = best[2] if args.rebalance else 0
+        # every candidate cut is measured and the best kept (sharding.tune_partition); all ranks see the same gathered times
+        rebalance_kept = 0
+        if args.rebalance:
+            sharded, rebalance_kept, log = shd.tune_partition(sharded, build, local_times, rounds=args.rebalance, damp=args.rebalance_damp)
+            rebalance_log = [[round(t, 4) for t in times] for times in log]
         chain = sharded.chain
         apply_fn = sharded.apply
     else:
@@ -791,7 +779,7 @@ def measure_heff(args, env):
     if rank_phase is not None:
         line["rank_phases"] = rank_phase
         line["partition_feedback"] = {"iterations": args.rebalance, "kept_partition": rebalance_kept, "local_ms_by_rank_of_each_partition": rebalance_log,
-                                      "how": "rows of the split bond re-weighted by measured time / modelled flops per rank, cut again (set-up time)"}
+                                      "how": "sharding.tune_partition at set-up: rows of the split bond re-weighted by (measured time / modelled flops)^damp of the rank that owned them and cut again; every cut measured, the best kept", "damp": args.rebalance_damp}
     if args.breakdown:
         for rp in rank_phase or []:
             print(f"  rank {rp['rank']}: local steps {rp['local_steps_ms']:.3f} ms, exchange + wait {rp['exchange_and_wait_ms']:.3f} ms", file=sys.stderr)

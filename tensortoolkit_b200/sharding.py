@@ -155,6 +155,30 @@ def reweigh_pieces(pieces, ranges_per_rank, times_ms: Sequence[float], damp: flo
     return out
 
 
+def tune_partition(chain, build, measure, rounds: int = 4, damp: float = 0.5):
+    """Partition feedback loop (set-up time autotuning, like the planner's split-K simulation): `chain` is the sharded chain
+    built on the flop-balanced cuts (anything with `.info.pieces`, `.info.sector_ranges` and `.close()`), `build(pieces)` builds one
+    on other weights, `measure(chain)` returns the local time of EVERY rank (the same list on all ranks, e.g. all-gathered), so
+    all ranks take the same decisions without talking.  Every candidate cut is measured; the one whose slowest rank is fastest
+    is kept (a step can overshoot: moving rows changes tile counts).  Returns (chain, index of the kept cut, measured times of
+    every cut)."""
+    log, best = [], None
+    for it in range(rounds + 1):
+        times = [float(t) for t in measure(chain)]
+        log.append(times)
+        if best is None or max(times) < best[0]:
+            best = (max(times), chain.info.pieces, it)
+        if it == rounds:
+            break
+        pieces = reweigh_pieces(chain.info.pieces, chain.info.sector_ranges, times, damp=damp)
+        chain.close()
+        chain = build(pieces)
+    if best[2] != rounds:
+        chain.close()
+        chain = build(best[1])
+    return chain, best[2], log
+
+
 def restrict_tensor(t: BlockSparseTensor, axis: int, ranges: Sequence[Tuple[int, int]]) -> BlockSparseTensor:
     """Sub-tensor keeping rows [lo, hi) of every sector of index `axis` (empty sectors dropped)."""
     ix = t.indexes[axis]

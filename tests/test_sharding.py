@@ -100,6 +100,42 @@ def test_partition_feedback_moves_rows_from_slow_ranks():
         assert segs[0][0] == 0 and segs[-1][1] == d and all(a[1] == b[0] for a, b in zip(segs, segs[1:]))
 
 
+def test_tune_partition_keeps_the_best_measured_cut():
+    """sharding.tune_partition on a synthetic machine whose rank 1 is 30 % slow and whose time has a per-tile step (64 rows):
+    the kept cut is never worse than the flop-balanced one, every abandoned chain is closed, and the loop is deterministic."""
+    import types
+    degs = [40, 200, 680, 200, 40]
+    cost = np.array([1.0, 2.0, 3.0, 2.0, 1.0])
+    world = 4
+    slow = [1.0, 1.3, 1.0, 1.0]
+    closed = []
+
+    def build(pieces):
+        cuts = sh.cut_line(pieces, len(degs), degs, world, snap=8)
+        c = types.SimpleNamespace(info=types.SimpleNamespace(pieces=pieces, sector_ranges=cuts))
+        c.close = lambda c=c: closed.append(id(c))
+        return c
+
+    def measure(c):
+        out = []
+        for r in range(world):
+            t = 0.0
+            for s, (lo, hi) in enumerate(c.info.sector_ranges[r]):
+                t += -(-(hi - lo) // 64) * 64 * cost[s]      # whole tiles of 64 rows
+            out.append(t * slow[r])
+        return out
+
+    first = build(sh.line_pieces(cost, degs))
+    t0 = max(measure(first))
+    chain, kept, log = sh.tune_partition(first, build, measure, rounds=4, damp=0.5)
+    assert len(log) == 5 and max(measure(chain)) == min(max(t) for t in log) <= t0
+    assert max(log[kept]) == max(measure(chain))
+    assert max(measure(chain)) < t0                        # the slow rank did get fewer rows
+    assert len(closed) == (4 if kept == 4 else 5) and id(chain) not in closed
+    chain2, kept2, log2 = sh.tune_partition(build(sh.line_pieces(cost, degs)), build, measure, rounds=4, damp=0.5)
+    assert kept2 == kept and log2 == log
+
+
 def test_restricted_operand_is_a_row_slice():
     ts = make_tensors(64, np.complex128, 2)
     mine, info = sh.shard_heff_tensors(ts, 4, 1)
