@@ -29,7 +29,7 @@ template<typename T>
 __global__ void __launch_bounds__(kPermThreads)
 PermuteKernel(const PermBlk *__restrict__ blks, const uint32_t *__restrict__ tile_base, uint32_t nblk,
               uint32_t ntiles, const T *__restrict__ srcA, const T *__restrict__ srcB,
-              T *__restrict__ dstA, T *__restrict__ dstB) {
+              T *__restrict__ dstA, T *__restrict__ dstB, uint32_t allow_bulk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *s = reinterpret_cast<T *>(smem_raw);
   __shared__ PermBlk sd;
@@ -90,7 +90,7 @@ PermuteKernel(const PermBlk *__restrict__ blks, const uint32_t *__restrict__ til
     const float scale = sd.scale;
     const uint32_t s_out = sd.sstr[jout], d_in = sd.dstr[jin], d_out = sd.dstr[jout];
 
-    if (V != 0u && sd.bulk != 0u) {
+    if (V != 0u && sd.bulk != 0u && allow_bulk != 0u) {
       // run mode, bulk asynchronous copies (no per-element instructions at all): thread 0 queues TOa copies of TIa*V contiguous
       // source elements into shared memory, completing on the mbarrier; then every thread queues one shared -> global copy
       // per V-element run of the tile (TIa*TOa runs), commits them and waits until shared memory has been read
@@ -259,16 +259,20 @@ cudaError_t LaunchPermute(int dtype, const PermBlk *blks, const uint32_t *tile_b
                           int num_sms, cudaStream_t stream) {
   if (ntiles == 0) return cudaSuccess;
   const uint32_t grid = ntiles < uint32_t(num_sms) * 6u ? ntiles : uint32_t(num_sms) * 6u;
+  // the plan marks runs whose ELEMENT offsets are 16-byte aligned; bulk copies also need 16-byte aligned base pointers, which
+  // only the caller's buffers can break (a double buffer at an odd element of a larger allocation)
+  const auto misaligned = [](const void *q) { return q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
+  const uint32_t allow_bulk = (misaligned(srcA) || misaligned(srcB) || misaligned(dstA) || misaligned(dstB)) ? 0u : 1u;
   if (dtype == 0) {
     const size_t smem = kPermSmemElems * sizeof(double);
     PermuteKernel<double><<<grid, kPermThreads, smem, stream>>>(
         blks, tile_base, nblk, ntiles, static_cast<const double *>(srcA), static_cast<const double *>(srcB),
-        static_cast<double *>(dstA), static_cast<double *>(dstB));
+        static_cast<double *>(dstA), static_cast<double *>(dstB), allow_bulk);
   } else {
     const size_t smem = kPermSmemElems * sizeof(double2);
     PermuteKernel<double2><<<grid, kPermThreads, smem, stream>>>(
         blks, tile_base, nblk, ntiles, static_cast<const double2 *>(srcA), static_cast<const double2 *>(srcB),
-        static_cast<double2 *>(dstA), static_cast<double2 *>(dstB));
+        static_cast<double2 *>(dstA), static_cast<double2 *>(dstB), allow_bulk);
   }
   return cudaGetLastError();
 }

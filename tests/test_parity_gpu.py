@@ -185,6 +185,43 @@ def test_deterministic_repeat(ctx):
     assert np.array_equal(c1.data, c2.data)
 
 
+def test_permute_pass_on_device_buffers_that_are_only_8_byte_aligned(ctx):
+    """The permute kernel's bulk-copy path (cp.async.bulk) needs 16-byte aligned base pointers; the plan only knows element
+    offsets.  Double operands handed over at an odd element of a larger allocation must take the element path and still give
+    the same numbers as the aligned call (which takes the bulk path: every run here is 16-byte aligned)."""
+    import ctypes as C
+    from tensortoolkit_b200.heff import DeviceBuffer
+    rng = np.random.default_rng(7)
+    n1, k, n2, m = 6, 40, 8, 24                      # B stored (n1, k, n2), contracted over k; runs of n2 = 8 doubles
+    a = rng.random((m, k)); b = rng.random((n1, k, n2))
+    want = (a @ np.transpose(b, (1, 0, 2)).reshape(k, n1 * n2)).reshape(-1)
+    t = _lib.Task()
+    t.a_ord = t.b_ord = t.c_ord = 0
+    t.a_off = t.b_off = t.c_off = 0
+    t.m, t.k, t.n, t.sign, t.first = m, k, n1 * n2, 1, 1
+    tarr = (_lib.Task * 1)(t)
+    ash = np.array([(m, k)], np.uint32); bsh = np.array([(n1, k, n2)], np.uint32)
+    zero = np.zeros(1, np.uint64)
+    h = C.c_void_p()
+    _lib.check(_lib.lib.qlb200_plan_create_raw(
+        ctx.h, _lib.F64, _lib.PLAN_DETERMINISTIC | 256, 2, (C.c_int32 * 2)(0, 1), 1, ash.ctypes.data_as(C.POINTER(C.c_uint32)),
+        zero.ctypes.data_as(C.POINTER(C.c_uint64)), 3, (C.c_int32 * 3)(1, 0, 2), 1, bsh.ctypes.data_as(C.POINTER(C.c_uint32)),
+        zero.ctypes.data_as(C.POINTER(C.c_uint64)), 1, tarr, m * n1 * n2, C.byref(h)), "plan_create_raw")     # 256 = QLB200_PLAN_NO_VIEW
+    bufs = [DeviceBuffer(ctx, x.nbytes + 16) for x in (a, b)] + [DeviceBuffer(ctx, want.nbytes + 16)]
+    for shift in (0, 8):
+        for buf, x in zip(bufs, (a, b)):
+            _lib.check(_lib.lib.qlb200_memcpy_h2d(ctx.h, C.c_void_p(buf.ptr + shift), x.ctypes.data, x.nbytes), "h2d")
+        _lib.check(_lib.lib.qlb200_execute(ctx.h, h, C.c_void_p(bufs[0].ptr + shift), C.c_void_p(bufs[1].ptr + shift),
+                                           C.c_void_p(bufs[2].ptr + shift), _lib.MEM_DEVICE), "execute")
+        got = np.empty_like(want)
+        _lib.check(_lib.lib.qlb200_memcpy_d2h(ctx.h, got.ctypes.data, C.c_void_p(bufs[2].ptr + shift), got.nbytes), "d2h")
+        ctx.sync()
+        assert util.rel_fro(got, want) <= TOL, shift
+    _lib.lib.qlb200_plan_destroy(h)
+    for buf in bufs:
+        buf.free()
+
+
 def test_ragged_raw_plan_vs_numpy(ctx):
     """Config 5 in miniature: descriptor table built directly (no shells), ragged m/k/n in [1, 300],
     several pairs per output block, rank-3 operand blocks with the config-5 permutations."""
