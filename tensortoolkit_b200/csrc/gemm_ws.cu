@@ -221,7 +221,7 @@ __device__ __noinline__ void FixupTile(const GemmParams &p, const GemmTile &tile
   const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * WBM, col0 = uint32_t(tile.tn) * WBN;
   const double2 *src0 = static_cast<const double2 *>(p.partials) + (unsigned long long) tile.part_base * (WBM * WBN) +
                         g4 * WBN + q * 8 + 2 * t4;
-#pragma unroll 1
+#pragma unroll 2
   for (int i = 0; i < 4; ++i) {
     double2 sum[NT][2];
 #pragma unroll

@@ -114,7 +114,7 @@ __device__ __noinline__ void FixupTileR(const GemmParams &p, const GemmTile &til
   const uint32_t row0 = g.row_begin + uint32_t(tile.tm) * RBM, col0 = uint32_t(tile.tn) * RBN;
   const double *src0 = static_cast<const double *>(p.partials) + (unsigned long long) tile.part_base * (RBM * RBN) +
                        g4 * RBN + q * 8 + 2 * t4;
-#pragma unroll 1
+#pragma unroll 4
   for (int i = 0; i < 8; ++i) {
     double2 sum[4];
 #pragma unroll
