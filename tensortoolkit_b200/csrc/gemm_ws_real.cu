@@ -20,7 +20,8 @@
 // stages from now; the copy that comes for it later finds a short, uniform latency.  Measured (exp/r2_call23.sh): step 4 of the
 // U(1) chain 0.76 -> 0.82 of DGEMM at D=4096, 0.79 -> 0.85 on the Hubbard chain; the distance (4 / 8 / 16) does not matter.
 // Prefetching the other three operand layouts as well (k x m stored A, both B layouts: 16 rows of 512 .. 1024 contiguous
-// bytes per stage, or an L2-resident operand) was measured too and LOSES 1 - 4 % (exp/r2_call24.sh): not done.  The complex
+// bytes per stage, or an L2-resident operand) was measured too and LOSES 1 - 4 % (exp/r2_call24.sh); k x m stored A alone
+// changes nothing (exp/r2_call44.sh): not done.  The complex
 // kernel (16-byte elements: 256 bytes per row and stage) gains nothing from it either (exp/r2_call25.sh).
 #ifndef QLB200_REAL_PF_STAGES
 #define QLB200_REAL_PF_STAGES 8
