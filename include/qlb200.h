@@ -219,6 +219,13 @@ typedef struct qlb200_unit {
 } qlb200_unit;
 uint64_t qlb200_plan_units(const qlb200_plan *p, uint64_t cap, qlb200_unit *out, uint32_t *tile_rows, uint32_t *tile_cols,
                            uint32_t *stage_k);
+/* Work items of the narrow-pair kernel (output blocks with n <= 8 and every k <= 32): item i covers rows
+ * [row0, row0 + rows) of output block `group`.  Returns their number; fills at most `cap`. */
+typedef struct qlb200_item {
+  uint32_t group, row0, rows;
+  uint32_t n;                      /* columns of the output block */
+} qlb200_item;
+uint64_t qlb200_plan_items(const qlb200_plan *p, uint64_t cap, qlb200_item *out);
 /* QLB200_PLAN_STREAM_K plans: CTA b runs units [seg[b], seg[b+1]).  Returns the number of table entries (CTAs + 1; 0 for
  * plans whose units are pulled dynamically); fills at most `cap`. */
 uint64_t qlb200_plan_segments(const qlb200_plan *p, uint64_t cap, uint32_t *seg_out);

@@ -72,6 +72,10 @@ class AccumStats(C.Structure):
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 
 
+class Item(C.Structure):
+    _fields_ = [("group", C.c_uint32), ("row0", C.c_uint32), ("rows", C.c_uint32), ("n", C.c_uint32)]
+
+
 class Unit(C.Structure):
     _fields_ = [("group", C.c_uint32), ("tm", C.c_uint32), ("tn", C.c_uint32), ("s_begin", C.c_uint32), ("s_end", C.c_uint32),
                 ("split", C.c_uint32), ("nsplit", C.c_uint32), ("rows", C.c_uint32), ("cols", C.c_uint32)]
@@ -125,6 +129,7 @@ SYMBOLS = {
     "qlb200_plan_operand_block": (C.c_int, [_P, C.c_int, C.c_uint64, _U64P]),
     "qlb200_plan_read_workspace": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, _P]),
     "qlb200_plan_units": (C.c_uint64, [_P, C.c_uint64, C.POINTER(Unit), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "qlb200_plan_items": (C.c_uint64, [_P, C.c_uint64, C.POINTER(Item)]),
     "qlb200_plan_segments": (C.c_uint64, [_P, C.c_uint64, C.POINTER(C.c_uint32)]),
     "qlb200_execute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "qlb200_execute_permute": (C.c_int, [_P, _P, _P, _P]),

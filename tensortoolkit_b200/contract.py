@@ -189,6 +189,13 @@ class ContractionPlan:
         lib.qlb200_plan_units(self.h, n, arr, C.byref(bm), C.byref(bn), C.byref(bk))
         return [arr[i] for i in range(n)], (bm.value, bn.value, bk.value)
 
+    def items(self):
+        """Work items of the narrow-pair kernel: list of (group, row0, rows, n) -- qlb200_plan_items."""
+        n = int(lib.qlb200_plan_items(self.h, 0, None))
+        arr = (_lib.Item * max(n, 1))()
+        lib.qlb200_plan_items(self.h, n, arr)
+        return [(arr[i].group, arr[i].row0, arr[i].rows, arr[i].n) for i in range(n)]
+
     def segments(self):
         """Stream-K plans: unit range boundaries per CTA (qlb200_plan_segments); [] for dynamically scheduled plans."""
         n = int(lib.qlb200_plan_segments(self.h, 0, None))

@@ -475,6 +475,19 @@ uint64_t qlb200_plan_units(const qlb200_plan *p, uint64_t cap, qlb200_unit *out,
   return n;
 }
 
+uint64_t qlb200_plan_items(const qlb200_plan *p, uint64_t cap, qlb200_item *out) {
+  if (!p) return 0;
+  const uint64_t n = p->h.items.size();
+  for (uint64_t i = 0; i < n && i < cap && out; ++i) {
+    const SkinnyItem &it = p->h.items[i];
+    const GemmGroup &g = p->h.part_groups[it.group];
+    const uint32_t sub_rows = uint32_t(kSkinnyElems) / g.n;       // as the kernel computes it
+    out[i].group = it.group; out[i].row0 = it.row0; out[i].n = g.n;
+    out[i].rows = std::min<uint32_t>(sub_rows * p->h.skinny_sub, g.row_end - it.row0);
+  }
+  return n;
+}
+
 uint64_t qlb200_plan_segments(const qlb200_plan *p, uint64_t cap, uint32_t *seg_out) {
   if (!p) return 0;
   for (uint64_t i = 0; i < p->h.seg.size() && i < cap && seg_out; ++i) seg_out[i] = p->h.seg[i];

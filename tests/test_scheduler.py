@@ -60,6 +60,43 @@ def check_units(plan, match, dtype, stream_k=False):
     return sum(c["elems"] for c in cover.values())
 
 
+def check_items(plan):
+    """Narrow-pair work items: the items of a block are consecutive row ranges starting at row 0, none empty, none longer than
+    the kernel's item size; returns the output elements they cover."""
+    by_group = {}
+    for g, row0, rows, n in plan.items():
+        assert rows >= 1 and 1 <= n <= 8
+        by_group.setdefault(g, []).append((row0, rows, n))
+    elems = 0
+    for g, its in by_group.items():
+        its.sort()
+        assert its[0][0] == 0
+        for (r0, nr, n), (r1, _, n1) in zip(its, its[1:]):
+            assert r0 + nr == r1 and n == n1                         # contiguous, no overlap
+        per = {nr for _, nr, _ in its[:-1]}
+        assert len(per) <= 1 and all(its[-1][1] <= x for x in per)   # equal items, a shorter tail
+        elems += sum(nr * n for _, nr, n in its)
+    return elems
+
+
+@pytest.mark.parametrize("per_slot", ["1", "2", "8"])
+def test_narrow_pair_items_tile_their_blocks(per_slot, monkeypatch):
+    """The MPO-application steps of the chain at two sizes, with the item-size tuning switch at several settings."""
+    monkeypatch.setenv("QLB200_SKINNY_ITEMS_PER_SLOT", per_slot)
+    seen = 0
+    for D in (300, 1500):
+        ms = heff_matches(wl.u1_heisenberg_indexes(D), np.complex128)
+        for m in ms:
+            plan = tk.ContractionPlan(None, m, np.complex128, _lib.PLAN_DETERMINISTIC)
+            st = plan.stats()
+            n = check_items(plan)
+            if st.ntile_dmma == 0:
+                assert n == m.c_elems                                # a pure narrow-pair step: the items are all of C
+                seen += 1
+            plan.close(); m.close()
+    assert seen == 4                                                 # steps 2 and 3 of both chains
+
+
 @pytest.mark.parametrize("dtype", [np.complex128, np.float64])
 @pytest.mark.parametrize("flags", [0, _lib.PLAN_STAGGER_OUTPUT, _lib.PLAN_NO_SPLIT_K, _lib.PLAN_CPLX_4M, _lib.PLAN_NO_SKINNY | _lib.PLAN_STAGGER_OUTPUT,
                                    _lib.PLAN_STREAM_K, _lib.PLAN_STREAM_K | _lib.PLAN_CPLX_4M | _lib.PLAN_NO_SKINNY])
@@ -73,6 +110,7 @@ def test_units_cover_every_tile_once(workload, flags, dtype):
         covered = check_units(plan, m, dtype, stream_k=bool(flags & _lib.PLAN_STREAM_K))
         if st.nrow_skinny == 0 and st.ntile_dmma:
             assert covered == m.c_elems                              # all of C comes from DMMA tiles
+        assert covered + check_items(plan) == m.c_elems              # DMMA tiles + narrow-pair items = every element of C, once
         plan.close(); m.close()
 
 
