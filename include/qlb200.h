@@ -335,6 +335,29 @@ int qlb200_ipc_export(qlb200_ctx *ctx, const void *dev_ptr, unsigned char *handl
 int qlb200_ipc_open(qlb200_ctx *ctx, const unsigned char *handle64, void **peer_ptr);
 int qlb200_ipc_close(qlb200_ctx *ctx, void *peer_ptr);
 
+/* ---- row-slab partitioner of a contraction chain (host only) ------------------------------------------------------- */
+/* The reference distributes the DMRG mat-vec over MPI ranks by restricting one FREE index of the first operand to one QN
+ * sector per work unit (dmrg::Contract1Sector, dmrg/contract_1sector.h:181-228).  Here the unit is a range of ROWS of a
+ * sector: the rows of the split index form one line (sector-major) of weighted pieces, rank r owns the r-th equal-weight
+ * segment.  All ranks compute the same cuts from the same numbers.  (tensortoolkit_b200/sharding.py is the Python face.) */
+typedef struct qlb200_piece {
+  uint32_t sector, lo, hi;         /* rows [lo, hi) of one sector of the split index */
+  uint32_t pad_;
+  double weight;                   /* cost per row */
+} qlb200_piece;
+/* cost[s] += flops of every matched pair whose A block lies in sector s of A's index `axis` (2 m k n, 8 m k n complex):
+ * summed over the steps of a chain (the split index stays a free index of the left operand) this is the line's weight */
+int qlb200_shard_sector_flops(const qlb200_match *m, int32_t axis, int dtype, double *cost);
+/* ranges_out[(r * nsct + s) * 2 + {0, 1}] = rows [lo, hi) of sector s owned by rank r; cuts inside a sector are multiples of
+ * `snap` rows.  A rank may come out empty (world larger than what can be cut). */
+int qlb200_shard_cut_line(const qlb200_piece *pieces, uint64_t npieces, const uint32_t *degs, uint32_t nsct, int32_t world,
+                          int32_t snap, uint32_t *ranges_out);
+/* Feedback step: times[r] = measured time of rank r's share under `ranges` (cut from `pieces`); every rank's rows are
+ * re-weighted by ((time share) / (modelled share)) ^ damp and returned as pieces split at the old cuts (sorted by sector,
+ * row).  Returns their number (at most npieces + world - 1 ... npieces * world); fills at most `cap`. */
+uint64_t qlb200_shard_reweigh(const qlb200_piece *pieces, uint64_t npieces, const uint32_t *ranges, uint32_t nsct, int32_t world,
+                              const double *times, double damp, uint64_t cap, qlb200_piece *out);
+
 /* ---- multi-GPU plumbing without torch / NCCL: symmetric buffers, multicast mapping, device barrier -------------- */
 /* One communicator per rank (a process, or a thread driving its own context) of ONE NVLink domain, world <= 8.  The only
  * thing the caller supplies is an all-gather of a few bytes for the bootstrap -- MPI_Allgather in a TensorToolkit program

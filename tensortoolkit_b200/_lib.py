@@ -72,6 +72,10 @@ class AccumStats(C.Structure):
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 
 
+class Piece(C.Structure):
+    _fields_ = [("sector", C.c_uint32), ("lo", C.c_uint32), ("hi", C.c_uint32), ("pad_", C.c_uint32), ("weight", C.c_double)]
+
+
 class Item(C.Structure):
     _fields_ = [("group", C.c_uint32), ("row0", C.c_uint32), ("rows", C.c_uint32), ("n", C.c_uint32)]
 
@@ -130,6 +134,10 @@ SYMBOLS = {
     "qlb200_plan_read_workspace": (C.c_int, [_P, _P, C.c_int, C.c_uint64, C.c_uint64, _P]),
     "qlb200_plan_units": (C.c_uint64, [_P, C.c_uint64, C.POINTER(Unit), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "qlb200_plan_items": (C.c_uint64, [_P, C.c_uint64, C.POINTER(Item)]),
+    "qlb200_shard_sector_flops": (C.c_int, [_P, C.c_int32, C.c_int, C.POINTER(C.c_double)]),
+    "qlb200_shard_cut_line": (C.c_int, [C.POINTER(Piece), C.c_uint64, _U32P, C.c_uint32, C.c_int32, C.c_int32, _U32P]),
+    "qlb200_shard_reweigh": (C.c_uint64, [C.POINTER(Piece), C.c_uint64, _U32P, C.c_uint32, C.c_int32, C.POINTER(C.c_double), C.c_double,
+                                          C.c_uint64, C.POINTER(Piece)]),
     "qlb200_plan_segments": (C.c_uint64, [_P, C.c_uint64, C.POINTER(C.c_uint32)]),
     "qlb200_execute": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "qlb200_execute_permute": (C.c_int, [_P, _P, _P, _P]),

@@ -475,6 +475,15 @@ uint64_t qlb200_plan_units(const qlb200_plan *p, uint64_t cap, qlb200_unit *out,
   return n;
 }
 
+int qlb200_shard_sector_flops(const qlb200_match *m, int32_t axis, int dtype, double *cost) {
+  if (!m || !cost || axis < 0 || axis >= m->m.a.rank) return Fail(QLB200_ERR_ARG, "bad argument");
+  const Shell &a = m->m.a;
+  const double f = dtype == QLB200_C64 ? 8.0 : 2.0;
+  for (const qlb200_task &t : m->m.tasks)
+    cost[a.coors[uint64_t(t.a_ord) * a.rank + axis]] += f * double(t.m) * double(t.k) * double(t.n);
+  return QLB200_OK;
+}
+
 uint64_t qlb200_plan_items(const qlb200_plan *p, uint64_t cap, qlb200_item *out) {
   if (!p) return 0;
   const uint64_t n = p->h.items.size();

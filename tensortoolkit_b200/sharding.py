@@ -19,6 +19,10 @@ from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 
+import ctypes as C
+
+from . import _lib
+from ._lib import check, lib
 from .contract import Match
 from .tensor import BlockSparseTensor, Index, QNSector
 
@@ -66,12 +70,10 @@ def sector_costs(tensors: Dict[str, BlockSparseTensor], steps, name: str, axis: 
     track, out_axis = _track_axis(steps, ranks, name, axis)
     nsct = tensors[name].indexes[axis].nsct
     cost = np.zeros(nsct)
-    f = 8.0 if np.dtype(dtype) == np.complex128 else 2.0
+    code = _lib.C64 if np.dtype(dtype) == np.complex128 else _lib.F64
     for (lhs, rhs, axes, res), p in zip(steps, track):
         m = Match(shells[lhs], shells[rhs], axes)
-        a_coors = shells[lhs].blk_coors
-        for t in m.tasks():
-            cost[int(a_coors[t.a_ord, p])] += f * t.m * t.k * t.n
+        check(lib.qlb200_shard_sector_flops(m.h, p, code, cost.ctypes.data_as(C.POINTER(C.c_double))), "qlb200_shard_sector_flops")
         shells[res] = m.result_shell(dtype)
         m.close()
     return cost, shells, out_axis
@@ -83,42 +85,21 @@ def line_pieces(cost: np.ndarray, degs: Sequence[int]) -> List[Tuple[int, int, i
     return [(s, 0, int(d), (float(c) / int(d)) if d else 0.0) for s, (c, d) in enumerate(zip(cost, degs))]
 
 
+def _pieces_array(pieces):
+    arr = (_lib.Piece * max(len(pieces), 1))()
+    for i, (s, lo, hi, w) in enumerate(pieces):
+        arr[i].sector, arr[i].lo, arr[i].hi, arr[i].weight = int(s), int(lo), int(hi), float(w)
+    return arr
+
+
 def cut_line(pieces, nsct: int, degs: Sequence[int], world: int, snap: int = 8) -> List[List[Tuple[int, int]]]:
     """Cut the line of rows (sector-major) into `world` contiguous segments of equal weight.  Cuts are snapped to
-    multiples of `snap` rows inside a sector.  Returns [rank][sector] -> (lo, hi)."""
-    degs = [int(d) for d in degs]
-    total = sum((hi - lo) * w for _, lo, hi, w in pieces)
-
-    def locate(target):
-        acc = 0.0
-        for s, lo, hi, w in pieces:
-            c = (hi - lo) * w
-            if acc + c > target and c > 0:
-                r = lo + (target - acc) / w
-                r = int(round(r / snap)) * snap
-                return s, max(0, min(degs[s], r))
-            acc += c
-        return nsct, 0
-    cuts = [(0, 0)] + [locate(total * r / world) for r in range(1, world)] + [(nsct, 0)]
-    for i in range(1, len(cuts)):                      # snapping must not make the cuts run backwards
-        if cuts[i] < cuts[i - 1]:
-            cuts[i] = cuts[i - 1]
-    out = []
-    for r in range(world):
-        (s0, r0), (s1, r1) = cuts[r], cuts[r + 1]
-        ranges = []
-        for s, d in enumerate(degs):
-            lo, hi = 0, d
-            if s < s0 or s > s1:
-                lo = hi = 0
-            else:
-                if s == s0:
-                    lo = r0
-                if s == s1:
-                    hi = r1
-            ranges.append((lo, max(lo, hi)))
-        out.append(ranges)
-    return out
+    multiples of `snap` rows inside a sector.  Returns [rank][sector] -> (lo, hi).  (qlb200_shard_cut_line)"""
+    d = np.ascontiguousarray(degs, dtype=np.uint32)
+    out = np.zeros((world, nsct, 2), np.uint32)
+    check(lib.qlb200_shard_cut_line(_pieces_array(pieces), len(pieces), d.ctypes.data_as(C.POINTER(C.c_uint32)), nsct, world, snap,
+                                    out.ctypes.data_as(C.POINTER(C.c_uint32))), "qlb200_shard_cut_line")
+    return [[(int(lo), int(hi)) for lo, hi in out[r]] for r in range(world)]
 
 
 def row_line_cuts(cost: np.ndarray, degs: Sequence[int], world: int, snap: int = 8) -> List[List[Tuple[int, int]]]:
@@ -132,27 +113,17 @@ def reweigh_pieces(pieces, ranges_per_rank, times_ms: Sequence[float], damp: flo
     so every rank's rows are re-weighted by (measured time / modelled weight) of that rank; cutting the re-weighted line
     into equal parts moves rows from slow ranks to fast ones.  `damp` < 1 takes only part of the step (factor ** damp): moving
     rows changes tile counts, so the full step tends to overshoot and swap the roles of the ranks.  Returns the new pieces
-    (split at the old cuts)."""
+    (split at the old cuts).  (qlb200_shard_reweigh)"""
     world = len(ranges_per_rank)
-    model = []
-    for r in range(world):
-        w = 0.0
-        for s, lo, hi, wt in pieces:
-            a, b = max(lo, ranges_per_rank[r][s][0]), min(hi, ranges_per_rank[r][s][1])
-            if b > a:
-                w += (b - a) * wt
-        model.append(w)
-    mean_t = float(np.mean([t for t, m in zip(times_ms, model) if m > 0])) or 1.0
-    mean_m = float(np.mean([m for m in model if m > 0])) or 1.0
-    out = []
-    for s, lo, hi, wt in pieces:
-        for r in range(world):
-            a, b = max(lo, ranges_per_rank[r][s][0]), min(hi, ranges_per_rank[r][s][1])
-            if b > a:
-                f = (times_ms[r] / mean_t) / (model[r] / mean_m) if model[r] > 0 else 1.0
-                out.append((s, a, b, wt * f ** damp))
-    out.sort(key=lambda p: (p[0], p[1]))
-    return out
+    nsct = len(ranges_per_rank[0]) if world else 0
+    rg = np.ascontiguousarray(ranges_per_rank, dtype=np.uint32).reshape(world, nsct, 2)
+    t = np.ascontiguousarray(times_ms, dtype=np.float64)
+    arr = _pieces_array(pieces)
+    args = (arr, len(pieces), rg.ctypes.data_as(C.POINTER(C.c_uint32)), nsct, world, t.ctypes.data_as(C.POINTER(C.c_double)), float(damp))
+    n = int(lib.qlb200_shard_reweigh(*args, 0, None))
+    out = (_lib.Piece * max(n, 1))()
+    lib.qlb200_shard_reweigh(*args, n, out)
+    return [(int(out[i].sector), int(out[i].lo), int(out[i].hi), float(out[i].weight)) for i in range(n)]
 
 
 def tune_partition(chain, build, measure, rounds: int = 4, damp: float = 0.5):

@@ -136,6 +136,51 @@ def test_tune_partition_keeps_the_best_measured_cut():
     assert kept2 == kept and log2 == log
 
 
+def test_c_partitioner_equals_the_python_restatement():
+    """qlb200_shard_cut_line / qlb200_shard_reweigh (the product) against their Python restatement (tests/util.py) on random
+    lines: identical cuts (integers) and identical pieces (weights to the last bit: same operations in the same order)."""
+    from tests import util
+    rng = np.random.default_rng(5)
+    for case in range(200):
+        nsct = int(rng.integers(1, 20))
+        degs = [int(x) for x in rng.integers(1, 700, nsct)]
+        cost = rng.random(nsct) * rng.integers(0, 2, nsct).clip(0, 1) if case % 7 == 0 else rng.random(nsct) + 0.01
+        world = int(rng.integers(1, 9))
+        snap = int(rng.choice([1, 4, 8, 16]))
+        pieces = sh.line_pieces(cost * np.array(degs), degs)
+        cuts = sh.cut_line(pieces, nsct, degs, world, snap)
+        assert cuts == util.cut_line_py(pieces, nsct, degs, world, snap), case
+        times = list(rng.random(world) + 0.5)
+        for damp in (1.0, 0.5):
+            got = sh.reweigh_pieces(pieces, cuts, times, damp)
+            want = util.reweigh_pieces_py(pieces, cuts, times, damp)
+            assert [(a, b, c) for a, b, c, _ in got] == [(a, b, c) for a, b, c, _ in want], case
+            assert np.array_equal([w for *_, w in got], [w for *_, w in want]) or np.allclose([w for *_, w in got], [w for *_, w in want], rtol=1e-15, atol=0), case
+            cuts2 = sh.cut_line(got, nsct, degs, world, snap)
+            assert cuts2 == util.cut_line_py(want, nsct, degs, world, snap), case
+
+
+def test_sector_costs_attribute_every_flop_once():
+    """qlb200_shard_sector_flops over the four steps of the chain: the line's total weight is the chain's flop count
+    (qlb200_estimate_cost), and it equals a task-by-task restatement."""
+    ti = wl.heff_tensor_indexes(wl.hubbard_indexes(120))
+    rng = np.random.default_rng(3)
+    t = {n: tk.BlockSparseTensor(ix, np.float64).random((0, 0), rng) for n, ix in ti.items()}
+    cost, shells, out_axis = sh.sector_costs(t, wl.HEFF_STEPS, "lenv", 2, np.float64)
+    want = np.zeros_like(cost)
+    total = 0.0
+    cur = dict(t)
+    track, _ = sh._track_axis(wl.HEFF_STEPS, {k: v.rank for k, v in t.items()}, "lenv", 2)
+    for (lhs, rhs, axes, res), p in zip(wl.HEFF_STEPS, track):
+        m = tk.Match(cur[lhs], cur[rhs], axes)
+        for task in m.tasks():
+            want[int(cur[lhs].blk_coors[task.a_ord, p])] += 2.0 * task.m * task.k * task.n
+        total += m.cost(np.float64).flops if hasattr(m, "cost") else sum(2.0 * x.m * x.k * x.n for x in m.tasks())
+        cur[res] = m.result_shell(np.float64)
+        m.close()
+    assert np.allclose(cost, want, rtol=1e-14) and np.isclose(cost.sum(), total, rtol=1e-12)
+
+
 def test_restricted_operand_is_a_row_slice():
     ts = make_tensors(64, np.complex128, 2)
     mine, info = sh.shard_heff_tensors(ts, 4, 1)

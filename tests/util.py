@@ -111,3 +111,66 @@ def assert_same_as_ref(c_bst, c_ref, tol):
     assert c_bst.data.shape == raw.shape
     if raw.size:
         assert rel_fro(c_bst.data, raw) <= tol
+
+
+# ---- Python restatement of the row-slab partitioner (the product calls qlb200_shard_* in the library) ----
+def cut_line_py(pieces, nsct, degs, world, snap=8):
+    degs = [int(d) for d in degs]
+    total = sum((hi - lo) * w for _, lo, hi, w in pieces)
+
+    def locate(target):
+        acc = 0.0
+        for s, lo, hi, w in pieces:
+            c = (hi - lo) * w
+            if acc + c > target and c > 0:
+                r = lo + (target - acc) / w
+                r = int(round(r / snap)) * snap
+                return s, max(0, min(degs[s], r))
+            acc += c
+        return nsct, 0
+    cuts = [(0, 0)] + [locate(total * r / world) for r in range(1, world)] + [(nsct, 0)]
+    for i in range(1, len(cuts)):
+        if cuts[i] < cuts[i - 1]:
+            cuts[i] = cuts[i - 1]
+    out = []
+    for r in range(world):
+        (s0, r0), (s1, r1) = cuts[r], cuts[r + 1]
+        ranges = []
+        for s, d in enumerate(degs):
+            lo, hi = 0, d
+            if s < s0 or s > s1:
+                lo = hi = 0
+            else:
+                if s == s0:
+                    lo = r0
+                if s == s1:
+                    hi = r1
+            ranges.append((lo, max(lo, hi)))
+        out.append(ranges)
+    return out
+
+
+def reweigh_pieces_py(pieces, ranges_per_rank, times_ms, damp=1.0):
+    import numpy as np
+    world = len(ranges_per_rank)
+    model = []
+    for r in range(world):
+        w = 0.0
+        for s, lo, hi, wt in pieces:
+            a, b = max(lo, ranges_per_rank[r][s][0]), min(hi, ranges_per_rank[r][s][1])
+            if b > a:
+                w += (b - a) * wt
+        model.append(w)
+    ts = [t for t, m in zip(times_ms, model) if m > 0]
+    ms = [m for m in model if m > 0]
+    mean_t = (float(np.mean(ts)) if ts else 1.0) or 1.0
+    mean_m = (float(np.mean(ms)) if ms else 1.0) or 1.0
+    out = []
+    for s, lo, hi, wt in pieces:
+        for r in range(world):
+            a, b = max(lo, ranges_per_rank[r][s][0]), min(hi, ranges_per_rank[r][s][1])
+            if b > a:
+                f = (times_ms[r] / mean_t) / (model[r] / mean_m) if model[r] > 0 else 1.0
+                out.append((s, a, b, wt * f ** damp))
+    out.sort(key=lambda p: (p[0], p[1]))
+    return out
