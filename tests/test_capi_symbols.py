@@ -55,3 +55,36 @@ def test_product_never_imports_oracle():
                     assert bad not in src, f"{f} uses the oracle ({bad})"
     for f in ("qlb200.h", os.path.join("qlten_b200", "contract.h")):
         assert "oracle/" not in open(os.path.join(ROOT, "include", f)).read()
+
+
+def test_header_is_plain_c_and_the_partitioner_answers_from_c(tmp_path):
+    """include/qlb200.h must compile as C (the boundary is a C ABI: plain pointers and sizes), and a C program linked
+    against the library gets the known answer of a small partition: two sectors of 100 rows, the second twice as costly per
+    row, two ranks -> the cut lies at row 25 of the second sector (150 of 300 weight units), snapped to a multiple of 8."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "cuts.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "qlb200.h"
+int main(void) {
+  qlb200_piece line[2] = {{0, 0, 100, 0, 1.0}, {1, 0, 100, 0, 2.0}};
+  uint32_t degs[2] = {100, 100}, ranges[2][2][2];
+  if (qlb200_shard_cut_line(line, 2, degs, 2, 2, 8, &ranges[0][0][0]) != QLB200_OK) return 2;
+  printf("%u %u %u %u | %u %u %u %u\n", ranges[0][0][0], ranges[0][0][1], ranges[0][1][0], ranges[0][1][1],
+         ranges[1][0][0], ranges[1][0][1], ranges[1][1][0], ranges[1][1][1]);
+  double t[2] = {1.0, 3.0};
+  qlb200_piece out[4];
+  unsigned long long n = qlb200_shard_reweigh(line, 2, &ranges[0][0][0], 2, 2, t, 1.0, 4, out);
+  printf("%llu %s\n", n, qlb200_version());
+  return 0;
+}
+''')
+    exe = tmp_path / "cuts"
+    lib_dir = os.path.join(root, "tensortoolkit_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-lqlb200", "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0] == "0 100 0 24 | 0 0 24 100"          # 25 snaps to 24
+    assert out[1].split()[0] == "3"                      # sector 0 (rank 0), sector 1 split at the cut
