@@ -358,6 +358,22 @@ int qlb200_shard_cut_line(const qlb200_piece *pieces, uint64_t npieces, const ui
 uint64_t qlb200_shard_reweigh(const qlb200_piece *pieces, uint64_t npieces, const uint32_t *ranges, uint32_t nsct, int32_t world,
                               const double *times, double damp, uint64_t cap, qlb200_piece *out);
 
+/* Row slab of a tensor: keep rows [ranges[2 s], ranges[2 s + 1]) of every sector s of index `axis`; sectors left empty
+ * disappear, and their blocks with them (the restricted operand of a rank; the reference restricts to ONE sector,
+ * dmrg/contract_1sector.h:181-228).  Call once with the output arrays NULL for the counts in *info, then with arrays of those
+ * sizes.  kept_sectors[i] = old number of the slab's sector i (new_deg[i] its degeneracy); kept_blocks[j] = old ordinal of
+ * the slab's block j, new_coors[j * rank ..] its coordinates in the slab; (copy_src, copy_dst, copy_len)[k] = element ranges
+ * that build the slab's raw buffer from the full one (blocks packed in order) -- directly, or on the device with
+ * qlb200_cplan_create. */
+typedef struct qlb200_slab_info {
+  uint32_t nsct_kept;
+  uint32_t pad_;
+  uint64_t nblk_kept, elems, ncopy;
+} qlb200_slab_info;
+int qlb200_shard_restrict(const qlb200_shell *t, int32_t axis, const uint32_t *ranges, qlb200_slab_info *info,
+                          uint32_t *kept_sectors, uint32_t *new_deg, uint32_t *kept_blocks, uint32_t *new_coors,
+                          uint64_t *copy_src, uint64_t *copy_dst, uint64_t *copy_len);
+
 /* ---- multi-GPU plumbing without torch / NCCL: symmetric buffers, multicast mapping, device barrier -------------- */
 /* One communicator per rank (a process, or a thread driving its own context) of ONE NVLink domain, world <= 8.  The only
  * thing the caller supplies is an all-gather of a few bytes for the bootstrap -- MPI_Allgather in a TensorToolkit program

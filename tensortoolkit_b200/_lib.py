@@ -76,6 +76,10 @@ class Piece(C.Structure):
     _fields_ = [("sector", C.c_uint32), ("lo", C.c_uint32), ("hi", C.c_uint32), ("pad_", C.c_uint32), ("weight", C.c_double)]
 
 
+class SlabInfo(C.Structure):
+    _fields_ = [("nsct_kept", C.c_uint32), ("pad_", C.c_uint32), ("nblk_kept", C.c_uint64), ("elems", C.c_uint64), ("ncopy", C.c_uint64)]
+
+
 class Item(C.Structure):
     _fields_ = [("group", C.c_uint32), ("row0", C.c_uint32), ("rows", C.c_uint32), ("n", C.c_uint32)]
 
@@ -135,6 +139,7 @@ SYMBOLS = {
     "qlb200_plan_units": (C.c_uint64, [_P, C.c_uint64, C.POINTER(Unit), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "qlb200_plan_items": (C.c_uint64, [_P, C.c_uint64, C.POINTER(Item)]),
     "qlb200_shard_sector_flops": (C.c_int, [_P, C.c_int32, C.c_int, C.POINTER(C.c_double)]),
+    "qlb200_shard_restrict": (C.c_int, [_P, C.c_int32, _U32P, C.POINTER(SlabInfo), _U32P, _U32P, _U32P, _U32P, _U64P, _U64P, _U64P]),
     "qlb200_shard_cut_line": (C.c_int, [C.POINTER(Piece), C.c_uint64, _U32P, C.c_uint32, C.c_int32, C.c_int32, _U32P]),
     "qlb200_shard_reweigh": (C.c_uint64, [C.POINTER(Piece), C.c_uint64, _U32P, C.c_uint32, C.c_int32, C.POINTER(C.c_double), C.c_double,
                                           C.c_uint64, C.POINTER(Piece)]),

@@ -105,3 +105,65 @@ uint64_t qlb200_shard_reweigh(const qlb200_piece *pieces, uint64_t npieces, cons
 }
 
 }  // extern "C"
+
+// Row slab of a tensor: keep rows [lo, hi) of every sector of index `axis`; sectors with hi <= lo disappear and their blocks
+// with them.  The relabelling of the kept sectors is monotone, so the kept blocks stay in ascending blk_idx order and the slab's
+// raw buffer is the kept blocks' slices packed in that order.  The slice of a block is `outer` runs of (hi - lo) * inner
+// contiguous elements (outer / inner = the extents in front of / behind `axis`): the copy list below builds the slab's buffer
+// from the full one on the host or, through qlb200_cplan_create, on the device.
+extern "C" int qlb200_shard_restrict(const qlb200_shell *t, int32_t axis, const uint32_t *ranges, qlb200_slab_info *info,
+                                     uint32_t *kept_sectors, uint32_t *new_deg, uint32_t *kept_blocks, uint32_t *new_coors,
+                                     uint64_t *copy_src, uint64_t *copy_dst, uint64_t *copy_len) {
+  if (!t || !ranges || !info || axis < 0 || axis >= t->rank || !t->nsct || !t->deg || (t->nblk && !t->blk_coors)) return QLB200_ERR_ARG;
+  const int rank = t->rank;
+  std::vector<uint32_t> base(rank + 1, 0);
+  for (int i = 0; i < rank; ++i) base[i + 1] = base[i] + t->nsct[i];
+  const uint32_t nsct = t->nsct[axis];
+  std::vector<int64_t> new_pos(nsct, -1);
+  uint32_t nkept = 0;
+  for (uint32_t s = 0; s < nsct; ++s) {
+    const uint32_t lo = ranges[2 * s], hi = ranges[2 * s + 1];
+    if (hi > t->deg[base[axis] + s]) return QLB200_ERR_ARG;
+    if (hi > lo) {
+      if (kept_sectors) kept_sectors[nkept] = s;
+      if (new_deg) new_deg[nkept] = hi - lo;
+      new_pos[s] = nkept++;
+    }
+  }
+  uint64_t nblk = 0, elems = 0, ncopy = 0, src_off = 0;
+  for (uint64_t b = 0; b < t->nblk; ++b) {
+    const uint32_t *c = t->blk_coors + b * rank;
+    uint64_t outer = 1, inner = 1, size = 1;
+    for (int i = 0; i < rank; ++i) {
+      if (c[i] >= t->nsct[i]) return QLB200_ERR_ARG;
+      const uint64_t d = t->deg[base[i] + c[i]];
+      size *= d;
+      if (i < axis) outer *= d;
+      if (i > axis) inner *= d;
+    }
+    const uint32_t s = c[axis];
+    if (new_pos[s] >= 0) {
+      const uint64_t lo = ranges[2 * s], hi = ranges[2 * s + 1], rows = t->deg[base[axis] + s];
+      if (kept_blocks) kept_blocks[nblk] = uint32_t(b);
+      if (new_coors) {
+        for (int i = 0; i < rank; ++i) new_coors[nblk * rank + i] = c[i];
+        new_coors[nblk * rank + axis] = uint32_t(new_pos[s]);
+      }
+      const uint64_t run = (hi - lo) * inner;
+      if (hi - lo == rows || outer == 1) {                 // one contiguous piece
+        if (copy_src) { copy_src[ncopy] = src_off + lo * inner; copy_dst[ncopy] = elems; copy_len[ncopy] = run * outer; }
+        ++ncopy;
+      } else {
+        for (uint64_t o = 0; o < outer; ++o) {
+          if (copy_src) { copy_src[ncopy] = src_off + (o * rows + lo) * inner; copy_dst[ncopy] = elems + o * run; copy_len[ncopy] = run; }
+          ++ncopy;
+        }
+      }
+      elems += run * outer;
+      ++nblk;
+    }
+    src_off += size;
+  }
+  info->nsct_kept = nkept; info->nblk_kept = nblk; info->elems = elems; info->ncopy = ncopy;
+  return QLB200_OK;
+}

@@ -150,26 +150,40 @@ def tune_partition(chain, build, measure, rounds: int = 4, damp: float = 0.5):
     return chain, best[2], log
 
 
+def slab_layout(t: BlockSparseTensor, axis: int, ranges: Sequence[Tuple[int, int]]):
+    """qlb200_shard_restrict: (kept old sector numbers, their new degeneracies, kept old block ordinals, the blocks' coordinates
+    in the slab, (src, dst, len) element ranges that build the slab's raw buffer from the full one)."""
+    sv = t.shell()
+    rg = np.ascontiguousarray(ranges, dtype=np.uint32).reshape(-1)
+    info = _lib.SlabInfo()
+    u32, u64 = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    rgp = rg.ctypes.data_as(u32)
+    check(lib.qlb200_shard_restrict(sv.ptr(), axis, rgp, C.byref(info), None, None, None, None, None, None, None), "qlb200_shard_restrict")
+    ks, nd = np.zeros(max(info.nsct_kept, 1), np.uint32), np.zeros(max(info.nsct_kept, 1), np.uint32)
+    kb, nc = np.zeros(max(info.nblk_kept, 1), np.uint32), np.zeros((max(info.nblk_kept, 1), max(t.rank, 1)), np.uint32)
+    cs, cd, cl = (np.zeros(max(info.ncopy, 1), np.uint64) for _ in range(3))
+    check(lib.qlb200_shard_restrict(sv.ptr(), axis, rgp, C.byref(info), ks.ctypes.data_as(u32), nd.ctypes.data_as(u32), kb.ctypes.data_as(u32),
+                                    nc.ctypes.data_as(u32), cs.ctypes.data_as(u64), cd.ctypes.data_as(u64), cl.ctypes.data_as(u64)),
+          "qlb200_shard_restrict")
+    n = int(info.ncopy)
+    return ks[:info.nsct_kept], nd[:info.nsct_kept], kb[:info.nblk_kept], nc[:info.nblk_kept], (cs[:n], cd[:n], cl[:n]), int(info.elems)
+
+
 def restrict_tensor(t: BlockSparseTensor, axis: int, ranges: Sequence[Tuple[int, int]]) -> BlockSparseTensor:
-    """Sub-tensor keeping rows [lo, hi) of every sector of index `axis` (empty sectors dropped)."""
+    """Sub-tensor keeping rows [lo, hi) of every sector of index `axis` (empty sectors dropped): structure and copy list from
+    the library (qlb200_shard_restrict), applied here on the host buffer."""
     ix = t.indexes[axis]
-    keep = [s for s, (lo, hi) in enumerate(ranges) if hi > lo]
-    new_pos = {s: i for i, s in enumerate(keep)}
-    new_ix = Index(ix.kind, [QNSector(ix.sectors[s].qn, ranges[s][1] - ranges[s][0]) for s in keep], ix.dir)
+    kept, new_deg, blocks, coors, (src, dst, ln), elems = slab_layout(t, axis, ranges)
+    new_ix = Index(ix.kind, [QNSector(ix.sectors[int(s)].qn, int(d)) for s, d in zip(kept, new_deg)], ix.dir)
     idxs = list(t.indexes)
     idxs[axis] = new_ix
     out = BlockSparseTensor(idxs, t.dtype)
-    sel = [b for b in range(t.nblk) if int(t.blk_coors[b, axis]) in new_pos]
-    if not sel or not keep:
+    if not len(blocks) or not len(kept):
         return out
-    coors = t.blk_coors[sel].copy()
-    coors[:, axis] = [new_pos[int(c)] for c in coors[:, axis]]
     out.set_blocks(coors)          # relabelling is monotone, so block order is preserved
-    for nb, b in enumerate(sel):
-        lo, hi = ranges[int(t.blk_coors[b, axis])]
-        sl = [slice(None)] * t.rank
-        sl[axis] = slice(lo, hi)
-        out.block(nb)[...] = t.block(b)[tuple(sl)]
+    assert out.data.size == elems
+    for s0, d0, n in zip(src.tolist(), dst.tolist(), ln.tolist()):
+        out.data[d0:d0 + n] = t.data[s0:s0 + n]
     return out
 
 

@@ -181,6 +181,27 @@ def test_sector_costs_attribute_every_flop_once():
     assert np.allclose(cost, want, rtol=1e-14) and np.isclose(cost.sum(), total, rtol=1e-12)
 
 
+def test_c_row_slab_equals_the_numpy_restatement():
+    """qlb200_shard_restrict (structure + copy list, applied by sharding.restrict_tensor) against block-by-block numpy slicing:
+    every axis of a rank-4 fermionic tensor, random row ranges incl. empty and full sectors."""
+    from tests import util
+    rng = np.random.default_rng(11)
+    ti = wl.heff_tensor_indexes(wl.hubbard_indexes(60))
+    for name, div in (("psi", (0, 0)), ("lenv", (0, 0))):
+        t = tk.BlockSparseTensor(ti[name], np.complex128).random(div, rng)
+        for axis in range(t.rank):
+            for trial in range(4):
+                ranges = []
+                for sct in t.indexes[axis].sectors:
+                    d = int(sct.dgnc)
+                    kind = rng.integers(0, 4)
+                    lo, hi = (0, d) if kind == 0 else (0, 0) if kind == 1 else sorted(int(x) for x in rng.integers(0, d + 1, 2))
+                    ranges.append((lo, hi))
+                got, want = sh.restrict_tensor(t, axis, ranges), util.restrict_tensor_py(t, axis, ranges)
+                assert got.same_structure(want) and got.indexes == want.indexes
+                assert np.array_equal(got.data, want.data)
+
+
 def test_restricted_operand_is_a_row_slice():
     ts = make_tensors(64, np.complex128, 2)
     mine, info = sh.shard_heff_tensors(ts, 4, 1)

@@ -174,3 +174,28 @@ def reweigh_pieces_py(pieces, ranges_per_rank, times_ms, damp=1.0):
                 out.append((s, a, b, wt * f ** damp))
     out.sort(key=lambda p: (p[0], p[1]))
     return out
+
+
+def restrict_tensor_py(t, axis, ranges):
+    """numpy restatement of sharding.restrict_tensor (block-by-block slicing)."""
+    import tensortoolkit_b200 as tk
+    from tensortoolkit_b200.tensor import Index, QNSector
+    ix = t.indexes[axis]
+    keep = [s for s, (lo, hi) in enumerate(ranges) if hi > lo]
+    new_pos = {s: i for i, s in enumerate(keep)}
+    new_ix = Index(ix.kind, [QNSector(ix.sectors[s].qn, ranges[s][1] - ranges[s][0]) for s in keep], ix.dir)
+    idxs = list(t.indexes)
+    idxs[axis] = new_ix
+    out = tk.BlockSparseTensor(idxs, t.dtype)
+    sel = [b for b in range(t.nblk) if int(t.blk_coors[b, axis]) in new_pos]
+    if not sel or not keep:
+        return out
+    coors = t.blk_coors[sel].copy()
+    coors[:, axis] = [new_pos[int(c)] for c in coors[:, axis]]
+    out.set_blocks(coors)
+    for nb, b in enumerate(sel):
+        lo, hi = ranges[int(t.blk_coors[b, axis])]
+        sl = [slice(None)] * t.rank
+        sl[axis] = slice(lo, hi)
+        out.block(nb)[...] = t.block(b)[tuple(sl)]
+    return out
