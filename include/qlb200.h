@@ -354,7 +354,8 @@ int qlb200_shard_cut_line(const qlb200_piece *pieces, uint64_t npieces, const ui
                           int32_t snap, uint32_t *ranges_out);
 /* Feedback step: times[r] = measured time of rank r's share under `ranges` (cut from `pieces`); every rank's rows are
  * re-weighted by ((time share) / (modelled share)) ^ damp and returned as pieces split at the old cuts (sorted by sector,
- * row).  Returns their number (at most npieces + world - 1 ... npieces * world); fills at most `cap`. */
+ * row).  Returns their number (every old piece appears once per rank that owns rows of it: at most npieces + world - 1 for
+ * cuts made from the same pieces); fills at most `cap` -- call with cap = 0 first. */
 uint64_t qlb200_shard_reweigh(const qlb200_piece *pieces, uint64_t npieces, const uint32_t *ranges, uint32_t nsct, int32_t world,
                               const double *times, double damp, uint64_t cap, qlb200_piece *out);
 
