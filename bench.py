@@ -585,14 +585,15 @@ def measure_heff(args, env):
                 ctx.sync()
             h2d_b, d2h_b = int(psi_host.nbytes), 0
         else:
-            # N GPUs: every rank uploads 1/N of psi and fans it out over NVLink; every rank downloads its own result slabs
+            # N GPUs: every rank uploads 1/N of psi and fans it out over NVLink; every rank downloads 1/N of the (replicated) result
             # into the one shared host buffer (ShardedChain.apply_host)
             e2e_apply = lambda: sharded.apply_host(psi_host, out_host, apply_fn)
             e2e_how = (f"each rank uploads 1/{world} of psi over its own PCIe link and fans it out to all GPUs "
                        f"({'multimem.st through the NVSwitch' if sharded.in_mc else 'unicast peer stores'}), barrier, sharded apply, each rank "
-                       "downloads its own row slabs of the result into one shared-memory host buffer")
+                       f"downloads 1/{world} of the result (every GPU holds all of it after the exchange) into one shared-memory host buffer")
             h2d_b = int(-(-psi_host.nbytes // world))
-            d2h_b = int(sum(ln for _, ln in sharded.own_ranges()) * es)
+            dl_lo, dl_hi = sharded.download_slice(int(sharded.info.full_elems))
+            d2h_b = int((dl_hi - dl_lo) * es)
         for _ in range(2):
             e2e_apply()
         barrier()

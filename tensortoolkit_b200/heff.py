@@ -560,8 +560,8 @@ class ShardedChain:
         every rank uploads only ITS 1/world share of the input over its own PCIe link and fans it out to all GPUs
         (multimem.st through the NVSwitch, or unicast peer stores); after one barrier the whole input is everywhere.
         Then the sharded apply (`apply_fn`, default self.apply; a captured graph's launch works too) and the download of
-        this rank's OWN row slabs of the result into host_out at their place in the full layout -- the ranks' downloads
-        together are the full result (host_out may be one shared-memory buffer mapped by all ranks)."""
+        this rank's equal slice of the full result (download_slice) into host_out at its place in the full layout -- the
+        ranks' downloads together are the full result (host_out may be one shared-memory buffer mapped by all ranks)."""
         es = self.dtype.itemsize
         if self.host_input is None:
             raise RuntimeError("ShardedChain was built without host_input")
@@ -584,10 +584,20 @@ class ShardedChain:
         else:
             check(lib.qlb200_memcpy_h2d(self.ctx.h, C.c_void_p(self.in_ptr), host_in.ctypes.data, host_in.nbytes), "h2d")
         n_launch = (apply_fn or self.apply)()
-        for off, ln in self.own_ranges():
-            check(lib.qlb200_memcpy_d2h(self.ctx.h, host_out.ctypes.data + off * es, C.c_void_p(self.full_ptr + off * es), ln * es), "d2h")
+        # after the apply's barrier EVERY GPU holds the whole result, so the download need not follow ownership (the edge ranks
+        # own many small-sector rows: up to 1.5 x the mean output): rank r takes the r-th equal slice of the full buffer
+        lo, hi = self.download_slice(host_out.size)
+        if hi > lo:
+            check(lib.qlb200_memcpy_d2h(self.ctx.h, host_out.ctypes.data + lo * es, C.c_void_p(self.full_ptr + lo * es), (hi - lo) * es), "d2h")
         self.ctx.sync()
         return n_launch
+
+    def download_slice(self, n_elems: int):
+        """Element range [lo, hi) of the full result this rank downloads in apply_host (equal slices, 16-byte aligned cuts)."""
+        unit = max(1, 16 // self.dtype.itemsize)
+        per = -(-n_elems // self.world)
+        per = -(-per // unit) * unit
+        return min(n_elems, self.rank * per), min(n_elems, (self.rank + 1) * per)
 
     def download_full(self, host: np.ndarray):
         check(lib.qlb200_memcpy_d2h(self.ctx.h, host.ctypes.data, C.c_void_p(self.full_ptr), host.nbytes), "qlb200_memcpy_d2h")
