@@ -202,6 +202,48 @@ def test_c_row_slab_equals_the_numpy_restatement():
                 assert np.array_equal(got.data, want.data)
 
 
+def test_cpp_client_shards_step_one_like_the_python_face(tmp_path):
+    """tests/cpp/shard_host.cc: a C++ program using only include/qlb200.h reads the shells of lenv and psi, matches, attributes
+    the flops, cuts the row line, builds every rank's slab and matches it -- same rows, slab sizes, task counts and result
+    sizes as tensortoolkit_b200/sharding.py."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ti = wl.heff_tensor_indexes(wl.u1_heisenberg_indexes(700))
+    rng = np.random.default_rng(4)
+    t = {n: tk.BlockSparseTensor(ti[n], np.complex128).random((0,), rng) for n in ("lenv", "psi")}
+    path = tmp_path / "shells.txt"
+    with open(path, "w") as f:
+        for name in ("lenv", "psi"):
+            x = t[name]
+            f.write(f"{x.rank} {x.nblk}\n")
+            for ix in x.indexes:
+                f.write(f"{ix.nsct} {int(ix.dir)}\n")
+            f.write(" ".join(str(int(d)) for ix in x.indexes for d in ix.degs()) + "\n")
+            f.write(" ".join(str(int(c)) for c in x.blk_coors.reshape(-1)) + "\n")
+    exe = tmp_path / "shard_host"
+    lib_dir = os.path.join(root, "tensortoolkit_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "shard_host.cc"), "-o", str(exe), "-L", lib_dir, "-lqlb200", "-Wl,-rpath," + lib_dir])
+    world = 4
+    out = subprocess.run([str(exe), str(path), str(world)], capture_output=True, text=True, check=True).stdout.splitlines()
+    steps = [("lenv", "psi", ([0], [0]), "t1")]
+    m = tk.Match(t["lenv"], t["psi"], ([0], [0]))
+    assert out[0] == f"whole: tasks {len(m.tasks())} c_elems {m.c_elems}"
+    m.close()
+    cost, _, _ = sh.sector_costs(t, steps, "lenv", 2, np.complex128)
+    degs = [int(d) for d in t["lenv"].indexes[2].degs()]
+    cuts = sh.row_line_cuts(cost, degs, world, snap=8)
+    for r in range(world):
+        slab = sh.restrict_tensor(t["lenv"], 2, cuts[r])
+        rows = sum(hi - lo for lo, hi in cuts[r])
+        copies = len(sh.slab_layout(t["lenv"], 2, cuts[r])[4][0])
+        ms = tk.Match(slab, t["psi"], ([0], [0])) if slab.nblk else None
+        want = f"rank {r}: rows {rows} slab_elems {slab.data.size if slab.nblk else 0} copies {copies} tasks {len(ms.tasks()) if ms else 0} c_elems {ms.c_elems if ms else 0}"
+        assert out[1 + r] == want
+        if ms:
+            ms.close()
+
+
 def test_restricted_operand_is_a_row_slice():
     ts = make_tensors(64, np.complex128, 2)
     mine, info = sh.shard_heff_tensors(ts, 4, 1)
