@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--no-cold", action="store_true", help="skip the cold drop-in measurement (4 Contract calls on host tensors incl. match + plan build)")
     ap.add_argument("--pipe-in", default="", help="N=1 e2e: cumulative fractions of the streamed input at which the parts of step 1 are cut (tuning; default ContractionChain.pipe_fractions)")
     ap.add_argument("--pipe-out", default="", help="N=1 e2e: cumulative fractions of the output at which the parts of the last step are cut (tuning)")
+    ap.add_argument("--self-check", action="store_true", help="N=1: compare the apply with the same apply through the alternate kernels of the library (reference-free; for A/B runs with --no-cpu-baseline)")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--plan-flags", type=int, default=1, help="qlb200_plan_create flags (kernel A/B testing; 1 = default)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "multicast", "fused", "allgather"],
@@ -477,6 +478,26 @@ def measure_heff(args, env):
         if not verified <= 1e-12:
             _fatal(f"rank {rank}: sharded apply differs from the unsharded one, rel err {verified:.3e}")
         del got
+    self_check = None
+    if args.self_check and world == 1 and not args.shard_of:
+        # reference-free check for kernel A/B runs that skip the CPU baseline (and with it the parity key): the same apply through
+        # DIFFERENT kernels of this library -- every block through the permute kernel, the four-product complex GEMM, no
+        # narrow-pair kernel -- must give the same tensor.  (A variant that skips or repeats work is wrong in only one of the two.)
+        alt_flags = (tk._lib.PLAN_DETERMINISTIC | tk._lib.PLAN_NO_SKINNY | tk._lib.PLAN_PERMUTE_ALL |
+                     (tk._lib.PLAN_CPLX_4M if dtype == "c128" else 0))
+        with torch.cuda.stream(stream):
+            alt = ContractionChain(ctx, tensors, wl.HEFF_STEPS, np_dtype(dtype), alt_flags)
+            alt.apply_device()
+            want_alt = alt.result("out").data
+            alt.close()
+            chain.apply_device()
+            got_alt = chain.result("out").data
+        sc = float(np.linalg.norm(got_alt - want_alt) / np.linalg.norm(want_alt))
+        if not sc <= 1e-12:
+            _fatal(f"self-check FAILED: this plan's kernels and the alternate kernel path disagree, rel err {sc:.3e}")
+        self_check = {"rel_err_vs_alternate_kernels": sc, "alternate": "PLAN_NO_SKINNY | PLAN_PERMUTE_ALL" + (" | PLAN_CPLX_4M" if dtype == "c128" else ""),
+                      "tolerance": 1e-12}
+        del want_alt, got_alt
     graph = None
     if not args.no_graph:
         # one apply = one CUDA graph launch (kernels, and for N>1 the exchange barrier): no per-kernel host launch cost
@@ -777,6 +798,8 @@ def measure_heff(args, env):
     }
     if verified is not None:
         line["sharded_vs_unsharded_rel_err"] = verified
+    if self_check is not None:
+        line["self_check"] = self_check
     if rank_phase is not None:
         line["rank_phases"] = rank_phase
         line["partition_feedback"] = {"iterations": args.rebalance, "kept_partition": rebalance_kept, "local_ms_by_rank_of_each_partition": rebalance_log,
