@@ -8,6 +8,7 @@
 
 #include "qlten_b200/contract.h"
 #include "qlten_b200/axis_ops.h"
+#include "qlten_b200/sharding.h"
 
 using namespace qlref;
 
@@ -142,6 +143,39 @@ int qlref_b200_transpose(void *t, const int64_t *perm, void *ctx) {
       return 0;
     });
   } catch (const std::exception &e) { std::fprintf(stderr, "qlref_b200_transpose: %s\n", e.what()); return -1; }
+}
+
+// qlten::b200::RowSlab: rows [lo_hi[2 s], lo_hi[2 s + 1]) of every sector s of index `axis` (host only)
+void *qlref_b200_row_slab(const void *t, int64_t axis, int64_t nsct, const int64_t *lo_hi) {
+  return Guard("qlref_b200_row_slab", [&]() -> void * {
+    return Dispatch<TenBase *>(static_cast<const TenBase *>(t), [&](auto *T) -> TenBase * {
+      qlten::b200::RowRanges ranges;
+      for (int64_t s = 0; s < nsct; ++s) ranges.push_back({uint32_t(lo_hi[2 * s]), uint32_t(lo_hi[2 * s + 1])});
+      return T->wrap(qlten::b200::RowSlab(T->t, size_t(axis), ranges));
+    });
+  });
+}
+
+// qlten::b200::SectorFlops + CutRowLine for one contraction: ranges_out[(r * nsct + s) * 2 + {0, 1}]
+int qlref_b200_cut_rows(const void *a, const void *b, int n, const int64_t *aa, const int64_t *ba, int64_t split_axis, int world,
+                        int snap, int64_t *ranges_out) {
+  void *ok = Guard("qlref_b200_cut_rows", [&]() -> void * {
+    return Dispatch<void *>(static_cast<const TenBase *>(a), [&](auto *A) -> void * {
+      std::vector<double> cost;
+      qlten::b200::SectorFlops(A->t, Same(A, static_cast<const TenBase *>(b))->t, MakeAxes(n, aa, ba), size_t(split_axis), cost);
+      const auto &idx = A->t.GetIndex(size_t(split_axis));
+      std::vector<uint32_t> degs;
+      for (size_t s = 0; s < idx.GetQNSctNum(); ++s) degs.push_back(uint32_t(idx.GetQNSct(s).GetDegeneracy()));
+      const auto cuts = qlten::b200::CutRowLine(cost, degs, world, snap);
+      for (int r = 0; r < world; ++r)
+        for (size_t s = 0; s < degs.size(); ++s) {
+          ranges_out[(size_t(r) * degs.size() + s) * 2] = cuts[r][s].first;
+          ranges_out[(size_t(r) * degs.size() + s) * 2 + 1] = cuts[r][s].second;
+        }
+      return const_cast<void *>(a);
+    });
+  });
+  return ok ? 0 : 1;
 }
 
 }  // extern "C"

@@ -92,6 +92,8 @@ def adapter():
             "qlref_b200_contract_1sector": (_P, [_P, C.c_int64, C.c_int64, _P, C.c_int, _I64P, _I64P, _P]),
             "qlref_b200_transpose": (C.c_int, [_P, _I64P, _P]),
             "qlref_b200_contract_contiguous": (_P, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, _P]),
+            "qlref_b200_row_slab": (_P, [_P, C.c_int64, C.c_int64, _I64P]),
+            "qlref_b200_cut_rows": (C.c_int, [_P, _P, C.c_int, _I64P, _I64P, C.c_int64, C.c_int, C.c_int, _I64P]),
             "qlref_b200_apply_rank2": (_P, [_P, _P, C.c_int64, _P, C.c_int64, _P]),
             "qlref_b200_contract_accumulate": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), _P,
                                                          C.c_int, C.POINTER(C.c_uint64), _P]),
@@ -274,6 +276,25 @@ def b200_contract(a: RefTensor, b: RefTensor, axes, ctx_handle=None) -> RefTenso
     if not h:
         raise RuntimeError("qlten::b200::Contract failed")
     return RefTensor(h, _c_indexes(a, b, axes), a.dtype)
+
+
+def b200_row_slab(t: RefTensor, axis: int, ranges, new_indexes) -> RefTensor:
+    """qlten::b200::RowSlab on a reference QLTensor (host only); `new_indexes` = the index list the caller expects."""
+    flat = [int(x) for r in ranges for x in r]
+    h = adapter().qlref_b200_row_slab(t.h, axis, len(ranges), _i64(flat))
+    if not h:
+        raise RuntimeError("qlten::b200::RowSlab failed")
+    return RefTensor(h, new_indexes, t.dtype)
+
+
+def b200_cut_rows(a: RefTensor, b: RefTensor, axes, split_axis: int, world: int, snap: int = 8):
+    """qlten::b200::SectorFlops + CutRowLine for one contraction: [rank][sector] -> (lo, hi)."""
+    nsct = a.indexes[split_axis].nsct
+    out = (C.c_int64 * (world * nsct * 2))()
+    rc = adapter().qlref_b200_cut_rows(a.h, b.h, len(axes[0]), _i64(axes[0]), _i64(axes[1]), split_axis, world, snap, out)
+    if rc != 0:
+        raise RuntimeError("qlten::b200::CutRowLine failed")
+    return [[(int(out[(r * nsct + s) * 2]), int(out[(r * nsct + s) * 2 + 1])) for s in range(nsct)] for r in range(world)]
 
 
 def b200_contract_1sector(a: RefTensor, axis, sct, b: RefTensor, axes, ctx_handle=None) -> RefTensor:

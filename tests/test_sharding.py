@@ -244,6 +244,38 @@ def test_cpp_client_shards_step_one_like_the_python_face(tmp_path):
             ms.close()
 
 
+def test_cpp_adapter_row_slab_and_cuts_on_reference_tensors(ref):
+    """include/qlten_b200/sharding.h instantiated on the reference's own QLTensor types (oracle/_ref/libqladapter.so, host only):
+    qlten::b200::RowSlab gives the tensor sharding.restrict_tensor gives -- same indexes (checked by the reference's own
+    Index ==), same blocks, same raw data -- for bosonic and fermionic tensors, and SectorFlops + CutRowLine give sharding.py's
+    cuts."""
+    rng = np.random.default_rng(21)
+    for ixf, div, dtype in ((wl.u1_heisenberg_indexes, (0,), np.complex128), (wl.hubbard_indexes, (0, 0), np.float64)):
+        ti = wl.heff_tensor_indexes(ixf(90))
+        ref.set_seed(5)
+        lenv = ref.RefTensor.new(ti["lenv"], dtype).random(div)
+        psi = ref.RefTensor.new(ti["psi"], dtype).random(div)
+        tl, tp = lenv.to_bst(), psi.to_bst()
+        steps = [("lenv", "psi", ([0], [0]), "t1")]
+        cost, _, _ = sh.sector_costs({"lenv": tl, "psi": tp}, steps, "lenv", 2, dtype)
+        degs = [int(d) for d in tl.indexes[2].degs()]
+        for world in (2, 5):
+            want_cuts = sh.row_line_cuts(cost, degs, world, snap=8)
+            assert ref.b200_cut_rows(lenv, psi, ([0], [0]), 2, world, 8) == want_cuts
+            for r in range(world):
+                want = sh.restrict_tensor(tl, 2, want_cuts[r])
+                got = ref.b200_row_slab(lenv, 2, want_cuts[r], want.indexes)
+                expect = ref.RefTensor.from_bst(want)
+                assert got.indexes_equal(expect)                       # the reference's own Index comparison
+                g = got.to_bst()
+                assert g.same_structure(want) and np.array_equal(g.data, want.data)
+        for axis in (0, 1):                                            # other axes, arbitrary ranges
+            ranges = [(0, int(d)) if i % 2 else (int(d) // 3, int(d)) for i, d in enumerate(tl.indexes[axis].degs())]
+            want = sh.restrict_tensor(tl, axis, ranges)
+            g = ref.b200_row_slab(lenv, axis, ranges, want.indexes).to_bst()
+            assert g.same_structure(want) and np.array_equal(g.data, want.data)
+
+
 def test_restricted_operand_is_a_row_slice():
     ts = make_tensors(64, np.complex128, 2)
     mine, info = sh.shard_heff_tensors(ts, 4, 1)
